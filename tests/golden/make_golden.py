@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(qutip 5.4.0.dev built into oracle/_ref by oracle/build_ref.py) in this container.
+
+    python tests/golden/make_golden.py
+
+The reference cannot travel to the GPU box's tests as a hard requirement, so its outputs
+on reduced-size versions of BASELINE.json's five configs are committed as small .npz
+files; tests/test_oracle.py pins oracle/ against them and the GPU tests compare the CUDA
+path with them too.  Operators are stored exactly as the reference's constructors built
+them (CSR / Dia arrays), so layouts match SURVEY.md section 8d.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+warnings.filterwarnings("ignore")
+
+import qutip  # noqa: E402
+from qutip import (basis, destroy, liouvillian, mcsolve, mesolve, qeye, sigmam,  # noqa
+                   sigmax, sigmaz, tensor, QobjEvo, operator_to_vector, num)
+from qutip.core import data as _data  # noqa: E402
+
+
+def pack_op(prefix, d, out):
+    """Store a data-layer object under keys prefix_*."""
+    if isinstance(d, _data.CSR):
+        s = d.as_scipy()
+        out[prefix + "_kind"] = "csr"
+        out[prefix + "_data"] = s.data.copy()
+        out[prefix + "_col"] = s.indices.astype(np.int32)
+        out[prefix + "_rowptr"] = s.indptr.astype(np.int32)
+    elif isinstance(d, _data.Dia):
+        s = d.as_scipy()
+        out[prefix + "_kind"] = "dia"
+        out[prefix + "_data"] = s.data.copy()
+        out[prefix + "_offsets"] = s.offsets.astype(np.int32)
+    else:
+        out[prefix + "_kind"] = "dense"
+        out[prefix + "_arr"] = d.to_array()
+    out[prefix + "_shape"] = np.array(d.shape)
+
+
+def tfim(n, gamma=0.1):
+    sx, sz, sm = [], [], []
+    for i in range(n):
+        ops = [qeye(2)] * n
+        ops[i] = sigmax(); sx.append(tensor(ops))
+        ops[i] = sigmaz(); sz.append(tensor(ops))
+        ops[i] = sigmam(); sm.append(tensor(ops))
+    H = 0
+    for i in range(n - 1):
+        H = H - sz[i] * sz[i + 1]
+    for i in range(n):
+        H = H - sx[i]
+    c_ops = [np.sqrt(gamma) * s for s in sm]
+    return H, c_ops, sz
+
+
+def save(name, **kw):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **kw)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+OPT = {"progress_bar": False, "store_states": True}
+
+
+def golden_mesolve(name, H, psi0, tlist, c_ops, e_ops, methods=("vern7", "vern9"), args=None,
+                   force=None):
+    out = {}
+    solver = qutip.MESolver(H if isinstance(H, QobjEvo) else QobjEvo(H, args=args) if
+                            isinstance(H, list) else H, c_ops,
+                            options=dict(OPT, method=methods[0]))
+    rhs = solver.rhs
+    if force is not None:
+        rhs = rhs.to(force)
+    lst = rhs.to_list()
+    nel = 0
+    for el in lst:
+        if isinstance(el, qutip.Qobj):
+            pack_op("el%d" % nel, el.data, out)
+            out["el%d_coeff" % nel] = ""
+        else:
+            pack_op("el%d" % nel, el[0].data, out)
+            # StrCoefficient state: (values..., args, code, names...); conj wraps it
+            out["el%d_coeff" % nel] = describe_coeff(el[1])
+        nel += 1
+    out["n_elements"] = nel
+    out["tlist"] = np.asarray(tlist, dtype=float)
+    rho0 = qutip.ket2dm(psi0) if psi0.isket else psi0
+    out["y0"] = rho0.full().ravel("F")
+    out["n"] = rho0.shape[0]
+    for i, e in enumerate(e_ops):
+        out["eop%d" % i] = e.full()
+    out["n_eops"] = len(e_ops)
+    for m in methods:
+        r = mesolve(H, psi0, tlist, c_ops, e_ops=e_ops, args=args,
+                    options=dict(OPT, method=m))
+        out["states_" + m] = np.array([s.full().ravel("F") for s in r.states])
+        out["expect_" + m] = np.array(r.expect)
+    save(name, **out)
+
+
+def describe_coeff(c):
+    """Text form of a Coefficient for the fixtures: 'str:<expr>|k=v,...' or
+    'conj(<...>)'."""
+    cls = type(c).__name__
+    if cls == "ConjCoefficient":
+        return "conj(" + describe_coeff(c.__reduce__()[2][1]) + ")"
+    if cls.startswith("StrCoefficient"):
+        st = c.__reduce__()
+        # generated class, auto_pickle -> (rebuild, (cls, checksum, state))
+        state = st[2] if len(st) > 2 and st[2] is not None else st[1][2]
+        n = (len(state) - 2) // 2
+        vals, code, names = state[:n], state[n + 1], state[n + 2:]
+        return "str:" + code + "|" + ",".join("%s=%r" % (k, complex(v))
+                                              for k, v in zip(names, vals))
+    raise NotImplementedError(cls)
+
+
+def golden_mcsolve(name, H, c_ops, psi0, tlist, e_ops, ntraj, seed, method="vern7"):
+    out = {}
+    solver = qutip.MCSolver(H, c_ops, options={"progress_bar": False, "method": method,
+                                               "keep_runs_results": True,
+                                               "store_final_state": True})
+    # NB: the reference keeps -iH and every -0.5*n_op as separate constant elements
+    els = solver.rhs().to_list()
+    for i, el in enumerate(els):
+        pack_op("el%d" % i, el.data, out)
+        out["el%d_coeff" % i] = ""
+    out["n_elements"] = len(els)
+    for i, (c, n) in enumerate(zip(solver._c_ops, solver._n_ops)):
+        pack_op("cop%d" % i, c.to_list()[0].data, out)
+        pack_op("nop%d" % i, n.to_list()[0].data, out)
+    out["n_cops"] = len(c_ops)
+    for i, e in enumerate(e_ops):
+        pack_op("eop%d" % i, e.data, out)
+    out["n_eops"] = len(e_ops)
+    out["tlist"] = np.asarray(tlist, dtype=float)
+    out["psi0"] = psi0.full().ravel()
+    ss = np.random.SeedSequence(seed)
+    r = solver.run(psi0, tlist, ntraj=ntraj, e_ops=e_ops, seeds=ss)
+    out["seed"] = seed
+    out["ntraj"] = ntraj
+    out["runs_expect"] = np.array(r.runs_expect)        # [n_e][ntraj][nt]
+    out["avg_expect"] = np.array(r.average_expect)
+    ncol = np.array([len(c) for c in r.col_times])
+    out["col_count"] = ncol
+    out["col_times"] = np.concatenate([np.asarray(c, dtype=float) for c in r.col_times]
+                                      + [np.zeros(0)])
+    out["col_which"] = np.concatenate([np.asarray(c, dtype=np.int64) for c in r.col_which]
+                                      + [np.zeros(0, dtype=np.int64)])
+    out["final_states"] = np.array([s.full().ravel() for s in r.runs_final_states])
+    # thresholds exactly as the reference draws them
+    kids = np.random.SeedSequence(seed).spawn(ntraj)
+    out["draws"] = np.stack([np.random.default_rng(k).random(64) for k in kids])
+    save(name, **out)
+
+
+def golden_matmul():
+    rng = np.random.default_rng(0)
+    out = {}
+    n = 96
+    dense = rng.random((n, n)) + 1j * rng.random((n, n))
+    mask = rng.random((n, n)) < 0.1
+    A = dense * mask
+    csr = _data.to(_data.CSR, _data.Dense(A))
+    # unsorted column indices, as the reference's tests cover
+    s = csr.as_scipy()
+    for r in range(n):
+        lo, hi = s.indptr[r], s.indptr[r + 1]
+        perm = rng.permutation(hi - lo)
+        s.indices[lo:hi] = s.indices[lo:hi][perm]
+        s.data[lo:hi] = s.data[lo:hi][perm]
+    pack_op("csr", csr, out)
+    B = np.zeros((n, n), dtype=complex)
+    for off in (-40, -3, -1, 0, 2, 7, 50):
+        B += np.diag(rng.random(n - abs(off)) + 1j * rng.random(n - abs(off)), off)
+    dia = _data.to(_data.Dia, _data.Dense(B))
+    pack_op("dia", dia, out)
+    pack_op("dense", _data.Dense(dense), out)
+    x = rng.random(n) + 1j * rng.random(n)
+    out["x"] = x
+    xd = _data.Dense(x.reshape(-1, 1))
+    for nm, op in (("csr", csr), ("dia", dia), ("dense", _data.Dense(dense))):
+        for si, sc in enumerate((1.0, 0.5, 0.5j, -0.3 + 0.7j)):
+            pre = np.ones((n, 1), dtype=complex)
+            o = _data.Dense(pre.copy())
+            r = _data.matmul(op, xd, sc)
+            out["%s_mul_s%d" % (nm, si)] = r.to_array().ravel()
+    out["scales"] = np.array([1.0, 0.5, 0.5j, -0.3 + 0.7j])
+    save("matmul", **out)
+
+
+def main():
+    golden_matmul()
+
+    # C1: damped Jaynes-Cummings, cavity N=10 (x) qubit  
+    N = 10
+    a = tensor(destroy(N), qeye(2)); sm = tensor(qeye(N), destroy(2))
+    H = 2 * np.pi * a.dag() * a + 2 * np.pi * sm.dag() * sm \
+        + 2 * np.pi * 0.05 * (a.dag() * sm + a * sm.dag())
+    c_ops = [np.sqrt(0.1) * a, np.sqrt(0.05) * sm]
+    psi0 = tensor(basis(N, 3), basis(2, 0))
+    golden_mesolve("c1_jc", H, psi0, np.linspace(0, 10, 101), c_ops,
+                   [a.dag() * a, tensor(qeye(N), sigmaz())])
+
+    # C2 reduced: dissipative TFIM, 4 spins (L 256^2), CSR from the reference ctor
+    H, c_ops, sz = tfim(4)
+    psi0 = basis([2] * 4, [0] * 4)
+    golden_mesolve("c2_tfim4", H, psi0, np.linspace(0, 1, 11), c_ops, [sz[0]])
+
+    # C3 reduced: mcsolve TFIM 6 spins (dim 64), 24 trajectories, SeedSequence(7)
+    H, c_ops, sz = tfim(6)
+    psi0 = basis([2] * 6, [0] * 6)
+    golden_mcsolve("c3_tfim6_mc", H, c_ops, psi0, np.linspace(0, 2, 21), [sz[0]], 24, 7)
+    # stronger damping -> many jumps per trajectory
+    H, c_ops, sz = tfim(4, gamma=1.5)
+    psi0 = basis([2] * 4, [0] * 4)
+    golden_mcsolve("c3_tfim4_mc_strong", H, c_ops, psi0, np.linspace(0, 3, 16),
+                   [sz[0], sz[1]], 16, 11, method="vern9")
+
+    # C4 reduced: cos-driven cavity 8 (x) transmon 3, string coefficient
+    Nc = 8
+    a = tensor(destroy(Nc), qeye(3)); b = tensor(qeye(Nc), destroy(3))
+    H0 = 5 * a.dag() * a + 4.5 * b.dag() * b - 0.15 * b.dag() * b.dag() * b * b \
+        + 0.1 * (a.dag() * b + a * b.dag())
+    H1 = a + a.dag()
+    args = {"A": 0.2, "w": 5.0}
+    Ht = QobjEvo([H0, [H1, "A*cos(w*t)"]], args=args)
+    c_ops = [np.sqrt(0.01) * a, np.sqrt(0.02) * b, np.sqrt(0.03) * b.dag() * b]
+    psi0 = tensor(basis(Nc, 0), basis(3, 0))
+    golden_mesolve("c4_driven", Ht, psi0, np.linspace(0, 5, 51), c_ops,
+                   [a.dag() * a, b.dag() * b], methods=("vern7",))
+
+    # C5 reduced: driven Kerr N=12, 4 parameter points
+    Nk = 12
+    a = destroy(Nk)
+    for i, (U, D, F) in enumerate([(0.5, 0.2, 0.4), (1.0, -0.5, 0.8), (0.1, 1.0, 0.3),
+                                   (2.0, 0.0, 1.0)]):
+        H = 0.5 * U * a.dag() * a.dag() * a * a - D * a.dag() * a + F * (a + a.dag())
+        golden_mesolve("c5_kerr_%d" % i, H, basis(Nk, 0), np.linspace(0, 10, 21), [a],
+                       [a.dag() * a], methods=("vern7",))
+
+
+if __name__ == "__main__":
+    main()
