@@ -1,0 +1,11 @@
+#!/bin/bash
+# Build libqutip_b200.so for sm_100a (cross-compiles without a GPU).
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2,-pthread ${QB_NVCC_EXTRA}"
+$NVCC $FLAGS -c qb_ops.cu -o qb_ops.o &
+$NVCC $FLAGS -c qb_engine.cu -o qb_engine.o &
+wait
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libqutip_b200.so qb_ops.o qb_engine.o -lcudart
+echo "built $(cd .. && pwd)/libqutip_b200.so"

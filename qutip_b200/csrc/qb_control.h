@@ -1,0 +1,557 @@
+// qb_control.h -- per-trajectory step controller ("scalar unit" of the engine).
+//
+// The engine advances every trajectory by alternating two kernels:
+//   pass kernel  : executes ONE vector instruction (QbPass) per trajectory -- an operator
+//                  application fused with the RK linear combinations and reductions;
+//   control kernel: reduces the partial sums and runs qb_advance() below, which consumes
+//                  the reductions, takes every scalar decision of the reference's
+//                  integrator / Monte-Carlo logic and emits the next QbPass.
+// No host round trip happens between steps.
+//
+// qb_advance() is a flattened, resumable restatement of
+//   Explicit_RungeKutta       qutip/solver/integrator/explicit_rk.pyx:204-467
+//   IntegratorVern7/9 wrapper qutip/solver/integrator/qutip_integrator.py:69-92
+//   MCIntegrator              qutip/solver/mcsolve.py:245-406
+//   Solver.run / _run_one_traj loops  solver_base.py:159-226, multitraj.py:260-283
+// Every label cites the reference lines it mirrors.  The code is host+device so that the
+// control flow can be unit-tested without a GPU (tests/emul); it contains no vector work.
+#pragma once
+#include <math.h>
+#include "qb_types.h"
+#include "qb_coeff.h"
+
+struct QbProgRef { int off, len; };   // len == 0: constant coefficient 1
+
+struct QbCtl {
+    QbTableau tab;
+    QbOptions opt;
+    int N, ntiles;
+    int nelem, ncops, neops, nargs;
+    int eop_functional;         // e_ops are linear functionals (mesolve tr(E rho))
+    int maxcoef;
+    int nt, ndraws;
+    const QbProgRef* elem_prog;  // [nelem]
+    const QbProgRef* cop_prog;   // [ncops]
+    const QbProgRef* nop_prog;   // [ncops]
+    const QbProgRef* eop_prog;   // [neops]
+    const QbInstr* instr;
+    const QbSpline* splines;
+    const double* spool;
+    const qb_c128* args;         // [ntraj][nargs]
+    const double* tlist;         // [nt]
+    const double* draws;         // [ntraj][ndraws]
+    qb_c128* out_expect;         // [ntraj][neops][nt]
+    int* out_ncol;               // [ntraj]
+    double* out_col_t;           // [ntraj][max_collapses]
+    int* out_col_which;          // [ntraj][max_collapses]
+};
+
+// ------------------------------------------------------------------ small helpers
+QB_HD void qb_pass_clear(QbPass& p) {
+    p.kind = QB_PASS_NONE; p.opset = 0; p.op_lo = 0; p.op_hi = 0; p.x = -1; p.zdst = -1;
+    p.dst1 = -1; p.nsrc = 0; p.red = 0; p.out_index = 0; p.zscale = 1.0; p.w1z = 0.0;
+    p.w2z = 0.0;
+}
+// reference iadd_data skips exact-zero factors (explicit_rk.pyx:38-39)
+QB_HD void qb_pass_src(QbPass& p, int slot, double w1, double w2) {
+    if (w1 == 0.0 && w2 == 0.0) return;
+    p.src[p.nsrc] = slot; p.w1[p.nsrc] = w1; p.w2[p.nsrc] = w2; p.nsrc++;
+}
+QB_HD int qb_eval_ref(const QbCtl& g, const QbTraj& c, QbProgRef pr, double t, qb_c128* out) {
+    if (pr.len == 0) { out->re = 1.0; out->im = 0.0; return 0; }
+    return qb_eval_prog(g.instr + pr.off, pr.len, t, g.args + (size_t)c.traj_id * g.nargs,
+                        g.splines, g.spool, out);
+}
+// coefficients of all RHS elements at time t -> coef[0..nelem)
+QB_HD int qb_eval_rhs_coefs(const QbCtl& g, const QbTraj& c, double t, qb_c128* coef) {
+    for (int e = 0; e < g.nelem; e++)
+        if (qb_eval_ref(g, c, g.elem_prog[e], t, &coef[e])) return -1;
+    return 0;
+}
+QB_HD int qb_stage_x(const QbTraj& c, int i, int first) {
+    // stage `first` reads sTA (or y_prev for stage 0); then TB, TA, ... alternate
+    return ((i - first) & 1) ? c.sTB : c.sTA;
+}
+
+// internal labels (not resumable)
+enum {
+    QL_RETURN = 1000, QL_FAIL, QL_SET_BEGIN, QL_SET_DONE, QL_INT_BEGIN, QL_RK_LOOP,
+    QL_STEP_ATTEMPT, QL_STAGE_ISSUE, QL_AFTER_LOOP, QL_DENSE_BEGIN, QL_DENSE_ISSUE,
+    QL_INTERP_ISSUE, QL_INT_DONE, QL_ME_REACHED, QL_ME_NEXT, QL_MC_ENTRY, QL_MC_LOOP,
+    QL_MC_TARGET, QL_RECORD, QL_EXPECT_ISSUE, QL_AFTER_RECORD, QL_RF_LOOP, QL_RF_END,
+    QL_COLLAPSE, QL_APPLY_ISSUE, QL_FINISH
+};
+
+// Run the controller until it has emitted a pass (returns 1), the trajectory finished or
+// paused (returns 0) or failed (returns 0 with c.done < 0).
+//   red   : reductions of the pass just executed (red[0]=|o1|^2, red[1]=wrms sum,
+//           red[2]=|z|^2 ; EXPECT: red[2m], red[2m+1] = <x|O_m|x>)
+//   coef  : per-slot coefficient buffer the next pass will read
+//   probs : per-slot scratch [ncops]
+QB_HD int qb_advance(const QbCtl& g, QbTraj& c, QbPass& p, const double* red,
+                     qb_c128* coef, double* probs)
+{
+    const QbTableau& T = g.tab;
+    const int s = T.s, S = T.S;
+    int L = c.pc;
+    int dense_i = 0, stage_i = 0;
+    double set_t = 0.0;
+    for (int guard = 0; guard < 4096; guard++) {
+        switch (L) {
+        case QB_PC_IDLE:
+            qb_pass_clear(p);
+            return 0;
+
+        // ================================================================ entry points
+        case QB_PC_ME_BEGIN:        // Solver.run: set_state, record t0 (solver_base.py:200-205)
+            c.mode = 0; c.done = 0; c.ncol = 0; c.rng = 0;
+            c.n_rhs = c.n_accept = c.n_reject = c.n_pass = 0;
+            c.set_t = g.tlist[c.tl_idx]; c.set_x = QB_SLOT_INIT; c.set_scale = 1.0;
+            c.after_set = QB_K_ME_START;
+            L = QL_SET_BEGIN; break;
+        case QB_PC_MC_BEGIN: {      // MCIntegrator.set_state (mcsolve.py:245-281)
+            c.mode = 1; c.done = 0; c.ncol = 0; c.rng = 0;
+            c.n_rhs = c.n_accept = c.n_reject = c.n_pass = 0;
+            if (g.opt.no_jump) c.target_norm = 0.0;
+            else {
+                if (c.rng >= g.ndraws) { c.status = QB_ST_RNG_EXHAUSTED; L = QL_FAIL; break; }
+                double u = g.draws[(size_t)c.traj_id * g.ndraws + c.rng++];
+                c.target_norm = u * (1.0 - g.opt.jump_prob_floor) + g.opt.jump_prob_floor;
+            }
+            c.set_t = g.tlist[c.tl_idx]; c.set_x = QB_SLOT_INIT; c.set_scale = 1.0;
+            c.after_set = QB_K_MC_START;
+            L = QL_SET_BEGIN; break;
+        }
+        case QB_PC_ME_NEXT: L = QL_ME_NEXT; break;       // host appended targets
+        case QB_PC_MC_ENTRY: L = QL_MC_ENTRY; break;
+        case QB_PC_STEP_ENTRY:      // Integrator.mcstep(t) from the host (qutip_integrator.py:84-87)
+            c.done = 0;
+            c.int_t = g.tlist[c.tl_idx]; c.int_step = 1; c.after_int = QB_K_PAUSE;
+            L = QL_INT_BEGIN; break;
+
+        // ================================================================ set_initial_value
+        case QL_SET_BEGIN: {        // explicit_rk.pyx:204-230 ; y0 = set_scale * V[set_x]
+            set_t = c.set_t;
+            c.t = c.t_prev = c.t_front = set_t;
+            c.dt_int = 0.0;
+            if (c.set_x == c.sF) { int tmp = c.sP; c.sP = c.sF; c.sF = tmp; }
+            c.sY = c.sF;
+            qb_pass_clear(p);
+            if (g.opt.first_step != 0.0) {          // :227-230, no estimate
+                c.dt_safe = g.opt.first_step;
+                p.kind = QB_PASS_COMBINE; p.dst1 = c.sF; p.red = QB_RED_NORM2_O1;
+                qb_pass_src(p, c.set_x, c.set_scale, 0.0);
+                c.pc = QB_PC_SET_DONE; return 1;
+            }
+            // _estimate_first_step (:232-276), first RHS evaluation k0 = f(t, y0)
+            p.kind = QB_PASS_RHS; p.x = c.set_x; p.zscale = c.set_scale; p.zdst = 0;
+            p.dst1 = c.sF; p.red = QB_RED_NORM2_O1 | QB_RED_NORM2_Z;
+            qb_pass_src(p, c.set_x, c.set_scale, 0.0);
+            if (qb_eval_rhs_coefs(g, c, set_t, coef)) { c.status = QB_ST_BAD_PROGRAM; L = QL_FAIL; break; }
+            c.n_rhs++;
+            c.pc = QB_PC_EST0_DONE; return 1;
+        }
+        case QB_PC_SET_DONE:
+            c.norm2_y = red[0];
+            L = QL_SET_DONE; break;
+        case QB_PC_EST0_DONE: {     // :237-256
+            double norm = sqrt(red[0]);
+            c.norm2_y = red[0];
+            double tol = g.opt.atol + norm * g.opt.rtol;
+            if (norm <= g.opt.atol) norm = 1.0;
+            double tmp_norm = sqrt(red[2]);
+            double fact = 1.0;
+            for (int i = 1; i <= T.order; i++) fact *= i;
+            double dt1;
+            if (tmp_norm >= g.opt.atol * 1e-6)
+                dt1 = pow(tol * fact * pow(norm, (double)T.order), 1.0 / (T.order + 1)) / tmp_norm;
+            else
+                dt1 = pow(tol * fact, 1.0 / (T.order + 1)) * norm * 0.5;
+            c.est_norm = norm; c.est_tol = tol; c.est_dt1 = dt1;
+            // y_temp = y0 + (dt1/100) k0   (:258-261)
+            qb_pass_clear(p);
+            p.kind = QB_PASS_COMBINE; p.dst1 = c.sTB;
+            qb_pass_src(p, c.sF, 1.0, 0.0);
+            qb_pass_src(p, 0, dt1 / 100, 0.0);
+            c.pc = QB_PC_EST1IN_DONE; return 1;
+        }
+        case QB_PC_EST1IN_DONE: {   // k1 = f(t + dt1/100, y_temp)   (:262-263)
+            qb_pass_clear(p);
+            p.kind = QB_PASS_RHS; p.x = c.sTB; p.zdst = 1; p.red = QB_RED_NORM2_Z;
+            if (qb_eval_rhs_coefs(g, c, c.t + c.est_dt1 / 100, coef)) { c.status = QB_ST_BAD_PROGRAM; L = QL_FAIL; break; }
+            c.n_rhs++;
+            c.pc = QB_PC_EST1_DONE; return 1;
+        }
+        case QB_PC_EST1_DONE: {     // :264-276
+            double tmp_norm = sqrt(red[2]);
+            double fact = 1.0;
+            for (int i = 1; i <= T.order; i++) fact *= i;
+            double dt2;
+            if (tmp_norm >= g.opt.atol * 1e-6)
+                dt2 = pow(c.est_tol * fact * pow(c.est_norm, (double)T.order),
+                          1.0 / (T.order + 1)) / tmp_norm;
+            else
+                dt2 = c.est_dt1;
+            double dt = c.est_dt1 < dt2 ? c.est_dt1 : dt2;
+            double min_step = g.opt.min_step != 0.0 ? g.opt.min_step : 1e-15;   // :115
+            if (g.opt.max_step != 0.0 && g.opt.max_step < dt) dt = g.opt.max_step;
+            if (min_step > dt) dt = min_step;
+            c.dt_safe = dt;
+            L = QL_SET_DONE; break;
+        }
+        case QL_SET_DONE:
+            switch (c.after_set) {
+            case QB_K_ME_START: case QB_K_MC_START: L = QL_RECORD; break;   // record tlist[0]
+            case QB_K_MC_AFTER_COLLAPSE:                  // mcsolve.py:297-298
+                c.mc_t_old = c.t; c.mc_n_old = 1.0; L = QL_MC_LOOP; break;
+            default: L = QL_FINISH; break;               // host-driven set_state
+            }
+            break;
+
+        // ================================================================ integrate(t, step)
+        case QL_INT_BEGIN: {        // explicit_rk.pyx:278-310
+            double t = c.int_t;
+            if (t == c.t) { L = QL_INT_DONE; break; }                       // :291
+            if (t < c.t_prev) { c.status = QB_ST_OUTSIDE_RANGE; L = QL_FAIL; break; }   // :294
+            if (g.opt.interpolate && t < c.t_front) {                       // :298-304
+                if (c.status != QB_ST_INTERPOLATED) { L = QL_DENSE_BEGIN; break; }
+                L = QL_INTERP_ISSUE; break;
+            }
+            c.status = QB_ST_NORMAL;
+            if (c.int_step && c.t < c.t_front && t > c.t_front) c.int_t = c.t_front;  // :308-310
+            c.nsteps_left = g.opt.nsteps;
+            L = QL_RK_LOOP; break;
+        }
+        case QL_RK_LOOP:            // while self._t_front < t and self._status >= 0   (:312)
+            if (c.t_front < c.int_t && c.status >= 0) {
+                int tmp = c.sP; c.sP = c.sF; c.sF = tmp;     // y_prev <- y_front (:313), by relabel
+                c.t_prev = c.t_front;
+                c.step_n = 0;
+                L = QL_STEP_ATTEMPT; break;
+            }
+            L = QL_AFTER_LOOP; break;
+        case QL_STEP_ATTEMPT: {     // _step_in_err body (:339-343) + _get_timestep (:440-449)
+            double dt_needed = c.int_t - c.t_prev, dt;
+            if (g.opt.interpolate) dt = c.dt_safe;
+            else if (dt_needed <= c.dt_safe) dt = dt_needed;
+            else dt = dt_needed / ((int)(dt_needed / c.dt_safe) + 1);
+            c.dt_cur = dt;
+            stage_i = 0;
+            L = QL_STAGE_ISSUE; break;
+        }
+        case QL_STAGE_ISSUE: {      // _compute_step (:358-389), one stage per pass
+            const int i = stage_i;
+            const double dt = c.dt_cur;
+            qb_pass_clear(p);
+            p.kind = QB_PASS_RHS;
+            p.x = (i == 0) ? c.sP : qb_stage_x(c, i, 1);
+            p.zdst = i;
+            qb_pass_src(p, c.sP, 1.0, 0.0);
+            if (i < s - 1) {        // epilogue builds the next stage input (:374-375)
+                const int n = i + 1;
+                p.dst1 = qb_stage_x(c, n, 1);
+                for (int j = 0; j < i; j++) qb_pass_src(p, j, dt * T.a[n][j], 0.0);
+                p.w1z = dt * T.a[n][i];
+            } else {                // y_front, error vector (:380-397)
+                p.dst1 = c.sF;
+                for (int j = 0; j < i; j++) qb_pass_src(p, j, dt * T.b[j], dt * T.e[j]);
+                p.w1z = dt * T.b[i]; p.w2z = dt * T.e[i];
+                p.red = QB_RED_NORM2_O1 | QB_RED_WRMS;
+            }
+            if (qb_eval_rhs_coefs(g, c, i == 0 ? c.t_prev : c.t_prev + T.c[i] * dt, coef)) {
+                c.status = QB_ST_BAD_PROGRAM; L = QL_FAIL; break;
+            }
+            c.stage = i; c.n_rhs++;
+            c.pc = QB_PC_STAGE_DONE; return 1;
+        }
+        case QB_PC_STAGE_DONE: {
+            if (c.stage < s - 1) { stage_i = c.stage + 1; L = QL_STAGE_ISSUE; break; }
+            // step finished: error, controller (:341-352, :451-467)
+            const double dt = c.dt_cur;
+            const double err = sqrt(red[1] / (double)g.N);
+            c.t_front = c.t_prev + dt;
+            c.dt_int = dt;
+            c.norm2_front = red[0];
+            double factor;
+            if (err == 0.0) factor = 10.0;
+            else {
+                factor = 0.9 * pow(err, -1.0 / (T.order + 1));
+                if (factor > 10.0) factor = 10.0;
+                if (factor < 0.2) factor = 0.2;
+            }
+            double min_step = g.opt.min_step != 0.0 ? g.opt.min_step : 1e-15;
+            double dts = dt * factor;
+            if (g.opt.max_step != 0.0 && g.opt.max_step < dts) dts = g.opt.max_step;
+            if (min_step > dts) dts = min_step;
+            c.dt_safe = dts;
+            if (err >= 1.0) c.n_reject++; else c.n_accept++;
+            bool stop = false;
+            if (dt == min_step && err > 1.0) { c.status = QB_ST_DT_UNDERFLOW; stop = true; }
+            else {
+                c.step_n++;
+                if (c.step_n > c.nsteps_left) { c.status = QB_ST_TOO_MUCH_WORK; stop = true; }
+            }
+            if (!stop && err >= 1.0) { L = QL_STEP_ATTEMPT; break; }   // while error >= 1
+            c.nsteps_left -= c.step_n;                                  // :315
+            L = c.int_step ? QL_AFTER_LOOP : QL_RK_LOOP;                // :317-318
+            break;
+        }
+        case QL_AFTER_LOOP:         // :320-331
+            if (c.status < 0) { L = QL_FAIL; break; }
+            if (c.t_front > c.int_t) { L = QL_DENSE_BEGIN; break; }
+            c.status = QB_ST_AT_FRONT;
+            c.t = c.t_front; c.sY = c.sF; c.norm2_y = c.norm2_front;
+            L = QL_INT_DONE; break;
+
+        // ---------------------------------------------------------------- dense output
+        case QL_DENSE_BEGIN: {      // _prep_dense_out (:399-410), input of the first extra stage
+            if (S == s) { c.status = QB_ST_INTERPOLATED; L = QL_INTERP_ISSUE; break; }
+            const double dt = c.dt_int;
+            qb_pass_clear(p);
+            p.kind = QB_PASS_COMBINE; p.dst1 = c.sTA;
+            qb_pass_src(p, c.sP, 1.0, 0.0);
+            for (int j = 0; j < s; j++) qb_pass_src(p, j, dt * T.a[s][j], 0.0);
+            c.pc = QB_PC_DENSEIN_DONE; return 1;
+        }
+        case QB_PC_DENSEIN_DONE: dense_i = s; L = QL_DENSE_ISSUE; break;
+        case QL_DENSE_ISSUE: {
+            const int i = dense_i;
+            const double dt = c.dt_int;
+            qb_pass_clear(p);
+            p.kind = QB_PASS_RHS; p.x = qb_stage_x(c, i, s); p.zdst = i;
+            qb_pass_src(p, c.sP, 1.0, 0.0);
+            if (i < S - 1) {
+                const int n = i + 1;
+                p.dst1 = qb_stage_x(c, n, s);
+                for (int j = 0; j < i; j++) qb_pass_src(p, j, dt * T.a[n][j], 0.0);
+                p.w1z = dt * T.a[n][i];
+            } else {                // last extra stage: fuse _interpolate_step(int_t) (:412-430)
+                const double tau = (c.int_t - c.t_prev) / dt;
+                p.dst1 = c.sI; p.red = QB_RED_NORM2_O1;
+                for (int j = 0; j < S; j++) {
+                    double bf = 0.0;
+                    for (int q = T.dense_order - 1; q >= 0; q--) { bf += T.bi[j][q]; bf *= tau; }
+                    if (j < i) qb_pass_src(p, j, dt * bf, 0.0); else p.w1z = dt * bf;
+                }
+            }
+            if (qb_eval_rhs_coefs(g, c, c.t_prev + T.c[i] * dt, coef)) {
+                c.status = QB_ST_BAD_PROGRAM; L = QL_FAIL; break;
+            }
+            c.stage = i; c.n_rhs++;
+            c.pc = QB_PC_DENSE_DONE; return 1;
+        }
+        case QB_PC_DENSE_DONE:
+            if (c.stage < S - 1) { dense_i = c.stage + 1; L = QL_DENSE_ISSUE; break; }
+            c.status = QB_ST_INTERPOLATED;
+            c.t = c.int_t; c.sY = c.sI; c.norm2_y = red[0];
+            L = QL_INT_DONE; break;
+        case QL_INTERP_ISSUE: {     // _interpolate_step (:412-430) with k already complete
+            const double dt = c.dt_int;
+            const double tau = (c.int_t - c.t_prev) / dt;
+            qb_pass_clear(p);
+            p.kind = QB_PASS_COMBINE; p.dst1 = c.sI; p.red = QB_RED_NORM2_O1;
+            qb_pass_src(p, c.sP, 1.0, 0.0);
+            for (int j = 0; j < S; j++) {
+                double bf = 0.0;
+                for (int q = T.dense_order - 1; q >= 0; q--) { bf += T.bi[j][q]; bf *= tau; }
+                qb_pass_src(p, j, dt * bf, 0.0);
+            }
+            c.pc = QB_PC_INTERP_DONE; return 1;
+        }
+        case QB_PC_INTERP_DONE:
+            c.status = QB_ST_INTERPOLATED;
+            c.t = c.int_t; c.sY = c.sI; c.norm2_y = red[0];
+            L = QL_INT_DONE; break;
+
+        case QL_INT_DONE:
+            switch (c.after_int) {
+            case QB_K_ME_REACHED: L = QL_RECORD; break;
+            case QB_K_MC_AFTER_STEP: {      // mcsolve.py:290-300
+                const double norm = c.norm2_y;
+                if (norm <= c.target_norm) {
+                    c.rf_n_old = c.mc_n_old; c.rf_n = norm;
+                    c.rf_t_prev = c.mc_t_old; c.rf_t_final = c.t;
+                    c.rf_tries = 0;
+                    L = QL_RF_LOOP;
+                } else {
+                    c.mc_t_old = c.t; c.mc_n_old = norm;
+                    L = QL_MC_LOOP;
+                }
+                break;
+            }
+            case QB_K_RF_AFTER_GUESS: {     // mcsolve.py:348-361
+                const double n2 = c.norm2_y;
+                if (fabs(c.target_norm - n2) < g.opt.norm_tol * c.target_norm) { L = QL_RF_END; break; }
+                if (n2 < c.target_norm) { c.rf_t_final = c.rf_t_guess; c.rf_n = n2; }
+                else { c.rf_t_prev = c.rf_t_guess; c.rf_n_old = n2; }
+                L = QL_RF_LOOP; break;
+            }
+            default: L = QL_FINISH; break;
+            }
+            break;
+
+        // ================================================================ mesolve driver
+        case QL_ME_NEXT:            // for t in tlist[1:]: integrate(t)   (integrator.py:197-212)
+            if (c.tl_idx >= c.tl_end) { L = QL_FINISH; break; }
+            c.done = 0;
+            c.int_t = g.tlist[c.tl_idx]; c.int_step = 0; c.after_int = QB_K_ME_REACHED;
+            L = QL_INT_BEGIN; break;
+
+        // ---- record the state at tlist[tl_idx]: e_ops, optional stored state ----
+        case QL_RECORD:
+            c.exp_set = QB_OPSET_EOPS; c.exp_lo = 0; c.expect_mode = 0; c.exp_t = c.t;
+            if (g.neops > 0) { L = QL_EXPECT_ISSUE; break; }
+            L = QL_AFTER_RECORD; break;
+        case QL_EXPECT_ISSUE: {
+            const int nops = (c.exp_set == QB_OPSET_EOPS) ? g.neops : g.ncops;
+            qb_pass_clear(p);
+            p.kind = QB_PASS_EXPECT; p.opset = c.exp_set; p.x = c.sY;
+            p.op_lo = c.exp_lo;
+            p.op_hi = (c.exp_lo + QB_MAXRED / 2 < nops) ? c.exp_lo + QB_MAXRED / 2 : nops;
+            c.pc = QB_PC_EXPECT_DONE; return 1;
+        }
+        case QB_PC_EXPECT_DONE: {
+            const int nops = (c.exp_set == QB_OPSET_EOPS) ? g.neops : g.ncops;
+            const int lo = c.exp_lo;
+            const int hi = (lo + QB_MAXRED / 2 < nops) ? lo + QB_MAXRED / 2 : nops;
+            bool bad = false;
+            for (int m = lo; m < hi; m++) {
+                qb_c128 v, cf; v.re = red[2 * (m - lo)]; v.im = red[2 * (m - lo) + 1];
+                QbProgRef pr = (c.exp_set == QB_OPSET_EOPS) ? g.eop_prog[m] : g.nop_prog[m];
+                if (qb_eval_ref(g, c, pr, c.exp_t, &cf)) { bad = true; break; }
+                v = qb_cmul(cf, v);
+                if (c.expect_mode == 0) {
+                    // mcsolve returns y/||y|| (mcsolve.py:302); tlist[0] is recorded as given
+                    if (c.mode == 1 && c.tl_idx > 0) { v.re /= c.norm2_y; v.im /= c.norm2_y; }
+                    g.out_expect[((size_t)c.traj_id * g.neops + m) * g.nt + c.tl_idx] = v;
+                } else {
+                    probs[m] = v.re;        // mcsolve.py:384-387
+                }
+            }
+            if (bad) { c.status = QB_ST_BAD_PROGRAM; L = QL_FAIL; break; }
+            c.exp_lo = hi;
+            if (hi < nops) { L = QL_EXPECT_ISSUE; break; }
+            L = (c.expect_mode == 0) ? QL_AFTER_RECORD : QL_APPLY_ISSUE;
+            break;
+        }
+        case QL_AFTER_RECORD:
+            if (g.opt.store_states) {
+                qb_pass_clear(p);
+                p.kind = QB_PASS_COMBINE; p.dst1 = QB_SLOT_OUT; p.out_index = c.tl_idx;
+                double sc = 1.0;
+                if (c.mode == 1 && c.tl_idx > 0) sc = 1.0 / sqrt(c.norm2_y);
+                qb_pass_src(p, c.sY, sc, 0.0);
+                c.pc = QB_PC_STORE_DONE; return 1;
+            }
+            /* fallthrough */
+        case QB_PC_STORE_DONE:
+            c.tl_idx++;
+            L = (c.mode == 0) ? QL_ME_NEXT : QL_MC_ENTRY;
+            break;
+
+        // ================================================================ mcsolve driver
+        case QL_MC_ENTRY:           // MCIntegrator.integrate(t)   (mcsolve.py:286-289)
+            if (c.tl_idx >= c.tl_end) { L = QL_FINISH; break; }
+            c.done = 0;
+            c.mc_t_old = c.t; c.mc_n_old = c.norm2_y;
+            L = QL_MC_LOOP; break;
+        case QL_MC_LOOP:            // while t_old < t   (:289)
+            if (c.mc_t_old < g.tlist[c.tl_idx]) {
+                c.int_t = g.tlist[c.tl_idx]; c.int_step = 1; c.after_int = QB_K_MC_AFTER_STEP;
+                L = QL_INT_BEGIN; break;
+            }
+            L = QL_RECORD; break;   // return t_old, y_old/||y_old||   (:302)
+
+        // ---------------------------------------------------------------- _find_collapse_time
+        case QL_RF_LOOP: {          // mcsolve.py:321-347
+            if (c.rf_tries >= g.opt.norm_steps) { L = QL_RF_END; break; }
+            c.rf_tries++;
+            if ((c.rf_t_final - c.rf_t_prev) < g.opt.norm_t_tol) {
+                c.rf_t_guess = c.rf_t_final;      // state = integrator.get_state()
+                L = QL_RF_END; break;
+            }
+            const double dt = c.rf_t_final - c.rf_t_prev;
+            double ratio = log(c.rf_n_old / c.target_norm) / log(c.rf_n_old / c.rf_n);
+            if (ratio < g.opt.norm_min_step) ratio = g.opt.norm_min_step;
+            if (ratio > (1.0 - g.opt.norm_min_step)) ratio = 1.0 - g.opt.norm_min_step;
+            double t_guess = c.rf_t_prev + dt * ratio;
+            if ((t_guess - c.rf_t_prev) < g.opt.norm_t_tol) t_guess = c.rf_t_prev + g.opt.norm_t_tol;
+            c.rf_t_guess = t_guess;
+            c.int_t = t_guess; c.int_step = 1; c.after_int = QB_K_RF_AFTER_GUESS;
+            L = QL_INT_BEGIN; break;
+        }
+        case QL_RF_END:             // :363-369
+            if (c.rf_tries >= g.opt.norm_steps) { c.status = QB_ST_ROOTFIND_FAILED; L = QL_FAIL; break; }
+            L = QL_COLLAPSE; break;
+
+        // ---------------------------------------------------------------- _do_collapse
+        case QL_COLLAPSE:           // mcsolve.py:371-392 ; state = V[sY], time = rf_t_guess
+            if (g.ncops == 1) { c.which = 0; L = QL_APPLY_ISSUE; c.expect_mode = 2; break; }
+            c.exp_set = QB_OPSET_NOPS; c.exp_lo = 0; c.expect_mode = 1;
+            // n_ops are evaluated at the collapse time (expect_data(collapse_time, state))
+            c.exp_t = c.rf_t_guess;
+            L = QL_EXPECT_ISSUE; break;
+        case QL_APPLY_ISSUE: {
+            if (c.expect_mode == 1) {       // choose the operator (:388-392)
+                if (c.rng >= g.ndraws) { c.status = QB_ST_RNG_EXHAUSTED; L = QL_FAIL; break; }
+                const double u = g.draws[(size_t)c.traj_id * g.ndraws + c.rng++];
+                double sum = 0.0;
+                for (int k = 0; k < g.ncops; k++) sum += probs[k];   // python sum(), left to right
+                double target = sum * u - probs[0];
+                int which = 0;
+                bool bad = false;
+                while (target > 0.0 && which <= g.ncops) {
+                    which++;
+                    if (which >= g.ncops) { bad = true; break; }      // reference: IndexError
+                    target -= probs[which];
+                }
+                if (bad) { c.status = QB_ST_COLLAPSE_INDEX; L = QL_FAIL; break; }
+                c.which = which;
+            }
+            qb_pass_clear(p);
+            p.kind = QB_PASS_APPLY; p.opset = QB_OPSET_COPS; p.op_lo = c.which; p.op_hi = c.which + 1;
+            p.x = c.sY; p.zdst = c.sTA; p.red = QB_RED_NORM2_Z;
+            if (qb_eval_ref(g, c, g.cop_prog[c.which], c.rf_t_guess, &coef[0])) {
+                c.status = QB_ST_BAD_PROGRAM; L = QL_FAIL; break;
+            }
+            c.pc = QB_PC_APPLY_DONE; return 1;
+        }
+        case QB_PC_PROBS_DONE: L = QL_FAIL; c.status = QB_ST_BAD_PROGRAM; break;   // unused
+        case QB_PC_APPLY_DONE: {    // mcsolve.py:394-406
+            const double new_norm = sqrt(red[2]);
+            if (new_norm < g.opt.mc_corr_eps) {
+                // numerical-error collapse: keep the state, renormalise, no record, no draw
+                c.set_x = c.sY; c.set_scale = 1.0 / sqrt(c.norm2_y);
+            } else {
+                c.set_x = c.sTA; c.set_scale = 1.0 / new_norm;
+                if (c.ncol >= g.opt.max_collapses) { c.status = QB_ST_TOO_MANY_COLLAPSES; L = QL_FAIL; break; }
+                g.out_col_t[(size_t)c.traj_id * g.opt.max_collapses + c.ncol] = c.rf_t_guess;
+                g.out_col_which[(size_t)c.traj_id * g.opt.max_collapses + c.ncol] = c.which;
+                c.ncol++;
+                if (c.rng >= g.ndraws) { c.status = QB_ST_RNG_EXHAUSTED; L = QL_FAIL; break; }
+                c.target_norm = g.draws[(size_t)c.traj_id * g.ndraws + c.rng++];
+            }
+            c.set_t = c.rf_t_guess;
+            c.after_set = QB_K_MC_AFTER_COLLAPSE;
+            L = QL_SET_BEGIN; break;
+        }
+
+        // ================================================================ exits
+        case QL_FINISH:
+            qb_pass_clear(p);
+            c.pc = QB_PC_IDLE; c.done = 1;
+            if (c.mode == 1) g.out_ncol[c.traj_id] = c.ncol;
+            return 0;
+        case QL_FAIL:
+        default:
+            qb_pass_clear(p);
+            if (L != QL_FAIL) c.status = QB_ST_BAD_PROGRAM;
+            c.pc = QB_PC_IDLE; c.done = c.status < 0 ? c.status : QB_ST_BAD_PROGRAM;
+            if (c.mode == 1 && g.out_ncol) g.out_ncol[c.traj_id] = c.ncol;
+            return 0;
+        }
+    }
+    qb_pass_clear(p);
+    c.pc = QB_PC_IDLE; c.done = QB_ST_BAD_PROGRAM;
+    return 0;
+}

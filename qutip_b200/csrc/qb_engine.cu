@@ -1,0 +1,801 @@
+// qb_engine.cu -- fused evolution engine: pass kernel (vector unit), control kernel
+// (scalar unit, qb_control.h) and the host driver behind the C ABI.
+//
+// Data layout in HBM
+//   pool[nslots][V][N] complex128 : per trajectory slot V = S + 5 state-sized vectors:
+//       k[0..S-1] (RK stage derivatives), y_prev, y_front, y_interp, tmpA, tmpB.
+//       "y_prev <- y_front" etc. are slot relabels in QbTraj, never copies.
+//   pass[nslots], traj[nslots]    : the next vector instruction and the controller state
+//   partials[nslots][ntiles][64]  : per-CTA partial reductions, summed in a fixed order
+// A "round" = pass kernel + control kernel; the host enqueues rounds back to back and only
+// looks at a device counter every chunk, so there is no host synchronisation per step.
+#include <algorithm>
+#include <string.h>
+#include <vector>
+#include "qb_host.h"
+#include "qb_kernels.cuh"
+#include "qb_tableaux.h"
+
+struct QbEngineDev {
+    QbCtl ctl;
+    QbOpDev elem[QB_MAX_ELEMS];
+    const QbOpDev* cops;
+    const QbOpDev* nops;
+    const QbOpDev* eops;
+    double2* pool;
+    int V, nslots;
+    const double2* init_states;
+    const int* init_map;
+    double2* out_states;
+    QbTraj* traj;
+    QbPass* pass;
+    qb_c128* coef;
+    double* probs;
+    double* partials;
+    int* queue_head;       // next trajectory id to start
+    int* n_active;         // slots still working
+    int ntraj_total;
+    int mode;
+    int* out_status;
+    int* out_stats;
+};
+
+// ------------------------------------------------------------------ pass kernel
+__device__ __forceinline__ const double2* qb_vsrc(const QbEngineDev* E, int slot, int idx,
+                                                  int init_idx) {
+    if (idx >= 0) return E->pool + ((size_t)slot * E->V + idx) * (size_t)E->ctl.N;
+    return E->init_states + (size_t)init_idx * (size_t)E->ctl.N;
+}
+
+__global__ void __launch_bounds__(QB_TILE_ROWS)
+qb_pass_kernel(const QbEngineDev* __restrict__ E)
+{
+    const int ntiles = E->ctl.ntiles;
+    const int slot = blockIdx.x / ntiles;
+    const int tile = blockIdx.x - slot * ntiles;
+    const QbPass* gp = &E->pass[slot];
+    if (gp->kind == QB_PASS_NONE) return;
+
+    __shared__ QbPass sp;
+    __shared__ double2 scoef[QB_MAX_ELEMS];
+    __shared__ double sred[QB_TILE_ROWS / 32][QB_MAXRED];
+    __shared__ int s_ids[2];
+    {
+        const int nw = (int)(sizeof(QbPass) / sizeof(int));
+        const int* src = reinterpret_cast<const int*>(gp);
+        int* dst = reinterpret_cast<int*>(&sp);
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+        if (threadIdx.x < QB_MAX_ELEMS) {
+            const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef +
+                                      (threadIdx.x < E->ctl.maxcoef ? threadIdx.x : 0)];
+            scoef[threadIdx.x] = make_double2(c.re, c.im);
+        }
+        if (threadIdx.x == 0) { s_ids[0] = E->traj[slot].init_idx; s_ids[1] = E->traj[slot].traj_id; }
+    }
+    __syncthreads();
+
+    const int N = E->ctl.N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sl = tile * (QB_TILE_ROWS / 32) + warp;
+    const long long r = (long long)sl * 32 + lane;
+    const bool active = r < N;
+    const bool slice_ok = (long long)sl * 32 < N;
+    const int kind = sp.kind;
+    const int init_idx = s_ids[0];
+
+    if (kind == QB_PASS_EXPECT) {
+        const QbOpDev* ops = (sp.opset == QB_OPSET_EOPS) ? E->eops : E->nops;
+        const bool functional = (sp.opset == QB_OPSET_EOPS) && E->ctl.eop_functional;
+        const double2* x = qb_vsrc(E, slot, sp.x, init_idx);
+        double2 xr = make_double2(0.0, 0.0);
+        if (active) xr = x[r];
+        const int nops = sp.op_hi - sp.op_lo;
+        for (int m = 0; m < nops; m++) {
+            double2 q = make_double2(0.0, 0.0);
+            if (slice_ok) q = qb_rowdot(ops[sp.op_lo + m], sl, lane, r, active, x);
+            double2 pr;
+            if (functional) pr = q;
+            else pr = make_double2(xr.x * q.x + xr.y * q.y, xr.x * q.y - xr.y * q.x);  // conj(x)*q
+            if (!active) pr = make_double2(0.0, 0.0);
+            const double sre = qb_warp_sum(pr.x), sim = qb_warp_sum(pr.y);
+            if (lane == 0) { sred[warp][2 * m] = sre; sred[warp][2 * m + 1] = sim; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * nops) {
+            double s = 0.0;
+            for (int w = 0; w < QB_TILE_ROWS / 32; w++) s += sred[w][threadIdx.x];
+            E->partials[((size_t)slot * ntiles + tile) * QB_MAXRED + threadIdx.x] = s;
+        }
+        return;
+    }
+
+    // ---- operator application ----
+    double2 z = make_double2(0.0, 0.0);
+    if (slice_ok && (kind == QB_PASS_RHS || kind == QB_PASS_APPLY)) {
+        const double2* x = qb_vsrc(E, slot, sp.x, init_idx);
+        if (kind == QB_PASS_RHS) {
+            const int nelem = E->ctl.nelem;
+            for (int e = 0; e < nelem; e++) {
+                const double2 q = qb_rowdot(E->elem[e], sl, lane, r, active, x);
+                const double2 c = scoef[e];
+                z.x += c.x * q.x - c.y * q.y;
+                z.y += c.x * q.y + c.y * q.x;
+            }
+        } else {
+            const double2 q = qb_rowdot(E->cops[sp.op_lo], sl, lane, r, active, x);
+            const double2 c = scoef[0];
+            z.x = c.x * q.x - c.y * q.y;
+            z.y = c.x * q.y + c.y * q.x;
+        }
+        z.x *= sp.zscale; z.y *= sp.zscale;
+    }
+
+    // ---- fused linear combinations, stores, reductions ----
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    if (active) {
+        const size_t N_ = (size_t)N;
+        double2* base = E->pool + (size_t)slot * E->V * N_;
+        if (sp.zdst >= 0) base[(size_t)sp.zdst * N_ + r] = z;
+        double2 o1 = make_double2(0.0, 0.0), o2 = make_double2(0.0, 0.0);
+        const int nsrc = sp.nsrc;
+        for (int i = 0; i < nsrc; i++) {
+            const double2 v = qb_vsrc(E, slot, sp.src[i], init_idx)[r];
+            const double a = sp.w1[i], b = sp.w2[i];
+            o1.x = fma(a, v.x, o1.x); o1.y = fma(a, v.y, o1.y);
+            o2.x = fma(b, v.x, o2.x); o2.y = fma(b, v.y, o2.y);
+        }
+        o1.x = fma(sp.w1z, z.x, o1.x); o1.y = fma(sp.w1z, z.y, o1.y);
+        o2.x = fma(sp.w2z, z.x, o2.x); o2.y = fma(sp.w2z, z.y, o2.y);
+        if (sp.dst1 >= 0) base[(size_t)sp.dst1 * N_ + r] = o1;
+        else if (sp.dst1 == QB_SLOT_OUT)
+            E->out_states[((size_t)s_ids[1] * E->ctl.nt + sp.out_index) * N_ + r] = o1;
+        const double n1 = o1.x * o1.x + o1.y * o1.y;
+        r0 = n1;
+        if (sp.red & QB_RED_WRMS) {
+            const double q = sqrt(o2.x * o2.x + o2.y * o2.y)
+                             / (E->ctl.opt.atol + E->ctl.opt.rtol * sqrt(n1));
+            r1 = q * q;
+        }
+        r2 = z.x * z.x + z.y * z.y;
+    }
+    if (sp.red) {
+        r0 = qb_warp_sum(r0); r1 = qb_warp_sum(r1); r2 = qb_warp_sum(r2);
+        if (lane == 0) { sred[warp][0] = r0; sred[warp][1] = r1; sred[warp][2] = r2; }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double s = 0.0;
+            for (int w = 0; w < QB_TILE_ROWS / 32; w++) s += sred[w][threadIdx.x];
+            E->partials[((size_t)slot * ntiles + tile) * QB_MAXRED + threadIdx.x] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ control kernel
+__device__ void qb_start_traj(QbEngineDev* E, QbTraj& c, int traj_id) {
+    const int S = E->ctl.tab.S;
+    c.traj_id = traj_id;
+    c.init_idx = E->init_map ? E->init_map[traj_id] : 0;
+    c.mode = E->mode;
+    c.tl_idx = 0; c.tl_end = E->ctl.nt;
+    c.sP = S; c.sF = S + 1; c.sI = S + 2; c.sTA = S + 3; c.sTB = S + 4; c.sY = S + 1;
+    c.status = QB_ST_NORMAL; c.done = 0;
+    c.pc = E->mode ? QB_PC_MC_BEGIN : QB_PC_ME_BEGIN;
+}
+
+__global__ void __launch_bounds__(128)
+qb_control_kernel(QbEngineDev* __restrict__ E)
+{
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (slot >= E->nslots) return;
+    QbTraj* gc = &E->traj[slot];
+    if (gc->pc == QB_PC_IDLE) return;
+    QbPass* gp = &E->pass[slot];
+    __shared__ double sred[4][QB_MAXRED];
+
+    const int kind = gp->kind;
+    int nred = 0;
+    if (kind == QB_PASS_EXPECT) nred = 2 * (gp->op_hi - gp->op_lo);
+    else if (kind != QB_PASS_NONE && gp->red) nred = 3;
+    const int ntiles = E->ctl.ntiles;
+    for (int k = 0; k < nred; k++) {
+        double s = 0.0;
+        for (int tile = lane; tile < ntiles; tile += 32)
+            s += E->partials[((size_t)slot * ntiles + tile) * QB_MAXRED + k];
+        s = qb_warp_sum(s);
+        if (lane == 0) sred[w][k] = s;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+
+    QbTraj c = *gc;
+    QbPass p;
+    qb_c128* coef = E->coef + (size_t)slot * E->ctl.maxcoef;
+    double* probs = E->probs + (size_t)slot * (E->ctl.ncops > 0 ? E->ctl.ncops : 1);
+    for (;;) {
+        const int issued = qb_advance(E->ctl, c, p, sred[w], coef, probs);
+        if (issued) { c.n_pass++; break; }
+        // finished, paused or failed
+        if (E->out_status && c.traj_id >= 0) E->out_status[c.traj_id] = c.done;
+        if (E->out_stats && c.traj_id >= 0) {
+            int* st = E->out_stats + (size_t)c.traj_id * 4;
+            st[0] = c.n_rhs; st[1] = c.n_accept; st[2] = c.n_reject; st[3] = c.n_pass;
+        }
+        int next = E->ntraj_total;
+        if (E->queue_head) next = atomicAdd(E->queue_head, 1);
+        if (next >= E->ntraj_total) { atomicSub(E->n_active, 1); break; }
+        qb_start_traj(E, c, next);
+    }
+    *gc = c;
+    *gp = p;
+}
+
+// one RHS evaluation on plain device vectors (micro-benchmark / data-layer matmul of a
+// whole QobjEvo): out = sum_k coef_k A_k x
+__global__ void __launch_bounds__(QB_TILE_ROWS)
+qb_rhs_kernel(const QbEngineDev* __restrict__ E, const double2* __restrict__ x,
+              double2* __restrict__ out, const qb_c128* __restrict__ coef)
+{
+    const int N = E->ctl.N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sl = blockIdx.x * (QB_TILE_ROWS / 32) + warp;
+    const long long r = (long long)sl * 32 + lane;
+    if ((long long)sl * 32 >= N) return;
+    const bool active = r < N;
+    double2 z = make_double2(0.0, 0.0);
+    for (int e = 0; e < E->ctl.nelem; e++) {
+        const double2 q = qb_rowdot(E->elem[e], sl, lane, r, active, x);
+        const qb_c128 c = coef[e];
+        z.x += c.re * q.x - c.im * q.y;
+        z.y += c.re * q.y + c.im * q.x;
+    }
+    if (active) out[r] = z;
+}
+
+// sum over trajectories: sums[0][e][t] = sum_j v, sums[1][e][t] = sum_j (re^2, im^2)
+__global__ void qb_reduce_expect_kernel(const double2* __restrict__ ex, long long ntraj,
+                                        int n, double2* __restrict__ sums)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double2 s = make_double2(0.0, 0.0), s2 = make_double2(0.0, 0.0);
+    for (long long j = 0; j < ntraj; j++) {
+        const double2 v = ex[(size_t)j * n + i];
+        s.x += v.x; s.y += v.y; s2.x += v.x * v.x; s2.y += v.y * v.y;
+    }
+    sums[i] = s; sums[n + i] = s2;
+}
+
+// ================================================================== host side
+struct QbEngH : QbObj {
+    QbSysH* sys = nullptr;
+    int tableau = 0, nslots = 0, V = 0;
+    QbOptions opt;
+    QbEngineDev h;                 // host mirror of the device descriptor
+    QbEngineDev* d = nullptr;
+    std::vector<void*> owned;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int* h_active = nullptr;       // pinned
+    // buffers re-allocated per run when sizes change
+    void* d_tlist = nullptr; int cap_nt = 0;
+    void* d_init = nullptr; size_t cap_init = 0;
+    void* d_args = nullptr; size_t cap_args = 0;
+    long long last_rounds = 0;
+    double last_ms = 0.0;
+    int maxcoef = 1;
+    QbEngH() : QbObj(QB_TAG_ENG) { memset(&h, 0, sizeof h); }
+    ~QbEngH() override {
+        for (void* p : owned) cudaFree(p);
+        if (d_tlist) cudaFree(d_tlist);
+        if (d_init) cudaFree(d_init);
+        if (d_args) cudaFree(d_args);
+        if (h_active) cudaFreeHost(h_active);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+template <class T> static int qb_dev_array(QbEngH* e, const std::vector<T>& v, const T** out) {
+    *out = nullptr;
+    if (v.empty()) return QB_OK;
+    void* p = nullptr;
+    QB_CUDA(cudaMalloc(&p, v.size() * sizeof(T)));
+    e->owned.push_back(p);
+    QB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T*>(p);
+    return QB_OK;
+}
+template <class T> static int qb_dev_alloc(QbEngH* e, size_t n, T** out, bool zero = true) {
+    void* p = nullptr;
+    if (n == 0) n = 1;
+    QB_CUDA(cudaMalloc(&p, n * sizeof(T)));
+    e->owned.push_back(p);
+    if (zero) QB_CUDA(cudaMemset(p, 0, n * sizeof(T)));
+    *out = static_cast<T*>(p);
+    return QB_OK;
+}
+
+extern "C" int qb_options_default(qb_options* o) {
+    if (!o) QB_FAIL(QB_E_ARG, "null options");
+    o->atol = 1e-8; o->rtol = 1e-6; o->nsteps = 1000;
+    o->first_step = 0; o->min_step = 0; o->max_step = 0; o->interpolate = 1;
+    o->norm_steps = 25; o->norm_t_tol = 1e-6; o->norm_tol = 1e-4; o->norm_min_step = 0.1;
+    o->mc_corr_eps = 1e-10; o->store_states = 0; o->max_collapses = 64; o->no_jump = 0;
+    o->jump_prob_floor = 0.0;
+    return QB_OK;
+}
+
+// ---- system ----
+extern "C" int qb_system_create(int64_t N, int nargs, qb_handle* out) {
+    if (N <= 0 || N > 0x7fffffff || nargs < 0 || !out) QB_FAIL(QB_E_ARG, "bad system size");
+    QbSysH* s = new QbSysH();
+    s->N = N; s->nargs = nargs;
+    *out = s;
+    return QB_OK;
+}
+static int qb_get_opdev(qb_handle op, int64_t N, QbOpDev* out) {
+    if (QbOpH* o = qb_cast<QbOpH>(op, QB_TAG_OP)) {
+        if (o->dev.nrows != N || o->dev.ncols != N)
+            QB_FAIL(QB_E_SHAPE, "incompatible matrix shapes (%d, %d) and (%lld, 1)",
+                    o->dev.nrows, o->dev.ncols, (long long)N);
+        *out = o->dev; return QB_OK;
+    }
+    if (QbDenseH* dn = qb_cast<QbDenseH>(op, QB_TAG_DENSE)) {
+        if (dn->rows != N || dn->cols != N)
+            QB_FAIL(QB_E_SHAPE, "incompatible matrix shapes (%lld, %lld) and (%lld, 1)",
+                    (long long)dn->rows, (long long)dn->cols, (long long)N);
+        if (!dn->fortran) QB_FAIL(QB_E_TYPE, "dense operators must be column-major (fortran)");
+        memset(out, 0, sizeof *out);
+        out->fmt = QB_FMT_DENSE; out->nrows = (int)N; out->ncols = (int)N;
+        out->nnz = N * N; out->dense = reinterpret_cast<const qb_c128*>(dn->d);
+        return QB_OK;
+    }
+    QB_FAIL(QB_E_TYPE, "handle is not an operator");
+}
+static std::vector<QbInstr> qb_prog(const qb_instr* p, int n) {
+    std::vector<QbInstr> v;
+    for (int i = 0; i < n; i++) { QbInstr q; q.op = p[i].op; q.iarg = p[i].iarg; q.re = p[i].re; q.im = p[i].im; v.push_back(q); }
+    return v;
+}
+extern "C" int qb_system_add_element(qb_handle sys, qb_handle op, const qb_instr* prog, int nprog) {
+    QbSysH* s = qb_cast<QbSysH>(sys, QB_TAG_SYS);
+    if (!s) QB_FAIL(QB_E_TYPE, "not a system handle");
+    if ((int)s->elems.size() >= QB_MAX_ELEMS) QB_FAIL(QB_E_ARG, "too many elements (max %d)", QB_MAX_ELEMS);
+    QbOpDev d; int rc = qb_get_opdev(op, s->N, &d); if (rc) return rc;
+    s->elems.push_back(d); s->elem_prog.push_back(qb_prog(prog, nprog));
+    return QB_OK;
+}
+extern "C" int qb_system_add_collapse(qb_handle sys, qb_handle c_op, const qb_instr* cprog, int ncprog,
+                                      qb_handle n_op, const qb_instr* nprog, int nnprog) {
+    QbSysH* s = qb_cast<QbSysH>(sys, QB_TAG_SYS);
+    if (!s) QB_FAIL(QB_E_TYPE, "not a system handle");
+    QbOpDev c, n; int rc = qb_get_opdev(c_op, s->N, &c); if (rc) return rc;
+    rc = qb_get_opdev(n_op, s->N, &n); if (rc) return rc;
+    s->cops.push_back(c); s->nops.push_back(n);
+    s->cop_prog.push_back(qb_prog(cprog, ncprog)); s->nop_prog.push_back(qb_prog(nprog, nnprog));
+    return QB_OK;
+}
+extern "C" int qb_system_add_eop(qb_handle sys, qb_handle op, const qb_instr* prog, int nprog) {
+    QbSysH* s = qb_cast<QbSysH>(sys, QB_TAG_SYS);
+    if (!s) QB_FAIL(QB_E_TYPE, "not a system handle");
+    QbOpDev d; int rc = qb_get_opdev(op, s->N, &d); if (rc) return rc;
+    s->eops.push_back(d); s->eop_prog.push_back(qb_prog(prog, nprog));
+    return QB_OK;
+}
+extern "C" int qb_system_set_eop_functional(qb_handle sys, int functional) {
+    QbSysH* s = qb_cast<QbSysH>(sys, QB_TAG_SYS);
+    if (!s) QB_FAIL(QB_E_TYPE, "not a system handle");
+    s->eop_functional = functional ? 1 : 0;
+    return QB_OK;
+}
+extern "C" int qb_system_add_spline(qb_handle sys, const double* tlist, const void* poly,
+                                    int n, int order, double dt, int* id) {
+    QbSysH* s = qb_cast<QbSysH>(sys, QB_TAG_SYS);
+    if (!s || !tlist || !poly || n < 1 || order < 0) QB_FAIL(QB_E_ARG, "bad spline");
+    QbSpline sp; sp.n = n; sp.order = order; sp.uniform = dt != 0.0; sp.pad_ = 0; sp.dt = dt;
+    sp.t_off = (long long)s->spool.size();
+    s->spool.insert(s->spool.end(), tlist, tlist + n);
+    sp.p_off = (long long)s->spool.size();
+    const double* pp = static_cast<const double*>(poly);
+    s->spool.insert(s->spool.end(), pp, pp + 2 * (size_t)(order + 1) * n);
+    if (id) *id = (int)s->splines.size();
+    s->splines.push_back(sp);
+    return QB_OK;
+}
+
+// ---- engine ----
+extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb_options* opt,
+                                qb_handle* out) {
+    QbSysH* s = qb_cast<QbSysH>(sys, QB_TAG_SYS);
+    if (!s) QB_FAIL(QB_E_TYPE, "not a system handle");
+    if (tableau < 0 || tableau > 1) QB_FAIL(QB_E_ARG, "unknown tableau id %d (0 vern7, 1 vern9)", tableau);
+    if (nslots < 1 || !out || !opt) QB_FAIL(QB_E_ARG, "bad engine arguments");
+    if (s->elems.empty()) QB_FAIL(QB_E_STATE, "system has no elements");
+    QbEngH* e = new QbEngH();
+    e->sys = s; e->tableau = tableau; e->nslots = nslots;
+    static_assert(sizeof(qb_options) == sizeof(QbOptions), "options layout");
+    memcpy(&e->opt, opt, sizeof(QbOptions));
+    if (e->opt.max_collapses < 1) e->opt.max_collapses = 1;
+    QbEngineDev& h = e->h;
+    h.ctl.tab = *QB_TABLEAUX[tableau];
+    h.ctl.opt = e->opt;
+    h.ctl.N = (int)s->N;
+    h.ctl.ntiles = (int)((s->N + QB_TILE_ROWS - 1) / QB_TILE_ROWS);
+    h.ctl.nelem = (int)s->elems.size();
+    h.ctl.ncops = (int)s->cops.size();
+    h.ctl.neops = (int)s->eops.size();
+    h.ctl.nargs = s->nargs;
+    h.ctl.eop_functional = s->eop_functional;
+    e->maxcoef = std::max(1, h.ctl.nelem);
+    h.ctl.maxcoef = e->maxcoef;
+    e->V = h.ctl.tab.S + 5;
+    h.V = e->V; h.nslots = nslots;
+    int rc;
+#define QB_TRY(x) do { rc = (x); if (rc) { delete e; return rc; } } while (0)
+    // programs
+    std::vector<QbInstr> instr;
+    auto pack = [&](const std::vector<std::vector<QbInstr>>& progs) {
+        std::vector<QbProgRef> refs;
+        for (auto& p : progs) { QbProgRef r; r.off = (int)instr.size(); r.len = (int)p.size(); refs.push_back(r); instr.insert(instr.end(), p.begin(), p.end()); }
+        return refs;
+    };
+    std::vector<QbProgRef> r_el = pack(s->elem_prog), r_c = pack(s->cop_prog),
+                           r_n = pack(s->nop_prog), r_e = pack(s->eop_prog);
+    QB_TRY(qb_dev_array(e, r_el, &h.ctl.elem_prog));
+    QB_TRY(qb_dev_array(e, r_c, &h.ctl.cop_prog));
+    QB_TRY(qb_dev_array(e, r_n, &h.ctl.nop_prog));
+    QB_TRY(qb_dev_array(e, r_e, &h.ctl.eop_prog));
+    QB_TRY(qb_dev_array(e, instr, &h.ctl.instr));
+    QB_TRY(qb_dev_array(e, s->splines, &h.ctl.splines));
+    QB_TRY(qb_dev_array(e, s->spool, &h.ctl.spool));
+    for (size_t i = 0; i < s->elems.size(); i++) h.elem[i] = s->elems[i];
+    QB_TRY(qb_dev_array(e, s->cops, &h.cops));
+    QB_TRY(qb_dev_array(e, s->nops, &h.nops));
+    QB_TRY(qb_dev_array(e, s->eops, &h.eops));
+    // state
+    const size_t N = (size_t)s->N;
+    {
+        cudaError_t ce = cudaMalloc((void**)&h.pool, (size_t)nslots * e->V * N * sizeof(double2));
+        if (ce != cudaSuccess) { delete e; QB_FAIL(QB_E_ALLOC, "cannot allocate %.1f MB of state buffers: %s",
+            (double)nslots * e->V * N * 16 / 1e6, cudaGetErrorString(ce)); }
+        e->owned.push_back(h.pool);
+    }
+    QB_TRY(qb_dev_alloc(e, (size_t)nslots, &h.traj));
+    QB_TRY(qb_dev_alloc(e, (size_t)nslots, &h.pass));
+    QB_TRY(qb_dev_alloc(e, (size_t)nslots * e->maxcoef, &h.coef));
+    QB_TRY(qb_dev_alloc(e, (size_t)nslots * std::max(1, h.ctl.ncops), &h.probs));
+    QB_TRY(qb_dev_alloc(e, (size_t)nslots * h.ctl.ntiles * QB_MAXRED, &h.partials));
+    QB_TRY(qb_dev_alloc(e, 1, &h.queue_head));
+    QB_TRY(qb_dev_alloc(e, 1, &h.n_active));
+    {
+        void* p = nullptr;
+        cudaError_t ce = cudaMalloc(&p, sizeof(QbEngineDev));
+        if (ce != cudaSuccess) { delete e; QB_FAIL(QB_E_ALLOC, "cudaMalloc failed"); }
+        e->owned.push_back(p); e->d = static_cast<QbEngineDev*>(p);
+    }
+    if (cudaStreamCreate(&e->stream) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess ||
+        cudaEventCreate(&e->ev1) != cudaSuccess ||
+        cudaMallocHost((void**)&e->h_active, sizeof(int)) != cudaSuccess) {
+        delete e; QB_FAIL(QB_E_CUDA, "stream/event creation failed");
+    }
+#undef QB_TRY
+    *out = e;
+    return QB_OK;
+}
+
+// enqueue rounds until every slot is idle; one host sync per chunk
+static int qb_drive(QbEngH* e, int nslots_used) {
+    const int ntiles = e->h.ctl.ntiles;
+    const long long grid1 = (long long)nslots_used * ntiles;
+    const int grid2 = (nslots_used * 32 + 127) / 128;
+    if (grid1 > 0x7fffffffLL) QB_FAIL(QB_E_ARG, "grid too large");
+    int chunk = 8;
+    long long rounds = 0;
+    QB_CUDA(cudaEventRecord(e->ev0, e->stream));
+    // the very first control launch turns the *_BEGIN entry points into passes
+    qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
+    QB_LAUNCH_CHECK();
+    for (;;) {
+        for (int i = 0; i < chunk; i++) {
+            qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d);
+            QB_LAUNCH_CHECK();
+            qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
+            QB_LAUNCH_CHECK();
+        }
+        rounds += chunk;
+        QB_CUDA(cudaMemcpyAsync(e->h_active, e->h.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        QB_CUDA(cudaStreamSynchronize(e->stream));
+        if (*e->h_active <= 0) break;
+        if (chunk < 64) chunk *= 2;
+        if (rounds > 2000000000LL) QB_FAIL(QB_E_STATE, "engine did not terminate");
+    }
+    QB_CUDA(cudaEventRecord(e->ev1, e->stream));
+    QB_CUDA(cudaEventSynchronize(e->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->last_rounds = rounds; e->last_ms = ms;
+    return QB_OK;
+}
+
+static int qb_run_common(QbEngH* e, int mode, int64_t ntraj,
+                         const void* d_init, const int32_t* d_init_map,
+                         const double* d_tlist, int nt, const void* d_args,
+                         const double* d_draws, int ndraws,
+                         void* d_expect, int32_t* d_status, int32_t* d_ncol, double* d_col_t,
+                         int32_t* d_col_which, int32_t* d_stats, void* d_states) {
+    QbEngineDev& h = e->h;
+    if (mode == 1 && h.ctl.ncops == 0) QB_FAIL(QB_E_STATE, "mcsolve mode needs collapse operators");
+    if (mode == 1 && !d_draws && !e->opt.no_jump) QB_FAIL(QB_E_ARG, "mcsolve mode needs the threshold table");
+    if (h.ctl.neops > 0 && !d_expect) QB_FAIL(QB_E_ARG, "system has e_ops but no expect output buffer");
+    if (e->opt.store_states && !d_states) QB_FAIL(QB_E_ARG, "store_states set but no states buffer");
+    if (mode == 1 && (!d_ncol || !d_col_t || !d_col_which)) QB_FAIL(QB_E_ARG, "mcsolve mode needs collapse output buffers");
+    h.ctl.nt = nt; h.ctl.ndraws = ndraws;
+    h.ctl.neops = (int)e->sys->eops.size();      // (the Integrator protocol zeroes these)
+    h.ctl.opt = e->opt;
+    h.ctl.tlist = d_tlist; h.ctl.draws = d_draws;
+    h.ctl.args = static_cast<const qb_c128*>(d_args);
+    h.ctl.out_expect = static_cast<qb_c128*>(d_expect);
+    h.ctl.out_ncol = d_ncol; h.ctl.out_col_t = d_col_t; h.ctl.out_col_which = d_col_which;
+    h.init_states = static_cast<const double2*>(d_init);
+    h.init_map = d_init_map;
+    h.out_states = static_cast<double2*>(d_states);
+    h.out_status = d_status; h.out_stats = d_stats;
+    h.ntraj_total = (int)ntraj; h.mode = mode;
+    const int used = (int)std::min<int64_t>(e->nslots, ntraj);
+    // initial slots: trajectory i in slot i
+    std::vector<QbTraj> tr(used);
+    const int S = h.ctl.tab.S;
+    for (int i = 0; i < used; i++) {
+        QbTraj& c = tr[i];
+        memset(&c, 0, sizeof c);
+        c.traj_id = i; c.init_idx = 0; c.mode = mode; c.tl_idx = 0; c.tl_end = nt;
+        c.sP = S; c.sF = S + 1; c.sI = S + 2; c.sTA = S + 3; c.sTB = S + 4; c.sY = S + 1;
+        c.pc = mode ? QB_PC_MC_BEGIN : QB_PC_ME_BEGIN;
+    }
+    if (d_init_map) {
+        std::vector<int32_t> im(used);
+        QB_CUDA(cudaMemcpy(im.data(), d_init_map, used * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < used; i++) tr[i].init_idx = im[i];
+    }
+    QB_CUDA(cudaMemsetAsync(h.traj, 0, (size_t)e->nslots * sizeof(QbTraj), e->stream));
+    QB_CUDA(cudaMemsetAsync(h.pass, 0, (size_t)e->nslots * sizeof(QbPass), e->stream));
+    QB_CUDA(cudaMemcpyAsync(h.traj, tr.data(), used * sizeof(QbTraj), cudaMemcpyHostToDevice, e->stream));
+    int head = used, act = used;
+    QB_CUDA(cudaMemcpyAsync(h.queue_head, &head, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    QB_CUDA(cudaMemcpyAsync(h.n_active, &act, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    QB_CUDA(cudaMemcpyAsync(e->d, &h, sizeof(QbEngineDev), cudaMemcpyHostToDevice, e->stream));
+    QB_CUDA(cudaStreamSynchronize(e->stream));   // host vectors above go out of scope
+    return qb_drive(e, used);
+}
+
+extern "C" int qb_engine_run_device(qb_handle eng, int mode, int64_t ntraj,
+                         const void* d_init_states, int64_t ninit, const int32_t* d_init_map,
+                         const double* d_tlist, int nt, const void* d_args,
+                         const double* d_draws, int ndraws,
+                         void* d_expect, int32_t* d_status, int32_t* d_ncol, double* d_col_t,
+                         int32_t* d_col_which, int32_t* d_stats, void* d_states) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    if (ntraj < 1 || nt < 1 || !d_init_states || !d_tlist || ninit < 1) QB_FAIL(QB_E_ARG, "bad run arguments");
+    if (e->sys->nargs > 0 && !d_args) QB_FAIL(QB_E_ARG, "system has args but none were given");
+    return qb_run_common(e, mode, ntraj, d_init_states, d_init_map, d_tlist, nt, d_args, d_draws,
+                         ndraws, d_expect, d_status, d_ncol, d_col_t, d_col_which, d_stats, d_states);
+}
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { if (bytes == 0) bytes = 16; return cudaMalloc(&p, bytes) == cudaSuccess ? 0 : -1; }
+};
+}
+
+extern "C" int qb_engine_run(qb_handle eng, int mode, int64_t ntraj,
+                  const void* init_states, int64_t ninit, const int32_t* init_map,
+                  const double* tlist, int nt,
+                  const void* args, const double* draws, int ndraws,
+                  void* expect, int32_t* status, int32_t* ncol, double* col_t,
+                  int32_t* col_which, int32_t* stats, void* states, void* final_states) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    if (ntraj < 1 || nt < 1 || !init_states || !tlist || ninit < 1) QB_FAIL(QB_E_ARG, "bad run arguments");
+    const size_t N = (size_t)e->sys->N;
+    const int neops = e->h.ctl.neops, nargs = e->sys->nargs, maxcol = e->opt.max_collapses;
+    if (nargs > 0 && !args) QB_FAIL(QB_E_ARG, "system has args but none were given");
+    if (final_states && ntraj > e->nslots) QB_FAIL(QB_E_ARG, "final_states needs nslots >= ntraj");
+    DevBuf b_init, b_map, b_tl, b_args, b_draws, b_exp, b_st, b_ncol, b_ct, b_cw, b_stats, b_states;
+#define QB_A(buf, bytes) do { if (buf.alloc(bytes)) QB_FAIL(QB_E_ALLOC, "device allocation of %zu bytes failed", (size_t)(bytes)); } while (0)
+    QB_A(b_init, (size_t)ninit * N * 16);
+    QB_CUDA(cudaMemcpy(b_init.p, init_states, (size_t)ninit * N * 16, cudaMemcpyHostToDevice));
+    if (init_map) { QB_A(b_map, ntraj * 4); QB_CUDA(cudaMemcpy(b_map.p, init_map, ntraj * 4, cudaMemcpyHostToDevice)); }
+    QB_A(b_tl, (size_t)nt * 8);
+    QB_CUDA(cudaMemcpy(b_tl.p, tlist, (size_t)nt * 8, cudaMemcpyHostToDevice));
+    if (nargs > 0) { QB_A(b_args, (size_t)ntraj * nargs * 16); QB_CUDA(cudaMemcpy(b_args.p, args, (size_t)ntraj * nargs * 16, cudaMemcpyHostToDevice)); }
+    if (draws && ndraws > 0) { QB_A(b_draws, (size_t)ntraj * ndraws * 8); QB_CUDA(cudaMemcpy(b_draws.p, draws, (size_t)ntraj * ndraws * 8, cudaMemcpyHostToDevice)); }
+    QB_A(b_exp, (size_t)ntraj * std::max(1, neops) * nt * 16);
+    QB_CUDA(cudaMemset(b_exp.p, 0, (size_t)ntraj * std::max(1, neops) * nt * 16));
+    QB_A(b_st, ntraj * 4); QB_CUDA(cudaMemset(b_st.p, 0, ntraj * 4));
+    QB_A(b_ncol, ntraj * 4); QB_CUDA(cudaMemset(b_ncol.p, 0, ntraj * 4));
+    QB_A(b_ct, (size_t)ntraj * maxcol * 8); QB_A(b_cw, (size_t)ntraj * maxcol * 4);
+    QB_CUDA(cudaMemset(b_ct.p, 0, (size_t)ntraj * maxcol * 8));
+    QB_CUDA(cudaMemset(b_cw.p, 0, (size_t)ntraj * maxcol * 4));
+    QB_A(b_stats, ntraj * 16); QB_CUDA(cudaMemset(b_stats.p, 0, ntraj * 16));
+    if (e->opt.store_states) {
+        if (!states) QB_FAIL(QB_E_ARG, "store_states set but states == NULL");
+        QB_A(b_states, (size_t)ntraj * nt * N * 16);
+    }
+#undef QB_A
+    int rc = qb_run_common(e, mode, ntraj, b_init.p, static_cast<int32_t*>(b_map.p),
+                           static_cast<double*>(b_tl.p), nt, b_args.p,
+                           static_cast<double*>(b_draws.p), ndraws, b_exp.p,
+                           static_cast<int32_t*>(b_st.p), static_cast<int32_t*>(b_ncol.p),
+                           static_cast<double*>(b_ct.p), static_cast<int32_t*>(b_cw.p),
+                           static_cast<int32_t*>(b_stats.p), b_states.p);
+    if (rc) return rc;
+    if (expect && neops > 0) QB_CUDA(cudaMemcpy(expect, b_exp.p, (size_t)ntraj * neops * nt * 16, cudaMemcpyDeviceToHost));
+    if (status) QB_CUDA(cudaMemcpy(status, b_st.p, ntraj * 4, cudaMemcpyDeviceToHost));
+    if (ncol) QB_CUDA(cudaMemcpy(ncol, b_ncol.p, ntraj * 4, cudaMemcpyDeviceToHost));
+    if (col_t) QB_CUDA(cudaMemcpy(col_t, b_ct.p, (size_t)ntraj * maxcol * 8, cudaMemcpyDeviceToHost));
+    if (col_which) QB_CUDA(cudaMemcpy(col_which, b_cw.p, (size_t)ntraj * maxcol * 4, cudaMemcpyDeviceToHost));
+    if (stats) QB_CUDA(cudaMemcpy(stats, b_stats.p, ntraj * 16, cudaMemcpyDeviceToHost));
+    if (states && e->opt.store_states) QB_CUDA(cudaMemcpy(states, b_states.p, (size_t)ntraj * nt * N * 16, cudaMemcpyDeviceToHost));
+    if (final_states) {
+        // slot i holds trajectory i (ntraj <= nslots): copy V[sY]
+        std::vector<QbTraj> tr(ntraj);
+        QB_CUDA(cudaMemcpy(tr.data(), e->h.traj, ntraj * sizeof(QbTraj), cudaMemcpyDeviceToHost));
+        for (int64_t j = 0; j < ntraj; j++) {
+            const QbTraj& c = tr[j];
+            const double2* src = e->h.pool + ((size_t)j * e->V + c.sY) * N;
+            QB_CUDA(cudaMemcpy(static_cast<char*>(final_states) + (size_t)c.traj_id * N * 16, src, N * 16, cudaMemcpyDeviceToHost));
+        }
+    }
+    return QB_OK;
+}
+
+extern "C" int qb_reduce_expect(const void* d_expect, int64_t ntraj, int neops, int nt, void* d_sums) {
+    const int n = neops * nt;
+    if (n <= 0 || ntraj < 0 || !d_expect || !d_sums) QB_FAIL(QB_E_ARG, "bad reduce arguments");
+    qb_reduce_expect_kernel<<<(n + 127) / 128, 128>>>(static_cast<const double2*>(d_expect), ntraj, n,
+                                                       static_cast<double2*>(d_sums));
+    QB_LAUNCH_CHECK();
+    return QB_OK;
+}
+
+extern "C" int qb_engine_last_run_info(qb_handle eng, int64_t* rounds, double* gpu_ms) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    if (rounds) *rounds = e->last_rounds;
+    if (gpu_ms) *gpu_ms = e->last_ms;
+    return QB_OK;
+}
+
+// ---- Integrator protocol on slot 0 ----
+static int qb_integ_prepare(QbEngH* e) {
+    QbEngineDev& h = e->h;
+    if (!e->d_tlist) { QB_CUDA(cudaMalloc(&e->d_tlist, 8)); }
+    if (!e->d_init) { QB_CUDA(cudaMalloc(&e->d_init, (size_t)e->sys->N * 16)); }
+    if (e->sys->nargs > 0 && !e->d_args) {
+        QB_CUDA(cudaMalloc(&e->d_args, (size_t)e->sys->nargs * 16));
+        QB_CUDA(cudaMemset(e->d_args, 0, (size_t)e->sys->nargs * 16));
+    }
+    h.ctl.nt = 1; h.ctl.ndraws = 0; h.ctl.tlist = static_cast<const double*>(e->d_tlist);
+    h.ctl.draws = nullptr; h.ctl.args = static_cast<const qb_c128*>(e->d_args);
+    h.ctl.out_expect = nullptr; h.ctl.out_ncol = nullptr; h.ctl.out_col_t = nullptr;
+    h.ctl.out_col_which = nullptr;
+    h.ctl.neops = 0;                   // e_ops are evaluated by the caller in this protocol
+    h.ctl.opt.store_states = 0;
+    h.init_states = static_cast<const double2*>(e->d_init); h.init_map = nullptr;
+    h.out_states = nullptr; h.out_status = nullptr; h.out_stats = nullptr;
+    h.ntraj_total = 0; h.mode = 0;
+    return QB_OK;
+}
+static int qb_integ_launch(QbEngH* e, QbTraj& c) {
+    QbEngineDev& h = e->h;
+    int act = 1, head = 1;
+    QB_CUDA(cudaMemcpyAsync(h.traj, &c, sizeof(QbTraj), cudaMemcpyHostToDevice, e->stream));
+    QB_CUDA(cudaMemsetAsync(h.pass, 0, sizeof(QbPass), e->stream));
+    QB_CUDA(cudaMemcpyAsync(h.queue_head, &head, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    QB_CUDA(cudaMemcpyAsync(h.n_active, &act, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    QB_CUDA(cudaMemcpyAsync(e->d, &h, sizeof(QbEngineDev), cudaMemcpyHostToDevice, e->stream));
+    QB_CUDA(cudaStreamSynchronize(e->stream));
+    int rc = qb_drive(e, 1);
+    if (rc) return rc;
+    QB_CUDA(cudaMemcpy(&c, h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    return QB_OK;
+}
+
+extern "C" int qb_integ_set_args(qb_handle eng, const void* args) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    int rc = qb_integ_prepare(e); if (rc) return rc;
+    if (e->sys->nargs > 0) {
+        if (!args) QB_FAIL(QB_E_ARG, "null args");
+        QB_CUDA(cudaMemcpy(e->d_args, args, (size_t)e->sys->nargs * 16, cudaMemcpyHostToDevice));
+    }
+    return QB_OK;
+}
+
+extern "C" int qb_integ_set_state(qb_handle eng, double t, const void* y) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e || !y) QB_FAIL(QB_E_TYPE, "not an engine handle / null state");
+    int rc = qb_integ_prepare(e); if (rc) return rc;
+    QB_CUDA(cudaMemcpy(e->d_init, y, (size_t)e->sys->N * 16, cudaMemcpyHostToDevice));
+    QB_CUDA(cudaMemcpy(e->d_tlist, &t, 8, cudaMemcpyHostToDevice));
+    QbTraj c; memset(&c, 0, sizeof c);
+    const int S = e->h.ctl.tab.S;
+    c.traj_id = 0; c.init_idx = 0; c.mode = 0; c.tl_idx = 0; c.tl_end = 0;
+    c.sP = S; c.sF = S + 1; c.sI = S + 2; c.sTA = S + 3; c.sTB = S + 4; c.sY = S + 1;
+    c.status = QB_ST_NORMAL;
+    // ME_BEGIN with an empty target list: set_state, then the QL_RECORD/ME_NEXT chain
+    // finds nothing to do and pauses.
+    c.pc = QB_PC_ME_BEGIN;
+    rc = qb_integ_launch(e, c); if (rc) return rc;
+    if (c.done < 0) QB_FAIL(QB_E_STATE, "set_state failed with status %d", c.done);
+    return QB_OK;
+}
+
+extern "C" int qb_integ_integrate(qb_handle eng, double t, int step, double* t_out, int* status) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    int rc = qb_integ_prepare(e); if (rc) return rc;
+    QbTraj c;
+    QB_CUDA(cudaMemcpy(&c, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    if (c.sP == 0 && c.sF == 0) { if (status) *status = QB_ST_NOT_INITIATED; return QB_OK; }
+    QB_CUDA(cudaMemcpy(e->d_tlist, &t, 8, cudaMemcpyHostToDevice));
+    c.tl_idx = 0; c.tl_end = 1; c.done = 0;
+    c.pc = step ? QB_PC_STEP_ENTRY : QB_PC_ME_NEXT;
+    rc = qb_integ_launch(e, c); if (rc) return rc;
+    if (t_out) *t_out = c.t;
+    if (status) *status = c.done < 0 ? c.done : c.status;
+    return QB_OK;
+}
+
+extern "C" int qb_integ_get_state(qb_handle eng, double* t, void* y) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    QbTraj c;
+    QB_CUDA(cudaMemcpy(&c, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    if (t) *t = c.t;
+    if (y) {
+        const size_t N = (size_t)e->sys->N;
+        QB_CUDA(cudaMemcpy(y, e->h.pool + (size_t)c.sY * N, N * 16, cudaMemcpyDeviceToHost));
+    }
+    return QB_OK;
+}
+
+extern "C" int qb_integ_stats(qb_handle eng, int64_t stats[4]) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e || !stats) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    QbTraj c;
+    QB_CUDA(cudaMemcpy(&c, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    stats[0] = c.n_rhs; stats[1] = c.n_accept; stats[2] = c.n_reject; stats[3] = c.n_pass;
+    return QB_OK;
+}
+
+extern "C" int qb_engine_rhs(qb_handle eng, double t, qb_handle xh, qb_handle outh) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    QbDenseH* x = qb_cast<QbDenseH>(xh, QB_TAG_DENSE);
+    QbDenseH* o = qb_cast<QbDenseH>(outh, QB_TAG_DENSE);
+    if (!e || !x || !o) QB_FAIL(QB_E_TYPE, "bad handles");
+    if (x->size() != e->sys->N || o->size() != e->sys->N) QB_FAIL(QB_E_SHAPE, "incompatible shapes");
+    // coefficients on the host (same byte-code interpreter)
+    std::vector<qb_c128> coef(e->h.ctl.nelem);
+    std::vector<qb_c128> zero_args(std::max(1, e->sys->nargs));
+    if (e->d_args && e->sys->nargs > 0)
+        QB_CUDA(cudaMemcpy(zero_args.data(), e->d_args, (size_t)e->sys->nargs * 16, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < e->h.ctl.nelem; k++) {
+        const auto& p = e->sys->elem_prog[k];
+        if (p.empty()) { coef[k].re = 1.0; coef[k].im = 0.0; }
+        else if (qb_eval_prog(p.data(), (int)p.size(), t, zero_args.data(), e->sys->splines.data(),
+                              e->sys->spool.data(), &coef[k]))
+            QB_FAIL(QB_E_STATE, "coefficient program failed");
+    }
+    QB_CUDA(cudaMemcpyAsync(e->h.coef, coef.data(), coef.size() * 16, cudaMemcpyHostToDevice, e->stream));
+    QB_CUDA(cudaMemcpyAsync(e->d, &e->h, sizeof(QbEngineDev), cudaMemcpyHostToDevice, e->stream));
+    qb_rhs_kernel<<<e->h.ctl.ntiles, QB_TILE_ROWS, 0, e->stream>>>(e->d, x->d, o->d, e->h.coef);
+    QB_LAUNCH_CHECK();
+    QB_CUDA(cudaStreamSynchronize(e->stream));
+    return QB_OK;
+}

@@ -1,0 +1,365 @@
+"""Host-side mirror of the device objects: operators, dense states, systems, engines.
+
+Everything here is a thin owner of an opaque handle of libqutip_b200.so; numpy arrays go
+in and come out, all arithmetic happens in the CUDA kernels.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import QbOptions, as_c128, check, ptr
+from .coeffs import Program
+
+FMT_AUTO, FMT_CSR, FMT_DIAM = 0, 1, 2
+FMT_NAMES = {0: "csr", 1: "diam", 2: "dense"}
+TABLEAUX = {"vern7": 0, "vern9": 1}
+
+STATUS_MESSAGES = {
+    # texts of explicit_rk.pyx:476-492 so callers can raise the reference's messages
+    2: "Internal state at the desired time.",
+    1: "Internal state past the desired time and interpolation to step done.",
+    0: "No work done.",
+    -1: ("Too much work done in one call. Try to increase the nsteps parameter or "
+         "increasing the tolerance."),
+    -2: "Step size becomes too small. Try increasing tolerance.",
+    -3: "Step outside available range.",
+    -4: "Not initialized.",
+    -10: ("Could not find the collapse time within desired tolerance. Increase accuracy of "
+          "the ODE solver or lower the tolerance with the options 'norm_steps', 'norm_tol', "
+          "'norm_t_tol'."),
+    -11: "collapse operator selection ran past the last operator (IndexError in the reference)",
+    -12: "threshold table exhausted: more random draws are needed for this trajectory",
+    -13: "more collapses than max_collapses in one trajectory",
+    -14: "coefficient program failed on the device",
+}
+
+
+class _Handle:
+    def __init__(self, h):
+        self._h = h
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise ValueError("handle already freed")
+        return self._h
+
+    def free(self):
+        if getattr(self, "_h", None) is not None:
+            try:
+                _lib.load().qb_free(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    def __del__(self):
+        self.free()
+
+
+class DeviceDense(_Handle):
+    """complex128 matrix on the device (mirror of core/data/dense.pxd:9-22)."""
+
+    def __init__(self, h, shape, fortran):
+        super().__init__(h)
+        self.shape = tuple(shape)
+        self.fortran = bool(fortran)
+
+    @classmethod
+    def from_numpy(cls, arr):
+        arr = np.asarray(arr, dtype=np.complex128)
+        if arr.ndim == 1:
+            arr = arr.reshape(-1, 1)
+        fortran = arr.flags.f_contiguous and not (arr.flags.c_contiguous and arr.shape[1] != 1)
+        if not (arr.flags.f_contiguous or arr.flags.c_contiguous):
+            arr = np.asfortranarray(arr)
+            fortran = True
+        h = C.c_void_p()
+        check(_lib.load().qb_dense_upload(ptr(arr), arr.shape[0], arr.shape[1], int(fortran),
+                                          C.byref(h)))
+        return cls(h, arr.shape, fortran)
+
+    @classmethod
+    def zeros(cls, rows, cols, fortran=True):
+        h = C.c_void_p()
+        check(_lib.load().qb_dense_zeros(rows, cols, int(fortran), C.byref(h)))
+        return cls(h, (rows, cols), fortran)
+
+    def to_numpy(self):
+        out = np.empty(self.shape, dtype=np.complex128, order="F" if self.fortran else "C")
+        check(_lib.load().qb_dense_download(self.handle, ptr(out)))
+        return out
+
+    def copy(self):
+        h = C.c_void_p()
+        check(_lib.load().qb_dense_copy(self.handle, C.byref(h)))
+        return DeviceDense(h, self.shape, self.fortran)
+
+
+class DeviceOp(_Handle):
+    """Sparse operator on the device: diagonal-masked slices or CSR."""
+
+    def __init__(self, h, shape):
+        super().__init__(h)
+        self.shape = tuple(shape)
+
+    @classmethod
+    def from_csr(cls, data, col, rowptr, shape, fmt=FMT_AUTO):
+        data = as_c128(data)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        h = C.c_void_p()
+        check(_lib.load().qb_csr_upload(ptr(data), ptr(col), ptr(rowptr), shape[0], shape[1],
+                                        int(rowptr[-1]), fmt, C.byref(h)))
+        return cls(h, shape)
+
+    @classmethod
+    def from_dia(cls, data, offsets, shape, fmt=FMT_AUTO):
+        data = as_c128(data)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        if data.ndim != 2 or data.shape != (len(offsets), shape[1]):
+            raise ValueError("Dia data must be [num_diag][ncols]")
+        h = C.c_void_p()
+        check(_lib.load().qb_dia_upload(ptr(data), ptr(offsets), len(offsets), shape[0],
+                                        shape[1], fmt, C.byref(h)))
+        return cls(h, shape)
+
+    @classmethod
+    def from_scipy(cls, m, fmt=FMT_AUTO):
+        import scipy.sparse as sp
+        if isinstance(m, (sp.dia_matrix, sp.dia_array)):
+            return cls.from_dia(m.data, m.offsets, m.shape, fmt)
+        m = sp.csr_matrix(m)
+        return cls.from_csr(m.data, m.indices, m.indptr, m.shape, fmt)
+
+    def info(self):
+        fmt, rows, cols = C.c_int(), C.c_int64(), C.c_int64()
+        nnz, nbytes = C.c_int64(), C.c_int64()
+        check(_lib.load().qb_op_info(self.handle, C.byref(fmt), C.byref(rows), C.byref(cols),
+                                     C.byref(nnz), C.byref(nbytes)))
+        return dict(format=FMT_NAMES[fmt.value], rows=rows.value, cols=cols.value,
+                    nnz=nnz.value, device_bytes=nbytes.value)
+
+
+# --------------------------------------------------------------------- data-layer ops
+def matmul(op, x, scale=1.0, out=None):
+    """out += scale * op @ x  (matmul.pyx:226-347,429-507); allocates zeros if out is None."""
+    if out is None:
+        out = DeviceDense.zeros(op.shape[0], x.shape[1], x.fortran or x.shape[1] == 1)
+    s = complex(scale)
+    check(_lib.load().qb_matmul(op.handle, x.handle, s.real, s.imag, out.handle))
+    return out
+
+
+def axpy(x, a, y):
+    a = complex(a)
+    check(_lib.load().qb_axpy(x.handle, a.real, a.imag, y.handle))
+    return y
+
+
+def scal(x, a):
+    a = complex(a)
+    check(_lib.load().qb_scal(x.handle, a.real, a.imag))
+    return x
+
+
+def nrm2(x):
+    out = C.c_double()
+    check(_lib.load().qb_nrm2(x.handle, C.byref(out)))
+    return out.value
+
+
+def wrms_error(diff, state, atol, rtol):
+    out = C.c_double()
+    check(_lib.load().qb_wrms_error(diff.handle, state.handle, atol, rtol, C.byref(out)))
+    return out.value
+
+
+def _c2(fn, *args):
+    out = (C.c_double * 2)()
+    check(fn(*args, out))
+    return complex(out[0], out[1])
+
+
+def inner(a, b, conj=True):
+    return _c2(_lib.load().qb_inner, a.handle, b.handle, int(conj))
+
+
+def expect_ket(op, x):
+    return _c2(_lib.load().qb_expect_ket, op.handle, x.handle)
+
+
+def expect_dm(op, rho):
+    return _c2(_lib.load().qb_expect_dm, op.handle, rho.handle)
+
+
+def expect_super(op, vec):
+    return _c2(_lib.load().qb_expect_super, op.handle, vec.handle)
+
+
+def trace_oper_ket(vec):
+    return _c2(_lib.load().qb_trace_oper_ket, vec.handle)
+
+
+# --------------------------------------------------------------------- system / engine
+def _prog_args(prog):
+    if prog is None or len(prog) == 0:
+        return None, 0
+    return prog.as_ctypes(), len(prog)
+
+
+class System(_Handle):
+    """What QobjEvo.matmul_data sums, plus mcsolve's collapse operators and the e_ops."""
+
+    def __init__(self, N, nargs=0):
+        h = C.c_void_p()
+        check(_lib.load().qb_system_create(N, nargs, C.byref(h)))
+        super().__init__(h)
+        self.N, self.nargs = int(N), int(nargs)
+        self.nelem = self.ncops = self.neops = 0
+        self.functional = False
+        self._keep = []     # operators must outlive the system
+
+    def add_element(self, op, prog=None):
+        p, n = _prog_args(prog)
+        check(_lib.load().qb_system_add_element(self.handle, op.handle, p, n))
+        self._keep.append(op)
+        self.nelem += 1
+
+    def add_collapse(self, c_op, n_op, cprog=None, nprog=None):
+        cp, cn = _prog_args(cprog)
+        np_, nn = _prog_args(nprog)
+        check(_lib.load().qb_system_add_collapse(self.handle, c_op.handle, cp, cn,
+                                                 n_op.handle, np_, nn))
+        self._keep += [c_op, n_op]
+        self.ncops += 1
+
+    def add_eop(self, op, prog=None):
+        p, n = _prog_args(prog)
+        check(_lib.load().qb_system_add_eop(self.handle, op.handle, p, n))
+        self._keep.append(op)
+        self.neops += 1
+
+    def set_functional(self, flag=True):
+        check(_lib.load().qb_system_set_eop_functional(self.handle, int(flag)))
+        self.functional = bool(flag)
+
+    def add_spline(self, tlist, poly, dt=0.0):
+        tlist = np.ascontiguousarray(tlist, dtype=np.float64)
+        poly = as_c128(poly)
+        if poly.ndim == 1:
+            poly = poly.reshape(1, -1)
+        sid = C.c_int()
+        check(_lib.load().qb_system_add_spline(self.handle, ptr(tlist), ptr(poly), len(tlist),
+                                               poly.shape[0] - 1, float(dt), C.byref(sid)))
+        return sid.value
+
+
+def make_options(**kw):
+    o = QbOptions()
+    check(_lib.load().qb_options_default(C.byref(o)))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise KeyError("unknown engine option %r" % k)
+        setattr(o, k, v)
+    return o
+
+
+class RunResult(dict):
+    __getattr__ = dict.__getitem__
+
+
+class Engine(_Handle):
+    """Fused RK / Monte-Carlo engine bound to one system."""
+
+    def __init__(self, system, method="vern7", nslots=1, **options):
+        if method not in TABLEAUX:
+            raise ValueError("unknown method %r (device engine has %s)" % (method, list(TABLEAUX)))
+        self.system = system
+        self.method = method
+        self.nslots = int(nslots)
+        self.opt = make_options(**options)
+        h = C.c_void_p()
+        check(_lib.load().qb_engine_create(system.handle, TABLEAUX[method], self.nslots,
+                                           C.byref(self.opt), C.byref(h)))
+        super().__init__(h)
+
+    # ---- batched runs ------------------------------------------------------------
+    def run(self, mode, init_states, tlist, ntraj=1, init_map=None, args=None, draws=None,
+            final_states=False):
+        s = self.system
+        init_states = as_c128(np.atleast_2d(init_states))
+        if init_states.shape[1] != s.N:
+            raise ValueError("incompatible state size %d for a system of size %d"
+                             % (init_states.shape[1], s.N))
+        tlist = np.ascontiguousarray(tlist, dtype=np.float64)
+        nt = len(tlist)
+        maxcol = self.opt.max_collapses
+        expect = np.zeros((ntraj, max(1, s.neops), nt), dtype=np.complex128)
+        status = np.zeros(ntraj, dtype=np.int32)
+        ncol = np.zeros(ntraj, dtype=np.int32)
+        col_t = np.zeros((ntraj, maxcol), dtype=np.float64)
+        col_w = np.zeros((ntraj, maxcol), dtype=np.int32)
+        stats = np.zeros((ntraj, 4), dtype=np.int32)
+        states = (np.zeros((ntraj, nt, s.N), dtype=np.complex128)
+                  if self.opt.store_states else None)
+        fstates = np.zeros((ntraj, s.N), dtype=np.complex128) if final_states else None
+        ndraws = 0
+        if draws is not None:
+            draws = np.ascontiguousarray(draws, dtype=np.float64)
+            if draws.shape[0] != ntraj:
+                raise ValueError("draws must be [ntraj][ndraws]")
+            ndraws = draws.shape[1]
+        if args is not None:
+            args = as_c128(args).reshape(ntraj, s.nargs)
+        if init_map is not None:
+            init_map = np.ascontiguousarray(init_map, dtype=np.int32)
+        check(_lib.load().qb_engine_run(
+            self.handle, mode, ntraj, ptr(init_states), init_states.shape[0], ptr(init_map),
+            ptr(tlist), nt, ptr(args), ptr(draws), ndraws, ptr(expect), ptr(status), ptr(ncol),
+            ptr(col_t), ptr(col_w), ptr(stats), ptr(states), ptr(fstates)))
+        rounds, ms = C.c_int64(), C.c_double()
+        check(_lib.load().qb_engine_last_run_info(self.handle, C.byref(rounds), C.byref(ms)))
+        return RunResult(expect=expect[:, :s.neops], status=status, ncol=ncol, col_t=col_t,
+                         col_which=col_w, stats=stats, states=states, final_states=fstates,
+                         rounds=rounds.value, gpu_ms=ms.value)
+
+    def run_mesolve(self, y0, tlist, **kw):
+        return self.run(0, y0, tlist, **kw)
+
+    def run_mcsolve(self, psi0, tlist, draws, ntraj=None, **kw):
+        ntraj = len(draws) if ntraj is None else ntraj
+        return self.run(1, psi0, tlist, ntraj=ntraj, draws=draws, **kw)
+
+    # ---- Integrator protocol (slot 0) ---------------------------------------------
+    def set_args(self, args):
+        args = as_c128(args)
+        check(_lib.load().qb_integ_set_args(self.handle, ptr(args)))
+
+    def set_state(self, t, y):
+        y = as_c128(y).reshape(-1)
+        if y.size != self.system.N:
+            raise ValueError("incompatible state size")
+        check(_lib.load().qb_integ_set_state(self.handle, float(t), ptr(y)))
+
+    def integrate(self, t, step=False):
+        """returns (t_reached, status)."""
+        t_out, st = C.c_double(), C.c_int()
+        check(_lib.load().qb_integ_integrate(self.handle, float(t), int(step), C.byref(t_out),
+                                             C.byref(st)))
+        return t_out.value, st.value
+
+    def get_state(self):
+        t = C.c_double()
+        y = np.empty(self.system.N, dtype=np.complex128)
+        check(_lib.load().qb_integ_get_state(self.handle, C.byref(t), ptr(y)))
+        return t.value, y
+
+    def stats(self):
+        st = (C.c_int64 * 4)()
+        check(_lib.load().qb_integ_stats(self.handle, st))
+        return dict(rhs_evals=st[0], accepted=st[1], rejected=st[2], passes=st[3])
+
+    def rhs(self, t, x, out):
+        check(_lib.load().qb_engine_rhs(self.handle, float(t), x.handle, out.handle))
+        return out

@@ -1,0 +1,255 @@
+// tests/emul/emul.cpp -- TEST INFRASTRUCTURE ONLY (never part of libqutip_b200.so).
+//
+// Host-side unit-test harness for the engine's *control logic and data formats*: it
+// compiles the very same headers the CUDA kernels use
+//     qutip_b200/csrc/qb_control.h   (step controller / Monte-Carlo state machine)
+//     qutip_b200/csrc/qb_coeff.h     (coefficient byte-code)
+//     qutip_b200/csrc/qb_diam.h      (CSR/Dia -> diagonal-masked slices)
+// with g++ and executes each QbPass with a plain serial loop that follows the pass
+// kernel's semantics (qb_engine.cu:qb_pass_kernel).  This lets the no-GPU CI check the
+// flattened state machine against the oracle; it is not a product path and is not
+// importable from the package.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+#include "../../qutip_b200/csrc/qb_types.h"
+#include "../../qutip_b200/csrc/qb_coeff.h"
+#include "../../qutip_b200/csrc/qb_control.h"
+#include "../../qutip_b200/csrc/qb_diam.h"
+#include "../../qutip_b200/csrc/qb_tableaux.h"
+
+namespace {
+struct HostOp {
+    int fmt; int nrows, ncols;
+    std::vector<qb_c128> val; std::vector<int> col, rowptr;      // CSR
+    qbdiam::DiamHost dh;                                           // DIAM
+};
+struct Sys {
+    int64_t N = 0; int nargs = 0;
+    std::vector<HostOp> elems, cops, nops, eops;
+    std::vector<std::vector<QbInstr>> elem_prog, cop_prog, nop_prog, eop_prog;
+    int eop_functional = 0;
+};
+Sys g_sys;
+
+static int popc(unsigned x) { return __builtin_popcount(x); }
+
+// mirrors qb_kernels.cuh:qb_rowdot lane by lane
+static qb_c128 rowdot(const HostOp& A, int64_t r, const qb_c128* x) {
+    qb_c128 acc = {0.0, 0.0};
+    if (A.fmt == QB_FMT_CSR) {
+        for (int p = A.rowptr[r]; p < A.rowptr[r + 1]; p++) {
+            const qb_c128 a = A.val[p], b = x[A.col[p]];
+            acc.re += a.re * b.re - a.im * b.im; acc.im += a.re * b.im + a.im * b.re;
+        }
+        return acc;
+    }
+    const int sl = (int)(r / 32), lane = (int)(r % 32);
+    long long vb = A.dh.slice_vbase[sl];
+    const unsigned lt = (1u << lane) - 1u;
+    for (int e = A.dh.slice_ptr[sl]; e < A.dh.slice_ptr[sl + 1]; e++) {
+        const unsigned m = (unsigned)A.dh.ent[e].y;
+        if ((m >> lane) & 1u) {
+            const qb_c128 a = A.dh.val[vb + popc(m & lt)], b = x[r + A.dh.ent[e].x];
+            acc.re += a.re * b.re - a.im * b.im; acc.im += a.re * b.im + a.im * b.re;
+        }
+        vb += popc(m);
+    }
+    return acc;
+}
+
+static HostOp make_op(const qb_c128* data, const int32_t* col, const int32_t* rowptr,
+                      int64_t rows, int64_t cols, int fmt) {
+    HostOp o; o.fmt = fmt; o.nrows = (int)rows; o.ncols = (int)cols;
+    const int64_t nnz = rowptr[rows];
+    if (fmt == QB_FMT_CSR) {
+        o.val.assign(data, data + nnz); o.col.assign(col, col + nnz);
+        o.rowptr.assign(rowptr, rowptr + rows + 1);
+    } else {
+        qbdiam::build_diam(rows, [&](int64_t sl, std::vector<qbdiam::Entry>& es) {
+            const int64_t r0 = sl * 32, r1 = std::min<int64_t>(rows, r0 + 32);
+            for (int64_t r = r0; r < r1; r++)
+                for (int p = rowptr[r]; p < rowptr[r + 1]; p++) {
+                    qbdiam::Entry e; e.off = (int)(col[p] - r); e.lane = (int)(r - r0); e.v = data[p];
+                    es.push_back(e);
+                }
+        }, o.dh);
+    }
+    return o;
+}
+static std::vector<QbInstr> prog(const QbInstr* p, int n) { return std::vector<QbInstr>(p, p + n); }
+}  // namespace
+
+extern "C" {
+void emul_reset(int64_t N, int nargs) { g_sys = Sys(); g_sys.N = N; g_sys.nargs = nargs; }
+void emul_add_element(const void* data, const int32_t* col, const int32_t* rowptr, int fmt,
+                      const QbInstr* p, int np) {
+    g_sys.elems.push_back(make_op((const qb_c128*)data, col, rowptr, g_sys.N, g_sys.N, fmt));
+    g_sys.elem_prog.push_back(prog(p, np));
+}
+void emul_add_collapse(const void* cd, const int32_t* cc, const int32_t* cr,
+                       const void* nd, const int32_t* nc, const int32_t* nr, int fmt) {
+    g_sys.cops.push_back(make_op((const qb_c128*)cd, cc, cr, g_sys.N, g_sys.N, fmt));
+    g_sys.nops.push_back(make_op((const qb_c128*)nd, nc, nr, g_sys.N, g_sys.N, fmt));
+    g_sys.cop_prog.push_back({}); g_sys.nop_prog.push_back({});
+}
+void emul_add_eop(const void* d, const int32_t* c, const int32_t* r, int fmt) {
+    g_sys.eops.push_back(make_op((const qb_c128*)d, c, r, g_sys.N, g_sys.N, fmt));
+    g_sys.eop_prog.push_back({});
+}
+void emul_set_functional(int f) { g_sys.eop_functional = f; }
+double emul_diam_avg_lanes(int which) {
+    const HostOp& o = g_sys.elems[which];
+    return o.dh.ent.empty() ? 0.0 : (double)o.dh.val.size() / (double)o.dh.ent.size();
+}
+// y = A x with the element `which` (format check)
+void emul_matvec(int which, const void* x, void* y) {
+    const HostOp& o = g_sys.elems[which];
+    for (int64_t r = 0; r < g_sys.N; r++) ((qb_c128*)y)[r] = rowdot(o, r, (const qb_c128*)x);
+}
+int emul_eval_prog(const QbInstr* p, int np, double t, const void* args, double out[2]) {
+    qb_c128 r; int rc = qb_eval_prog(p, np, t, (const qb_c128*)args, nullptr, nullptr, &r);
+    out[0] = r.re; out[1] = r.im; return rc;
+}
+
+int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nslots,
+             const void* init_states, const int32_t* init_map, const double* tlist, int nt,
+             const void* args, const double* draws, int ndraws,
+             void* expect, int32_t* status, int32_t* ncol, double* col_t, int32_t* col_which,
+             int32_t* stats, void* states, int64_t max_rounds)
+{
+    Sys& s = g_sys;
+    const int64_t N = s.N;
+    QbCtl g; memset(&g, 0, sizeof g);
+    g.tab = *QB_TABLEAUX[tableau];
+    g.opt = *opt;
+    g.N = (int)N; g.ntiles = 1;
+    g.nelem = (int)s.elems.size(); g.ncops = (int)s.cops.size(); g.neops = (int)s.eops.size();
+    g.nargs = s.nargs; g.eop_functional = s.eop_functional;
+    g.maxcoef = std::max(1, g.nelem);
+    g.nt = nt; g.ndraws = ndraws;
+    std::vector<QbInstr> instr;
+    auto pack = [&](const std::vector<std::vector<QbInstr>>& ps) {
+        std::vector<QbProgRef> refs;
+        for (auto& p : ps) { QbProgRef r; r.off = (int)instr.size(); r.len = (int)p.size(); refs.push_back(r); instr.insert(instr.end(), p.begin(), p.end()); }
+        return refs;
+    };
+    auto r_el = pack(s.elem_prog), r_c = pack(s.cop_prog), r_n = pack(s.nop_prog), r_e = pack(s.eop_prog);
+    g.elem_prog = r_el.data(); g.cop_prog = r_c.data(); g.nop_prog = r_n.data(); g.eop_prog = r_e.data();
+    g.instr = instr.data();
+    g.args = (const qb_c128*)args; g.tlist = tlist; g.draws = draws;
+    g.out_expect = (qb_c128*)expect; g.out_ncol = ncol; g.out_col_t = col_t; g.out_col_which = col_which;
+    const int S = g.tab.S, V = S + 5;
+    std::vector<qb_c128> pool((size_t)nslots * V * N);
+    std::vector<QbTraj> traj(nslots); std::vector<QbPass> pass(nslots);
+    std::vector<qb_c128> coef((size_t)nslots * g.maxcoef);
+    std::vector<double> probs((size_t)nslots * std::max(1, g.ncops));
+    std::vector<double> red((size_t)nslots * QB_MAXRED);
+    memset(traj.data(), 0, traj.size() * sizeof(QbTraj));
+    memset(pass.data(), 0, pass.size() * sizeof(QbPass));
+    int64_t head = 0; int active = 0;
+    auto start = [&](QbTraj& c, int id) {
+        c.traj_id = id; c.init_idx = init_map ? init_map[id] : 0; c.mode = mode;
+        c.tl_idx = 0; c.tl_end = nt;
+        c.sP = S; c.sF = S + 1; c.sI = S + 2; c.sTA = S + 3; c.sTB = S + 4; c.sY = S + 1;
+        c.status = QB_ST_NORMAL; c.done = 0; c.pc = mode ? QB_PC_MC_BEGIN : QB_PC_ME_BEGIN;
+    };
+    for (int i = 0; i < nslots && head < ntraj; i++) { start(traj[i], (int)head++); active++; }
+    auto vsrc = [&](int slot, int idx) -> const qb_c128* {
+        if (idx >= 0) return pool.data() + ((size_t)slot * V + idx) * N;
+        return (const qb_c128*)init_states + (size_t)traj[slot].init_idx * N;
+    };
+    auto control = [&]() {
+        for (int slot = 0; slot < nslots; slot++) {
+            QbTraj& c = traj[slot];
+            if (c.pc == QB_PC_IDLE) continue;
+            for (;;) {
+                int issued = qb_advance(g, c, pass[slot], red.data() + (size_t)slot * QB_MAXRED,
+                                        coef.data() + (size_t)slot * g.maxcoef,
+                                        probs.data() + (size_t)slot * std::max(1, g.ncops));
+                if (issued) { c.n_pass++; break; }
+                if (status) status[c.traj_id] = c.done;
+                if (stats) { int* st = stats + (size_t)c.traj_id * 4; st[0] = c.n_rhs; st[1] = c.n_accept; st[2] = c.n_reject; st[3] = c.n_pass; }
+                if (head >= ntraj) { active--; break; }
+                start(c, (int)head++);
+            }
+        }
+    };
+    std::vector<qb_c128> zbuf(N), o1buf(N);
+    control();
+    int64_t rounds = 0;
+    while (active > 0) {
+        if (++rounds > max_rounds) return -1;
+        for (int slot = 0; slot < nslots; slot++) {
+            const QbPass& p = pass[slot];
+            if (p.kind == QB_PASS_NONE) continue;
+            double* rd = red.data() + (size_t)slot * QB_MAXRED;
+            const qb_c128* cf = coef.data() + (size_t)slot * g.maxcoef;
+            if (p.kind == QB_PASS_EXPECT) {
+                const std::vector<HostOp>& ops = p.opset == QB_OPSET_EOPS ? s.eops : s.nops;
+                const bool fun = p.opset == QB_OPSET_EOPS && s.eop_functional;
+                const qb_c128* x = vsrc(slot, p.x);
+                for (int m = p.op_lo; m < p.op_hi; m++) {
+                    double sre = 0, sim = 0;
+                    for (int64_t r = 0; r < N; r++) {
+                        qb_c128 q = rowdot(ops[m], r, x);
+                        if (fun) { sre += q.re; sim += q.im; }
+                        else { sre += x[r].re * q.re + x[r].im * q.im; sim += x[r].re * q.im - x[r].im * q.re; }
+                    }
+                    rd[2 * (m - p.op_lo)] = sre; rd[2 * (m - p.op_lo) + 1] = sim;
+                }
+                continue;
+            }
+            // operator application into zbuf (x must not alias any destination)
+            for (int64_t r = 0; r < N; r++) { zbuf[r].re = 0; zbuf[r].im = 0; }
+            if (p.kind == QB_PASS_RHS || p.kind == QB_PASS_APPLY) {
+                const qb_c128* x = vsrc(slot, p.x);
+                if (p.x >= 0 && (p.x == p.zdst || p.x == p.dst1)) return -2;   // gather hazard
+                for (int64_t r = 0; r < N; r++) {
+                    qb_c128 z = {0, 0};
+                    if (p.kind == QB_PASS_RHS) {
+                        for (int e = 0; e < g.nelem; e++) {
+                            qb_c128 q = rowdot(s.elems[e], r, x);
+                            z.re += cf[e].re * q.re - cf[e].im * q.im; z.im += cf[e].re * q.im + cf[e].im * q.re;
+                        }
+                    } else {
+                        qb_c128 q = rowdot(s.cops[p.op_lo], r, x);
+                        z.re = cf[0].re * q.re - cf[0].im * q.im; z.im = cf[0].re * q.im + cf[0].im * q.re;
+                    }
+                    z.re *= p.zscale; z.im *= p.zscale;
+                    zbuf[r] = z;
+                }
+            }
+            double r0 = 0, r1 = 0, r2 = 0;
+            qb_c128* base = pool.data() + (size_t)slot * V * N;
+            for (int64_t r = 0; r < N; r++) {
+                const qb_c128 z = zbuf[r];
+                qb_c128 o1 = {0, 0}, o2 = {0, 0};
+                for (int i = 0; i < p.nsrc; i++) {
+                    const qb_c128 v = vsrc(slot, p.src[i])[r];
+                    o1.re += p.w1[i] * v.re; o1.im += p.w1[i] * v.im;
+                    o2.re += p.w2[i] * v.re; o2.im += p.w2[i] * v.im;
+                }
+                o1.re += p.w1z * z.re; o1.im += p.w1z * z.im;
+                o2.re += p.w2z * z.re; o2.im += p.w2z * z.im;
+                o1buf[r] = o1;
+                const double n1 = o1.re * o1.re + o1.im * o1.im;
+                r0 += n1;
+                if (p.red & QB_RED_WRMS) {
+                    const double q = sqrt(o2.re * o2.re + o2.im * o2.im) / (g.opt.atol + g.opt.rtol * sqrt(n1));
+                    r1 += q * q;
+                }
+                r2 += z.re * z.re + z.im * z.im;
+            }
+            if (p.zdst >= 0) memcpy(base + (size_t)p.zdst * N, zbuf.data(), N * sizeof(qb_c128));
+            if (p.dst1 >= 0) memcpy(base + (size_t)p.dst1 * N, o1buf.data(), N * sizeof(qb_c128));
+            else if (p.dst1 == QB_SLOT_OUT)
+                memcpy((qb_c128*)states + ((size_t)traj[slot].traj_id * nt + p.out_index) * N, o1buf.data(), N * sizeof(qb_c128));
+            rd[0] = r0; rd[1] = r1; rd[2] = r2;
+        }
+        control();
+    }
+    return (int)std::min<int64_t>(rounds, 0x7fffffff);
+}
+}

@@ -1,0 +1,133 @@
+"""No-GPU check of the engine's control logic and operator format.
+
+tests/emul/emul.cpp compiles the SAME headers the CUDA kernels use (qb_control.h step
+controller, qb_coeff.h byte-code, qb_diam.h format conversion) with g++ and executes each
+vector pass with a serial loop.  Compared here with the golden fixtures of the reference:
+if these pass, the flattened state machine reproduces the reference's step sequence,
+RHS-evaluation counts and collapse records."""
+import numpy as np
+import pytest
+
+from _emul import FMT_CSR, FMT_DIAM, EmulSystem, default_options
+from _golden import coeff_spec, load, op_arrays, orc_op, orc_rhs
+from _systems import functional_of, merged_constant_rhs
+from qutip_b200 import coeffs
+
+
+def _sp_arrays(m):
+    import scipy.sparse as sp
+    m = sp.csr_matrix(m)
+    m.sort_indices()
+    return ("csr", m.shape, dict(data=m.data, col=m.indices, rowptr=m.indptr))
+
+
+@pytest.mark.parametrize("kind", ["csr", "dia"])
+def test_diam_format_matvec(kind):
+    g = load("matmul")
+    n = len(g["x"])
+    s = EmulSystem(n, 0, FMT_DIAM)
+    s.add_element(*op_arrays(g, kind))
+    np.testing.assert_allclose(s.matvec(0, g["x"]), g["%s_mul_s0" % kind], rtol=1e-13,
+                               atol=1e-13)
+
+
+def test_diam_duplicate_entries():
+    # duplicate (row, col) pairs are legal in CSR; they must be summed
+    data = np.array([1.0, 2.0, 3.0, 4.0], dtype=complex)
+    col = np.array([1, 1, 0, 2], dtype=np.int32)
+    rowptr = np.array([0, 2, 3, 4], dtype=np.int32)
+    s = EmulSystem(3, 0, FMT_DIAM)
+    s.add_element("csr", (3, 3), dict(data=data, col=col, rowptr=rowptr))
+    x = np.array([1.0, 10.0, 100.0], dtype=complex)
+    np.testing.assert_allclose(s.matvec(0, x), [30.0, 3.0, 400.0])
+
+
+@pytest.mark.parametrize("name,method", [("c1_jc", "vern7"), ("c1_jc", "vern9"),
+                                         ("c2_tfim4", "vern7"), ("c2_tfim4", "vern9"),
+                                         ("c4_driven", "vern7"), ("c5_kerr_0", "vern7")])
+@pytest.mark.parametrize("fmt", [FMT_DIAM, FMT_CSR])
+def test_mesolve_state_machine(name, method, fmt):
+    g = load(name)
+    s = EmulSystem(len(g["y0"]), 0, fmt)
+    for i in range(int(g["n_elements"])):
+        spec = coeff_spec(g["el%d_coeff" % i])
+        prog = coeffs.compile_expr(spec[0], spec[1]) if spec is not None else None
+        s.add_element(*op_arrays(g, "el%d" % i), prog=prog)
+    for i in range(int(g["n_eops"])):
+        s.add_eop(*_sp_arrays(functional_of(g["eop%d" % i])))
+    s.set_functional(1)
+    r = s.run(0, 0 if method == "vern7" else 1, g["y0"], g["tlist"],
+              opt=default_options(store_states=1))
+    assert r["status"][0] == 1
+    assert np.abs(r["states"][0] - g["states_" + method]).max() < 1e-10
+    assert np.abs(r["expect"][0] - g["expect_" + method]).max() < 1e-10
+
+
+def test_mesolve_counts_match_oracle():
+    from oracle.rk_oracle import mesolve_oracle
+    g = load("c1_jc")
+    rhs = orc_rhs(g)
+    o = mesolve_oracle(rhs, g["y0"], g["tlist"], "vern7")
+    s = EmulSystem(len(g["y0"]), 0, FMT_DIAM)
+    for i in range(int(g["n_elements"])):
+        s.add_element(*op_arrays(g, "el%d" % i))
+    r = s.run(0, 0, g["y0"], g["tlist"])
+    assert r["stats"][0][0] == rhs.nevals
+    assert (r["stats"][0][1], r["stats"][0][2]) == (o["rk"].n_accept, o["rk"].n_reject)
+
+
+@pytest.mark.parametrize("name,method,nslots", [("c3_tfim6_mc", "vern7", 24),
+                                               ("c3_tfim6_mc", "vern7", 5),
+                                               ("c3_tfim4_mc_strong", "vern9", 7)])
+def test_mcsolve_state_machine(name, method, nslots):
+    g = load(name)
+    s = EmulSystem(len(g["psi0"]), 0, FMT_DIAM)
+    s.add_element(*_sp_arrays(merged_constant_rhs(g)))
+    for i in range(int(g["n_cops"])):
+        s.add_collapse(op_arrays(g, "cop%d" % i), op_arrays(g, "nop%d" % i))
+    for i in range(int(g["n_eops"])):
+        s.add_eop(*op_arrays(g, "eop%d" % i))
+    ntraj = int(g["ntraj"])
+    r = s.run(1, 0 if method == "vern7" else 1, g["psi0"], g["tlist"], ntraj=ntraj,
+              nslots=nslots, draws=g["draws"], opt=default_options(store_states=1))
+    assert (r["status"] == 1).all()
+    cc = np.concatenate([[0], np.cumsum(g["col_count"])])
+    assert np.array_equal(r["ncol"], g["col_count"])
+    for j in range(ntraj):
+        n = r["ncol"][j]
+        assert np.array_equal(r["col_which"][j, :n], g["col_which"][cc[j]:cc[j + 1]])
+        np.testing.assert_allclose(r["col_t"][j, :n], g["col_times"][cc[j]:cc[j + 1]],
+                                   rtol=0, atol=1e-10)
+    assert np.abs(np.transpose(r["expect"], (1, 0, 2)) - g["runs_expect"]).max() < 1e-9
+    assert np.abs(r["states"][:, -1, :] - g["final_states"]).max() < 1e-9
+
+
+def test_rng_exhaustion_status():
+    g = load("c3_tfim4_mc_strong")
+    s = EmulSystem(len(g["psi0"]), 0, FMT_DIAM)
+    s.add_element(*_sp_arrays(merged_constant_rhs(g)))
+    for i in range(int(g["n_cops"])):
+        s.add_collapse(op_arrays(g, "cop%d" % i), op_arrays(g, "nop%d" % i))
+    r = s.run(1, 1, g["psi0"], g["tlist"], ntraj=int(g["ntraj"]), draws=g["draws"][:, :3])
+    assert (r["status"] == -12).any()
+
+
+def test_coefficient_bytecode():
+    import ctypes as C
+    from _emul import lib
+    L = lib()
+    cases = [("A*cos(w*t)", {"A": 0.2, "w": 5.0}), ("exp(-t/tau)*sin(2*pi*f*t)**2", {"tau": 3.0, "f": 0.7}),
+             ("conj(exp(1j*w*t))", {"w": 2.0}), ("sqrt(abs(t-1.5))+real((1+2j)*t)", {}),
+             ("-(t**2)/(1+t)", {}), ("tanh(t)+cosh(0.1*t)-sinh(0.2*t)", {})]
+    for expr, args in cases:
+        p = coeffs.compile_expr(expr, args)
+        for t in (0.0, 0.3, 1.7, 4.2):
+            out = (C.c_double * 2)()
+            rc = L.emul_eval_prog(p.as_ctypes(), len(p), C.c_double(t), None, out)
+            assert rc == 0
+            ref = coeffs.evaluate(p, t)
+            assert abs(complex(out[0], out[1]) - ref) < 1e-13 * max(1, abs(ref))
+    with pytest.raises(TypeError):
+        coeffs.compile_expr("__import__('os').system('x')")
+    with pytest.raises(TypeError):
+        coeffs.compile_expr("foo(t)")
