@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on B200:
+    mcsolve trajectories/s @1/2/4/8 B200 ; mesolve Liouvillian SpMV GB/s vs HBM
+
+A "step" is one pass of the hot path over one batch: mcsolve of `--ntraj` trajectories per
+GPU of config C3 (dissipative TFIM, 14 spins, dim 16384, vern7, tlist = linspace(0,2,21),
+e_op sigma_z on spin 0, seeds SeedSequence(7)).  Ranks shard the trajectories (weak
+scaling: the per-GPU batch is fixed) and the only collective is one all-reduce of the
+expectation sums.  The JSON line also carries the mesolve/C2 figures (TFIM 10 spins,
+Liouvillian 2^20, SpMV GB/s and RHS-evals/s) with their own roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm
+    python bench.py --impl reference ...                            reference CPU arm
+Multi-GPU: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mcsolve_trajectories_per_s"
+UNIT = "trajectories/s"
+C3 = dict(n_spins=14, gamma=0.1, t_end=2.0, nt=21, seed=7, method="vern7")
+C2 = dict(n_spins=10, gamma=0.1, t_end=1.0, nt=11, method="vern7")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path (unmodified qutip 5.4.0.dev from
+    oracle/_ref) through its public API: mcsolve(..., map='parallel', num_cpus=all cores) on
+    a bounded sample of the C3 workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    ref = oracle.ref_path()
+    if ref is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+        return 0
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    sys.path.insert(0, ref)
+    import warnings
+    warnings.filterwarnings("ignore")
+    import qutip
+    from qutip_b200 import models
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    n = args.ref_spins or C3["n_spins"]
+    H, c_ops, sz = models.tfim(n, C3["gamma"])
+    dims = [[2] * n, [2] * n]
+    Hq = qutip.Qobj(H, dims=dims)
+    cq = [qutip.Qobj(c, dims=dims) for c in c_ops]
+    eq = [qutip.Qobj(sz[0], dims=dims)]
+    psi0 = qutip.basis([2] * n, [0] * n)
+    tlist = np.linspace(0, C3["t_end"], C3["nt"])
+    sample = args.ref_sample or max(8, 2 * cores)
+    opts = {"progress_bar": False, "method": C3["method"], "map": "parallel" if cores > 1 else "serial",
+            "num_cpus": cores}
+    solver = qutip.MCSolver(Hq, cq, options=opts)
+    times = []
+    for i in range(args.warmup_ref + args.steps):
+        ss = np.random.SeedSequence(C3["seed"] + i)
+        t0 = time.perf_counter()
+        solver.run(psi0, tlist, ntraj=sample, e_ops=eq, seeds=ss)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup_ref:
+            times.append(dt)
+    total = sum(times)
+    value = sample * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup_ref, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C3 mcsolve dissipative TFIM %d spins (dim %d), vern7, tlist linspace(0,2,21), "
+                               "e_op sz_0; %d trajectories per step" % (n, 2 ** n, sample)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": "%d trajectories/step x %d steps, qutip 5.4.0.dev mcsolve map=parallel "
+                                   "num_cpus=%d" % (sample, len(times), cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+def mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=False):
+    """C2: Liouvillian SpMV GB/s (algorithmic CSR bytes / CUDA-event time) and a short
+    mesolve run for RHS-evals/s."""
+    import scipy.sparse as sp
+    n = 8 if quick else C2["n_spins"]
+    t0 = time.perf_counter()
+    H, c_ops, sz = models.tfim(n, C2["gamma"])
+    L = models.liouvillian(H, c_ops)
+    t_build = time.perf_counter() - t0
+    N = L.shape[0]
+    t0 = time.perf_counter()
+    op = qb.DeviceOp.from_scipy(L)
+    t_upload = time.perf_counter() - t0
+    info = op.info()
+    system = qb.System(N)
+    system.add_element(op)
+    system.add_eop(qb.DeviceOp.from_scipy(
+        __import__("qutip_b200.solve", fromlist=["x"]).trace_functional(sz[0])))
+    system.set_functional(True)
+    eng = qb.Engine(system, C2["method"], nslots=1)
+    rng = np.random.default_rng(0)
+    x = qb.DeviceDense.from_numpy(rng.random(N) + 1j * rng.random(N))
+    out = qb.DeviceDense.zeros(N, 1)
+    eng.rhs_bench(0.0, x, out, iters=5)
+    iters = 50
+    ms = eng.rhs_bench(0.0, x, out, iters=iters)
+    per = ms / iters * 1e-3
+    alg = models.csr_algorithmic_bytes(L.nnz, N, N)
+    gbs = alg / per / 1e9
+    # short mesolve: t in [0,1], 11 points, from |0...0><0...0|
+    rho0 = np.zeros(N, dtype=complex)
+    rho0[0] = 1.0
+    tlist = np.linspace(0, C2["t_end"], C2["nt"])
+    eng.set_profiling(True)
+    t0 = time.perf_counter()
+    r = eng.run_mesolve(rho0, tlist)
+    wall = time.perf_counter() - t0
+    prof = eng.profile()
+    nrhs = int(r.stats[0][0])
+    return {
+        "workload": "C2 mesolve dissipative TFIM %d spins, Liouvillian %d^2, nnz %d, vern7, tlist linspace(0,1,11)"
+                    % (n, N, L.nnz),
+        "operator_format": info["format"], "operator_device_bytes": info["device_bytes"],
+        "spmv_ms": per * 1e3, "spmv_gbs": gbs, "rhs_evals_per_s_kernel": 1.0 / per,
+        "mesolve_rhs_evals": nrhs, "mesolve_gpu_ms": r.gpu_ms, "mesolve_wall_s": wall,
+        "mesolve_rhs_evals_per_s": nrhs / (r.gpu_ms * 1e-3),
+        "mesolve_pass_kernel_share": prof["pass_ms"] / r.gpu_ms if r.gpu_ms else None,
+        "expect_sz0_final": float(r.expect[0][0][-1].real),
+        "host_build_s": t_build, "upload_and_convert_s": t_upload,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": gbs / hbm_peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                     "kernel": "qb_rhs_kernel (DIAM SpMV)"},
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    import qutip_b200 as qb
+    from qutip_b200 import models, solve
+    from qutip_b200 import _lib
+    _lib.check(_lib.load().qb_set_device(local))
+    hbm_peak, peak_src = peaks()
+    dev = torch.device("cuda", local)
+
+    n = args.spins or C3["n_spins"]
+    H, c_ops, sz = models.tfim(n, C3["gamma"])
+    heff = models.heff(H, c_ops)
+    N = heff.shape[0]
+    tlist = np.linspace(0, C3["t_end"], C3["nt"])
+    psi0 = models.basis_state(n)
+    ntraj = args.ntraj
+    nslots = min(ntraj, args.slots)
+    system = solve.build_system([heff], c_ops, e_ops=[sz[0]])
+    eng = qb.Engine(system, C3["method"], nslots=nslots)
+    eng.set_profiling(True)
+    ndraws = 64
+    # every rank / step uses its own block of the global seed list SeedSequence(7).spawn
+    total_steps = args.warmup + args.steps
+
+    def step_draws(i):
+        first = (i * world + rank) * ntraj
+        return solve.make_thresholds(C3["seed"], ntraj, ndraws, first=first)
+
+    draws_all = [step_draws(i) for i in range(total_steps)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: inputs already in HBM, outputs stay in HBM ----
+    lib = _lib.load()
+    neops, nt, maxcol = 1, len(tlist), eng.opt.max_collapses
+    d_psi = torch.from_numpy(psi0.view(np.float64).copy()).to(dev)
+    d_tl = torch.from_numpy(tlist.copy()).to(dev)
+    d_exp = torch.zeros(ntraj * neops * nt * 2, dtype=torch.float64, device=dev)
+    d_status = torch.zeros(ntraj, dtype=torch.int32, device=dev)
+    d_ncol = torch.zeros(ntraj, dtype=torch.int32, device=dev)
+    d_colt = torch.zeros(ntraj * maxcol, dtype=torch.float64, device=dev)
+    d_colw = torch.zeros(ntraj * maxcol, dtype=torch.int32, device=dev)
+    d_stats = torch.zeros(ntraj * 4, dtype=torch.int32, device=dev)
+    d_sums = torch.zeros(2 * neops * nt * 2, dtype=torch.float64, device=dev)
+    d_draws = [torch.from_numpy(d).to(dev) for d in draws_all]
+    import ctypes as C
+
+    def vp(t):
+        return C.c_void_p(t.data_ptr())
+
+    def device_step(i):
+        torch.cuda.synchronize()
+        _lib.check(lib.qb_engine_run_device(
+            eng.handle, 1, ntraj, vp(d_psi), 1, None, vp(d_tl), nt, None, vp(d_draws[i]), ndraws,
+            vp(d_exp), vp(d_status), vp(d_ncol), vp(d_colt), vp(d_colw), vp(d_stats), None))
+        _lib.check(lib.qb_reduce_expect(vp(d_exp), ntraj, neops, nt, vp(d_sums)))
+        if world > 1:
+            dist.all_reduce(d_sums)          # the single collective of the path
+        rounds, ms = C.c_int64(), C.c_double()
+        lib.qb_engine_last_run_info(eng.handle, C.byref(rounds), C.byref(ms))
+        return rounds.value, ms.value, eng.profile()
+
+    launches0 = qb.launch_count()
+    for i in range(args.warmup):
+        device_step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches1 = qb.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t0 = time.perf_counter()
+    gpu_ms = pass_ms = 0.0
+    rounds = pass_launches = 0
+    vec_acc = 0.0
+    for i in range(args.warmup, total_steps):
+        r_, ms_, prof = device_step(i)
+        rounds += r_; gpu_ms += ms_
+        pass_ms += prof["pass_ms"]; pass_launches += prof["pass_launches"]
+        vec_acc += prof["state_vector_accesses"]
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches2 = qb.launch_count()
+    elapsed = torch.tensor([gpu_ms * 1e-3, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    t_dev = float(elapsed[0])         # engine CUDA-event time, max over ranks
+    clocks = sampler.stop() if rank == 0 else None
+    status = d_status.cpu().numpy()
+    stats = d_stats.cpu().numpy().reshape(ntraj, 4)
+    ncol = d_ncol.cpu().numpy()
+    ok = bool((status == 1).all())
+    value = world * ntraj * args.steps / t_dev
+
+    # ---- end to end through the public API with host buffers (H2D + D2H inside) ----
+    pin_psi = torch.from_numpy(psi0.copy()).pin_memory()
+    pin_draws = [torch.from_numpy(d.copy()).pin_memory() for d in draws_all[args.warmup:]]
+    barrier()
+    t0 = time.perf_counter()
+    e2e_res = None
+    for i in range(args.steps):
+        e2e_res = eng.run_mcsolve(pin_psi.numpy(), tlist, pin_draws[i].numpy(), ntraj=ntraj)
+        if world > 1:
+            solve.reduce_expect_sums(np.transpose(e2e_res.expect, (1, 0, 2)), device=dev)
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * ntraj * args.steps / float(e2e_t[0])
+    h2d = psi0.nbytes + tlist.nbytes + draws_all[0].nbytes
+    d2h = e2e_res.expect.nbytes + e2e_res.status.nbytes + e2e_res.ncol.nbytes + \
+        e2e_res.col_t.nbytes + e2e_res.col_which.nbytes + e2e_res.stats.nbytes
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (pass kernel), live CUDA-event time ----
+    op_alg = models.csr_algorithmic_bytes(heff.nnz, N, N) - 32 * N   # operator part only
+    alg_bytes = vec_acc * 16.0 * N + pass_launches * op_alg
+    achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms else 0.0
+    roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "kernel": "qb_pass_kernel",
+            "algorithmic_bytes_per_launch": alg_bytes / max(1, pass_launches),
+            "avg_launch_ms": pass_ms / max(1, pass_launches),
+            "pass_kernel_share_of_step": pass_ms / gpu_ms if gpu_ms else None}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 mcsolve dissipative TFIM %d spins (dim %d), vern7, tlist linspace(0,2,21), "
+                               "e_op sz_0, seeds SeedSequence(7); %d trajectories per GPU per step, %d slots"
+                               % (n, N, ntraj, nslots),
+                   "l2": "state working set %.1f GB per GPU >> 126 MB L2" % (nslots * (16 + 5) * N * 16 / 1e9),
+                   "parallelism": "trajectories sharded over %d GPU(s), one all-reduce of expectation sums" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches2 - launches1),
+        "clocks": clocks,
+        "roofline": roof,
+        "all_trajectories_ok": ok,
+        "rhs_evals_per_trajectory": float(stats[:, 0].mean()),
+        "jumps_per_trajectory": float(ncol.mean()),
+        "rounds_per_step": rounds / args.steps,
+        "wall_s_timed_region": wall,
+    }
+    if world == 1 and not args.no_mesolve:
+        line["mesolve"] = mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=args.quick)
+    if world == 1 and not args.no_cpu:
+        # reference CPU arm on a bounded sample, in a subprocess (it forks worker processes)
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",
+                                  "--steps", "1", "--warmup-ref", "0"]
+                                 + (["--ref-spins", str(n)] if args.spins else []),
+                                 capture_output=True, text=True, timeout=900)
+            ref = json.loads(out.stdout.strip().splitlines()[-1])
+            line["cpu_baseline"] = ref.get("cpu_baseline", {"unavailable": ref.get("unavailable")})
+        except Exception as exc:       # never lose the GPU numbers to a baseline failure
+            line["cpu_baseline"] = {"unavailable": repr(exc)[:200]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ntraj", type=int, default=10000, help="trajectories per GPU per step")
+    ap.add_argument("--slots", type=int, default=4096, help="concurrent trajectory slots")
+    ap.add_argument("--spins", type=int, default=0, help="override C3's 14 spins (debug)")
+    ap.add_argument("--ref-spins", type=int, default=0)
+    ap.add_argument("--ref-sample", type=int, default=0)
+    ap.add_argument("--no-mesolve", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="small C2 (debug)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

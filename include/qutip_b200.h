@@ -161,8 +161,20 @@ int qb_integ_get_state(qb_handle eng, double* t, void* y);
 int qb_integ_set_args(qb_handle eng, const void* args);
 int qb_integ_stats(qb_handle eng, int64_t stats[4]);
 
-/* ---- micro-benchmark hooks: one RHS evaluation out = sum_k c_k A_k x on device vectors */
+/* ---- measurement hooks ----
+ * qb_engine_rhs      : one RHS evaluation out = sum_k c_k(t) A_k x on device vectors
+ *                      (QobjEvo.matmul_data, core/cy/qobjevo.pyx:1103-1116)
+ * qb_engine_rhs_bench: `iters` of them back to back, timed with CUDA events
+ * profiling          : when on, every pass-kernel launch of a run is bracketed by CUDA
+ *                      events on the launching stream; qb_engine_profile returns their
+ *                      summed duration, the launch count and the number of state-sized
+ *                      vector accesses the passes had to make (algorithmic traffic) */
 int qb_engine_rhs(qb_handle eng, double t, qb_handle x, qb_handle out);
+int qb_engine_rhs_bench(qb_handle eng, double t, qb_handle x, qb_handle out, int iters,
+                        double* ms_total);
+int qb_engine_set_profiling(qb_handle eng, int on);
+int qb_engine_profile(qb_handle eng, double* pass_ms, int64_t* pass_launches,
+                      double* state_vector_accesses);
 
 #ifdef __cplusplus
 }

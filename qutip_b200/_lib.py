@@ -46,6 +46,7 @@ SYMBOLS = [
     "qb_engine_create", "qb_engine_run", "qb_engine_run_device", "qb_reduce_expect",
     "qb_engine_last_run_info", "qb_integ_set_state", "qb_integ_integrate",
     "qb_integ_get_state", "qb_integ_set_args", "qb_integ_stats", "qb_engine_rhs",
+    "qb_engine_rhs_bench", "qb_engine_set_profiling", "qb_engine_profile",
 ]
 
 _lib = None
@@ -108,6 +109,9 @@ def load():
         "qb_integ_set_args": [vp, vp],
         "qb_integ_stats": [vp, C.POINTER(i64)],
         "qb_engine_rhs": [vp, dbl, vp, vp],
+        "qb_engine_rhs_bench": [vp, dbl, vp, vp, i32, C.POINTER(dbl)],
+        "qb_engine_set_profiling": [vp, i32],
+        "qb_engine_profile": [vp, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)],
         "qb_device_count": [C.POINTER(i32)],
         "qb_set_device": [i32],
     }

@@ -38,6 +38,7 @@ struct QbEngineDev {
     int mode;
     int* out_status;
     int* out_stats;
+    unsigned long long* vec_count;   // state-sized vector accesses issued (algorithmic traffic)
 };
 
 // ------------------------------------------------------------------ pass kernel
@@ -214,7 +215,16 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
     double* probs = E->probs + (size_t)slot * (E->ctl.ncops > 0 ? E->ctl.ncops : 1);
     for (;;) {
         const int issued = qb_advance(E->ctl, c, p, sred[w], coef, probs);
-        if (issued) { c.n_pass++; break; }
+        if (issued) {
+            c.n_pass++;
+            if (E->vec_count) {
+                // algorithmic state traffic of the pass: x once, every source once, stores
+                unsigned long long nv = (unsigned long long)p.nsrc + (p.zdst >= 0) + (p.dst1 != -1)
+                                        + (p.kind != QB_PASS_COMBINE ? 1 : 0);
+                atomicAdd(E->vec_count, nv);
+            }
+            break;
+        }
         // finished, paused or failed
         if (E->out_status && c.traj_id >= 0) E->out_status[c.traj_id] = c.done;
         if (E->out_stats && c.traj_id >= 0) {
@@ -283,6 +293,11 @@ struct QbEngH : QbObj {
     void* d_args = nullptr; size_t cap_args = 0;
     long long last_rounds = 0;
     double last_ms = 0.0;
+    int profiling = 0;
+    double prof_pass_ms = 0.0;
+    long long prof_pass_launches = 0;
+    unsigned long long prof_vec_count = 0;
+    std::vector<cudaEvent_t> prof_events;
     int maxcoef = 1;
     QbEngH() : QbObj(QB_TAG_ENG) { memset(&h, 0, sizeof h); }
     ~QbEngH() override {
@@ -293,6 +308,7 @@ struct QbEngH : QbObj {
         if (h_active) cudaFreeHost(h_active);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (auto ev : prof_events) cudaEventDestroy(ev);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -469,6 +485,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     QB_TRY(qb_dev_alloc(e, (size_t)nslots * h.ctl.ntiles * QB_MAXRED, &h.partials));
     QB_TRY(qb_dev_alloc(e, 1, &h.queue_head));
     QB_TRY(qb_dev_alloc(e, 1, &h.n_active));
+    QB_TRY(qb_dev_alloc(e, 1, &h.vec_count));
     {
         void* p = nullptr;
         cudaError_t ce = cudaMalloc(&p, sizeof(QbEngineDev));
@@ -493,14 +510,23 @@ static int qb_drive(QbEngH* e, int nslots_used) {
     if (grid1 > 0x7fffffffLL) QB_FAIL(QB_E_ARG, "grid too large");
     int chunk = 8;
     long long rounds = 0;
+    QB_CUDA(cudaMemsetAsync(e->h.vec_count, 0, sizeof(unsigned long long), e->stream));
     QB_CUDA(cudaEventRecord(e->ev0, e->stream));
     // the very first control launch turns the *_BEGIN entry points into passes
     qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
     QB_LAUNCH_CHECK();
     for (;;) {
         for (int i = 0; i < chunk; i++) {
+            cudaEvent_t pa = nullptr, pb = nullptr;
+            if (e->profiling) {
+                if (cudaEventCreate(&pa) != cudaSuccess || cudaEventCreate(&pb) != cudaSuccess)
+                    QB_FAIL(QB_E_CUDA, "event creation failed");
+                e->prof_events.push_back(pa); e->prof_events.push_back(pb);
+                cudaEventRecord(pa, e->stream);
+            }
             qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d);
             QB_LAUNCH_CHECK();
+            if (e->profiling) cudaEventRecord(pb, e->stream);
             qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
             QB_LAUNCH_CHECK();
         }
@@ -516,6 +542,18 @@ static int qb_drive(QbEngH* e, int nslots_used) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     e->last_rounds = rounds; e->last_ms = ms;
+    if (e->profiling) {
+        double tot = 0.0;
+        for (size_t i = 0; i + 1 < e->prof_events.size(); i += 2) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, e->prof_events[i], e->prof_events[i + 1]);
+            tot += t;
+        }
+        e->prof_pass_ms = tot; e->prof_pass_launches = (long long)(e->prof_events.size() / 2);
+        for (auto ev : e->prof_events) cudaEventDestroy(ev);
+        e->prof_events.clear();
+        QB_CUDA(cudaMemcpy(&e->prof_vec_count, e->h.vec_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
     return QB_OK;
 }
 
@@ -797,5 +835,44 @@ extern "C" int qb_engine_rhs(qb_handle eng, double t, qb_handle xh, qb_handle ou
     qb_rhs_kernel<<<e->h.ctl.ntiles, QB_TILE_ROWS, 0, e->stream>>>(e->d, x->d, o->d, e->h.coef);
     QB_LAUNCH_CHECK();
     QB_CUDA(cudaStreamSynchronize(e->stream));
+    return QB_OK;
+}
+
+// ---- measurement hooks ----
+extern "C" int qb_engine_set_profiling(qb_handle eng, int on) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    e->profiling = on ? 1 : 0;
+    return QB_OK;
+}
+extern "C" int qb_engine_profile(qb_handle eng, double* pass_ms, int64_t* pass_launches,
+                                 double* state_vector_accesses) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    if (pass_ms) *pass_ms = e->prof_pass_ms;
+    if (pass_launches) *pass_launches = e->prof_pass_launches;
+    if (state_vector_accesses) *state_vector_accesses = (double)e->prof_vec_count;
+    return QB_OK;
+}
+// `iters` back-to-back RHS evaluations out = sum_k c_k(t) A_k x, timed with CUDA events on
+// the engine's stream (ms_total covers all iterations)
+extern "C" int qb_engine_rhs_bench(qb_handle eng, double t, qb_handle xh, qb_handle outh,
+                                   int iters, double* ms_total) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    QbDenseH* x = qb_cast<QbDenseH>(xh, QB_TAG_DENSE);
+    QbDenseH* o = qb_cast<QbDenseH>(outh, QB_TAG_DENSE);
+    if (!e || !x || !o || iters < 1) QB_FAIL(QB_E_TYPE, "bad arguments");
+    int rc = qb_engine_rhs(eng, t, xh, outh);      // sets coefficients, warm-up
+    if (rc) return rc;
+    QB_CUDA(cudaEventRecord(e->ev0, e->stream));
+    for (int i = 0; i < iters; i++) {
+        qb_rhs_kernel<<<e->h.ctl.ntiles, QB_TILE_ROWS, 0, e->stream>>>(e->d, x->d, o->d, e->h.coef);
+        QB_LAUNCH_CHECK();
+    }
+    QB_CUDA(cudaEventRecord(e->ev1, e->stream));
+    QB_CUDA(cudaEventSynchronize(e->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    if (ms_total) *ms_total = ms;
     return QB_OK;
 }

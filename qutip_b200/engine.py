@@ -363,3 +363,18 @@ class Engine(_Handle):
     def rhs(self, t, x, out):
         check(_lib.load().qb_engine_rhs(self.handle, float(t), x.handle, out.handle))
         return out
+
+    def rhs_bench(self, t, x, out, iters=20):
+        """milliseconds for ``iters`` back-to-back RHS evaluations (CUDA events)."""
+        ms = C.c_double()
+        check(_lib.load().qb_engine_rhs_bench(self.handle, float(t), x.handle, out.handle,
+                                              int(iters), C.byref(ms)))
+        return ms.value
+
+    def set_profiling(self, on=True):
+        check(_lib.load().qb_engine_set_profiling(self.handle, int(on)))
+
+    def profile(self):
+        ms, n, v = C.c_double(), C.c_int64(), C.c_double()
+        check(_lib.load().qb_engine_profile(self.handle, C.byref(ms), C.byref(n), C.byref(v)))
+        return dict(pass_ms=ms.value, pass_launches=n.value, state_vector_accesses=v.value)

@@ -1,0 +1,192 @@
+"""mesolve / mcsolve on plain arrays (scipy.sparse operators, numpy states).
+
+These are the calls a user makes when the whole batch should run on the device: all
+trajectories (or sweep members) advance concurrently in the fused engine, per-trajectory
+records come back as arrays shaped like the reference's ``McResult`` fields
+(``runs_expect``, ``col_times``, ``col_which``; solver/multitrajresult.py).  The QuTiP-facing
+wrappers in plugin.py translate Qobj/QobjEvo into these calls.
+
+Multi-GPU: trajectories are independent given their seed-derived thresholds
+(multitraj.py:250-256), so each rank of a torch.distributed job takes a contiguous block
+of the spawned seed list and only the expectation sums are reduced (one NCCL all-reduce).
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from . import engine as E
+from ._lib import QbError  # noqa: F401
+
+
+def make_thresholds(seeds, ntraj, ndraws=64, bitgenerator=None, first=0):
+    """The successive ``generator.random()`` values of trajectories [first, first+ntraj),
+    drawn exactly as the reference does (multitraj.py:354-393): SeedSequence(seed).spawn
+    then default_rng(child) (PCG64) or the named bit generator.  ``Generator.random(K)``
+    returns the same K doubles as K scalar calls."""
+    if isinstance(seeds, (list, tuple)):
+        kids = [s if isinstance(s, np.random.SeedSequence) else np.random.SeedSequence(s)
+                for s in seeds[first:first + ntraj]]
+    else:
+        ss = seeds if isinstance(seeds, np.random.SeedSequence) else np.random.SeedSequence(seeds)
+        kids = ss.spawn(first + ntraj)[first:]
+    out = np.empty((ntraj, ndraws), dtype=np.float64)
+    for j, k in enumerate(kids):
+        if bitgenerator:
+            gen = np.random.Generator(getattr(np.random, bitgenerator)(k))
+        else:
+            gen = np.random.default_rng(k)
+        out[j] = gen.random(ndraws)
+    return out
+
+
+def _as_op(m, fmt=E.FMT_AUTO):
+    if isinstance(m, (E.DeviceOp, E.DeviceDense)):
+        return m
+    if sp.issparse(m):
+        return E.DeviceOp.from_scipy(m, fmt)
+    return E.DeviceDense.from_numpy(np.asfortranarray(np.asarray(m, dtype=np.complex128)))
+
+
+def trace_functional(E_op):
+    """diag(vec(E^T)): sum_r w[r] * vec(rho)[r] = tr(E rho) for a column-stacked rho
+    (the mesolve branch of expect, core/data/expect.pyx:146-158)."""
+    Ed = E_op.toarray() if sp.issparse(E_op) else np.asarray(E_op)
+    w = Ed.T.reshape(-1, order="F")
+    return sp.dia_matrix((w.reshape(1, -1), [0]), shape=(w.size, w.size))
+
+
+def build_system(elements, c_ops=(), n_ops=None, e_ops=(), functional=False, nargs=0,
+                 fmt=E.FMT_AUTO):
+    """elements: list of operator or (operator, Program) pairs (time-dependent first,
+    constant last, like QobjEvo.compress).  c_ops: operators (or (op, Program))."""
+    first = elements[0][0] if isinstance(elements[0], (tuple, list)) else elements[0]
+    N = first.shape[0]
+    s = E.System(N, nargs)
+    for el in elements:
+        op, prog = el if isinstance(el, (tuple, list)) else (el, None)
+        s.add_element(_as_op(op, fmt), prog)
+    for i, c in enumerate(c_ops):
+        cop, cprog = c if isinstance(c, (tuple, list)) else (c, None)
+        if n_ops is not None:
+            n = n_ops[i]
+            nop, nprog = n if isinstance(n, (tuple, list)) else (n, None)
+        else:
+            cm = sp.csr_matrix(cop)
+            nop, nprog = sp.csr_matrix(cm.conj().T @ cm), (cprog.norm() if cprog else None)
+        s.add_collapse(_as_op(cop, fmt), _as_op(nop, fmt), cprog, nprog)
+    for e in e_ops:
+        op, prog = e if isinstance(e, (tuple, list)) else (e, None)
+        s.add_eop(_as_op(op, fmt), prog)
+    if functional:
+        s.set_functional(True)
+    return s
+
+
+class McResult(dict):
+    __getattr__ = dict.__getitem__
+
+
+def mcsolve(heff_elements, c_ops, psi0, tlist, ntraj, seeds=None, e_ops=(), method="vern7",
+            nslots=None, ndraws=64, options=None, n_ops=None, draws=None, engine=None):
+    """Monte-Carlo trajectories on the device.  ``heff_elements`` is mcsolve's rhs
+    (-iH - 1/2 sum c^dag c, solver/mcsolve.py:493-496).  Returns per-trajectory
+    expectation values [n_e][ntraj][nt], their average / std as the reference computes
+    them (multitrajresult.py:261-279,1116-1124) and the collapse records."""
+    opts = dict(options or {})
+    if engine is None:
+        system = build_system(heff_elements, c_ops, n_ops, e_ops)
+        nslots = min(ntraj, nslots or 4096)
+        engine = E.Engine(system, method, nslots=nslots, **opts)
+    if draws is None:
+        draws = make_thresholds(seeds, ntraj, ndraws)
+    r = engine.run_mcsolve(psi0, tlist, draws, ntraj=ntraj)
+    # trajectories whose threshold table ran out are re-run with a longer one
+    todo = np.nonzero(r.status == -12)[0]
+    while todo.size:
+        ndraws *= 4
+        full = make_thresholds(seeds, ntraj, ndraws) if seeds is not None else None
+        if full is None:
+            raise QbError(-12, E.STATUS_MESSAGES[-12])
+        r2 = engine.run_mcsolve(psi0, tlist, full[todo], ntraj=len(todo))
+        for k in ("expect", "status", "ncol", "stats"):
+            r[k][todo] = r2[k]
+        w = r2.col_t.shape[1]
+        r.col_t[todo, :w] = r2.col_t
+        r.col_which[todo, :w] = r2.col_which
+        todo = todo[r2.status == -12]
+    bad = np.nonzero(r.status != 1)[0]
+    if bad.size:
+        st = int(r.status[bad[0]])
+        raise QbError(st, "trajectory %d: %s" % (bad[0], E.STATUS_MESSAGES.get(st, "failed")))
+    runs = np.transpose(r.expect, (1, 0, 2))
+    avg = runs.mean(axis=1)
+    avg2 = (np.abs(runs) ** 2).mean(axis=1) if np.iscomplexobj(runs) else (runs ** 2).mean(axis=1)
+    std = np.sqrt(np.abs(avg2 - np.abs(avg) ** 2))
+    col_times = [r.col_t[j, :r.ncol[j]].copy() for j in range(ntraj)]
+    col_which = [r.col_which[j, :r.ncol[j]].copy() for j in range(ntraj)]
+    return McResult(runs_expect=runs, average_expect=avg, std_expect=std, col_times=col_times,
+                    col_which=col_which, ncol=r.ncol, stats=r.stats, rounds=r.rounds,
+                    gpu_ms=r.gpu_ms, engine=engine)
+
+
+def mesolve(elements, y0, tlist, e_ops=(), method="vern7", args=None, nargs=0,
+            store_states=True, options=None, engine=None, ntraj=None, nslots=None):
+    """Integrate d y/dt = (sum_k c_k(t) A_k) y through tlist for one system or -- with
+    per-member ``args`` [nsys][nargs] -- a batched parameter sweep.  ``e_ops`` are n x n
+    operators; tr(E rho) is evaluated on the device as a linear functional of the
+    column-stacked rho."""
+    opts = dict(options or {})
+    y0 = np.atleast_2d(np.asarray(y0, dtype=np.complex128))
+    nsys = ntraj or (len(args) if args is not None else y0.shape[0])
+    if engine is None:
+        fun = [trace_functional(e) for e in e_ops]
+        system = build_system(elements, e_ops=fun, functional=True, nargs=nargs)
+        engine = E.Engine(system, method, nslots=min(nsys, nslots or 4096),
+                          store_states=int(bool(store_states)), **opts)
+    init_map = np.arange(nsys, dtype=np.int32) % y0.shape[0] if y0.shape[0] > 1 else None
+    r = engine.run_mesolve(y0, tlist, ntraj=nsys, args=args, init_map=init_map)
+    bad = np.nonzero(r.status != 1)[0]
+    if bad.size:
+        st = int(r.status[bad[0]])
+        raise QbError(st, "system %d: %s" % (bad[0], E.STATUS_MESSAGES.get(st, "failed")))
+    return McResult(expect=r.expect, states=r.states, stats=r.stats, rounds=r.rounds,
+                    gpu_ms=r.gpu_ms, engine=engine)
+
+
+# ------------------------------------------------------------------ multi-GPU sharding
+def shard_range(ntraj, rank, world):
+    """Contiguous block of the spawned seed list for this rank."""
+    per = (ntraj + world - 1) // world
+    lo = min(ntraj, rank * per)
+    return lo, min(ntraj, lo + per)
+
+
+def reduce_expect_sums(runs_expect, group=None, device=None):
+    """[2][n_e][nt] = (sum_j e_j, sum_j |e_j|^2) over the local trajectories, all-reduced
+    over the ranks with ONE collective (NCCL on GPUs, gloo in the CPU tests).  This is the
+    reduce of _TrajectorySum.reduce_expect (multitrajresult.py:1116-1124)."""
+    import torch
+    import torch.distributed as dist
+    local = np.stack([runs_expect.sum(axis=1), (np.abs(runs_expect) ** 2).sum(axis=1)])
+    buf = torch.from_numpy(np.ascontiguousarray(local.view(np.float64)))
+    if device is not None:
+        buf = buf.to(device)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    out = buf.cpu().numpy().view(np.complex128)
+    return out[0], out[1]
+
+
+def mcsolve_sharded(heff_elements, c_ops, psi0, tlist, ntraj, seeds, e_ops=(), rank=0, world=1,
+                    device=None, **kw):
+    """Each rank runs trajectories [lo, hi) of the global seed list and the averages are
+    formed from one all-reduce of the expectation sums."""
+    lo, hi = shard_range(ntraj, rank, world)
+    draws = make_thresholds(seeds, hi - lo, kw.pop("ndraws", 64), first=lo)
+    res = mcsolve(heff_elements, c_ops, psi0, tlist, hi - lo, e_ops=e_ops, draws=draws, **kw)
+    s1, s2 = reduce_expect_sums(res.runs_expect, device=device)
+    avg = s1 / ntraj
+    std = np.sqrt(np.abs(s2 / ntraj - np.abs(avg) ** 2))
+    res["global_average_expect"] = avg
+    res["global_std_expect"] = std
+    res["shard"] = (lo, hi)
+    return res
