@@ -1,0 +1,600 @@
+"""Registration with QuTiP's own extension surfaces (drop-in boundary).
+
+``import qutip_b200.plugin`` (with QuTiP importable) registers
+
+* data-layer types ``B200Dense`` (device state) and ``B200Operator`` (device sparse
+  operator) with ``qutip.core.data.to.add_conversions`` (core/data/convert.pyx:208-329) and
+  specialisations with ``Dispatcher.add_specialisations`` (core/data/dispatch.pyx:267-337)
+  for the operations the stock RK loop and solvers call on a state: matmul, add, mul,
+  imul, neg, zeros-like copies, norm.l2 / norm.frobenius, ode.wrmn_error, expect,
+  expect_super, trace_oper_ket, inner;
+* integrators ``"b200_vern7"`` / ``"b200_vern9"`` with ``MESolver.add_integrator``,
+  ``SESolver.add_integrator`` and ``MCSolver.add_integrator``
+  (solver/solver_base.py:475-492): the whole adaptive RK stepping of
+  ``Explicit_RungeKutta`` runs fused on the device, same ``integrator_options`` keys and
+  defaults as ``IntegratorVern7`` (solver/integrator/qutip_integrator.py:51-59);
+* the map ``options["map"] = "b200"`` in ``qutip.solver.parallel._maps``
+  (solver/parallel.py:541-559): ``MCSolver.run`` hands all seeds to the device engine,
+  which runs every trajectory (RK steps, jump detection, collapse selection) without
+  host round trips and feeds per-trajectory ``Result`` objects to ``McResult.add``.
+
+Anything that cannot run on the device (python-function coefficients or operators,
+feedback arguments, non-Qobj e_ops in the batched map) raises ``TypeError`` naming the
+stock method to use instead -- there is no CPU fallback in this package.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+import qutip
+from qutip.core import data as _data
+from qutip.core.cy.qobjevo import QobjEvo
+from qutip.core.cy.coefficient import Coefficient as _Coefficient
+from qutip.solver.integrator.integrator import Integrator, IntegratorException
+from qutip.solver.mcsolve import MCSolver
+from qutip.solver.mesolve import MESolver
+from qutip.solver.sesolve import SESolver
+from qutip.solver import parallel as _qparallel
+
+from . import coeffs, engine as E
+from .solve import make_thresholds  # noqa: F401
+
+__all__ = ["B200Dense", "B200Operator", "B200Vern7", "B200Vern9", "bind_qobjevo", "b200_map",
+           "register"]
+
+
+# ------------------------------------------------------------------ QobjEvo -> device system
+def _data_to_host(d):
+    """scipy / numpy view of a reference data-layer object."""
+    if isinstance(d, _data.CSR):
+        return d.as_scipy()
+    if isinstance(d, _data.Dia):
+        return d.as_scipy()
+    if isinstance(d, _data.Dense):
+        return np.asfortranarray(d.to_array())
+    if isinstance(d, B200Operator):
+        return d
+    return _data.to(_data.CSR, d).as_scipy()
+
+
+def _coeff_state(c):
+    st = c.__reduce__()
+    if len(st) > 2 and st[2] is not None:
+        return st[2]
+    return st[1][2]
+
+
+def coefficient_to_program(c, system=None):
+    """Compile a reference Coefficient (core/cy/coefficient.pyx) into device byte-code."""
+    name = type(c).__name__
+    if name == "ConstantCoefficient":
+        return coeffs.constant(_coeff_state(c)[1])
+    if name.startswith("StrCoefficient"):
+        state = _coeff_state(c)
+        n = (len(state) - 2) // 2
+        vals, code, names = state[:n], state[n + 1], state[n + 2:]
+        return coeffs.compile_expr(code, dict(zip(names, vals)))
+    if name == "ConjCoefficient":
+        return coefficient_to_program(_coeff_state(c)[1], system).conj()
+    if name == "NormCoefficient":
+        return coefficient_to_program(_coeff_state(c)[1], system).norm()
+    if name == "SumCoefficient":
+        s = _coeff_state(c)
+        return coefficient_to_program(s[1], system) + coefficient_to_program(s[2], system)
+    if name == "MulCoefficient":
+        s = _coeff_state(c)
+        return coefficient_to_program(s[1], system) * coefficient_to_program(s[2], system)
+    if name == "InterCoefficient":
+        if system is None:
+            raise TypeError("array coefficients need a system to hold the spline table")
+        tl, poly, dt = c.__reduce__()[1]
+        return coeffs.spline(system.add_spline(tl, poly, dt or 0.0))
+    raise TypeError(
+        "coefficient of type %s cannot be evaluated on the device (python callables have no "
+        "device form); use a string or array coefficient, or a stock method such as 'vern7'"
+        % name)
+
+
+def bind_qobjevo(qevo, system=None):
+    """[(host operator, Program|None)] for ``sum_k coeff_k(t) A_k`` with all constant
+    elements merged into one operator placed last (QobjEvo.compress order,
+    core/cy/qobjevo.pyx:816-867).  Raises TypeError for forms that only exist on the host."""
+    if isinstance(qevo, qutip.Qobj):
+        qevo = QobjEvo(qevo)
+    if getattr(qevo, "_feedback_functions", None):
+        raise TypeError("feedback arguments rebuild the operator from the state on the host at "
+                        "every RHS evaluation and cannot run on the device; use method='vern7'")
+    const = None
+    out = []
+    for el in qevo.to_list():
+        if isinstance(el, qutip.Qobj):
+            h = _data_to_host(el.data)
+            h = sp.csr_matrix(h)
+            const = h if const is None else const + h
+        elif isinstance(el, (list, tuple)) and isinstance(el[0], qutip.Qobj) \
+                and isinstance(el[1], _Coefficient):
+            out.append((_data_to_host(el[0].data), coefficient_to_program(el[1], system)))
+        else:
+            raise TypeError("QobjEvo contains a function / map / product element, which is a "
+                            "python callable returning a Qobj and cannot run on the device; "
+                            "use method='vern7'")
+    if const is not None:
+        const = sp.csr_matrix(const)
+        const.sum_duplicates()
+        const.sort_indices()
+        out.append((const, None))
+    if not out:
+        n = qevo.shape[0]
+        out.append((sp.csr_matrix((n, n), dtype=complex), None))
+    return out
+
+
+def _single_element(qevo, what):
+    els = bind_qobjevo(qevo)
+    if len(els) != 1:
+        raise TypeError("%s with several time-dependent terms is not supported on the device"
+                        % what)
+    return els[0]
+
+
+def _upload(h):
+    if isinstance(h, (E.DeviceOp, E.DeviceDense)):
+        return h
+    if isinstance(h, B200Operator):
+        return h.dev
+    if sp.issparse(h):
+        return E.DeviceOp.from_scipy(h)
+    return E.DeviceDense.from_numpy(np.asfortranarray(h))
+
+
+def system_from_qobjevo(qevo, c_ops=(), n_ops=(), e_ops=(), functional=False):
+    N = qevo.shape[0]
+    system = E.System(N)
+    for h, prog in bind_qobjevo(qevo, system):
+        system.add_element(_upload(h), prog)
+    for c, n in zip(c_ops, n_ops):
+        ch, cp = _single_element(c, "a collapse operator")
+        nh, npg = _single_element(n, "a collapse operator")
+        system.add_collapse(_upload(ch), _upload(nh), cp, npg)
+    for e in e_ops:
+        eh, ep = _single_element(e, "an e_op")
+        system.add_eop(_upload(eh), ep)
+    if functional:
+        system.set_functional(True)
+    return system
+
+
+# ------------------------------------------------------------------ integrators
+class _B200Integrator(Integrator):
+    """Device-resident adaptive Runge-Kutta (restates Explicit_RungeKutta,
+    solver/integrator/explicit_rk.pyx, on the GPU).  ``rhs_format`` is "callable" like the
+    stock Verner integrators: the derivative must be the bound ``QobjEvo.matmul_data`` of
+    the system (what Solver._get_integrator passes, solver_base.py:292-295)."""
+    integrator_options = {
+        'atol': 1e-8,
+        'rtol': 1e-6,
+        'nsteps': 1000,
+        'first_step': 0,
+        'max_step': 0,
+        'min_step': 0,
+        'interpolate': True,
+    }
+    rhs_format = "callable"
+    _tableau = "vern7"
+    method = "b200_vern7"
+
+    def _prepare(self):
+        qevo = getattr(self.derivative, "__self__", None)
+        if not isinstance(qevo, QobjEvo) or getattr(self.derivative, "__name__", "") != "matmul_data":
+            raise TypeError(
+                "%s integrates QobjEvo systems on the device; the derivative must be "
+                "`QobjEvo.matmul_data` (python functions cannot run on the GPU). Use "
+                "method='%s' for arbitrary callables." % (self.method, self._tableau))
+        self._qevo = qevo
+        self._build()
+        self.name = self.method
+
+    def _build(self):
+        o = self._options
+        self._system = system_from_qobjevo(self._qevo)
+        self._engine = E.Engine(
+            self._system, self._tableau, nslots=1, atol=o['atol'], rtol=o['rtol'],
+            nsteps=int(o['nsteps']), first_step=float(o['first_step'] or 0),
+            min_step=float(o['min_step'] or 0), max_step=float(o['max_step'] or 0),
+            interpolate=int(bool(o['interpolate'])))
+        self._shape = None
+
+    def arguments(self, args):
+        # QobjEvo.arguments() was already applied by the solver; re-bind the coefficients
+        if self._is_set:
+            state = self.get_state()
+        self._build()
+        if self._is_set:
+            self.set_state(*state)
+
+    def set_state(self, t, state):
+        arr = _data.to(_data.Dense, state).to_array()
+        self._shape = arr.shape
+        self._engine.set_state(t, np.ascontiguousarray(arr.reshape(-1, order="F")))
+        self._is_set = True
+
+    def _wrap(self, y):
+        return _data.Dense(y.reshape(self._shape, order="F"), copy=False)
+
+    def get_state(self, copy=True):
+        t, y = self._engine.get_state()
+        return t, self._wrap(y)
+
+    def _run(self, t, step):
+        t_out, status = self._engine.integrate(t, step)
+        if status < 0:
+            raise IntegratorException(E.STATUS_MESSAGES.get(status, "integration failed"))
+        return self.get_state(False)
+
+    def integrate(self, t, copy=True):
+        return self._run(t, False)
+
+    def mcstep(self, t, copy=True):
+        return self._run(t, True)
+
+    def stats(self):
+        return self._engine.stats()
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        saved = self.get_state() if self._is_set else None
+        for k in ("_system", "_engine"):
+            d.pop(k, None)
+        d["_saved_state"] = saved
+        return d
+
+    def __setstate__(self, d):
+        saved = d.pop("_saved_state", None)
+        self.__dict__.update(d)
+        self._build()
+        if saved is not None:
+            self.set_state(*saved)
+
+    @property
+    def options(self):
+        """
+        Supported options by the device Verner methods (same keys and defaults as the
+        stock ``vern7`` / ``vern9``):
+
+        atol : float, default: 1e-8
+            Absolute tolerance.
+
+        rtol : float, default: 1e-6
+            Relative tolerance.
+
+        nsteps : int, default: 1000
+            Max. number of internal steps/call.
+
+        first_step : float, default: 0
+            Size of initial step (0 = automatic).
+
+        min_step : float, default: 0
+            Minimum step size (0 = automatic).
+
+        max_step : float, default: 0
+            Maximum step size (0 = automatic)
+
+        interpolate : bool, default: True
+            Whether to use interpolation step, faster most of the time.
+        """
+        return self._options
+
+    @options.setter
+    def options(self, new_options):
+        Integrator.options.fset(self, new_options)
+
+
+class B200Vern7(_B200Integrator):
+    """Verner 7(6) "most efficient" pair, fused on the B200.  ``method="b200_vern7"``."""
+    _tableau = "vern7"
+    method = "b200_vern7"
+
+
+class B200Vern9(_B200Integrator):
+    """Verner 9(8) "most efficient" pair, fused on the B200.  ``method="b200_vern9"``."""
+    _tableau = "vern9"
+    method = "b200_vern9"
+
+
+# ------------------------------------------------------------------ data-layer types
+class B200Dense(_data.Data):
+    """Dense complex128 matrix resident in HBM (mirror of core/data/dense.pxd:9-22)."""
+
+    def __init__(self, dev, shape=None):
+        if not isinstance(dev, E.DeviceDense):
+            dev = E.DeviceDense.from_numpy(np.asarray(dev, dtype=complex))
+        super().__init__(tuple(dev.shape))
+        self.dev = dev
+
+    @classmethod
+    def sparcity(cls):
+        return "dense"
+
+    def to_array(self):
+        return self.dev.to_numpy()
+
+    def copy(self):
+        return B200Dense(self.dev.copy())
+
+    def conj(self):
+        return B200Dense(np.conj(self.to_array()))
+
+    def transpose(self):
+        return B200Dense(self.to_array().T)
+
+    def adjoint(self):
+        return B200Dense(np.conj(self.to_array().T))
+
+    def trace(self):
+        return complex(np.trace(self.to_array()))
+
+
+class B200Operator(_data.Data):
+    """Sparse operator resident in HBM (diagonal-masked slices or CSR).  Keeps the host
+    object it was converted from so that conversions back are exact."""
+
+    def __init__(self, host):
+        if not isinstance(host, (_data.CSR, _data.Dia)):
+            host = _data.to(_data.CSR, host)
+        super().__init__(tuple(host.shape))
+        self.host = host
+        self.dev = E.DeviceOp.from_scipy(host.as_scipy())
+
+    @classmethod
+    def sparcity(cls):
+        return "sparse"
+
+    def to_array(self):
+        return self.host.to_array()
+
+    def copy(self):
+        return B200Operator(self.host.copy())
+
+    def conj(self):
+        return B200Operator(self.host.conj())
+
+    def transpose(self):
+        return B200Operator(self.host.transpose())
+
+    def adjoint(self):
+        return B200Operator(self.host.adjoint())
+
+    def trace(self):
+        return self.host.trace()
+
+
+def _dense_from(d):
+    arr = d.to_array()
+    return B200Dense(E.DeviceDense.from_numpy(arr))
+
+
+def _to_dense(d):
+    return _data.Dense(d.to_array(), copy=False)
+
+
+def _check_mm(left, right):
+    if left.shape[1] != right.shape[0]:
+        raise ValueError("incompatible matrix shapes " + str(left.shape) + " and "
+                         + str(right.shape))
+
+
+def _matmul_op_dense(left, right, scale=1):
+    _check_mm(left, right)
+    return B200Dense(E.matmul(left.dev, right.dev, scale))
+
+
+def _matmul_dense_dense(left, right, scale=1):
+    _check_mm(left, right)
+    if not left.dev.fortran and min(left.shape) > 1:
+        left = B200Dense(np.asfortranarray(left.to_array()))
+    return B200Dense(E.matmul(left.dev, right.dev, scale))
+
+
+def _add_dense(left, right, scale=1):
+    if left.shape != right.shape:
+        raise ValueError("incompatible matrix shapes " + str(left.shape) + " and "
+                         + str(right.shape))
+    out = left.dev.copy()
+    E.axpy(right.dev, scale, out)
+    return B200Dense(out)
+
+
+def _iadd_dense(left, right, scale=1):
+    E.axpy(right.dev, scale, left.dev)
+    return left
+
+
+def _sub_dense(left, right):
+    return _add_dense(left, right, -1)
+
+
+def _mul_dense(matrix, value):
+    out = matrix.dev.copy()
+    E.scal(out, value)
+    return B200Dense(out)
+
+
+def _imul_dense(matrix, value):
+    E.scal(matrix.dev, value)
+    return matrix
+
+
+def _neg_dense(matrix):
+    return _mul_dense(matrix, -1)
+
+
+def _zeros_dense(rows, cols):
+    return B200Dense(E.DeviceDense.zeros(rows, cols, True))
+
+
+def _l2_dense(vector):
+    return E.nrm2(vector.dev)
+
+
+def _wrmn_dense(diff, state, atol, rtol):
+    return E.wrms_error(diff.dev, state.dev, atol, rtol)
+
+
+def _expect_op_dense(op, state):
+    if state.shape[1] == 1:
+        return E.expect_ket(op.dev, state.dev)
+    return E.expect_dm(op.dev, state.dev)
+
+
+def _expect_super_op_dense(op, state):
+    return E.expect_super(op.dev, state.dev)
+
+
+def _trace_oper_ket_dense(matrix):
+    return E.trace_oper_ket(matrix.dev)
+
+
+def _inner_dense(left, right, scalar_is_ket=False):
+    if left.shape[1] == 1 and left.shape[0] != 1 or (left.shape == (1, 1) and scalar_is_ket):
+        return E.inner(left.dev, right.dev, True)       # <left|right>, left a ket
+    return E.inner(left.dev, right.dev, False)          # left is a bra
+
+
+_registered = False
+
+
+def register():
+    """Idempotent registration of the types, specialisations, integrators and the map."""
+    global _registered
+    if _registered:
+        return
+    _data.to.add_conversions([
+        (B200Dense, _data.Dense, _dense_from, 1),
+        (_data.Dense, B200Dense, _to_dense, 1),
+        (B200Operator, _data.CSR, B200Operator, 1),
+        (B200Operator, _data.Dia, B200Operator, 1),
+        (_data.CSR, B200Operator, lambda d: _data.to(_data.CSR, d.host), 1),
+    ])
+    _data.to.register_aliases(["b200", "B200Dense", "b200_dense"], B200Dense)
+    _data.to.register_aliases(["B200Operator", "b200_operator", "b200_sparse"], B200Operator)
+    _data.matmul.add_specialisations([
+        (B200Operator, B200Dense, B200Dense, _matmul_op_dense),
+        (B200Dense, B200Dense, B200Dense, _matmul_dense_dense),
+    ])
+    _data.add.add_specialisations([(B200Dense, B200Dense, B200Dense, _add_dense)])
+    _data.sub.add_specialisations([(B200Dense, B200Dense, B200Dense, _sub_dense)])
+    _data.mul.add_specialisations([(B200Dense, B200Dense, _mul_dense)])
+    _data.imul.add_specialisations([(B200Dense, B200Dense, _imul_dense)])
+    _data.neg.add_specialisations([(B200Dense, B200Dense, _neg_dense)])
+    if hasattr(_data, "iadd"):
+        _data.iadd.add_specialisations([(B200Dense, B200Dense, B200Dense, _iadd_dense)])
+    _data.zeros.add_specialisations([(B200Dense, _zeros_dense)])
+    _data.norm.l2.add_specialisations([(B200Dense, _l2_dense)])
+    _data.norm.frobenius.add_specialisations([(B200Dense, _l2_dense)])
+    _data.ode.wrmn_error.add_specialisations([(B200Dense, B200Dense, _wrmn_dense)])
+    _data.expect.add_specialisations([(B200Operator, B200Dense, _expect_op_dense)])
+    _data.expect_super.add_specialisations([(B200Operator, B200Dense, _expect_super_op_dense)])
+    _data.trace_oper_ket.add_specialisations([(B200Dense, _trace_oper_ket_dense)])
+    _data.inner.add_specialisations([(B200Dense, B200Dense, _inner_dense)])
+
+    for solver in (MESolver, SESolver, MCSolver):
+        solver.add_integrator(B200Vern7, "b200_vern7")
+        solver.add_integrator(B200Vern9, "b200_vern9")
+    _qparallel._maps["b200"] = b200_map
+    _registered = True
+
+
+# ------------------------------------------------------------------ whole-batch mcsolve
+def _device_method(method):
+    if method in ("b200_vern7", "vern7"):
+        return "vern7"
+    if method in ("b200_vern9", "vern9"):
+        return "vern9"
+    raise TypeError("the b200 map runs vern7 / vern9 on the device, not method=%r" % (method,))
+
+
+def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, map_kw=None,
+             progress_bar=None, progress_bar_kwargs={}):
+    """Map function for ``MCSolver.run(..., options={"map": "b200"})`` (protocol of
+    solver/parallel.py:49-132).  ``task`` is ``MCSolver._run_one_traj`` bound to the solver,
+    ``values`` the per-trajectory seeds, ``task_args = (state0, tlist, e_ops)``.  All
+    trajectories run as one device batch; each one is handed to ``reduce_func`` as the
+    ``(seed, Result, weight)`` triple ``McResult.add`` expects
+    (solver/multitrajresult.py:402-434)."""
+    solver = getattr(task, "__self__", None)
+    if not isinstance(solver, MCSolver) or task_kwargs:
+        raise TypeError("the 'b200' map runs MCSolver trajectories on the device; other tasks "
+                        "(or improved_sampling / mixed initial states) need a stock map")
+    state0, tlist, e_ops = task_args
+    seeds = list(values)
+    ntraj = len(seeds)
+    opts = solver.options
+    method = _device_method(opts["method"])
+    rhs = solver.rhs
+    e_dict = e_ops if isinstance(e_ops, dict) else dict(enumerate(e_ops or []))
+    for k, e in e_dict.items():
+        if not isinstance(e, (qutip.Qobj, QobjEvo)):
+            raise TypeError("e_ops must be Qobj / QobjEvo for the 'b200' map (python callables "
+                            "cannot run on the device)")
+    if rhs.rhs.issuper:
+        raise TypeError("superoperator Hamiltonians are not supported by the 'b200' map")
+    want_states = bool(opts["store_states"]) or (opts["store_states"] is None and not e_dict)
+    want_final = bool(opts["store_final_state"])
+    system = system_from_qobjevo(rhs.rhs, rhs.c_ops, rhs.n_ops,
+                                 [QobjEvo(e) if isinstance(e, qutip.Qobj) else e
+                                  for e in e_dict.values()])
+    iopt = solver._integrator._integrator.options
+    eng = E.Engine(
+        system, method, nslots=min(ntraj, 4096), atol=iopt['atol'], rtol=iopt['rtol'],
+        nsteps=int(iopt['nsteps']), first_step=float(iopt['first_step'] or 0),
+        min_step=float(iopt['min_step'] or 0), max_step=float(iopt['max_step'] or 0),
+        interpolate=int(bool(iopt['interpolate'])), norm_steps=int(opts['norm_steps']),
+        norm_t_tol=opts['norm_t_tol'], norm_tol=opts['norm_tol'],
+        norm_min_step=opts['norm_min_step'], mc_corr_eps=opts['mc_corr_eps'],
+        store_states=int(want_states or want_final))
+    ndraws = 64
+    gens = [s if hasattr(s, "random") else solver._get_generator(s) for s in seeds]
+    draws = np.stack([g.random(ndraws) for g in gens])
+    psi0 = _data.to(_data.Dense, state0).to_array().reshape(-1, order="F")
+    tlist = np.asarray(tlist, dtype=float)
+    r = eng.run_mcsolve(psi0, tlist, draws, ntraj=ntraj)
+    while (r.status == -12).any():           # threshold table too short: extend and redo those
+        todo = np.nonzero(r.status == -12)[0]
+        more = np.stack([gens[j].random(3 * ndraws) for j in todo])
+        draws_ext = np.concatenate([draws[todo], more], axis=1)
+        r2 = eng.run_mcsolve(psi0, tlist, draws_ext, ntraj=len(todo))
+        for key in ("expect", "status", "ncol", "col_t", "col_which", "stats"):
+            r[key][todo] = r2[key]
+        if r.states is not None:
+            r.states[todo] = r2.states
+        full = np.zeros((ntraj, draws_ext.shape[1]))
+        full[:, :draws.shape[1]] = draws
+        full[todo] = draws_ext
+        draws, ndraws = full, draws_ext.shape[1]
+    herm = [bool(e.isherm) if isinstance(e, qutip.Qobj) else False for e in e_dict.values()]
+    for j in range(ntraj):
+        st = int(r.status[j])
+        if st == -10:
+            raise RuntimeError(E.STATUS_MESSAGES[-10])
+        if st != 1:
+            raise IntegratorException(E.STATUS_MESSAGES.get(st, "integration failed"))
+        res = solver._trajectory_resultclass(e_dict, solver.options)
+        res.times = list(tlist)
+        for m, k in enumerate(res.e_data):
+            vals = r.expect[j, m]
+            res.e_data[k].extend((vals.real if herm[m] else vals).tolist())
+        if want_states or want_final:
+            qs = [solver._restore_state(_data.Dense(r.states[j, i].reshape(-1, 1)), copy=False)
+                  for i in (range(len(tlist)) if want_states else [len(tlist) - 1])]
+            if want_states:
+                res.states = qs
+            res._final_state = qs[-1]
+        res.collapse = [(float(r.col_t[j, i]), int(r.col_which[j, i]))
+                        for i in range(r.ncol[j])]
+        if reduce_func is not None:
+            remaining = reduce_func((seeds[j], res, 1))
+            if remaining is not None and remaining <= 0:
+                break
+    return None
+
+
+register()

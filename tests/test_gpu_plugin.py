@@ -1,0 +1,221 @@
+"""GPU tests of the QuTiP plug-in: the registered integrators, data-layer types and the
+'b200' map against the reference's own solvers run side by side (unmodified qutip
+5.4.0.dev from oracle/_ref) with identical options."""
+import pickle
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+_ref = oracle.ref_path()
+if _ref is None:
+    pytest.skip("reference build (oracle/_ref) not present", allow_module_level=True)
+sys.path.insert(0, _ref)
+warnings.filterwarnings("ignore")
+import qutip  # noqa: E402
+from qutip import (QobjEvo, basis, destroy, mcsolve, mesolve, qeye, sigmam, sigmax,  # noqa
+                   sigmaz, tensor)
+import qutip_b200.plugin as plugin  # noqa: E402
+
+ATOL, RTOL = 1e-8, 1e-6
+OPT = {"progress_bar": False}
+
+
+def tfim(n, gamma=0.1):
+    sx, sz, sm = [], [], []
+    for i in range(n):
+        ops = [qeye(2)] * n
+        ops[i] = sigmax(); sx.append(tensor(ops))
+        ops[i] = sigmaz(); sz.append(tensor(ops))
+        ops[i] = sigmam(); sm.append(tensor(ops))
+    H = 0
+    for i in range(n - 1):
+        H = H - sz[i] * sz[i + 1]
+    for i in range(n):
+        H = H - sx[i]
+    return H, [np.sqrt(gamma) * s for s in sm], sz
+
+
+def jc():
+    N = 10
+    a = tensor(destroy(N), qeye(2)); sm = tensor(qeye(N), destroy(2))
+    H = 2 * np.pi * a.dag() * a + 2 * np.pi * sm.dag() * sm \
+        + 2 * np.pi * 0.05 * (a.dag() * sm + a * sm.dag())
+    c_ops = [np.sqrt(0.1) * a, np.sqrt(0.05) * sm]
+    psi0 = tensor(basis(N, 3), basis(2, 0))
+    return H, c_ops, psi0, [a.dag() * a, tensor(qeye(N), sigmaz())]
+
+
+def test_registered():
+    assert "b200_vern7" in qutip.MESolver.avail_integrators()
+    assert "b200_vern9" in qutip.MCSolver.avail_integrators()
+    assert plugin.B200Dense in qutip.core.data.to.dtypes
+    assert qutip.solver.parallel._maps["b200"] is plugin.b200_map
+
+
+@pytest.mark.parametrize("method", ["vern7", "vern9"])
+def test_mesolve_c1_jc(method):
+    H, c_ops, psi0, e_ops = jc()
+    tl = np.linspace(0, 10, 101)
+    ref = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method=method, store_states=True))
+    out = mesolve(H, psi0, tl, c_ops, e_ops=e_ops,
+                  options=dict(OPT, method="b200_" + method, store_states=True))
+    np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), rtol=RTOL, atol=ATOL)
+    for a, b in zip(out.states, ref.states):
+        np.testing.assert_allclose(a.full(), b.full(), rtol=RTOL, atol=ATOL)
+
+
+def test_mesolve_c4_time_dependent_string_and_array():
+    Nc = 8
+    a = tensor(destroy(Nc), qeye(3)); b = tensor(qeye(Nc), destroy(3))
+    H0 = 5 * a.dag() * a + 4.5 * b.dag() * b - 0.15 * b.dag() * b.dag() * b * b \
+        + 0.1 * (a.dag() * b + a * b.dag())
+    tl = np.linspace(0, 5, 51)
+    env = np.exp(-((tl - 2.5) / 1.0) ** 2)
+    H = QobjEvo([H0, [a + a.dag(), "A*cos(w*t)"], [b + b.dag(), env]],
+                args={"A": 0.2, "w": 5.0}, tlist=tl)
+    c_ops = [np.sqrt(0.01) * a, np.sqrt(0.02) * b, np.sqrt(0.03) * b.dag() * b]
+    psi0 = tensor(basis(Nc, 0), basis(3, 0))
+    e_ops = [a.dag() * a, b.dag() * b]
+    ref = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="vern7"))
+    out = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="b200_vern7"))
+    np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), rtol=RTOL, atol=ATOL)
+
+
+def test_sesolve_and_options():
+    H, _, psi0, e_ops = jc()
+    tl = np.linspace(0, 3, 31)
+    o = dict(OPT, atol=1e-10, rtol=1e-8, first_step=1e-3, max_step=0.05)
+    ref = qutip.sesolve(H, psi0, tl, e_ops=e_ops, options=dict(o, method="vern7"))
+    out = qutip.sesolve(H, psi0, tl, e_ops=e_ops, options=dict(o, method="b200_vern7"))
+    np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), rtol=RTOL, atol=ATOL)
+    with pytest.raises(KeyError):
+        qutip.sesolve(H, psi0, tl, options=dict(OPT, method="b200_vern7", bogus=1))
+
+
+def test_nsteps_failure_raises_reference_exception():
+    H, c_ops, psi0, e_ops = jc()
+    with pytest.raises(qutip.solver.integrator.IntegratorException, match="Too much work"):
+        mesolve(H, psi0, [0, 50], c_ops, options=dict(OPT, method="b200_vern7", nsteps=3))
+
+
+def test_refuses_host_only_forms():
+    a = destroy(5)
+    H = QobjEvo([a.dag() * a, [a + a.dag(), lambda t: np.cos(t)]])
+    with pytest.raises(TypeError, match="device"):
+        mesolve(H, basis(5, 0), [0, 1], [a], options=dict(OPT, method="b200_vern7"))
+    with pytest.raises(TypeError, match="QobjEvo.matmul_data"):
+        plugin.B200Vern7(lambda t, y: y, {})
+
+
+def test_integrator_pickle_roundtrip():
+    H, c_ops, psi0, e_ops = jc()
+    s = qutip.MESolver(H, c_ops, options=dict(OPT, method="b200_vern7"))
+    s.start(psi0, 0.0)
+    s.step(0.5)
+    integ = pickle.loads(pickle.dumps(s._integrator))
+    t1, y1 = s._integrator.integrate(1.0)
+    t2, y2 = integ.integrate(1.0)
+    assert t1 == t2 == 1.0
+    np.testing.assert_allclose(y1.to_array(), y2.to_array(), rtol=RTOL, atol=ATOL)
+
+
+def test_mcsolve_with_registered_integrator_python_driver():
+    """Stock MCIntegrator (python jump logic) on top of the device integrator."""
+    H, c_ops, sz = tfim(5)
+    psi0 = basis([2] * 5, [0] * 5)
+    tl = np.linspace(0, 2, 11)
+    kw = dict(e_ops=[sz[0]], ntraj=6, seeds=np.random.SeedSequence(3))
+    ref = mcsolve(H, psi0, tl, c_ops, options=dict(OPT, method="vern7", keep_runs_results=True), **kw)
+    kw["seeds"] = np.random.SeedSequence(3)
+    out = mcsolve(H, psi0, tl, c_ops, options=dict(OPT, method="b200_vern7", keep_runs_results=True), **kw)
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    for a, b in zip(out.col_times, ref.col_times):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("method", ["vern7", "vern9"])
+def test_mcsolve_b200_map_matches_reference(method):
+    """Whole batch on the device through options['map']='b200': identical collapse records
+    (TestSeeds-style determinism, reference tests/solver/test_mcsolve.py:326-404)."""
+    H, c_ops, sz = tfim(6)
+    psi0 = basis([2] * 6, [0] * 6)
+    tl = np.linspace(0, 2, 21)
+    e_ops = [sz[0], sz[2]]
+    ref = mcsolve(H, psi0, tl, c_ops, e_ops=e_ops, ntraj=20, seeds=np.random.SeedSequence(7),
+                  options=dict(OPT, method=method, keep_runs_results=True))
+    out = mcsolve(H, psi0, tl, c_ops, e_ops=e_ops, ntraj=20, seeds=np.random.SeedSequence(7),
+                  options=dict(OPT, method=method, map="b200", keep_runs_results=True))
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    for a, b in zip(out.col_times, ref.col_times):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(np.array(out.average_expect), np.array(ref.average_expect), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(np.array(out.std_expect), np.array(ref.std_expect), rtol=1e-5, atol=1e-7)
+    assert out.num_trajectories == 20
+
+
+def test_mcsolve_b200_map_states_and_time_dependent_cops():
+    a = destroy(6)
+    H = a.dag() * a
+    c_ops = [QobjEvo([a, "sqrt(g)*exp(-k*t)"], args={"g": 0.8, "k": 0.3}), 0.2 * a.dag() * a]
+    psi0 = basis(6, 4)
+    tl = np.linspace(0, 3, 13)
+    o = dict(OPT, method="vern7", keep_runs_results=True, store_final_state=True)
+    ref = mcsolve(H, psi0, tl, c_ops, e_ops=[a.dag() * a], ntraj=12, seeds=5, options=o)
+    out = mcsolve(H, psi0, tl, c_ops, e_ops=[a.dag() * a], ntraj=12, seeds=5,
+                  options=dict(o, map="b200"))
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=RTOL, atol=ATOL)
+    for x, y in zip(out.runs_final_states, ref.runs_final_states):
+        np.testing.assert_allclose(x.full(), y.full(), rtol=RTOL, atol=ATOL)
+
+
+def test_data_layer_types_in_stock_rk_loop():
+    """Stock vern7 running on the registered device data types through the dispatchers
+    (QobjEvo.matmul_data -> matmul[B200Operator, B200Dense], add, mul, norms ...)."""
+    H, c_ops, psi0, e_ops = jc()
+    tl = np.linspace(0, 2, 11)
+    ref = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="vern7"))
+    L = qutip.liouvillian(H, c_ops).to("B200Operator")
+    rho0 = qutip.operator_to_vector(qutip.ket2dm(psi0)).to("b200")
+    solver = qutip.MESolver(L, options=dict(OPT, method="vern7"))
+    integ = solver._integrator
+    integ.set_state(0.0, rho0.data)
+    assert isinstance(integ.get_state()[1], plugin.B200Dense)
+    for i, t in enumerate(tl[1:], 1):
+        _, y = integ.integrate(t)
+        assert isinstance(y, plugin.B200Dense)
+        rho = qutip.vector_to_operator(qutip.Qobj(y.to_array(), dims=rho0.dims))
+        for k, e in enumerate(e_ops):
+            assert abs(qutip.expect(e, rho) - ref.expect[k][i]) < 1e-7
+
+
+def test_data_layer_specialisations_direct():
+    from qutip.core import data as _data
+    rng = np.random.default_rng(0)
+    n = 40
+    A = qutip.rand_herm(n, density=0.2, seed=1).data
+    x = rng.random((n, 1)) + 1j * rng.random((n, 1))
+    dA = _data.to(plugin.B200Operator, A)
+    dx = _data.to(plugin.B200Dense, _data.Dense(x))
+    y = _data.matmul(dA, dx, 0.5j)
+    assert isinstance(y, plugin.B200Dense)
+    np.testing.assert_allclose(y.to_array(), 0.5j * A.to_array() @ x, atol=1e-13)
+    np.testing.assert_allclose(_data.add(dx, y, 2.0).to_array(), x + 2 * y.to_array(), atol=1e-13)
+    np.testing.assert_allclose(_data.mul(dx, 3j).to_array(), 3j * x, atol=1e-13)
+    assert abs(_data.norm.l2(dx) - np.linalg.norm(x)) < 1e-12
+    assert abs(_data.expect(dA, dx) - np.vdot(x, A.to_array() @ x)) < 1e-12
+    assert abs(_data.inner(dx, y) - np.vdot(x, y.to_array())) < 1e-12
+    z = _data.zeros[plugin.B200Dense](3, 1)
+    assert np.all(z.to_array() == 0)
+    back = _data.to(_data.Dense, y)
+    np.testing.assert_allclose(back.to_array(), y.to_array())
+    with pytest.raises(ValueError, match="incompatible matrix shapes"):
+        _data.matmul(dA, _data.to(plugin.B200Dense, _data.Dense(np.ones((3, 1), dtype=complex))))

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Small driver for ncu captures (never a source of bench numbers).
+    python tools/prof_run.py c3 [ntraj]   one mcsolve batch of config C3
+    python tools/prof_run.py c2           C2 SpMV x5 + one short mesolve
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import qutip_b200 as qb  # noqa: E402
+from qutip_b200 import models, solve  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "c3"
+if what == "c3":
+    ntraj = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+    n = 14
+    H, c_ops, sz = models.tfim(n)
+    system = solve.build_system([models.heff(H, c_ops)], c_ops, e_ops=[sz[0]])
+    eng = qb.Engine(system, "vern7", nslots=ntraj)
+    draws = solve.make_thresholds(7, ntraj, 64)
+    r = eng.run_mcsolve(models.basis_state(n), np.linspace(0, 2, 21), draws, ntraj=ntraj)
+    print("c3", ntraj, "traj", r.rounds, "rounds", r.gpu_ms, "ms", (r.status == 1).all())
+else:
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    H, c_ops, sz = models.tfim(n)
+    L = models.liouvillian(H, c_ops)
+    N = L.shape[0]
+    system = qb.System(N)
+    system.add_element(qb.DeviceOp.from_scipy(L))
+    eng = qb.Engine(system, "vern7", nslots=1)
+    x = qb.DeviceDense.from_numpy(np.random.default_rng(0).random(N) + 0j)
+    out = qb.DeviceDense.zeros(N, 1)
+    print("spmv ms", eng.rhs_bench(0.0, x, out, iters=5) / 5)
+    rho0 = np.zeros(N, dtype=complex); rho0[0] = 1
+    r = eng.run_mesolve(rho0, np.linspace(0, 0.2, 3))
+    print("c2 mesolve", r.stats[0], r.gpu_ms, "ms")
