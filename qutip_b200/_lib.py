@@ -13,7 +13,8 @@ import numpy as np
 from .coeffs import QbInstr
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqutip_b200.so")
+# QUTIP_B200_LIB selects another build of the same library (A/B kernel tuning only)
+LIB_PATH = os.environ.get("QUTIP_B200_LIB") or os.path.join(_HERE, "libqutip_b200.so")
 
 
 class QbError(RuntimeError):

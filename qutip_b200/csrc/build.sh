@@ -7,5 +7,6 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 $NVCC $FLAGS -c qb_ops.cu -o qb_ops.o &
 $NVCC $FLAGS -c qb_engine.cu -o qb_engine.o &
 wait
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libqutip_b200.so qb_ops.o qb_engine.o -lcudart
-echo "built $(cd .. && pwd)/libqutip_b200.so"
+OUT=${QB_OUT:-../libqutip_b200.so}
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT qb_ops.o qb_engine.o -lcudart
+echo "built $OUT"

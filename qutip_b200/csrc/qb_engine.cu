@@ -6,7 +6,7 @@
 //       k[0..S-1] (RK stage derivatives), y_prev, y_front, y_interp, tmpA, tmpB.
 //       "y_prev <- y_front" etc. are slot relabels in QbTraj, never copies.
 //   pass[nslots], traj[nslots]    : the next vector instruction and the controller state
-//   partials[nslots][ntiles][64]  : per-CTA partial reductions, summed in a fixed order
+//   partials[nslots][nslices][red_stride] : per-warp partial reductions, summed in a fixed order
 // A "round" = pass kernel + control kernel; the host enqueues rounds back to back and only
 // looks at a device counter every chunk, so there is no host synchronisation per step.
 #include <algorithm>
@@ -39,6 +39,7 @@ struct QbEngineDev {
     int* out_status;
     int* out_stats;
     unsigned long long* vec_count;   // state-sized vector accesses issued (algorithmic traffic)
+    int nslices, red_stride;
 };
 
 // ------------------------------------------------------------------ pass kernel
@@ -48,126 +49,137 @@ __device__ __forceinline__ const double2* qb_vsrc(const QbEngineDev* E, int slot
     return E->init_states + (size_t)init_idx * (size_t)E->ctl.N;
 }
 
-__global__ void __launch_bounds__(QB_TILE_ROWS)
+#ifndef QB_PF
+#define QB_PF 4      // epilogue source vectors prefetched before the operator sweep
+#endif
+
+// Warp-autonomous pass kernel: one warp = one 32-row slice of one trajectory slot.  There
+// is no shared memory and no block-level barrier: each warp reads the (L1/L2-resident)
+// pass descriptor itself, issues the loads of its epilogue sources BEFORE the operator
+// sweep so their HBM latency overlaps it, and writes its own partial reductions
+// (partials[slot][slice][k], summed in a fixed order by the control kernel).
+#ifndef QB_MINB
+#define QB_MINB 4
+#endif
+__global__ void __launch_bounds__(QB_TILE_ROWS, QB_MINB)
 qb_pass_kernel(const QbEngineDev* __restrict__ E)
 {
     const int ntiles = E->ctl.ntiles;
     const int slot = blockIdx.x / ntiles;
     const int tile = blockIdx.x - slot * ntiles;
-    const QbPass* gp = &E->pass[slot];
-    if (gp->kind == QB_PASS_NONE) return;
-
-    __shared__ QbPass sp;
-    __shared__ double2 scoef[QB_MAX_ELEMS];
-    __shared__ double sred[QB_TILE_ROWS / 32][QB_MAXRED];
-    __shared__ int s_ids[2];
-    {
-        const int nw = (int)(sizeof(QbPass) / sizeof(int));
-        const int* src = reinterpret_cast<const int*>(gp);
-        int* dst = reinterpret_cast<int*>(&sp);
-        for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
-        if (threadIdx.x < QB_MAX_ELEMS) {
-            const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef +
-                                      (threadIdx.x < E->ctl.maxcoef ? threadIdx.x : 0)];
-            scoef[threadIdx.x] = make_double2(c.re, c.im);
-        }
-        if (threadIdx.x == 0) { s_ids[0] = E->traj[slot].init_idx; s_ids[1] = E->traj[slot].traj_id; }
-    }
-    __syncthreads();
-
+    const QbPass* __restrict__ gp = &E->pass[slot];
+    const int kind = gp->kind;
+    if (kind == QB_PASS_NONE) return;
     const int N = E->ctl.N;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sl = tile * (QB_TILE_ROWS / 32) + warp;
+    if ((long long)sl * 32 >= N) return;          // warp-uniform
     const long long r = (long long)sl * 32 + lane;
     const bool active = r < N;
-    const bool slice_ok = (long long)sl * 32 < N;
-    const int kind = sp.kind;
-    const int init_idx = s_ids[0];
+    const size_t N_ = (size_t)N;
+    const int init_idx = E->traj[slot].init_idx;
+    double* __restrict__ part = E->partials + ((size_t)slot * E->nslices + sl) * E->red_stride;
 
     if (kind == QB_PASS_EXPECT) {
-        const QbOpDev* ops = (sp.opset == QB_OPSET_EOPS) ? E->eops : E->nops;
-        const bool functional = (sp.opset == QB_OPSET_EOPS) && E->ctl.eop_functional;
-        const double2* x = qb_vsrc(E, slot, sp.x, init_idx);
+        const int opset = gp->opset, op_lo = gp->op_lo, nops = gp->op_hi - gp->op_lo;
+        const QbOpDev* ops = (opset == QB_OPSET_EOPS) ? E->eops : E->nops;
+        const bool functional = (opset == QB_OPSET_EOPS) && E->ctl.eop_functional;
+        const double2* x = qb_vsrc(E, slot, gp->x, init_idx);
         double2 xr = make_double2(0.0, 0.0);
         if (active) xr = x[r];
-        const int nops = sp.op_hi - sp.op_lo;
         for (int m = 0; m < nops; m++) {
-            double2 q = make_double2(0.0, 0.0);
-            if (slice_ok) q = qb_rowdot(ops[sp.op_lo + m], sl, lane, r, active, x);
+            const double2 q = qb_rowdot<QB_UP>(ops[op_lo + m], sl, lane, r, active, x);
             double2 pr;
             if (functional) pr = q;
             else pr = make_double2(xr.x * q.x + xr.y * q.y, xr.x * q.y - xr.y * q.x);  // conj(x)*q
             if (!active) pr = make_double2(0.0, 0.0);
             const double sre = qb_warp_sum(pr.x), sim = qb_warp_sum(pr.y);
-            if (lane == 0) { sred[warp][2 * m] = sre; sred[warp][2 * m + 1] = sim; }
-        }
-        __syncthreads();
-        if (threadIdx.x < 2 * nops) {
-            double s = 0.0;
-            for (int w = 0; w < QB_TILE_ROWS / 32; w++) s += sred[w][threadIdx.x];
-            E->partials[((size_t)slot * ntiles + tile) * QB_MAXRED + threadIdx.x] = s;
+            if (lane == 0) { part[2 * m] = sre; part[2 * m + 1] = sim; }
         }
         return;
     }
 
-    // ---- operator application ----
-    double2 z = make_double2(0.0, 0.0);
-    if (slice_ok && (kind == QB_PASS_RHS || kind == QB_PASS_APPLY)) {
-        const double2* x = qb_vsrc(E, slot, sp.x, init_idx);
-        if (kind == QB_PASS_RHS) {
-            const int nelem = E->ctl.nelem;
-            for (int e = 0; e < nelem; e++) {
-                const double2 q = qb_rowdot(E->elem[e], sl, lane, r, active, x);
-                const double2 c = scoef[e];
-                z.x += c.x * q.x - c.y * q.y;
-                z.y += c.x * q.y + c.y * q.x;
-            }
-        } else {
-            const double2 q = qb_rowdot(E->cops[sp.op_lo], sl, lane, r, active, x);
-            const double2 c = scoef[0];
-            z.x = c.x * q.x - c.y * q.y;
-            z.y = c.x * q.y + c.y * q.x;
-        }
-        z.x *= sp.zscale; z.y *= sp.zscale;
+    // ---- epilogue sources: lane i holds (slot, w1, w2) of source i; prefetch the first QB_PF
+    const int nsrc = gp->nsrc;
+    int my_src = 0;
+    double my_w1 = 0.0, my_w2 = 0.0;
+    if (lane < nsrc) { my_src = gp->src[lane]; my_w1 = gp->w1[lane]; my_w2 = gp->w2[lane]; }
+    double2 pv[QB_PF];
+#pragma unroll
+    for (int u = 0; u < QB_PF; u++) {
+        const int sidx = __shfl_sync(0xffffffffu, my_src, u);
+        const double2* p = qb_vsrc(E, slot, sidx, init_idx);
+        pv[u] = (u < nsrc && active) ? p[r] : make_double2(0.0, 0.0);
     }
 
-    // ---- fused linear combinations, stores, reductions ----
+    // ---- operator application ----
+    double2 z = make_double2(0.0, 0.0);
+    if (kind == QB_PASS_RHS) {
+        const double2* x = qb_vsrc(E, slot, gp->x, init_idx);
+        const int nelem = E->ctl.nelem;
+        const qb_c128* cf = E->coef + (size_t)slot * E->ctl.maxcoef;
+        for (int e = 0; e < nelem; e++) {
+            const double2 q = qb_rowdot<QB_UP>(E->elem[e], sl, lane, r, active, x);
+            const qb_c128 c = cf[e];
+            z.x += c.re * q.x - c.im * q.y;
+            z.y += c.re * q.y + c.im * q.x;
+        }
+    } else if (kind == QB_PASS_APPLY) {
+        const double2 q = qb_rowdot<QB_UP>(E->cops[gp->op_lo], sl, lane, r, active,
+                                    qb_vsrc(E, slot, gp->x, init_idx));
+        const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef];
+        z = make_double2(c.re * q.x - c.im * q.y, c.re * q.y + c.im * q.x);
+    }
+    const double zscale = gp->zscale;
+    z.x *= zscale; z.y *= zscale;
+
+    // ---- fused linear combinations (sources in order, z last), stores, reductions ----
+    double2 o1 = make_double2(0.0, 0.0), o2 = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < QB_PF; u++) {
+        const double a = __shfl_sync(0xffffffffu, my_w1, u), b = __shfl_sync(0xffffffffu, my_w2, u);
+        o1.x = fma(a, pv[u].x, o1.x); o1.y = fma(a, pv[u].y, o1.y);
+        o2.x = fma(b, pv[u].x, o2.x); o2.y = fma(b, pv[u].y, o2.y);
+    }
+    for (int i = QB_PF; i < nsrc; i += 4) {            // rarely taken (dense-output rows)
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int sidx = __shfl_sync(0xffffffffu, my_src, (i + u) & 31);
+            const double2* p = qb_vsrc(E, slot, sidx, init_idx);
+            v[u] = (i + u < nsrc && active) ? p[r] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const double a = __shfl_sync(0xffffffffu, my_w1, (i + u) & 31);
+            const double b = __shfl_sync(0xffffffffu, my_w2, (i + u) & 31);
+            o1.x = fma(a, v[u].x, o1.x); o1.y = fma(a, v[u].y, o1.y);
+            o2.x = fma(b, v[u].x, o2.x); o2.y = fma(b, v[u].y, o2.y);
+        }
+    }
+    const double w1z = gp->w1z, w2z = gp->w2z;
+    o1.x = fma(w1z, z.x, o1.x); o1.y = fma(w1z, z.y, o1.y);
+    o2.x = fma(w2z, z.x, o2.x); o2.y = fma(w2z, z.y, o2.y);
+    const int zdst = gp->zdst, dst1 = gp->dst1, red = gp->red;
     double r0 = 0.0, r1 = 0.0, r2 = 0.0;
     if (active) {
-        const size_t N_ = (size_t)N;
         double2* base = E->pool + (size_t)slot * E->V * N_;
-        if (sp.zdst >= 0) base[(size_t)sp.zdst * N_ + r] = z;
-        double2 o1 = make_double2(0.0, 0.0), o2 = make_double2(0.0, 0.0);
-        const int nsrc = sp.nsrc;
-        for (int i = 0; i < nsrc; i++) {
-            const double2 v = qb_vsrc(E, slot, sp.src[i], init_idx)[r];
-            const double a = sp.w1[i], b = sp.w2[i];
-            o1.x = fma(a, v.x, o1.x); o1.y = fma(a, v.y, o1.y);
-            o2.x = fma(b, v.x, o2.x); o2.y = fma(b, v.y, o2.y);
-        }
-        o1.x = fma(sp.w1z, z.x, o1.x); o1.y = fma(sp.w1z, z.y, o1.y);
-        o2.x = fma(sp.w2z, z.x, o2.x); o2.y = fma(sp.w2z, z.y, o2.y);
-        if (sp.dst1 >= 0) base[(size_t)sp.dst1 * N_ + r] = o1;
-        else if (sp.dst1 == QB_SLOT_OUT)
-            E->out_states[((size_t)s_ids[1] * E->ctl.nt + sp.out_index) * N_ + r] = o1;
+        if (zdst >= 0) base[(size_t)zdst * N_ + r] = z;
+        if (dst1 >= 0) base[(size_t)dst1 * N_ + r] = o1;
+        else if (dst1 == QB_SLOT_OUT)
+            E->out_states[((size_t)E->traj[slot].traj_id * E->ctl.nt + gp->out_index) * N_ + r] = o1;
         const double n1 = o1.x * o1.x + o1.y * o1.y;
         r0 = n1;
-        if (sp.red & QB_RED_WRMS) {
+        if (red & QB_RED_WRMS) {
             const double q = sqrt(o2.x * o2.x + o2.y * o2.y)
                              / (E->ctl.opt.atol + E->ctl.opt.rtol * sqrt(n1));
             r1 = q * q;
         }
         r2 = z.x * z.x + z.y * z.y;
     }
-    if (sp.red) {
+    if (red) {
         r0 = qb_warp_sum(r0); r1 = qb_warp_sum(r1); r2 = qb_warp_sum(r2);
-        if (lane == 0) { sred[warp][0] = r0; sred[warp][1] = r1; sred[warp][2] = r2; }
-        __syncthreads();
-        if (threadIdx.x < 3) {
-            double s = 0.0;
-            for (int w = 0; w < QB_TILE_ROWS / 32; w++) s += sred[w][threadIdx.x];
-            E->partials[((size_t)slot * ntiles + tile) * QB_MAXRED + threadIdx.x] = s;
-        }
+        if (lane == 0) { part[0] = r0; part[1] = r1; part[2] = r2; }
     }
 }
 
@@ -198,11 +210,11 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
     int nred = 0;
     if (kind == QB_PASS_EXPECT) nred = 2 * (gp->op_hi - gp->op_lo);
     else if (kind != QB_PASS_NONE && gp->red) nred = 3;
-    const int ntiles = E->ctl.ntiles;
+    const int nslices = E->nslices, stride = E->red_stride;
+    const double* __restrict__ part = E->partials + (size_t)slot * nslices * stride;
     for (int k = 0; k < nred; k++) {
         double s = 0.0;
-        for (int tile = lane; tile < ntiles; tile += 32)
-            s += E->partials[((size_t)slot * ntiles + tile) * QB_MAXRED + k];
+        for (int i = lane; i < nslices; i += 32) s += part[(size_t)i * stride + k];
         s = qb_warp_sum(s);
         if (lane == 0) sred[w][k] = s;
     }
@@ -482,7 +494,12 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     QB_TRY(qb_dev_alloc(e, (size_t)nslots, &h.pass));
     QB_TRY(qb_dev_alloc(e, (size_t)nslots * e->maxcoef, &h.coef));
     QB_TRY(qb_dev_alloc(e, (size_t)nslots * std::max(1, h.ctl.ncops), &h.probs));
-    QB_TRY(qb_dev_alloc(e, (size_t)nslots * h.ctl.ntiles * QB_MAXRED, &h.partials));
+    h.nslices = (int)((s->N + 31) / 32);
+    {
+        const int nops = std::max(h.ctl.ncops, h.ctl.neops);
+        h.red_stride = std::max(4, 2 * std::min(QB_MAXRED / 2, nops));
+    }
+    QB_TRY(qb_dev_alloc(e, (size_t)nslots * h.nslices * h.red_stride, &h.partials));
     QB_TRY(qb_dev_alloc(e, 1, &h.queue_head));
     QB_TRY(qb_dev_alloc(e, 1, &h.n_active));
     QB_TRY(qb_dev_alloc(e, 1, &h.vec_count));

@@ -7,15 +7,27 @@
 //   contiguous run of the value array (coalesced, 16 B per lane) and x[r + offset] is a
 //   contiguous run of the state too.  No per-nonzero column index is read: 16 B per
 //   non-zero + 8 B per (slice, diagonal) instead of CSR's 20 B per non-zero.
+//   The entry list of a slice is fetched once by the warp (lane e holds entry e), the
+//   value offsets come from a warp prefix sum of the mask popcounts, and the main loop
+//   broadcasts (offset, mask, base) by shuffle -- so no global load in the loop depends on
+//   another one and the unrolled loop keeps 8 x (1 + G) independent 16-byte loads per lane
+//   in flight.  G state vectors (trajectories) can share one pass over the operator.
 // * CSR   : generic fallback, one lane per row (handles unsorted / duplicate indices).
 // * DENSE : column-major A, lanes read consecutive rows of a column (coalesced).
 #pragma once
 #include <cuda_runtime.h>
 #include "qb_types.h"
 
-__device__ __forceinline__ double2 qb_ld(const qb_c128* p) {
-    return *reinterpret_cast<const double2*>(p);
-}
+// Entries kept in flight per lane by the DIAM sweep.  Measured on B200 (tools/perf_ab.sh):
+// occupancy beats deeper unrolling -- U=3 at 64 registers (32 warps/SM) gives the best
+// stand-alone SpMV, U=2 the best fused pass kernel.
+#ifndef QB_U1
+#define QB_U1 3     // stand-alone SpMV / matmul / expect kernels
+#endif
+#ifndef QB_UP
+#define QB_UP 2     // inside the fused pass kernel
+#endif
+
 __device__ __forceinline__ void qb_fma(double2& acc, const double2 a, const double2 b) {
     acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
     acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
@@ -23,50 +35,74 @@ __device__ __forceinline__ void qb_fma(double2& acc, const double2 a, const doub
 __device__ __forceinline__ double2 qb_mul(const double2 a, const double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+// acc[g] += (A x_g)[r] for the lane's row of slice sl, g < G.  DIAM only.  Whole-warp call.
+// A.pad_ != 0 marks an operator far larger than L2: its values are read with the
+// cache-streaming policy so they do not evict the (re-used) state vectors.
+template <int G, int QB_UNROLL>
+__device__ __forceinline__ void qb_rowdot_diam(const QbOpDev& A, int sl, int lane, long long r,
+                                               const double2* const* x, double2 (&acc)[G])
+{
+    const int e0 = A.slice_ptr[sl], e1 = A.slice_ptr[sl + 1];
+    long long vbase = A.slice_vbase[sl];
+    const unsigned lt = (1u << lane) - 1u;
+    const bool stream = A.pad_ != 0;
+    const int2* __restrict__ ent = reinterpret_cast<const int2*>(A.ent_off);
+    const double2* __restrict__ val = reinterpret_cast<const double2*>(A.val);
+    const double2 zero = make_double2(0.0, 0.0);
+    for (int c0 = e0; c0 < e1; c0 += 32) {
+        const int ne = min(32, e1 - c0);
+        int2 my = make_int2(0, 0);
+        if (lane < ne) my = ent[c0 + lane];
+        // exclusive prefix sum of popc(mask) over the chunk's entries
+        const int cnt = __popc((unsigned)my.y);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int my_vb = incl - cnt;
+        const int chunk_total = __shfl_sync(0xffffffffu, incl, 31);
+        const double2* vchunk = val + vbase;
+        // every iteration is a full unrolled batch: entries past `ne` come from lanes whose
+        // mask is zero (lanes >= ne hold (0, 0)), so they are predicated off -- no serial tail
+        for (int e = 0; e < ne; e += QB_UNROLL) {
+            double2 v[QB_UNROLL];
+            double2 xv[QB_UNROLL][G];
+#pragma unroll
+            for (int u = 0; u < QB_UNROLL; u++) {
+                const int src = (e + u) & 31;
+                const int off = __shfl_sync(0xffffffffu, my.x, src);
+                unsigned m = (unsigned)__shfl_sync(0xffffffffu, my.y, src);
+                const int vb = __shfl_sync(0xffffffffu, my_vb, src);
+                if (e + u >= ne) m = 0u;
+                const bool hit = (m >> lane) & 1u;
+                const double2* vp = vchunk + vb + __popc(m & lt);
+                if (stream) v[u] = hit ? __ldcs(vp) : zero;
+                else v[u] = hit ? __ldg(vp) : zero;
+#pragma unroll
+                for (int g = 0; g < G; g++) xv[u][g] = hit ? x[g][r + off] : zero;
+            }
+#pragma unroll
+            for (int u = 0; u < QB_UNROLL; u++)
+#pragma unroll
+                for (int g = 0; g < G; g++) qb_fma(acc[g], v[u], xv[u][g]);
+        }
+        vbase += chunk_total;
+    }
+}
 
-// (A x)[r] for the lane's row r of slice sl.  `active` lanes have r < nrows.
-// x is a plain vector (stride 1).
+// (A x)[r] for the lane's row r of slice sl, any format.  `active` lanes have r < nrows.
+template <int U = QB_U1>
 __device__ __forceinline__ double2 qb_rowdot(const QbOpDev& A, int sl, int lane, long long r,
                                              bool active, const double2* __restrict__ x)
 {
     double2 acc = make_double2(0.0, 0.0);
     if (A.fmt == QB_FMT_DIAM) {
-        const int e0 = A.slice_ptr[sl], e1 = A.slice_ptr[sl + 1];
-        long long vb = A.slice_vbase[sl];
-        const unsigned lt = (1u << lane) - 1u;
-        const int2* __restrict__ ent = reinterpret_cast<const int2*>(A.ent_off);
-        const double2* __restrict__ val = reinterpret_cast<const double2*>(A.val);
-        int e = e0;
-        for (; e + 4 <= e1; e += 4) {
-            int2 d0 = ent[e], d1 = ent[e + 1], d2 = ent[e + 2], d3 = ent[e + 3];
-            const unsigned m0 = (unsigned)d0.y, m1 = (unsigned)d1.y, m2 = (unsigned)d2.y,
-                           m3 = (unsigned)d3.y;
-            const long long b0 = vb, b1 = b0 + __popc(m0), b2 = b1 + __popc(m1),
-                            b3 = b2 + __popc(m2);
-            vb = b3 + __popc(m3);
-            const bool h0 = (m0 >> lane) & 1u, h1 = (m1 >> lane) & 1u, h2 = (m2 >> lane) & 1u,
-                       h3 = (m3 >> lane) & 1u;
-            const double2 zero = make_double2(0.0, 0.0);
-            double2 v0 = h0 ? val[b0 + __popc(m0 & lt)] : zero;
-            double2 v1 = h1 ? val[b1 + __popc(m1 & lt)] : zero;
-            double2 v2 = h2 ? val[b2 + __popc(m2 & lt)] : zero;
-            double2 v3 = h3 ? val[b3 + __popc(m3 & lt)] : zero;
-            double2 x0 = h0 ? x[r + d0.x] : zero;
-            double2 x1 = h1 ? x[r + d1.x] : zero;
-            double2 x2 = h2 ? x[r + d2.x] : zero;
-            double2 x3 = h3 ? x[r + d3.x] : zero;
-            qb_fma(acc, v0, x0); qb_fma(acc, v1, x1); qb_fma(acc, v2, x2); qb_fma(acc, v3, x3);
-        }
-        for (; e < e1; e++) {
-            int2 d0 = ent[e];
-            const unsigned m0 = (unsigned)d0.y;
-            if ((m0 >> lane) & 1u) {
-                double2 v0 = val[vb + __popc(m0 & lt)];
-                double2 x0 = x[r + d0.x];
-                qb_fma(acc, v0, x0);
-            }
-            vb += __popc(m0);
-        }
+        const double2* xs[1] = {x};
+        double2 a1[1] = {acc};
+        qb_rowdot_diam<1, U>(A, sl, lane, r, xs, a1);
+        acc = a1[0];
     } else if (A.fmt == QB_FMT_CSR) {
         if (active) {
             const double2* __restrict__ val = reinterpret_cast<const double2*>(A.val);

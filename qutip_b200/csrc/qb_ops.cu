@@ -104,6 +104,8 @@ static int finish_diam(QbOpH* h, DiamHost& dh, int64_t rows, int64_t cols) {
     h->dev.ent_mask = nullptr;
     if ((rc = to_device(h, dh.slice_vbase, &h->dev.slice_vbase))) return rc;
     if ((rc = to_device(h, dh.val, &h->dev.val))) return rc;
+    // operators much larger than the 126 MB L2 are streamed (read once per pass)
+    h->dev.pad_ = h->device_bytes > (int64_t)96 << 20 ? 1 : 0;
     return QB_OK;
 }
 }  // namespace
