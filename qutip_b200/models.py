@@ -63,3 +63,54 @@ def basis_state(n_spins):
 def csr_algorithmic_bytes(nnz, rows, cols, ncols_x=1):
     """bytes one CSR RHS evaluation must move (single column)."""
     return nnz * 20 + (rows + 1) * 4 + 16 * cols * ncols_x + 16 * rows * ncols_x
+
+
+# ---------------------------------------------------------------- bosonic configs (C1, C4, C5)
+def destroy(n):
+    return sp.diags(np.sqrt(np.arange(1, n, dtype=float)), 1, format="csr", dtype=complex)
+
+
+def commutator_super(H):
+    """-i (I kron H - H^T kron I): the Hamiltonian part of the Liouvillian."""
+    n = H.shape[0]
+    I = sp.identity(n, dtype=complex, format="csr")
+    return sp.csr_matrix(-1j * (sp.kron(I, H) - sp.kron(H.T, I)))
+
+
+def dissipator_super(c_ops):
+    n = c_ops[0].shape[0]
+    I = sp.identity(n, dtype=complex, format="csr")
+    L = sp.csr_matrix((n * n, n * n), dtype=complex)
+    for c in c_ops:
+        cdc = c.conj().T @ c
+        L = L + sp.kron(c.conj(), c) - 0.5 * sp.kron(I, cdc) - 0.5 * sp.kron(cdc.T, I)
+    return sp.csr_matrix(L)
+
+
+def kerr_sweep(N=30, grid=16):
+    """C5: H = U/2 a^dag^2 a^2 - Delta a^dag a + F (a + a^dag), c = [a], (U, Delta, F) on a
+    fixed grid^3 lattice.  Returns the four superoperators [L_U, L_Delta, L_F, L_diss], the
+    per-system argument table [grid^3][3] and a, so that
+    L(U, Delta, F) = U L_U + Delta L_Delta + F L_F + L_diss."""
+    a = destroy(N)
+    ad = sp.csr_matrix(a.conj().T)
+    H_U = 0.5 * ad @ ad @ a @ a
+    H_D = -(ad @ a)
+    H_F = a + ad
+    Us = np.linspace(0.1, 1.0, grid)
+    Ds = np.linspace(-1.0, 1.0, grid)
+    Fs = np.linspace(0.1, 1.5, grid)
+    args = np.array([(u, d, f) for u in Us for d in Ds for f in Fs], dtype=complex)
+    return ([commutator_super(H_U), commutator_super(H_D), commutator_super(H_F),
+             dissipator_super([a])], args, a)
+
+
+def driven_cavity_transmon(Nc=40):
+    """C4: H0 + A cos(w t) (a + a^dag) with decay/dephasing; returns (H0, H1, c_ops, a, b)."""
+    a = sp.kron(destroy(Nc), sp.identity(3, dtype=complex), format="csr")
+    b = sp.kron(sp.identity(Nc, dtype=complex), destroy(3), format="csr")
+    ad, bd = sp.csr_matrix(a.conj().T), sp.csr_matrix(b.conj().T)
+    H0 = 5 * ad @ a + 4.5 * bd @ b - 0.15 * bd @ bd @ b @ b + 0.1 * (ad @ b + a @ bd)
+    H1 = a + ad
+    c_ops = [np.sqrt(0.01) * a, np.sqrt(0.02) * b, np.sqrt(0.03) * (bd @ b)]
+    return sp.csr_matrix(H0), sp.csr_matrix(H1), c_ops, a, b

@@ -219,3 +219,45 @@ def test_data_layer_specialisations_direct():
     np.testing.assert_allclose(back.to_array(), y.to_array())
     with pytest.raises(ValueError, match="incompatible matrix shapes"):
         _data.matmul(dA, _data.to(plugin.B200Dense, _data.Dense(np.ones((3, 1), dtype=complex))))
+
+
+def test_c4_full_size_time_dependent():
+    """C4 at full size (cavity 40 x transmon 3, Liouvillian 14400^2, 4 elements with the
+    string coefficient and its conjugate evaluated on the device)."""
+    Nc = 40
+    a = tensor(destroy(Nc), qeye(3)); b = tensor(qeye(Nc), destroy(3))
+    H0 = 5 * a.dag() * a + 4.5 * b.dag() * b - 0.15 * b.dag() * b.dag() * b * b \
+        + 0.1 * (a.dag() * b + a * b.dag())
+    H = QobjEvo([H0, [a + a.dag(), "A*cos(w*t)"]], args={"A": 0.2, "w": 5.0})
+    c_ops = [np.sqrt(0.01) * a, np.sqrt(0.02) * b, np.sqrt(0.03) * b.dag() * b]
+    psi0 = tensor(basis(Nc, 0), basis(3, 0))
+    tl = np.linspace(0, 5, 51)
+    e_ops = [a.dag() * a, b.dag() * b]
+    ref = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="vern7"))
+    out = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="b200_vern7"))
+    np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), rtol=RTOL, atol=ATOL)
+
+
+def test_c5_sweep_members_match_reference():
+    """Batched parameter sweep: per-member constant coefficients (U, Delta, F) read from the
+    per-trajectory argument table; a few members checked against the reference mesolve."""
+    from qutip_b200 import coeffs, models, solve
+    N = 30
+    Ls, args, a_sp = models.kerr_sweep(N, grid=16)
+    idx = {"U": 0, "D": 1, "F": 2}
+    elements = [(Ls[0], coeffs.compile_expr("U", arg_index=idx)),
+                (Ls[1], coeffs.compile_expr("D", arg_index=idx)),
+                (Ls[2], coeffs.compile_expr("F", arg_index=idx)),
+                (Ls[3], None)]
+    n_op = (a_sp.conj().T @ a_sp).toarray()
+    rho0 = np.zeros(N * N, dtype=complex); rho0[0] = 1.0
+    tl = np.linspace(0, 10, 21)
+    pick = [0, 17, 255, 1000, 2222, 4095]
+    r = solve.mesolve(elements, rho0, tl, e_ops=[n_op], args=args[pick], nargs=3,
+                      store_states=False)
+    a = destroy(N)
+    for k, j in enumerate(pick):
+        U, D, F = args[j].real
+        Hq = 0.5 * U * a.dag() * a.dag() * a * a - D * a.dag() * a + F * (a + a.dag())
+        ref = mesolve(Hq, basis(N, 0), tl, [a], e_ops=[a.dag() * a], options=dict(OPT, method="vern7"))
+        np.testing.assert_allclose(r.expect[k, 0].real, ref.expect[0], rtol=RTOL, atol=ATOL)
