@@ -69,6 +69,11 @@ int qb_free(qb_handle h);
  * qb_expect_super  : expect_super_csr_dense       core/data/expect.pyx:223-236
  * qb_trace_oper_ket: trace_oper_ket_dense         core/data/trace.pyx:78-86 */
 int qb_matmul(qb_handle op, qb_handle x, double scale_re, double scale_im, qb_handle out);
+/* dense column-major A times a block of columns as a complex128 GEMM on the FP64 tensor
+ * cores (DMMA): out += scale * A @ X   (matmul_dense zgemm branch, matmul.pyx:329-346).
+ * qb_matmul routes here for dense operands with >= 8 columns. */
+int qb_zgemm(qb_handle a, qb_handle x, double scale_re, double scale_im, qb_handle out);
+int qb_zgemm_bench(qb_handle a, qb_handle x, qb_handle out, int iters, double* ms_total);
 int qb_axpy(qb_handle x, double a_re, double a_im, qb_handle y);
 int qb_scal(qb_handle x, double a_re, double a_im);
 int qb_copy(qb_handle src, qb_handle dst);

@@ -48,6 +48,7 @@ SYMBOLS = [
     "qb_engine_last_run_info", "qb_integ_set_state", "qb_integ_integrate",
     "qb_integ_get_state", "qb_integ_set_args", "qb_integ_stats", "qb_engine_rhs",
     "qb_engine_rhs_bench", "qb_engine_set_profiling", "qb_engine_profile",
+    "qb_zgemm", "qb_zgemm_bench",
 ]
 
 _lib = None
@@ -80,6 +81,8 @@ def load():
         "qb_free": [vp],
         "qb_matmul": [vp, vp, dbl, dbl, vp],
         "qb_axpy": [vp, dbl, dbl, vp],
+        "qb_zgemm": [vp, vp, dbl, dbl, vp],
+        "qb_zgemm_bench": [vp, vp, vp, i32, C.POINTER(dbl)],
         "qb_scal": [vp, dbl, dbl],
         "qb_copy": [vp, vp],
         "qb_zero": [vp],

@@ -6,7 +6,8 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2,-pthread ${QB_NVCC_EXTRA}"
 $NVCC $FLAGS -c qb_ops.cu -o qb_ops.o &
 $NVCC $FLAGS -c qb_engine.cu -o qb_engine.o &
+$NVCC $FLAGS -c qb_dense.cu -o qb_dense.o &
 wait
 OUT=${QB_OUT:-../libqutip_b200.so}
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT qb_ops.o qb_engine.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT qb_ops.o qb_engine.o qb_dense.o -lcudart
 echo "built $OUT"

@@ -40,7 +40,14 @@ struct QbEngineDev {
     int* out_stats;
     unsigned long long* vec_count;   // state-sized vector accesses issued (algorithmic traffic)
     int nslices, red_stride;
+    // dense batched path (qb_dense.cu): z of every slot precomputed by one DMMA ZGEMM
+    double2* zbuf;              // [nslots][N] or null
+    const double2** xcols;      // [nslots] column pointers of the GEMM's right operand
+    double2** zcols;            // [nslots]
 };
+
+int qb_launch_dense_rhs(cudaStream_t stream, const qb_c128* A, int N, const void* const* xcols,
+                        void* const* zcols, int ncols);
 
 // ------------------------------------------------------------------ pass kernel
 __device__ __forceinline__ const double2* qb_vsrc(const QbEngineDev* E, int slot, int idx,
@@ -118,6 +125,12 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
         const double2* x = qb_vsrc(E, slot, gp->x, init_idx);
         const int nelem = E->ctl.nelem;
         const qb_c128* cf = E->coef + (size_t)slot * E->ctl.maxcoef;
+        if (E->zbuf) {             // dense batched path: A x was computed by the ZGEMM pre-pass
+            const double2 q = active ? E->zbuf[(size_t)slot * N_ + r] : make_double2(0.0, 0.0);
+            const qb_c128 c = cf[0];
+            z.x = c.re * q.x - c.im * q.y;
+            z.y = c.re * q.y + c.im * q.x;
+        } else
         for (int e = 0; e < nelem; e++) {
             const double2 q = qb_rowdot<QB_UP>(E->elem[e], sl, lane, r, active, x);
             const qb_c128 c = cf[e];
@@ -250,6 +263,11 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
     }
     *gc = c;
     *gp = p;
+    if (E->zbuf) {
+        double2* zrow = E->zbuf + (size_t)slot * (size_t)E->ctl.N;
+        E->zcols[slot] = zrow;
+        E->xcols[slot] = (p.kind == QB_PASS_RHS) ? qb_vsrc(E, slot, p.x, c.init_idx) : zrow;
+    }
 }
 
 // one RHS evaluation on plain device vectors (micro-benchmark / data-layer matmul of a
@@ -503,6 +521,18 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     QB_TRY(qb_dev_alloc(e, 1, &h.queue_head));
     QB_TRY(qb_dev_alloc(e, 1, &h.n_active));
     QB_TRY(qb_dev_alloc(e, 1, &h.vec_count));
+    h.zbuf = nullptr; h.xcols = nullptr; h.zcols = nullptr;
+    if (s->elems.size() == 1 && s->elems[0].fmt == QB_FMT_DENSE && nslots >= 8) {
+        QB_TRY(qb_dev_alloc(e, (size_t)nslots * N, &h.zbuf));
+        QB_TRY(qb_dev_alloc(e, (size_t)nslots, &h.xcols));
+        QB_TRY(qb_dev_alloc(e, (size_t)nslots, &h.zcols));
+        std::vector<double2*> rows(nslots);
+        for (int i = 0; i < nslots; i++) rows[i] = h.zbuf + (size_t)i * N;
+        if (cudaMemcpy(h.xcols, rows.data(), nslots * sizeof(void*), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(h.zcols, rows.data(), nslots * sizeof(void*), cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete e; QB_FAIL(QB_E_CUDA, "column pointer upload failed");
+        }
+    }
     {
         void* p = nullptr;
         cudaError_t ce = cudaMalloc(&p, sizeof(QbEngineDev));
@@ -540,6 +570,12 @@ static int qb_drive(QbEngH* e, int nslots_used) {
                     QB_FAIL(QB_E_CUDA, "event creation failed");
                 e->prof_events.push_back(pa); e->prof_events.push_back(pb);
                 cudaEventRecord(pa, e->stream);
+            }
+            if (e->h.zbuf) {
+                int rcg = qb_launch_dense_rhs(e->stream, e->h.elem[0].dense, e->h.ctl.N,
+                                              (const void* const*)e->h.xcols, (void* const*)e->h.zcols,
+                                              nslots_used);
+                if (rcg) return rcg;
             }
             qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d);
             QB_LAUNCH_CHECK();

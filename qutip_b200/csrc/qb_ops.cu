@@ -411,10 +411,16 @@ static int reduce2(int mode, long long n, const double2* a, const double2* b, do
 }
 }  // namespace
 
+extern "C" int qb_zgemm(qb_handle ah, qb_handle xh, double sre, double sim, qb_handle oh);
+
 extern "C" int qb_matmul(qb_handle op, qb_handle xh, double sre, double sim, qb_handle outh) {
     QbOpDev A; int rc = get_opdev(op, &A); if (rc) return rc;
     QbDenseH* x = qb_cast<QbDenseH>(xh, QB_TAG_DENSE);
     QbDenseH* o = qb_cast<QbDenseH>(outh, QB_TAG_DENSE);
+    // dense x multi-column column-major state: true ZGEMM on the FP64 tensor cores
+    if (A.fmt == QB_FMT_DENSE && x && o && x->cols >= 8 && x->fortran && o->fortran &&
+        A.ncols == x->rows && A.nrows == o->rows && x->cols == o->cols)
+        return qb_zgemm(op, xh, sre, sim, outh);
     if (!x || !o) QB_FAIL(QB_E_TYPE, "matmul needs dense right operand and output");
     if (A.ncols != x->rows || A.nrows != o->rows || x->cols != o->cols)
         QB_FAIL(QB_E_SHAPE, "incompatible matrix shapes (%d, %d) and (%lld, %lld)", A.nrows, A.ncols,

@@ -151,6 +151,13 @@ def matmul(op, x, scale=1.0, out=None):
     return out
 
 
+def zgemm_bench(a, x, out, iters=10):
+    """milliseconds for ``iters`` back-to-back dense ZGEMMs out += a @ x (CUDA events)."""
+    ms = C.c_double()
+    check(_lib.load().qb_zgemm_bench(a.handle, x.handle, out.handle, int(iters), C.byref(ms)))
+    return ms.value
+
+
 def axpy(x, a, y):
     a = complex(a)
     check(_lib.load().qb_axpy(x.handle, a.real, a.imag, y.handle))
