@@ -197,6 +197,68 @@ def mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=False):
     }
 
 
+def extra_figures(qb, models, quick=False):
+    """Secondary configs of BASELINE.json (C4 time-dependent mesolve, C5 sweep + dense ZGEMM).
+    Parity of these paths is asserted in tests/; here only timings are recorded."""
+    from qutip_b200 import coeffs, solve
+    from qutip_b200 import engine as E
+    out = {}
+    # ---- C5: 4096-member driven-Kerr sweep, one batched run with per-member (U, Delta, F)
+    grid = 4 if quick else 16
+    Ls, sargs, a = models.kerr_sweep(30, grid)
+    idx = {"U": 0, "D": 1, "F": 2}
+    elements = [(Ls[0], coeffs.compile_expr("U", arg_index=idx)),
+                (Ls[1], coeffs.compile_expr("D", arg_index=idx)),
+                (Ls[2], coeffs.compile_expr("F", arg_index=idx)), (Ls[3], None)]
+    n_op = (a.conj().T @ a).toarray()
+    rho0 = np.zeros(900, dtype=complex); rho0[0] = 1.0
+    tl = np.linspace(0, 10, 21)
+    r = solve.mesolve(elements, rho0, tl, e_ops=[n_op], args=sargs, nargs=3, store_states=False)
+    t0 = time.perf_counter()
+    r = solve.mesolve(elements, rho0, tl, e_ops=[n_op], args=sargs, nargs=3, store_states=False,
+                      engine=r.engine)
+    wall = time.perf_counter() - t0
+    out["sweep_c5"] = {"workload": "C5 driven-Kerr N=30 (Liouvillian 900^2), %d systems, vern7, t in [0,10]" % len(sargs),
+                       "systems_per_s": len(sargs) / (r.gpu_ms * 1e-3), "gpu_ms": r.gpu_ms,
+                       "wall_s_incl_transfers": wall, "rounds": r.rounds,
+                       "rhs_evals_per_system": float(r.stats[:, 0].mean())}
+    # ---- C4: cos-driven cavity 40 x transmon 3, fused coefficient evaluation
+    H0, H1, c_ops, a4, b4 = models.driven_cavity_transmon(12 if quick else 40)
+    L0 = models.liouvillian(H0, c_ops)
+    n = H0.shape[0]
+    import scipy.sparse as sp
+    I = sp.identity(n, dtype=complex, format="csr")
+    pre, post = sp.kron(I, H1), sp.kron(H1.T, I)
+    els = [(sp.csr_matrix(-1j * pre), coeffs.compile_expr("A*cos(w*t)", {"A": 0.2, "w": 5.0})),
+           (sp.csr_matrix(1j * post), coeffs.compile_expr("conj(A*cos(w*t))", {"A": 0.2, "w": 5.0})),
+           (L0, None)]
+    rho0 = np.zeros(n * n, dtype=complex); rho0[0] = 1.0
+    tl = np.linspace(0, 5, 51)
+    r = solve.mesolve(els, rho0, tl, e_ops=[(a4.conj().T @ a4).toarray()], store_states=False)
+    r = solve.mesolve(els, rho0, tl, e_ops=[(a4.conj().T @ a4).toarray()], store_states=False,
+                      engine=r.engine)
+    out["td_mesolve_c4"] = {"workload": "C4 cos-driven cavity x transmon 3, Liouvillian %d^2, 3 elements, vern7, t in [0,5]" % (n * n),
+                            "gpu_ms": r.gpu_ms, "rhs_evals": int(r.stats[0][0]),
+                            "rhs_evals_per_s": float(r.stats[0][0]) / (r.gpu_ms * 1e-3)}
+    # ---- dense H_eff block: complex128 ZGEMM on the FP64 tensor cores
+    dz = []
+    rng = np.random.default_rng(0)
+    for dim, ncols in ((256, 256), (1024, 256), (1024, 4096), (4096, 256), (4096, 4096)):
+        if quick and dim > 1024:
+            continue
+        A = qb.DeviceDense.from_numpy(np.asfortranarray(rng.random((dim, dim)) + 1j * rng.random((dim, dim))))
+        X = qb.DeviceDense.from_numpy(np.asfortranarray(rng.random((dim, ncols)) + 1j * rng.random((dim, ncols))))
+        O = qb.DeviceDense.zeros(dim, ncols)
+        iters = 3 if dim * ncols >= 1 << 24 else 20
+        ms = E.zgemm_bench(A, X, O, iters) / iters
+        dz.append({"dim": dim, "ntraj": ncols, "ms": ms,
+                   "tflops": 8.0 * dim * dim * ncols / (ms * 1e-3) / 1e12})
+        del A, X, O
+    out["dense_zgemm"] = {"kernel": "qb_zgemm_dmma_kernel (mma.sync m8n8k4 f64)", "cases": dz,
+                          "note": "FP64 tensor peak is not in MEASURED_PEAKS.json; nominal B200 FP64 is 37-40 TFLOP/s"}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -360,6 +422,10 @@ def run_ours(args):
     }
     if world == 1 and not args.no_mesolve:
         line["mesolve"] = mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=args.quick)
+        try:
+            line.update(extra_figures(qb, models, quick=args.quick))
+        except Exception as exc:
+            line["extra_figures_error"] = repr(exc)[:300]
     if world == 1 and not args.no_cpu:
         # reference CPU arm on a bounded sample, in a subprocess (it forks worker processes)
         try:
