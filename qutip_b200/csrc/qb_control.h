@@ -84,14 +84,14 @@ enum {
 
 // Run the controller until it has emitted a pass (returns 1), the trajectory finished or
 // paused (returns 0) or failed (returns 0 with c.done < 0).
+//   T     : the Butcher tableau (g.tab on the host; a __constant__ copy on the device)
 //   red   : reductions of the pass just executed (red[0]=|o1|^2, red[1]=wrms sum,
 //           red[2]=|z|^2 ; EXPECT: red[2m], red[2m+1] = <x|O_m|x>)
 //   coef  : per-slot coefficient buffer the next pass will read
 //   probs : per-slot scratch [ncops]
-QB_HD int qb_advance(const QbCtl& g, QbTraj& c, QbPass& p, const double* red,
-                     qb_c128* coef, double* probs)
+QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
+                     const double* red, qb_c128* coef, double* probs)
 {
-    const QbTableau& T = g.tab;
     const int s = T.s, S = T.S;
     int L = c.pc;
     int dense_i = 0, stage_i = 0;

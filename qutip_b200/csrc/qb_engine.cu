@@ -16,8 +16,13 @@
 #include "qb_kernels.cuh"
 #include "qb_tableaux.h"
 
+// both tableaux live in constant memory: the controller's single active lane reads them
+// through the constant cache instead of serial global loads
+__constant__ QbTableau c_tabs[2];
+
 struct QbEngineDev {
     QbCtl ctl;
+    int tableau_id, pad0_;
     QbOpDev elem[QB_MAX_ELEMS];
     const QbOpDev* cops;
     const QbOpDev* nops;
@@ -56,6 +61,9 @@ __device__ __forceinline__ const double2* qb_vsrc(const QbEngineDev* E, int slot
     return E->init_states + (size_t)init_idx * (size_t)E->ctl.N;
 }
 
+#ifndef QB_SPW
+#define QB_SPW 1     // consecutive 32-row slices handled by one warp
+#endif
 #ifndef QB_PF
 #define QB_PF 4      // epilogue source vectors prefetched before the operator sweep
 #endif
@@ -79,19 +87,31 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
     if (kind == QB_PASS_NONE) return;
     const int N = E->ctl.N;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sl = tile * (QB_TILE_ROWS / 32) + warp;
+    const size_t N_ = (size_t)N;
+    const int init_idx = E->traj[slot].init_idx;
+    const int nsrc = gp->nsrc;
+    int my_src = 0;
+    double my_w1 = 0.0, my_w2 = 0.0;
+    if (lane < nsrc) { my_src = gp->src[lane]; my_w1 = gp->w1[lane]; my_w2 = gp->w2[lane]; }
+    const double zscale = gp->zscale, w1z = gp->w1z, w2z = gp->w2z;
+    const int zdst = gp->zdst, dst1 = gp->dst1, red = gp->red;
+    const int xslot = gp->x;
+  for (int it = 0; it < QB_SPW; it++) {
+    const int sl = (tile * (QB_TILE_ROWS / 32) + warp) * QB_SPW + it;
     if ((long long)sl * 32 >= N) return;          // warp-uniform
     const long long r = (long long)sl * 32 + lane;
     const bool active = r < N;
-    const size_t N_ = (size_t)N;
-    const int init_idx = E->traj[slot].init_idx;
+    // vector `idx` of this slot: one IMAD.WIDE (idx * N) instead of 64-bit multiplies
+    const double2* const slot_base = E->pool + (size_t)slot * E->V * N_;
+    const double2* const init_ptr = E->init_states + (size_t)init_idx * N_;
+#define QB_VS(idx) ((idx) >= 0 ? slot_base + (long long)(idx) * N : init_ptr)
     double* __restrict__ part = E->partials + ((size_t)slot * E->nslices + sl) * E->red_stride;
 
     if (kind == QB_PASS_EXPECT) {
         const int opset = gp->opset, op_lo = gp->op_lo, nops = gp->op_hi - gp->op_lo;
         const QbOpDev* ops = (opset == QB_OPSET_EOPS) ? E->eops : E->nops;
         const bool functional = (opset == QB_OPSET_EOPS) && E->ctl.eop_functional;
-        const double2* x = qb_vsrc(E, slot, gp->x, init_idx);
+        const double2* x = QB_VS(gp->x);
         double2 xr = make_double2(0.0, 0.0);
         if (active) xr = x[r];
         for (int m = 0; m < nops; m++) {
@@ -103,26 +123,22 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
             const double sre = qb_warp_sum(pr.x), sim = qb_warp_sum(pr.y);
             if (lane == 0) { part[2 * m] = sre; part[2 * m + 1] = sim; }
         }
-        return;
+        continue;
     }
 
     // ---- epilogue sources: lane i holds (slot, w1, w2) of source i; prefetch the first QB_PF
-    const int nsrc = gp->nsrc;
-    int my_src = 0;
-    double my_w1 = 0.0, my_w2 = 0.0;
-    if (lane < nsrc) { my_src = gp->src[lane]; my_w1 = gp->w1[lane]; my_w2 = gp->w2[lane]; }
     double2 pv[QB_PF];
 #pragma unroll
     for (int u = 0; u < QB_PF; u++) {
         const int sidx = __shfl_sync(0xffffffffu, my_src, u);
-        const double2* p = qb_vsrc(E, slot, sidx, init_idx);
+        const double2* p = QB_VS(sidx);
         pv[u] = (u < nsrc && active) ? p[r] : make_double2(0.0, 0.0);
     }
 
     // ---- operator application ----
     double2 z = make_double2(0.0, 0.0);
     if (kind == QB_PASS_RHS) {
-        const double2* x = qb_vsrc(E, slot, gp->x, init_idx);
+        const double2* x = QB_VS(xslot);
         const int nelem = E->ctl.nelem;
         const qb_c128* cf = E->coef + (size_t)slot * E->ctl.maxcoef;
         if (E->zbuf) {             // dense batched path: A x was computed by the ZGEMM pre-pass
@@ -139,11 +155,10 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
         }
     } else if (kind == QB_PASS_APPLY) {
         const double2 q = qb_rowdot<QB_UP>(E->cops[gp->op_lo], sl, lane, r, active,
-                                    qb_vsrc(E, slot, gp->x, init_idx));
+                                    QB_VS(gp->x));
         const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef];
         z = make_double2(c.re * q.x - c.im * q.y, c.re * q.y + c.im * q.x);
     }
-    const double zscale = gp->zscale;
     z.x *= zscale; z.y *= zscale;
 
     // ---- fused linear combinations (sources in order, z last), stores, reductions ----
@@ -159,7 +174,7 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int sidx = __shfl_sync(0xffffffffu, my_src, (i + u) & 31);
-            const double2* p = qb_vsrc(E, slot, sidx, init_idx);
+            const double2* p = QB_VS(sidx);
             v[u] = (i + u < nsrc && active) ? p[r] : make_double2(0.0, 0.0);
         }
 #pragma unroll
@@ -170,13 +185,11 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
             o2.x = fma(b, v[u].x, o2.x); o2.y = fma(b, v[u].y, o2.y);
         }
     }
-    const double w1z = gp->w1z, w2z = gp->w2z;
     o1.x = fma(w1z, z.x, o1.x); o1.y = fma(w1z, z.y, o1.y);
     o2.x = fma(w2z, z.x, o2.x); o2.y = fma(w2z, z.y, o2.y);
-    const int zdst = gp->zdst, dst1 = gp->dst1, red = gp->red;
     double r0 = 0.0, r1 = 0.0, r2 = 0.0;
     if (active) {
-        double2* base = E->pool + (size_t)slot * E->V * N_;
+        double2* base = const_cast<double2*>(slot_base);
         if (zdst >= 0) base[(size_t)zdst * N_ + r] = z;
         if (dst1 >= 0) base[(size_t)dst1 * N_ + r] = o1;
         else if (dst1 == QB_SLOT_OUT)
@@ -194,6 +207,8 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
         r0 = qb_warp_sum(r0); r1 = qb_warp_sum(r1); r2 = qb_warp_sum(r2);
         if (lane == 0) { part[0] = r0; part[1] = r1; part[2] = r2; }
     }
+  }
+#undef QB_VS
 }
 
 // ------------------------------------------------------------------ control kernel
@@ -239,7 +254,7 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
     qb_c128* coef = E->coef + (size_t)slot * E->ctl.maxcoef;
     double* probs = E->probs + (size_t)slot * (E->ctl.ncops > 0 ? E->ctl.ncops : 1);
     for (;;) {
-        const int issued = qb_advance(E->ctl, c, p, sred[w], coef, probs);
+        const int issued = qb_advance(E->ctl, c_tabs[E->tableau_id], c, p, sred[w], coef, probs);
         if (issued) {
             c.n_pass++;
             if (E->vec_count) {
@@ -272,7 +287,7 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
 
 // one RHS evaluation on plain device vectors (micro-benchmark / data-layer matmul of a
 // whole QobjEvo): out = sum_k coef_k A_k x
-__global__ void __launch_bounds__(QB_TILE_ROWS)
+__global__ void __launch_bounds__(QB_TILE_ROWS, 4)
 qb_rhs_kernel(const QbEngineDev* __restrict__ E, const double2* __restrict__ x,
               double2* __restrict__ out, const qb_c128* __restrict__ coef)
 {
@@ -466,9 +481,19 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     if (e->opt.max_collapses < 1) e->opt.max_collapses = 1;
     QbEngineDev& h = e->h;
     h.ctl.tab = *QB_TABLEAUX[tableau];
+    h.tableau_id = tableau;
+    {
+        static bool tabs_uploaded = false;
+        if (!tabs_uploaded) {
+            QbTableau both[2] = {*QB_TABLEAUX[0], *QB_TABLEAUX[1]};
+            cudaError_t ce = cudaMemcpyToSymbol(c_tabs, both, sizeof(both));
+            if (ce != cudaSuccess) { delete e; QB_FAIL(QB_E_CUDA, "tableau upload: %s", cudaGetErrorString(ce)); }
+            tabs_uploaded = true;
+        }
+    }
     h.ctl.opt = e->opt;
     h.ctl.N = (int)s->N;
-    h.ctl.ntiles = (int)((s->N + QB_TILE_ROWS - 1) / QB_TILE_ROWS);
+    h.ctl.ntiles = (int)((s->N + QB_TILE_ROWS * QB_SPW - 1) / (QB_TILE_ROWS * QB_SPW));
     h.ctl.nelem = (int)s->elems.size();
     h.ctl.ncops = (int)s->cops.size();
     h.ctl.neops = (int)s->eops.size();
@@ -885,7 +910,7 @@ extern "C" int qb_engine_rhs(qb_handle eng, double t, qb_handle xh, qb_handle ou
     }
     QB_CUDA(cudaMemcpyAsync(e->h.coef, coef.data(), coef.size() * 16, cudaMemcpyHostToDevice, e->stream));
     QB_CUDA(cudaMemcpyAsync(e->d, &e->h, sizeof(QbEngineDev), cudaMemcpyHostToDevice, e->stream));
-    qb_rhs_kernel<<<e->h.ctl.ntiles, QB_TILE_ROWS, 0, e->stream>>>(e->d, x->d, o->d, e->h.coef);
+    qb_rhs_kernel<<<(e->h.ctl.N + QB_TILE_ROWS - 1) / QB_TILE_ROWS, QB_TILE_ROWS, 0, e->stream>>>(e->d, x->d, o->d, e->h.coef);
     QB_LAUNCH_CHECK();
     QB_CUDA(cudaStreamSynchronize(e->stream));
     return QB_OK;
@@ -919,7 +944,7 @@ extern "C" int qb_engine_rhs_bench(qb_handle eng, double t, qb_handle xh, qb_han
     if (rc) return rc;
     QB_CUDA(cudaEventRecord(e->ev0, e->stream));
     for (int i = 0; i < iters; i++) {
-        qb_rhs_kernel<<<e->h.ctl.ntiles, QB_TILE_ROWS, 0, e->stream>>>(e->d, x->d, o->d, e->h.coef);
+        qb_rhs_kernel<<<(e->h.ctl.N + QB_TILE_ROWS - 1) / QB_TILE_ROWS, QB_TILE_ROWS, 0, e->stream>>>(e->d, x->d, o->d, e->h.coef);
         QB_LAUNCH_CHECK();
     }
     QB_CUDA(cudaEventRecord(e->ev1, e->stream));

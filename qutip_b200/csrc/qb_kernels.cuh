@@ -39,11 +39,12 @@ __device__ __forceinline__ double2 qb_mul(const double2 a, const double2 b) {
 // A.pad_ != 0 marks an operator far larger than L2: its values are read with the
 // cache-streaming policy so they do not evict the (re-used) state vectors.
 template <int G, int QB_UNROLL>
-__device__ __forceinline__ void qb_rowdot_diam(const QbOpDev& A, int sl, int lane, long long r,
+__device__ __forceinline__ void qb_rowdot_diam(const QbOpDev& A, int sl, int lane, long long r64,
                                                const double2* const* x, double2 (&acc)[G])
 {
     const int e0 = A.slice_ptr[sl], e1 = A.slice_ptr[sl + 1];
     long long vbase = A.slice_vbase[sl];
+    const int r = (int)r64;                 // 32-bit indexing: rows, cols < 2^31
     const unsigned lt = (1u << lane) - 1u;
     const bool stream = A.pad_ != 0;
     const int2* __restrict__ ent = reinterpret_cast<const int2*>(A.ent_off);
@@ -77,7 +78,7 @@ __device__ __forceinline__ void qb_rowdot_diam(const QbOpDev& A, int sl, int lan
                 const int vb = __shfl_sync(0xffffffffu, my_vb, src);
                 if (e + u >= ne) m = 0u;
                 const bool hit = (m >> lane) & 1u;
-                const double2* vp = vchunk + vb + __popc(m & lt);
+                const double2* vp = vchunk + (vb + __popc(m & lt));
                 if (stream) v[u] = hit ? __ldcs(vp) : zero;
                 else v[u] = hit ? __ldg(vp) : zero;
 #pragma unroll

@@ -165,7 +165,7 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
             QbTraj& c = traj[slot];
             if (c.pc == QB_PC_IDLE) continue;
             for (;;) {
-                int issued = qb_advance(g, c, pass[slot], red.data() + (size_t)slot * QB_MAXRED,
+                int issued = qb_advance(g, g.tab, c, pass[slot], red.data() + (size_t)slot * QB_MAXRED,
                                         coef.data() + (size_t)slot * g.maxcoef,
                                         probs.data() + (size_t)slot * std::max(1, g.ncops));
                 if (issued) { c.n_pass++; break; }
