@@ -44,6 +44,7 @@ int64_t qb_launch_count(void);
 int qb_dense_upload(const void* host, int64_t rows, int64_t cols, int fortran, qb_handle* out);
 int qb_dense_zeros(int64_t rows, int64_t cols, int fortran, qb_handle* out);
 int qb_dense_download(qb_handle h, void* host);
+int qb_dense_write(qb_handle h, const void* host);      /* overwrite from host memory */
 int qb_dense_copy(qb_handle h, qb_handle* out);
 int qb_dense_info(qb_handle h, int64_t* rows, int64_t* cols, int* fortran, void** devptr);
 /* operator formats: 0 auto (diagonal-masked slices when the matrix is diagonal

@@ -38,7 +38,7 @@ class QbOptions(C.Structure):
 SYMBOLS = [
     "qb_version", "qb_last_error", "qb_device_count", "qb_set_device", "qb_synchronize",
     "qb_launch_count",
-    "qb_dense_upload", "qb_dense_zeros", "qb_dense_download", "qb_dense_copy", "qb_dense_info",
+    "qb_dense_upload", "qb_dense_zeros", "qb_dense_download", "qb_dense_write", "qb_dense_copy", "qb_dense_info",
     "qb_csr_upload", "qb_dia_upload", "qb_op_info", "qb_free",
     "qb_matmul", "qb_axpy", "qb_scal", "qb_copy", "qb_zero", "qb_nrm2", "qb_wrms_error",
     "qb_inner", "qb_expect_ket", "qb_expect_dm", "qb_expect_super", "qb_trace_oper_ket",
@@ -72,6 +72,7 @@ def load():
         "qb_dense_upload": [vp, i64, i64, i32, pp],
         "qb_dense_zeros": [i64, i64, i32, pp],
         "qb_dense_download": [vp, vp],
+        "qb_dense_write": [vp, vp],
         "qb_dense_copy": [vp, pp],
         "qb_dense_info": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), pp],
         "qb_csr_upload": [vp, vp, vp, i64, i64, i64, i32, pp],

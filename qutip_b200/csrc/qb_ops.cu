@@ -53,6 +53,12 @@ extern "C" int qb_dense_download(qb_handle h, void* host) {
     QB_CUDA(cudaMemcpy(host, d->d, (size_t)d->size() * 16, cudaMemcpyDeviceToHost));
     return QB_OK;
 }
+extern "C" int qb_dense_write(qb_handle h, const void* host) {
+    QbDenseH* d = qb_cast<QbDenseH>(h, QB_TAG_DENSE);
+    if (!d || !host) QB_FAIL(QB_E_TYPE, "not a dense handle");
+    QB_CUDA(cudaMemcpy(d->d, host, (size_t)d->size() * 16, cudaMemcpyHostToDevice));
+    return QB_OK;
+}
 extern "C" int qb_dense_copy(qb_handle h, qb_handle* out) {
     QbDenseH* d = qb_cast<QbDenseH>(h, QB_TAG_DENSE);
     if (!d) QB_FAIL(QB_E_TYPE, "not a dense handle");

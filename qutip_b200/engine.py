@@ -95,6 +95,17 @@ class DeviceDense(_Handle):
         check(_lib.load().qb_dense_copy(self.handle, C.byref(h)))
         return DeviceDense(h, self.shape, self.fortran)
 
+    def write(self, arr):
+        """overwrite the device buffer from a host array of the same size"""
+        arr = as_c128(arr)
+        if arr.size != self.shape[0] * self.shape[1]:
+            raise ValueError("size mismatch")
+        check(_lib.load().qb_dense_write(self.handle, ptr(arr)))
+
+    def read_into(self, out):
+        check(_lib.load().qb_dense_download(self.handle, ptr(out)))
+        return out
+
 
 class DeviceOp(_Handle):
     """Sparse operator on the device: diagonal-masked slices or CSR."""

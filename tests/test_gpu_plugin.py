@@ -261,3 +261,21 @@ def test_c5_sweep_members_match_reference():
         Hq = 0.5 * U * a.dag() * a.dag() * a * a - D * a.dag() * a + F * (a + a.dag())
         ref = mesolve(Hq, basis(N, 0), tl, [a], e_ops=[a.dag() * a], options=dict(OPT, method="vern7"))
         np.testing.assert_allclose(r.expect[k, 0].real, ref.expect[0], rtol=RTOL, atol=ATOL)
+
+
+def test_adams_with_device_rhs():
+    """method='b200_adams': SciPy zvode (the reference's Adams) with the RHS on the device."""
+    H, c_ops, psi0, e_ops = jc()
+    tl = np.linspace(0, 5, 26)
+    ref = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="adams"))
+    out = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="b200_adams"))
+    np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), rtol=RTOL, atol=ATOL)
+    # time-dependent + mcsolve driver on top of it
+    a = destroy(6)
+    Ht = QobjEvo([a.dag() * a, [a + a.dag(), "0.3*sin(2*t)"]])
+    ref = mcsolve(Ht, basis(6, 2), np.linspace(0, 2, 9), [0.5 * a], e_ops=[a.dag() * a], ntraj=5,
+                  seeds=3, options=dict(OPT, method="adams", keep_runs_results=True))
+    out = mcsolve(Ht, basis(6, 2), np.linspace(0, 2, 9), [0.5 * a], e_ops=[a.dag() * a], ntraj=5,
+                  seeds=3, options=dict(OPT, method="b200_adams", keep_runs_results=True))
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=1e-5, atol=1e-7)
