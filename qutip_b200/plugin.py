@@ -71,8 +71,11 @@ def coefficient_to_program(c, system=None):
         return coeffs.constant(_coeff_state(c)[1])
     if name.startswith("StrCoefficient"):
         state = _coeff_state(c)
-        n = (len(state) - 2) // 2
-        vals, code, names = state[:n], state[n + 1], state[n + 2:]
+        # (named values..., extracted numeric constants..., args, code, names...): the code
+        # string is the first str; the names follow it and own the leading values
+        i_code = next(i for i, x in enumerate(state) if isinstance(x, str))
+        code, names = state[i_code], state[i_code + 1:]
+        vals = state[:len(names)]
         return coeffs.compile_expr(code, dict(zip(names, vals)))
     if name == "ConjCoefficient":
         return coefficient_to_program(_coeff_state(c)[1], system).conj()

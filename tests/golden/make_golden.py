@@ -117,8 +117,11 @@ def describe_coeff(c):
         st = c.__reduce__()
         # generated class, auto_pickle -> (rebuild, (cls, checksum, state))
         state = st[2] if len(st) > 2 and st[2] is not None else st[1][2]
-        n = (len(state) - 2) // 2
-        vals, code, names = state[:n], state[n + 1], state[n + 2:]
+        # (named values..., extracted numeric constants..., args, code, names...): the code
+        # string is the first str; the names follow it and own the leading values
+        i_code = next(i for i, x in enumerate(state) if isinstance(x, str))
+        code, names = state[i_code], state[i_code + 1:]
+        vals = state[:len(names)]
         return "str:" + code + "|" + ",".join("%s=%r" % (k, complex(v))
                                               for k, v in zip(names, vals))
     raise NotImplementedError(cls)
