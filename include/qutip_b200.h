@@ -164,6 +164,14 @@ int qb_engine_last_run_info(qb_handle eng, int64_t* rounds, double* gpu_ms);
 int qb_integ_set_state(qb_handle eng, double t, const void* y);
 int qb_integ_integrate(qb_handle eng, double t, int step, double* t_out, int* status);
 int qb_integ_get_state(qb_handle eng, double* t, void* y);
+/* Python-callable coefficients (FunctionCoefficient, core/cy/coefficient.pyx:176) cannot run
+ * on the device: elements whose program is the single instruction QB_I_HOST are evaluated
+ * by the host.  qb_integ_set_state returns 3 / qb_integ_integrate reports status 3 when the
+ * controller needs their values at the time given by qb_integ_pending_coef; the host calls
+ * qb_integ_resume with vals[nelem] (complex) until the status is no longer 3.  The matvecs,
+ * stage combinations and the step controller stay on the device. */
+int qb_integ_pending_coef(qb_handle eng, double* t);
+int qb_integ_resume(qb_handle eng, const void* vals, double* t_out, int* status);
 int qb_integ_set_args(qb_handle eng, const void* args);
 int qb_integ_stats(qb_handle eng, int64_t stats[4]);
 
@@ -176,6 +184,8 @@ int qb_integ_stats(qb_handle eng, int64_t stats[4]);
  *                      summed duration, the launch count and the number of state-sized
  *                      vector accesses the passes had to make (algorithmic traffic) */
 int qb_engine_rhs(qb_handle eng, double t, qb_handle x, qb_handle out);
+/* same with the coefficient values vals[nelem] (complex) supplied by the caller */
+int qb_engine_rhs_coef(qb_handle eng, const void* vals, qb_handle x, qb_handle out);
 int qb_engine_rhs_bench(qb_handle eng, double t, qb_handle x, qb_handle out, int iters,
                         double* ms_total);
 int qb_engine_set_profiling(qb_handle eng, int on);

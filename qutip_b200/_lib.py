@@ -48,7 +48,8 @@ SYMBOLS = [
     "qb_engine_last_run_info", "qb_integ_set_state", "qb_integ_integrate",
     "qb_integ_get_state", "qb_integ_set_args", "qb_integ_stats", "qb_engine_rhs",
     "qb_engine_rhs_bench", "qb_engine_set_profiling", "qb_engine_profile",
-    "qb_zgemm", "qb_zgemm_bench",
+    "qb_zgemm", "qb_zgemm_bench", "qb_integ_pending_coef", "qb_integ_resume",
+    "qb_engine_rhs_coef",
 ]
 
 _lib = None
@@ -111,9 +112,12 @@ def load():
         "qb_integ_set_state": [vp, dbl, vp],
         "qb_integ_integrate": [vp, dbl, i32, C.POINTER(dbl), C.POINTER(i32)],
         "qb_integ_get_state": [vp, C.POINTER(dbl), vp],
+        "qb_integ_pending_coef": [vp, C.POINTER(dbl)],
+        "qb_integ_resume": [vp, vp, C.POINTER(dbl), C.POINTER(i32)],
         "qb_integ_set_args": [vp, vp],
         "qb_integ_stats": [vp, C.POINTER(i64)],
         "qb_engine_rhs": [vp, dbl, vp, vp],
+        "qb_engine_rhs_coef": [vp, vp, vp, vp],
         "qb_engine_rhs_bench": [vp, dbl, vp, vp, i32, C.POINTER(dbl)],
         "qb_engine_set_profiling": [vp, i32],
         "qb_engine_profile": [vp, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)],

@@ -26,7 +26,7 @@ import numpy as np
 # op-codes: keep in sync with csrc/qb_types.h
 (I_CONST, I_T, I_ARG, I_ADD, I_SUB, I_MUL, I_DIV, I_NEG, I_CONJ, I_SIN, I_COS, I_TAN, I_EXP,
  I_LOG, I_SQRT, I_ABS, I_REAL, I_IMAG, I_POW, I_SINH, I_COSH, I_TANH, I_SPLINE, I_ASIN,
- I_ACOS, I_ATAN, I_NORM2, I_HEAVISIDE_GE) = range(28)
+ I_ACOS, I_ATAN, I_NORM2, I_HEAVISIDE_GE, I_HOST) = range(29)
 
 _FUNCS = {
     "sin": I_SIN, "cos": I_COS, "tan": I_TAN, "exp": I_EXP, "log": I_LOG, "sqrt": I_SQRT,
@@ -78,6 +78,12 @@ class Program:
 def constant(z):
     z = complex(z)
     return Program([(I_CONST, 0, z.real, z.imag)])
+
+
+def host():
+    """Placeholder program: the value is supplied by the host for every evaluation time
+    (python-callable coefficients)."""
+    return Program([(I_HOST, 0, 0.0, 0.0)])
 
 
 def spline(spline_id):

@@ -28,6 +28,7 @@ struct QbCtl {
     int N, ntiles;
     int nelem, ncops, neops, nargs;
     int eop_functional;         // e_ops are linear functionals (mesolve tr(E rho))
+    int has_host_coef;          // some RHS element's coefficient is evaluated by the host
     int maxcoef;
     int nt, ndraws;
     const QbProgRef* elem_prog;  // [nelem]
@@ -63,11 +64,25 @@ QB_HD int qb_eval_ref(const QbCtl& g, const QbTraj& c, QbProgRef pr, double t, q
                         g.splines, g.spool, out);
 }
 // coefficients of all RHS elements at time t -> coef[0..nelem)
-QB_HD int qb_eval_rhs_coefs(const QbCtl& g, const QbTraj& c, double t, qb_c128* coef) {
-    for (int e = 0; e < g.nelem; e++)
-        if (qb_eval_ref(g, c, g.elem_prog[e], t, &coef[e])) return -1;
+// returns 0 ok, -1 bad program, 1 = values of host-evaluated elements are needed for time t
+QB_HD int qb_eval_rhs_coefs(const QbCtl& g, QbTraj& c, double t, qb_c128* coef) {
+    if (g.has_host_coef && !(c.hc_valid && c.hc_t == t)) { c.hc_t = t; c.hc_valid = 0; return 1; }
+    for (int e = 0; e < g.nelem; e++) {
+        const QbProgRef pr = g.elem_prog[e];
+        if (pr.len == 1 && g.instr[pr.off].op == QB_I_HOST) continue;   // written by the host
+        if (qb_eval_ref(g, c, pr, t, &coef[e])) return -1;
+    }
+    c.hc_valid = 0;
     return 0;
 }
+// common handling of the three outcomes at a pass-issuing label `label`
+#define QB_COEFS_OR_PAUSE(tval, label)                                              \
+    {                                                                               \
+        const int rcq_ = qb_eval_rhs_coefs(g, c, (tval), coef);                     \
+        if (rcq_ < 0) { c.status = QB_ST_BAD_PROGRAM; L = QL_FAIL; break; }         \
+        if (rcq_ > 0) { qb_pass_clear(p); c.pc = QB_PC_IDLE; c.hc_resume = (label); \
+                        c.done = 2; return 0; }                                     \
+    }
 QB_HD int qb_stage_x(const QbTraj& c, int i, int first) {
     // stage `first` reads sTA (or y_prev for stage 0); then TB, TA, ... alternate
     return ((i - first) & 1) ? c.sTB : c.sTA;
@@ -94,7 +109,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
 {
     const int s = T.s, S = T.S;
     int L = c.pc;
-    int dense_i = 0, stage_i = 0;
+    int dense_i = c.stage_arg, stage_i = c.stage_arg;   // used when resuming at an *_ISSUE label
     double set_t = 0.0;
     for (int guard = 0; guard < 4096; guard++) {
         switch (L) {
@@ -147,7 +162,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             p.kind = QB_PASS_RHS; p.x = c.set_x; p.zscale = c.set_scale; p.zdst = 0;
             p.dst1 = c.sF; p.red = QB_RED_NORM2_O1 | QB_RED_NORM2_Z;
             qb_pass_src(p, c.set_x, c.set_scale, 0.0);
-            if (qb_eval_rhs_coefs(g, c, set_t, coef)) { c.status = QB_ST_BAD_PROGRAM; L = QL_FAIL; break; }
+            QB_COEFS_OR_PAUSE(set_t, QL_SET_BEGIN)
             c.n_rhs++;
             c.pc = QB_PC_EST0_DONE; return 1;
         }
@@ -178,7 +193,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
         case QB_PC_EST1IN_DONE: {   // k1 = f(t + dt1/100, y_temp)   (:262-263)
             qb_pass_clear(p);
             p.kind = QB_PASS_RHS; p.x = c.sTB; p.zdst = 1; p.red = QB_RED_NORM2_Z;
-            if (qb_eval_rhs_coefs(g, c, c.t + c.est_dt1 / 100, coef)) { c.status = QB_ST_BAD_PROGRAM; L = QL_FAIL; break; }
+            QB_COEFS_OR_PAUSE(c.t + c.est_dt1 / 100, QB_PC_EST1IN_DONE)
             c.n_rhs++;
             c.pc = QB_PC_EST1_DONE; return 1;
         }
@@ -258,9 +273,8 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
                 p.w1z = dt * T.b[i]; p.w2z = dt * T.e[i];
                 p.red = QB_RED_NORM2_O1 | QB_RED_WRMS;
             }
-            if (qb_eval_rhs_coefs(g, c, i == 0 ? c.t_prev : c.t_prev + T.c[i] * dt, coef)) {
-                c.status = QB_ST_BAD_PROGRAM; L = QL_FAIL; break;
-            }
+            c.stage_arg = i;
+            QB_COEFS_OR_PAUSE(i == 0 ? c.t_prev : c.t_prev + T.c[i] * dt, QL_STAGE_ISSUE)
             c.stage = i; c.n_rhs++;
             c.pc = QB_PC_STAGE_DONE; return 1;
         }
@@ -334,9 +348,8 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
                     if (j < i) qb_pass_src(p, j, dt * bf, 0.0); else p.w1z = dt * bf;
                 }
             }
-            if (qb_eval_rhs_coefs(g, c, c.t_prev + T.c[i] * dt, coef)) {
-                c.status = QB_ST_BAD_PROGRAM; L = QL_FAIL; break;
-            }
+            c.stage_arg = i;
+            QB_COEFS_OR_PAUSE(c.t_prev + T.c[i] * dt, QL_DENSE_ISSUE)
             c.stage = i; c.n_rhs++;
             c.pc = QB_PC_DENSE_DONE; return 1;
         }

@@ -266,6 +266,7 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
             break;
         }
         // finished, paused or failed
+        if (c.done == 2) { atomicSub(E->n_active, 1); break; }   // waits for host coefficients
         if (E->out_status && c.traj_id >= 0) E->out_status[c.traj_id] = c.done;
         if (E->out_stats && c.traj_id >= 0) {
             int* st = E->out_stats + (size_t)c.traj_id * 4;
@@ -499,6 +500,9 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     h.ctl.neops = (int)s->eops.size();
     h.ctl.nargs = s->nargs;
     h.ctl.eop_functional = s->eop_functional;
+    h.ctl.has_host_coef = 0;
+    for (auto& pr : s->elem_prog)
+        if (pr.size() == 1 && pr[0].op == QB_I_HOST) h.ctl.has_host_coef = 1;
     e->maxcoef = std::max(1, h.ctl.nelem);
     h.ctl.maxcoef = e->maxcoef;
     e->V = h.ctl.tab.S + 5;
@@ -642,6 +646,7 @@ static int qb_run_common(QbEngH* e, int mode, int64_t ntraj,
                          void* d_expect, int32_t* d_status, int32_t* d_ncol, double* d_col_t,
                          int32_t* d_col_which, int32_t* d_stats, void* d_states) {
     QbEngineDev& h = e->h;
+    if (h.ctl.has_host_coef) QB_FAIL(QB_E_STATE, "host-evaluated (python) coefficients are only supported by the integrator protocol, not by batched runs");
     if (mode == 1 && h.ctl.ncops == 0) QB_FAIL(QB_E_STATE, "mcsolve mode needs collapse operators");
     if (mode == 1 && !d_draws && !e->opt.no_jump) QB_FAIL(QB_E_ARG, "mcsolve mode needs the threshold table");
     if (h.ctl.neops > 0 && !d_expect) QB_FAIL(QB_E_ARG, "system has e_ops but no expect output buffer");
@@ -849,7 +854,7 @@ extern "C" int qb_integ_set_state(qb_handle eng, double t, const void* y) {
     c.pc = QB_PC_ME_BEGIN;
     rc = qb_integ_launch(e, c); if (rc) return rc;
     if (c.done < 0) QB_FAIL(QB_E_STATE, "set_state failed with status %d", c.done);
-    return QB_OK;
+    return c.done == 2 ? 3 : QB_OK;      // 3: coefficient values needed (qb_integ_resume)
 }
 
 extern "C" int qb_integ_integrate(qb_handle eng, double t, int step, double* t_out, int* status) {
@@ -864,7 +869,35 @@ extern "C" int qb_integ_integrate(qb_handle eng, double t, int step, double* t_o
     c.pc = step ? QB_PC_STEP_ENTRY : QB_PC_ME_NEXT;
     rc = qb_integ_launch(e, c); if (rc) return rc;
     if (t_out) *t_out = c.t;
-    if (status) *status = c.done < 0 ? c.done : c.status;
+    if (status) *status = c.done == 2 ? 3 : (c.done < 0 ? c.done : c.status);
+    return QB_OK;
+}
+
+// ---- host-evaluated coefficients (python callables) ----
+// After qb_integ_set_state / qb_integ_integrate returned status QB_ST_NEED_COEF (3) the
+// controller waits for the values of the host-evaluated elements at *t:
+//   qb_integ_pending_coef(eng, &t) ; qb_integ_resume(eng, vals[nelem] complex, &t_out, &status)
+extern "C" int qb_integ_pending_coef(qb_handle eng, double* t) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e || !t) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    QbTraj c;
+    QB_CUDA(cudaMemcpy(&c, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    if (c.done != 2) QB_FAIL(QB_E_STATE, "no coefficient request pending");
+    *t = c.hc_t;
+    return QB_OK;
+}
+extern "C" int qb_integ_resume(qb_handle eng, const void* vals, double* t_out, int* status) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e || !vals) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    QbTraj c;
+    QB_CUDA(cudaMemcpy(&c, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    if (c.done != 2) QB_FAIL(QB_E_STATE, "no coefficient request pending");
+    // values of ALL elements are accepted; the controller overwrites the device-evaluated ones
+    QB_CUDA(cudaMemcpy(e->h.coef, vals, (size_t)e->h.ctl.nelem * 16, cudaMemcpyHostToDevice));
+    c.hc_valid = 1; c.done = 0; c.pc = c.hc_resume;
+    int rc = qb_integ_launch(e, c); if (rc) return rc;
+    if (t_out) *t_out = c.t;
+    if (status) *status = c.done == 2 ? 3 : (c.done < 0 ? c.done : c.status);
     return QB_OK;
 }
 
@@ -887,6 +920,22 @@ extern "C" int qb_integ_stats(qb_handle eng, int64_t stats[4]) {
     QbTraj c;
     QB_CUDA(cudaMemcpy(&c, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
     stats[0] = c.n_rhs; stats[1] = c.n_accept; stats[2] = c.n_reject; stats[3] = c.n_pass;
+    return QB_OK;
+}
+
+// out = sum_k vals[k] A_k x with coefficient values supplied by the caller (python-callable
+// coefficients evaluated on the host; used by the zvode-driven Adams path)
+extern "C" int qb_engine_rhs_coef(qb_handle eng, const void* vals, qb_handle xh, qb_handle outh) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    QbDenseH* x = qb_cast<QbDenseH>(xh, QB_TAG_DENSE);
+    QbDenseH* o = qb_cast<QbDenseH>(outh, QB_TAG_DENSE);
+    if (!e || !x || !o || !vals) QB_FAIL(QB_E_TYPE, "bad handles");
+    if (x->size() != e->sys->N || o->size() != e->sys->N) QB_FAIL(QB_E_SHAPE, "incompatible shapes");
+    QB_CUDA(cudaMemcpyAsync(e->h.coef, vals, (size_t)e->h.ctl.nelem * 16, cudaMemcpyHostToDevice, e->stream));
+    QB_CUDA(cudaMemcpyAsync(e->d, &e->h, sizeof(QbEngineDev), cudaMemcpyHostToDevice, e->stream));
+    qb_rhs_kernel<<<(e->h.ctl.N + QB_TILE_ROWS - 1) / QB_TILE_ROWS, QB_TILE_ROWS, 0, e->stream>>>(e->d, x->d, o->d, e->h.coef);
+    QB_LAUNCH_CHECK();
+    QB_CUDA(cudaStreamSynchronize(e->stream));
     return QB_OK;
 }
 

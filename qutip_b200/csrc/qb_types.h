@@ -55,7 +55,8 @@ enum {
     QB_I_CONST = 0, QB_I_T, QB_I_ARG, QB_I_ADD, QB_I_SUB, QB_I_MUL, QB_I_DIV, QB_I_NEG,
     QB_I_CONJ, QB_I_SIN, QB_I_COS, QB_I_TAN, QB_I_EXP, QB_I_LOG, QB_I_SQRT, QB_I_ABS,
     QB_I_REAL, QB_I_IMAG, QB_I_POW, QB_I_SINH, QB_I_COSH, QB_I_TANH, QB_I_SPLINE,
-    QB_I_ASIN, QB_I_ACOS, QB_I_ATAN, QB_I_NORM2, QB_I_HEAVISIDE_GE
+    QB_I_ASIN, QB_I_ACOS, QB_I_ATAN, QB_I_NORM2, QB_I_HEAVISIDE_GE,
+    QB_I_HOST     // value supplied by the host for the pending evaluation time (python callables)
 };
 struct QbInstr { int op; int iarg; double re, im; };
 
@@ -144,6 +145,11 @@ struct QbTraj {
     int exp_set;               // opset of the running EXPECT chain
     int exp_lo;
     int expect_mode;           // what the EXPECT chain feeds (0 e_ops record, 1 probs)
+    // ---- host-evaluated coefficients (python callables): the controller pauses with
+    //      done == 2 and hc_t = the time it needs them for; the host writes the values into
+    //      the slot's coefficient buffer, sets hc_valid and resumes at pc = hc_resume ----
+    double hc_t;
+    int hc_valid, hc_resume, stage_arg;
     // ---- statistics ----
     int n_rhs, n_accept, n_reject, n_pass;
 };

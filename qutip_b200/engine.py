@@ -354,18 +354,41 @@ class Engine(_Handle):
         args = as_c128(args)
         check(_lib.load().qb_integ_set_args(self.handle, ptr(args)))
 
+    # host_coeffs: callable t -> sequence of nelem complex values, used when some element's
+    # coefficient is a python callable (program coeffs.host()); see qb_integ_resume
+    host_coeffs = None
+
+    def _serve_coefficients(self, status, t_out=0.0):
+        lib = _lib.load()
+        while status == 3:
+            if self.host_coeffs is None:
+                raise _lib.QbError(-6, "engine needs host-evaluated coefficients but none are bound")
+            t = C.c_double()
+            check(lib.qb_integ_pending_coef(self.handle, C.byref(t)))
+            vals = as_c128(np.asarray(self.host_coeffs(t.value), dtype=complex))
+            tt, st = C.c_double(), C.c_int()
+            check(lib.qb_integ_resume(self.handle, ptr(vals), C.byref(tt), C.byref(st)))
+            t_out, status = tt.value, st.value
+        return t_out, status
+
     def set_state(self, t, y):
         y = as_c128(y).reshape(-1)
         if y.size != self.system.N:
             raise ValueError("incompatible state size")
-        check(_lib.load().qb_integ_set_state(self.handle, float(t), ptr(y)))
+        rc = _lib.load().qb_integ_set_state(self.handle, float(t), ptr(y))
+        if rc == 3:
+            _, st = self._serve_coefficients(3)
+            if st < 0:
+                raise _lib.QbError(st, STATUS_MESSAGES.get(st, "set_state failed"))
+            return
+        check(rc)
 
     def integrate(self, t, step=False):
         """returns (t_reached, status)."""
         t_out, st = C.c_double(), C.c_int()
         check(_lib.load().qb_integ_integrate(self.handle, float(t), int(step), C.byref(t_out),
                                              C.byref(st)))
-        return t_out.value, st.value
+        return self._serve_coefficients(st.value, t_out.value)
 
     def get_state(self):
         t = C.c_double()
@@ -380,6 +403,11 @@ class Engine(_Handle):
 
     def rhs(self, t, x, out):
         check(_lib.load().qb_engine_rhs(self.handle, float(t), x.handle, out.handle))
+        return out
+
+    def rhs_coef(self, vals, x, out):
+        vals = as_c128(vals)
+        check(_lib.load().qb_engine_rhs_coef(self.handle, ptr(vals), x.handle, out.handle))
         return out
 
     def rhs_bench(self, t, x, out, iters=20):

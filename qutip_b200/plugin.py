@@ -98,7 +98,16 @@ def coefficient_to_program(c, system=None):
         % name)
 
 
-def bind_qobjevo(qevo, system=None):
+class _HostCoefficient(coeffs.Program):
+    """Program placeholder for a coefficient only the host can evaluate (python callable);
+    ``coeff(t)`` is the reference Coefficient itself."""
+
+    def __init__(self, coeff):
+        super().__init__(coeffs.host().instrs)
+        self.coeff = coeff
+
+
+def bind_qobjevo(qevo, system=None, allow_host=False):
     """[(host operator, Program|None)] for ``sum_k coeff_k(t) A_k`` with all constant
     elements merged into one operator placed last (QobjEvo.compress order,
     core/cy/qobjevo.pyx:816-867).  Raises TypeError for forms that only exist on the host."""
@@ -116,7 +125,13 @@ def bind_qobjevo(qevo, system=None):
             const = h if const is None else const + h
         elif isinstance(el, (list, tuple)) and isinstance(el[0], qutip.Qobj) \
                 and isinstance(el[1], _Coefficient):
-            out.append((_data_to_host(el[0].data), coefficient_to_program(el[1], system)))
+            try:
+                prog = coefficient_to_program(el[1], system)
+            except TypeError:
+                if not allow_host:
+                    raise
+                prog = _HostCoefficient(el[1])        # python callable: evaluated by the host
+            out.append((_data_to_host(el[0].data), prog))
         else:
             raise TypeError("QobjEvo contains a function / map / product element, which is a "
                             "python callable returning a Qobj and cannot run on the device; "
@@ -150,11 +165,16 @@ def _upload(h):
     return E.DeviceDense.from_numpy(np.asfortranarray(h))
 
 
-def system_from_qobjevo(qevo, c_ops=(), n_ops=(), e_ops=(), functional=False):
+def system_from_qobjevo(qevo, c_ops=(), n_ops=(), e_ops=(), functional=False, allow_host=False):
     N = qevo.shape[0]
     system = E.System(N)
-    for h, prog in bind_qobjevo(qevo, system):
+    system.coeff_objects = []       # per element: host-evaluated reference Coefficient or None
+    system.programs = []            # per element: compiled Program or None (constant 1)
+    for h, prog in bind_qobjevo(qevo, system, allow_host):
         system.add_element(_upload(h), prog)
+        system.coeff_objects.append(getattr(prog, "coeff", None))
+        system.programs.append(prog)
+    system.has_host = any(c is not None for c in system.coeff_objects)
     for c, n in zip(c_ops, n_ops):
         ch, cp = _single_element(c, "a collapse operator")
         nh, npg = _single_element(n, "a collapse operator")
@@ -199,12 +219,15 @@ class _B200Integrator(Integrator):
 
     def _build(self):
         o = self._options
-        self._system = system_from_qobjevo(self._qevo)
+        self._system = system_from_qobjevo(self._qevo, allow_host=True)
         self._engine = E.Engine(
             self._system, self._tableau, nslots=1, atol=o['atol'], rtol=o['rtol'],
             nsteps=int(o['nsteps']), first_step=float(o['first_step'] or 0),
             min_step=float(o['min_step'] or 0), max_step=float(o['max_step'] or 0),
             interpolate=int(bool(o['interpolate'])))
+        if self._system.has_host:
+            objs = self._system.coeff_objects
+            self._engine.host_coeffs = lambda t: [1.0 if c is None else complex(c(t)) for c in objs]
         self._shape = None
 
     def arguments(self, args):
@@ -320,19 +343,28 @@ class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
             raise TypeError("b200_adams integrates QobjEvo systems on the device; use "
                             "method='adams' for arbitrary callables")
         self._qevo = qevo
-        self._system = system_from_qobjevo(qevo)
+        self._system = system_from_qobjevo(qevo, allow_host=True)
         self._engine = E.Engine(self._system, "vern7", nslots=1)
         n = self._system.N
         self._dx = E.DeviceDense.zeros(n, 1)
         self._dout = E.DeviceDense.zeros(n, 1)
         self._hout = np.empty(n, dtype=np.complex128)
+        self._progs = self._system.programs
         super()._prepare()
         self.name = "b200 device RHS + scipy zvode adams"
 
     @staticmethod
     def _mul_np_vec(t, vec, self):
         self._dx.write(vec)
-        self._engine.rhs(t, self._dx, self._dout)
+        if self._system.has_host:
+            vals = [1.0 if c is None else complex(c(t)) for c in self._system.coeff_objects]
+            # device-compiled elements are evaluated by the same byte-code on the host side
+            for k, c in enumerate(self._system.coeff_objects):
+                if c is None and self._progs[k] is not None:
+                    vals[k] = coeffs.evaluate(self._progs[k], t)
+            self._engine.rhs_coef(vals, self._dx, self._dout)
+        else:
+            self._engine.rhs(t, self._dx, self._dout)
         return self._dout.read_into(self._hout)
 
     def set_state(self, t, state0):
@@ -341,8 +373,9 @@ class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
         super().set_state(t, _data.to(_data.Dense, state0))
 
     def arguments(self, args):
-        self._system = system_from_qobjevo(self._qevo)
+        self._system = system_from_qobjevo(self._qevo, allow_host=True)
         self._engine = E.Engine(self._system, "vern7", nslots=1)
+        self._progs = self._system.programs
 
     def __getstate__(self):
         raise TypeError("b200_adams integrators hold device handles and SciPy zvode state; "
@@ -591,7 +624,11 @@ def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, m
     want_final = bool(opts["store_final_state"])
     system = system_from_qobjevo(rhs.rhs, rhs.c_ops, rhs.n_ops,
                                  [QobjEvo(e) if isinstance(e, qutip.Qobj) else e
-                                  for e in e_dict.values()])
+                                  for e in e_dict.values()], allow_host=True)
+    if system.has_host:
+        raise TypeError("python-callable coefficients need a host evaluation per RHS call; the "
+                        "'b200' map runs whole batches on the device and cannot use them. Use "
+                        "string/array coefficients, or method='b200_vern7' with a stock map.")
     iopt = solver._integrator._integrator.options
     eng = E.Engine(
         system, method, nslots=min(ntraj, 4096), atol=iopt['atol'], rtol=iopt['rtol'],

@@ -106,11 +106,38 @@ def test_nsteps_failure_raises_reference_exception():
 
 def test_refuses_host_only_forms():
     a = destroy(5)
-    H = QobjEvo([a.dag() * a, [a + a.dag(), lambda t: np.cos(t)]])
+    # operator-valued python functions cannot be split into (operator, scalar coefficient)
+    H = QobjEvo(lambda t: a.dag() * a * np.cos(t))
     with pytest.raises(TypeError, match="device"):
         mesolve(H, basis(5, 0), [0, 1], [a], options=dict(OPT, method="b200_vern7"))
     with pytest.raises(TypeError, match="QobjEvo.matmul_data"):
         plugin.B200Vern7(lambda t, y: y, {})
+    # python-callable scalar coefficients cannot be used by the whole-batch map
+    Hc = QobjEvo([a.dag() * a, [a + a.dag(), lambda t: np.cos(t)]])
+    with pytest.raises(TypeError, match="b200"):
+        mcsolve(Hc, basis(5, 1), [0, 1], [a], ntraj=2, options=dict(OPT, map="b200"))
+
+
+@pytest.mark.parametrize("method", ["vern7", "adams"])
+def test_python_function_coefficients_evaluated_by_host(method):
+    """FunctionCoefficient: the scalar is evaluated on the host for each stage time while the
+    matvecs, stage combinations and step control stay on the device."""
+    a = destroy(8)
+    H = QobjEvo([a.dag() * a, [a + a.dag(), lambda t, A: A * np.cos(2 * t)]], args={"A": 0.4})
+    c_ops = [QobjEvo([a, lambda t, k: np.sqrt(k * np.exp(-t))], args={"k": 0.5})]
+    tl = np.linspace(0, 3, 16)
+    ref = mesolve(H, basis(8, 3), tl, c_ops, e_ops=[a.dag() * a], options=dict(OPT, method=method))
+    out = mesolve(H, basis(8, 3), tl, c_ops, e_ops=[a.dag() * a],
+                  options=dict(OPT, method="b200_" + method))
+    np.testing.assert_allclose(out.expect[0], ref.expect[0], rtol=RTOL, atol=ATOL)
+    # args updated between steps (Solver.step(t, args=...), reference test_mesolver_stepping)
+    s_ref = qutip.MESolver(H, c_ops, options=dict(OPT, method=method))
+    s_out = qutip.MESolver(H, c_ops, options=dict(OPT, method="b200_" + method))
+    for s in (s_ref, s_out):
+        s.start(basis(8, 3), 0)
+    for t, args in ((1.0, None), (2.0, {"k": 0.0, "A": 0.1})):
+        x, y = s_ref.step(t, args=args), s_out.step(t, args=args)
+        np.testing.assert_allclose(y.full(), x.full(), rtol=1e-5, atol=1e-7)
 
 
 def test_integrator_pickle_roundtrip():
