@@ -238,6 +238,11 @@ class _B200Integrator(Integrator):
         if self._is_set:
             self.set_state(*state)
 
+    def reset(self, hard=False):
+        # Solver._argument() updates the QobjEvo's args and then calls reset()
+        # (solver_base.py:456-460): the coefficient programs hold the bound args, so re-bind
+        self.arguments(None)
+
     def set_state(self, t, state):
         arr = _data.to(_data.Dense, state).to_array()
         self._shape = arr.shape
@@ -376,6 +381,10 @@ class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
         self._system = system_from_qobjevo(self._qevo, allow_host=True)
         self._engine = E.Engine(self._system, "vern7", nslots=1)
         self._progs = self._system.programs
+
+    def reset(self, hard=False):
+        self.arguments(None)
+        super().reset(hard)
 
     def __getstate__(self):
         raise TypeError("b200_adams integrators hold device handles and SciPy zvode state; "
