@@ -165,12 +165,20 @@ def _upload(h):
     return E.DeviceDense.from_numpy(np.asfortranarray(h))
 
 
-def system_from_qobjevo(qevo, c_ops=(), n_ops=(), e_ops=(), functional=False, allow_host=False):
-    N = qevo.shape[0]
+def system_from_qobjevo(qevo, c_ops=(), n_ops=(), e_ops=(), functional=False, allow_host=False,
+                        ncols=1):
+    """``ncols`` > 1: the state is an N x ncols matrix (propagator-style evolution,
+    solver/propagator.py:401-417); its columns are stacked and every operator becomes
+    block-diagonal kron(I_ncols, A), so one error norm covers the whole matrix exactly as
+    in the reference's RK loop."""
+    N = qevo.shape[0] * ncols
     system = E.System(N)
     system.coeff_objects = []       # per element: host-evaluated reference Coefficient or None
     system.programs = []            # per element: compiled Program or None (constant 1)
     for h, prog in bind_qobjevo(qevo, system, allow_host):
+        if ncols > 1:
+            h = sp.kron(sp.identity(ncols, dtype=complex, format="csr"), sp.csr_matrix(h),
+                        format="csr")
         system.add_element(_upload(h), prog)
         system.coeff_objects.append(getattr(prog, "coeff", None))
         system.programs.append(prog)
@@ -217,9 +225,11 @@ class _B200Integrator(Integrator):
         self._build()
         self.name = self.method
 
+    _ncols = 1
+
     def _build(self):
         o = self._options
-        self._system = system_from_qobjevo(self._qevo, allow_host=True)
+        self._system = system_from_qobjevo(self._qevo, allow_host=True, ncols=self._ncols)
         self._engine = E.Engine(
             self._system, self._tableau, nslots=1, atol=o['atol'], rtol=o['rtol'],
             nsteps=int(o['nsteps']), first_step=float(o['first_step'] or 0),
@@ -245,6 +255,9 @@ class _B200Integrator(Integrator):
 
     def set_state(self, t, state):
         arr = _data.to(_data.Dense, state).to_array()
+        if arr.shape[1] != self._ncols:          # matrix-valued state: re-bind block-diagonal
+            self._ncols = arr.shape[1]
+            self._build()
         self._shape = arr.shape
         self._engine.set_state(t, np.ascontiguousarray(arr.reshape(-1, order="F")))
         self._is_set = True

@@ -306,3 +306,14 @@ def test_adams_with_device_rhs():
                   seeds=3, options=dict(OPT, method="b200_adams", keep_runs_results=True))
     assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
     np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=1e-5, atol=1e-7)
+
+
+def test_matrix_valued_state_unitary_evolution():
+    """sesolve of an operator (propagator-style): N x N state through the device integrator."""
+    H = qutip.rand_herm(6, seed=2)
+    U0 = qutip.qeye(6)
+    tl = np.linspace(0, 2, 9)
+    ref = qutip.sesolve(H, U0, tl, options=dict(OPT, method="vern7"))
+    out = qutip.sesolve(H, U0, tl, options=dict(OPT, method="b200_vern7"))
+    for a, b in zip(out.states, ref.states):
+        np.testing.assert_allclose(a.full(), b.full(), rtol=RTOL, atol=ATOL)
