@@ -355,19 +355,24 @@ class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
     SURVEY 8f's next row)."""
     method = "adams"
 
-    def _prepare(self):
-        qevo = getattr(self.derivative, "__self__", None)
-        if not isinstance(qevo, QobjEvo) or getattr(self.derivative, "__name__", "") != "matmul_data":
-            raise TypeError("b200_adams integrates QobjEvo systems on the device; use "
-                            "method='adams' for arbitrary callables")
-        self._qevo = qevo
-        self._system = system_from_qobjevo(qevo, allow_host=True)
+    _ncols = 1
+
+    def _bind(self):
+        self._system = system_from_qobjevo(self._qevo, allow_host=True, ncols=self._ncols)
         self._engine = E.Engine(self._system, "vern7", nslots=1)
         n = self._system.N
         self._dx = E.DeviceDense.zeros(n, 1)
         self._dout = E.DeviceDense.zeros(n, 1)
         self._hout = np.empty(n, dtype=np.complex128)
         self._progs = self._system.programs
+
+    def _prepare(self):
+        qevo = getattr(self.derivative, "__self__", None)
+        if not isinstance(qevo, QobjEvo) or getattr(self.derivative, "__name__", "") != "matmul_data":
+            raise TypeError("b200_adams integrates QobjEvo systems on the device; use "
+                            "method='adams' for arbitrary callables")
+        self._qevo = qevo
+        self._bind()
         super()._prepare()
         self.name = "b200 device RHS + scipy zvode adams"
 
@@ -386,14 +391,13 @@ class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
         return self._dout.read_into(self._hout)
 
     def set_state(self, t, state0):
-        if state0.shape[1] > 1:
-            raise TypeError("b200_adams supports vectorised (column) states only")
+        if state0.shape[1] != self._ncols:       # matrix-valued state: block-diagonal binding
+            self._ncols = state0.shape[1]
+            self._bind()
         super().set_state(t, _data.to(_data.Dense, state0))
 
     def arguments(self, args):
-        self._system = system_from_qobjevo(self._qevo, allow_host=True)
-        self._engine = E.Engine(self._system, "vern7", nslots=1)
-        self._progs = self._system.programs
+        self._bind()
 
     def reset(self, hard=False):
         self.arguments(None)
