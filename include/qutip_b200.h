@@ -47,8 +47,9 @@ int qb_dense_download(qb_handle h, void* host);
 int qb_dense_write(qb_handle h, const void* host);      /* overwrite from host memory */
 int qb_dense_copy(qb_handle h, qb_handle* out);
 int qb_dense_info(qb_handle h, int64_t* rows, int64_t* cols, int* fortran, void** devptr);
-/* operator formats: 0 auto (diagonal-masked slices when the matrix is diagonal
- * structured, CSR otherwise), 1 force CSR, 2 force DIAM */
+/* operator formats: 0 auto (sliced ELLPACK for small L2-resident operators with little
+ * padding, diagonal-masked slices when the matrix is diagonal structured, CSR otherwise),
+ * 1 force CSR, 2 force DIAM, 3 force SELL */
 int qb_csr_upload(const void* data, const int32_t* col, const int32_t* rowptr,
                   int64_t rows, int64_t cols, int64_t nnz, int format, qb_handle* out);
 int qb_dia_upload(const void* data, const int32_t* offsets, int64_t ndiag,

@@ -97,4 +97,50 @@ template <class F> inline void build_diam(int64_t nrows, F fill_slice, DiamHost&
     }
 }
 
+// ---- sliced ELLPACK (32-row slices, slot-major, explicit column indices) ----
+// Used for operators that stay L2-resident (many trajectories re-read them): the sweep is
+// three coalesced loads and four FMAs per slot with no mask/shuffle arithmetic, i.e. far
+// fewer instructions than DIAM, at 20 B instead of ~16.3 B per stored element.
+struct SellHost {
+    std::vector<int> slice_ptr;          // [nslices + 1], in slots
+    std::vector<qb_c128> val;            // [nslots * 32]
+    std::vector<int> col;                // [nslots * 32]
+    long long nnz = 0;
+};
+
+template <class RowFn>   // row_fn(r, std::vector<std::pair<int, qb_c128>>& out) appends (col, val)
+inline void build_sell(int64_t nrows, int64_t ncols, RowFn row_fn, SellHost& out) {
+    const int64_t nslices = (nrows + 31) / 32;
+    out.slice_ptr.assign(1, 0);
+    std::vector<std::vector<std::pair<int, qb_c128>>> rows(32);
+    for (int64_t sl = 0; sl < nslices; sl++) {
+        int width = 0;
+        for (int l = 0; l < 32; l++) {
+            rows[l].clear();
+            const int64_t r = sl * 32 + l;
+            if (r < nrows) {
+                row_fn(r, rows[l]);
+                std::stable_sort(rows[l].begin(), rows[l].end(),
+                                 [](const std::pair<int, qb_c128>& a, const std::pair<int, qb_c128>& b) {
+                                     return a.first < b.first; });
+                out.nnz += (long long)rows[l].size();
+            }
+            width = std::max(width, (int)rows[l].size());
+        }
+        const size_t base = out.val.size();
+        out.val.resize(base + (size_t)width * 32);
+        out.col.resize(base + (size_t)width * 32);
+        for (int k = 0; k < width; k++)
+            for (int l = 0; l < 32; l++) {
+                const int64_t r = sl * 32 + l;
+                qb_c128 v = {0.0, 0.0};
+                int c = (int)std::min<int64_t>(r, ncols - 1);
+                if (c < 0) c = 0;
+                if (k < (int)rows[l].size()) { c = rows[l][k].first; v = rows[l][k].second; }
+                out.val[base + (size_t)k * 32 + l] = v;
+                out.col[base + (size_t)k * 32 + l] = c;
+            }
+        out.slice_ptr.push_back(out.slice_ptr.back() + width);
+    }
+}
 }  // namespace qbdiam

@@ -12,6 +12,9 @@
 //   broadcasts (offset, mask, base) by shuffle -- so no global load in the loop depends on
 //   another one and the unrolled loop keeps 8 x (1 + G) independent 16-byte loads per lane
 //   in flight.  G state vectors (trajectories) can share one pass over the operator.
+// * SELL  (sliced ELLPACK, slot-major, explicit column indices): for operators that stay
+//   L2-resident while many trajectories re-read them; three coalesced loads + four FMAs per
+//   slot and no mask arithmetic -> several times fewer instructions than DIAM.
 // * CSR   : generic fallback, one lane per row (handles unsorted / duplicate indices).
 // * DENSE : column-major A, lanes read consecutive rows of a column (coalesced).
 #pragma once
@@ -104,6 +107,20 @@ __device__ __forceinline__ double2 qb_rowdot(const QbOpDev& A, int sl, int lane,
         double2 a1[1] = {acc};
         qb_rowdot_diam<1, U>(A, sl, lane, r, xs, a1);
         acc = a1[0];
+    } else if (A.fmt == QB_FMT_SELL) {
+        const int s0 = A.slice_ptr[sl], w = A.slice_ptr[sl + 1] - s0;
+        const double2* __restrict__ v = reinterpret_cast<const double2*>(A.val) + ((size_t)s0 * 32 + lane);
+        const int* __restrict__ c = A.col + ((size_t)s0 * 32 + lane);
+        int k = 0;
+        for (; k + 4 <= w; k += 4) {          // 4 slots in flight: 12 coalesced loads per lane
+            const int c0 = __ldg(c + k * 32), c1 = __ldg(c + (k + 1) * 32),
+                      c2 = __ldg(c + (k + 2) * 32), c3 = __ldg(c + (k + 3) * 32);
+            const double2 v0 = __ldg(v + k * 32), v1 = __ldg(v + (k + 1) * 32),
+                          v2 = __ldg(v + (k + 2) * 32), v3 = __ldg(v + (k + 3) * 32);
+            const double2 x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+            qb_fma(acc, v0, x0); qb_fma(acc, v1, x1); qb_fma(acc, v2, x2); qb_fma(acc, v3, x3);
+        }
+        for (; k < w; k++) qb_fma(acc, __ldg(v + k * 32), x[__ldg(c + k * 32)]);
     } else if (A.fmt == QB_FMT_CSR) {
         if (active) {
             const double2* __restrict__ val = reinterpret_cast<const double2*>(A.val);

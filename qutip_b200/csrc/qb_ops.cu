@@ -114,6 +114,18 @@ static int finish_diam(QbOpH* h, DiamHost& dh, int64_t rows, int64_t cols) {
     h->dev.pad_ = h->device_bytes > (int64_t)96 << 20 ? 1 : 0;
     return QB_OK;
 }
+static int finish_sell(QbOpH* h, SellHost& sh, int64_t rows, int64_t cols) {
+    h->dev.fmt = QB_FMT_SELL; h->dev.nrows = (int)rows; h->dev.ncols = (int)cols;
+    h->dev.nnz = sh.nnz;
+    int rc;
+    if ((rc = to_device(h, sh.slice_ptr, &h->dev.slice_ptr))) return rc;
+    if ((rc = to_device(h, sh.val, &h->dev.val))) return rc;
+    if ((rc = to_device(h, sh.col, &h->dev.col))) return rc;
+    return QB_OK;
+}
+// operators up to this size stay L2-resident when many trajectories re-read them: prefer
+// the instruction-lean SELL sweep; larger ones are HBM streams: prefer the compact DIAM
+static const long long QB_SELL_MAX_BYTES = 48ll << 20;
 }  // namespace
 
 extern "C" int qb_csr_upload(const void* data, const int32_t* col, const int32_t* rowptr,
@@ -143,7 +155,20 @@ extern "C" int qb_csr_upload(const void* data, const int32_t* col, const int32_t
         // the warp keeps >= 8 lanes busy per entry
         if (format == 0) use_diam = (nnz == 0) || avg >= 8.0 || rows < 32;
     }
-    if (use_diam) rc = finish_diam(h, dh, rows, cols);
+    // format 3: force SELL; auto: SELL for small (L2-resident) operators with little padding
+    bool use_sell = (format == 3);
+    SellHost sh;
+    if (format == 3 || format == 0) {
+        build_sell(rows, cols, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o) {
+            for (int p = rowptr[r]; p < rowptr[r + 1]; p++) o.push_back({col[p], v[p]});
+        }, sh);
+        const long long padded = (long long)sh.val.size();
+        if (format == 0)
+            use_sell = nnz > 0 && rows >= 32 && padded * 20 <= QB_SELL_MAX_BYTES &&
+                       (double)padded <= 1.5 * (double)nnz;
+    }
+    if (use_sell) rc = finish_sell(h, sh, rows, cols);
+    else if (use_diam) rc = finish_diam(h, dh, rows, cols);
     else {
         h->dev.fmt = QB_FMT_CSR; h->dev.nrows = (int)rows; h->dev.ncols = (int)cols; h->dev.nnz = nnz;
         std::vector<qb_c128> vv(v, v + nnz);
@@ -187,7 +212,26 @@ extern "C" int qb_dia_upload(const void* data, const int32_t* offsets, int64_t n
     int rc = QB_OK;
     const double avg = dh.ent.empty() ? 0.0 : (double)dh.val.size() / (double)dh.ent.size();
     bool use_diam = format == 2 || (format == 0 && (dh.val.empty() || avg >= 8.0 || rows < 32));
-    if (use_diam) rc = finish_diam(h, dh, rows, cols);
+    bool use_sell = (format == 3);
+    SellHost sh;
+    if (format == 3 || format == 0) {
+        build_sell(rows, cols, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o) {
+            for (int k = 0; k < ndiag; k++) {
+                const int d = order[k];
+                const int64_t c = r + offsets[d];
+                if (c < 0 || c >= cols) continue;
+                const qb_c128 x = v[(size_t)d * cols + c];
+                if (x.re == 0.0 && x.im == 0.0) continue;
+                o.push_back({(int)c, x});
+            }
+        }, sh);
+        const long long padded = (long long)sh.val.size();
+        if (format == 0)
+            use_sell = sh.nnz > 0 && rows >= 32 && padded * 20 <= QB_SELL_MAX_BYTES &&
+                       (double)padded <= 1.5 * (double)sh.nnz;
+    }
+    if (use_sell) rc = finish_sell(h, sh, rows, cols);
+    else if (use_diam) rc = finish_diam(h, dh, rows, cols);
     else {
         // sparse diagonals: fall back to CSR built from the slices
         std::vector<std::vector<std::pair<int, qb_c128>>> rowsv(rows);
@@ -252,6 +296,12 @@ qb_matmul_kernel(QbOpDev A, const double2* __restrict__ X, long long xs_r, long 
                     const double2* a = reinterpret_cast<const double2*>(A.dense) + r;
                     for (int k = 0; k < A.ncols; k++)
                         qb_fma(q, a[(long long)k * A.nrows], X[(long long)k * xs_r + c * xs_c]);
+                } else if (A.fmt == QB_FMT_SELL) {
+                    const int s0 = A.slice_ptr[sl], w = A.slice_ptr[sl + 1] - s0;
+                    const double2* val = reinterpret_cast<const double2*>(A.val) + ((size_t)s0 * 32 + lane);
+                    const int* col = A.col + ((size_t)s0 * 32 + lane);
+                    for (int k = 0; k < w; k++)
+                        qb_fma(q, val[k * 32], X[(long long)col[k * 32] * xs_r + c * xs_c]);
                 }
             }
             if (A.fmt == QB_FMT_DIAM) {

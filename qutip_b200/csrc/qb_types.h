@@ -30,7 +30,7 @@ struct QbTableau {
 };
 
 // ---- operator storage on the device ----
-enum { QB_FMT_CSR = 0, QB_FMT_DIAM = 1, QB_FMT_DENSE = 2 };
+enum { QB_FMT_CSR = 0, QB_FMT_DIAM = 1, QB_FMT_DENSE = 2, QB_FMT_SELL = 3 };
 
 struct QbOpDev {
     int fmt, nrows, ncols, pad_;
@@ -46,6 +46,8 @@ struct QbOpDev {
     const int* ent_off;
     const unsigned* ent_mask;
     const long long* slice_vbase;
+    // SELL (sliced ELLPACK, 32-row slices, slot-major): slice_ptr[nslices+1] counts slots;
+    // slot k of slice s holds val/col[(slice_ptr[s] + k) * 32 + lane]; padding has val = 0
     // DENSE: column-major A[nrows x ncols]
     const qb_c128* dense;
 };

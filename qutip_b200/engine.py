@@ -11,8 +11,8 @@ from . import _lib
 from ._lib import QbOptions, as_c128, check, ptr
 from .coeffs import Program
 
-FMT_AUTO, FMT_CSR, FMT_DIAM = 0, 1, 2
-FMT_NAMES = {0: "csr", 1: "diam", 2: "dense"}
+FMT_AUTO, FMT_CSR, FMT_DIAM, FMT_SELL = 0, 1, 2, 3
+FMT_NAMES = {0: "csr", 1: "diam", 2: "dense", 3: "sell"}
 TABLEAUX = {"vern7": 0, "vern9": 1}
 
 STATUS_MESSAGES = {

@@ -12,7 +12,7 @@ from qutip_b200.coeffs import Program, QbInstr
 HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-FMT_CSR, FMT_DIAM = 0, 1
+FMT_CSR, FMT_DIAM, FMT_SELL = 0, 1, 3
 
 
 class QbOptions(C.Structure):

@@ -24,6 +24,7 @@ struct HostOp {
     int fmt; int nrows, ncols;
     std::vector<qb_c128> val; std::vector<int> col, rowptr;      // CSR
     qbdiam::DiamHost dh;                                           // DIAM
+    qbdiam::SellHost sh;                                           // SELL
 };
 struct Sys {
     int64_t N = 0; int nargs = 0;
@@ -46,6 +47,13 @@ static qb_c128 rowdot(const HostOp& A, int64_t r, const qb_c128* x) {
         return acc;
     }
     const int sl = (int)(r / 32), lane = (int)(r % 32);
+    if (A.fmt == QB_FMT_SELL) {
+        for (int k = A.sh.slice_ptr[sl]; k < A.sh.slice_ptr[sl + 1]; k++) {
+            const qb_c128 a = A.sh.val[(size_t)k * 32 + lane], b = x[A.sh.col[(size_t)k * 32 + lane]];
+            acc.re += a.re * b.re - a.im * b.im; acc.im += a.re * b.im + a.im * b.re;
+        }
+        return acc;
+    }
     long long vb = A.dh.slice_vbase[sl];
     const unsigned lt = (1u << lane) - 1u;
     for (int e = A.dh.slice_ptr[sl]; e < A.dh.slice_ptr[sl + 1]; e++) {
@@ -66,6 +74,10 @@ static HostOp make_op(const qb_c128* data, const int32_t* col, const int32_t* ro
     if (fmt == QB_FMT_CSR) {
         o.val.assign(data, data + nnz); o.col.assign(col, col + nnz);
         o.rowptr.assign(rowptr, rowptr + rows + 1);
+    } else if (fmt == QB_FMT_SELL) {
+        qbdiam::build_sell(rows, cols, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o2) {
+            for (int p = rowptr[r]; p < rowptr[r + 1]; p++) o2.push_back({col[p], data[p]});
+        }, o.sh);
     } else {
         qbdiam::build_diam(rows, [&](int64_t sl, std::vector<qbdiam::Entry>& es) {
             const int64_t r0 = sl * 32, r1 = std::min<int64_t>(rows, r0 + 32);

@@ -8,7 +8,7 @@ RHS-evaluation counts and collapse records."""
 import numpy as np
 import pytest
 
-from _emul import FMT_CSR, FMT_DIAM, EmulSystem, default_options
+from _emul import FMT_CSR, FMT_DIAM, FMT_SELL, EmulSystem, default_options
 from _golden import coeff_spec, load, op_arrays, orc_op, orc_rhs
 from _systems import functional_of, merged_constant_rhs
 from qutip_b200 import coeffs
@@ -22,10 +22,11 @@ def _sp_arrays(m):
 
 
 @pytest.mark.parametrize("kind", ["csr", "dia"])
-def test_diam_format_matvec(kind):
+@pytest.mark.parametrize("fmt", [FMT_DIAM, FMT_SELL])
+def test_diam_format_matvec(kind, fmt):
     g = load("matmul")
     n = len(g["x"])
-    s = EmulSystem(n, 0, FMT_DIAM)
+    s = EmulSystem(n, 0, fmt)
     s.add_element(*op_arrays(g, kind))
     np.testing.assert_allclose(s.matvec(0, g["x"]), g["%s_mul_s0" % kind], rtol=1e-13,
                                atol=1e-13)
@@ -40,12 +41,15 @@ def test_diam_duplicate_entries():
     s.add_element("csr", (3, 3), dict(data=data, col=col, rowptr=rowptr))
     x = np.array([1.0, 10.0, 100.0], dtype=complex)
     np.testing.assert_allclose(s.matvec(0, x), [30.0, 3.0, 400.0])
+    s = EmulSystem(3, 0, FMT_SELL)
+    s.add_element("csr", (3, 3), dict(data=data, col=col, rowptr=rowptr))
+    np.testing.assert_allclose(s.matvec(0, x), [30.0, 3.0, 400.0])
 
 
 @pytest.mark.parametrize("name,method", [("c1_jc", "vern7"), ("c1_jc", "vern9"),
                                          ("c2_tfim4", "vern7"), ("c2_tfim4", "vern9"),
                                          ("c4_driven", "vern7"), ("c5_kerr_0", "vern7")])
-@pytest.mark.parametrize("fmt", [FMT_DIAM, FMT_CSR])
+@pytest.mark.parametrize("fmt", [FMT_DIAM, FMT_CSR, FMT_SELL])
 def test_mesolve_state_machine(name, method, fmt):
     g = load(name)
     s = EmulSystem(len(g["y0"]), 0, fmt)
