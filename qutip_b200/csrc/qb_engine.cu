@@ -61,57 +61,62 @@ __device__ __forceinline__ const double2* qb_vsrc(const QbEngineDev* E, int slot
     return E->init_states + (size_t)init_idx * (size_t)E->ctl.N;
 }
 
-#ifndef QB_SPW
-#define QB_SPW 1     // consecutive 32-row slices handled by one warp
-#endif
 #ifndef QB_PF
 #define QB_PF 4      // epilogue source vectors prefetched before the operator sweep
 #endif
-
-// Warp-autonomous pass kernel: one warp = one 32-row slice of one trajectory slot.  There
-// is no shared memory and no block-level barrier: each warp reads the (L1/L2-resident)
-// pass descriptor itself, issues the loads of its epilogue sources BEFORE the operator
-// sweep so their HBM latency overlaps it, and writes its own partial reductions
-// (partials[slot][slice][k], summed in a fixed order by the control kernel).
 #ifndef QB_MINB
 #define QB_MINB 4
 #endif
-__global__ void __launch_bounds__(QB_TILE_ROWS, QB_MINB)
-qb_pass_kernel(const QbEngineDev* __restrict__ E)
+#define QB_SH_MAXW 40   // widest SELL slice the shared kernel stages (40*32*20 B = 25.6 KB)
+#ifndef QB_SH_T
+#define QB_SH_T 4       // consecutive slices one CTA of the shared kernel walks through
+#endif
+
+// per-warp view of a slot's pass descriptor (read straight from L1/L2-resident global memory)
+struct QbWarpHdr {
+    int kind, nsrc, zdst, dst1, red, xslot, my_src;
+    double my_w1, my_w2, zscale, w1z, w2z;
+    const double2* slot_base;
+    const double2* init_ptr;
+};
+
+__device__ __forceinline__ void qb_load_hdr(const QbEngineDev* __restrict__ E, int slot, int lane,
+                                            QbWarpHdr& h)
 {
-    const int ntiles = E->ctl.ntiles;
-    const int slot = blockIdx.x / ntiles;
-    const int tile = blockIdx.x - slot * ntiles;
     const QbPass* __restrict__ gp = &E->pass[slot];
-    const int kind = gp->kind;
-    if (kind == QB_PASS_NONE) return;
+    const size_t N_ = (size_t)E->ctl.N;
+    h.kind = gp->kind; h.nsrc = gp->nsrc; h.zdst = gp->zdst; h.dst1 = gp->dst1; h.red = gp->red;
+    h.xslot = gp->x;
+    h.my_src = 0; h.my_w1 = 0.0; h.my_w2 = 0.0;
+    if (lane < h.nsrc) { h.my_src = gp->src[lane]; h.my_w1 = gp->w1[lane]; h.my_w2 = gp->w2[lane]; }
+    h.zscale = gp->zscale; h.w1z = gp->w1z; h.w2z = gp->w2z;
+    h.slot_base = E->pool + (size_t)slot * E->V * N_;
+    h.init_ptr = E->init_states + (size_t)E->traj[slot].init_idx * N_;
+}
+
+// One 32-row slice of one trajectory slot, executed by one warp without any block-level
+// synchronisation: epilogue sources are requested BEFORE the operator sweep so their HBM
+// latency overlaps it; partial reductions go to partials[slot][slice][k].
+// sval/scol != nullptr: the slice of the (single, SELL) RHS operator is staged in shared
+// memory by the caller and shared by the CTA's warps (= 8 trajectories).
+__device__ __forceinline__ void qb_pass_one_slice(
+    const QbEngineDev* __restrict__ E, int slot, int sl, int lane, const QbWarpHdr& h,
+    const double2* __restrict__ sval, const int* __restrict__ scol, int sw)
+{
+    const QbPass* __restrict__ gp = &E->pass[slot];
     const int N = E->ctl.N;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t N_ = (size_t)N;
-    const int init_idx = E->traj[slot].init_idx;
-    const int nsrc = gp->nsrc;
-    int my_src = 0;
-    double my_w1 = 0.0, my_w2 = 0.0;
-    if (lane < nsrc) { my_src = gp->src[lane]; my_w1 = gp->w1[lane]; my_w2 = gp->w2[lane]; }
-    const double zscale = gp->zscale, w1z = gp->w1z, w2z = gp->w2z;
-    const int zdst = gp->zdst, dst1 = gp->dst1, red = gp->red;
-    const int xslot = gp->x;
-  for (int it = 0; it < QB_SPW; it++) {
-    const int sl = (tile * (QB_TILE_ROWS / 32) + warp) * QB_SPW + it;
-    if ((long long)sl * 32 >= N) return;          // warp-uniform
     const long long r = (long long)sl * 32 + lane;
     const bool active = r < N;
-    // vector `idx` of this slot: one IMAD.WIDE (idx * N) instead of 64-bit multiplies
-    const double2* const slot_base = E->pool + (size_t)slot * E->V * N_;
-    const double2* const init_ptr = E->init_states + (size_t)init_idx * N_;
-#define QB_VS(idx) ((idx) >= 0 ? slot_base + (long long)(idx) * N : init_ptr)
+    const int kind = h.kind, nsrc = h.nsrc;
+#define QB_VS(idx) ((idx) >= 0 ? h.slot_base + (long long)(idx) * N : h.init_ptr)
     double* __restrict__ part = E->partials + ((size_t)slot * E->nslices + sl) * E->red_stride;
 
     if (kind == QB_PASS_EXPECT) {
         const int opset = gp->opset, op_lo = gp->op_lo, nops = gp->op_hi - gp->op_lo;
         const QbOpDev* ops = (opset == QB_OPSET_EOPS) ? E->eops : E->nops;
         const bool functional = (opset == QB_OPSET_EOPS) && E->ctl.eop_functional;
-        const double2* x = QB_VS(gp->x);
+        const double2* x = QB_VS(h.xslot);
         double2 xr = make_double2(0.0, 0.0);
         if (active) xr = x[r];
         for (int m = 0; m < nops; m++) {
@@ -123,14 +128,14 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
             const double sre = qb_warp_sum(pr.x), sim = qb_warp_sum(pr.y);
             if (lane == 0) { part[2 * m] = sre; part[2 * m + 1] = sim; }
         }
-        continue;
+        return;
     }
 
     // ---- epilogue sources: lane i holds (slot, w1, w2) of source i; prefetch the first QB_PF
     double2 pv[QB_PF];
 #pragma unroll
     for (int u = 0; u < QB_PF; u++) {
-        const int sidx = __shfl_sync(0xffffffffu, my_src, u);
+        const int sidx = __shfl_sync(0xffffffffu, h.my_src, u);
         const double2* p = QB_VS(sidx);
         pv[u] = (u < nsrc && active) ? p[r] : make_double2(0.0, 0.0);
     }
@@ -138,10 +143,25 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
     // ---- operator application ----
     double2 z = make_double2(0.0, 0.0);
     if (kind == QB_PASS_RHS) {
-        const double2* x = QB_VS(xslot);
+        const double2* x = QB_VS(h.xslot);
         const int nelem = E->ctl.nelem;
         const qb_c128* cf = E->coef + (size_t)slot * E->ctl.maxcoef;
-        if (E->zbuf) {             // dense batched path: A x was computed by the ZGEMM pre-pass
+        if (sval) {                // SELL slice staged in shared memory, shared by 8 slots
+            double2 q = make_double2(0.0, 0.0);
+            const double2* v = sval + lane;
+            const int* c = scol + lane;
+            int k = 0;
+            for (; k + 4 <= sw; k += 4) {
+                const int c0 = c[k * 32], c1 = c[(k + 1) * 32], c2 = c[(k + 2) * 32], c3 = c[(k + 3) * 32];
+                const double2 x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+                qb_fma(q, v[k * 32], x0); qb_fma(q, v[(k + 1) * 32], x1);
+                qb_fma(q, v[(k + 2) * 32], x2); qb_fma(q, v[(k + 3) * 32], x3);
+            }
+            for (; k < sw; k++) qb_fma(q, v[k * 32], x[c[k * 32]]);
+            const qb_c128 cc = cf[0];
+            z.x = cc.re * q.x - cc.im * q.y;
+            z.y = cc.re * q.y + cc.im * q.x;
+        } else if (E->zbuf) {      // dense batched path: A x was computed by the ZGEMM pre-pass
             const double2 q = active ? E->zbuf[(size_t)slot * N_ + r] : make_double2(0.0, 0.0);
             const qb_c128 c = cf[0];
             z.x = c.re * q.x - c.im * q.y;
@@ -154,18 +174,17 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
             z.y += c.re * q.y + c.im * q.x;
         }
     } else if (kind == QB_PASS_APPLY) {
-        const double2 q = qb_rowdot<QB_UP>(E->cops[gp->op_lo], sl, lane, r, active,
-                                    QB_VS(gp->x));
+        const double2 q = qb_rowdot<QB_UP>(E->cops[gp->op_lo], sl, lane, r, active, QB_VS(h.xslot));
         const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef];
         z = make_double2(c.re * q.x - c.im * q.y, c.re * q.y + c.im * q.x);
     }
-    z.x *= zscale; z.y *= zscale;
+    z.x *= h.zscale; z.y *= h.zscale;
 
     // ---- fused linear combinations (sources in order, z last), stores, reductions ----
     double2 o1 = make_double2(0.0, 0.0), o2 = make_double2(0.0, 0.0);
 #pragma unroll
     for (int u = 0; u < QB_PF; u++) {
-        const double a = __shfl_sync(0xffffffffu, my_w1, u), b = __shfl_sync(0xffffffffu, my_w2, u);
+        const double a = __shfl_sync(0xffffffffu, h.my_w1, u), b = __shfl_sync(0xffffffffu, h.my_w2, u);
         o1.x = fma(a, pv[u].x, o1.x); o1.y = fma(a, pv[u].y, o1.y);
         o2.x = fma(b, pv[u].x, o2.x); o2.y = fma(b, pv[u].y, o2.y);
     }
@@ -173,42 +192,97 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
         double2 v[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const int sidx = __shfl_sync(0xffffffffu, my_src, (i + u) & 31);
+            const int sidx = __shfl_sync(0xffffffffu, h.my_src, (i + u) & 31);
             const double2* p = QB_VS(sidx);
             v[u] = (i + u < nsrc && active) ? p[r] : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const double a = __shfl_sync(0xffffffffu, my_w1, (i + u) & 31);
-            const double b = __shfl_sync(0xffffffffu, my_w2, (i + u) & 31);
+            const double a = __shfl_sync(0xffffffffu, h.my_w1, (i + u) & 31);
+            const double b = __shfl_sync(0xffffffffu, h.my_w2, (i + u) & 31);
             o1.x = fma(a, v[u].x, o1.x); o1.y = fma(a, v[u].y, o1.y);
             o2.x = fma(b, v[u].x, o2.x); o2.y = fma(b, v[u].y, o2.y);
         }
     }
-    o1.x = fma(w1z, z.x, o1.x); o1.y = fma(w1z, z.y, o1.y);
-    o2.x = fma(w2z, z.x, o2.x); o2.y = fma(w2z, z.y, o2.y);
+    o1.x = fma(h.w1z, z.x, o1.x); o1.y = fma(h.w1z, z.y, o1.y);
+    o2.x = fma(h.w2z, z.x, o2.x); o2.y = fma(h.w2z, z.y, o2.y);
     double r0 = 0.0, r1 = 0.0, r2 = 0.0;
     if (active) {
-        double2* base = const_cast<double2*>(slot_base);
-        if (zdst >= 0) base[(size_t)zdst * N_ + r] = z;
-        if (dst1 >= 0) base[(size_t)dst1 * N_ + r] = o1;
-        else if (dst1 == QB_SLOT_OUT)
+        double2* base = const_cast<double2*>(h.slot_base);
+        if (h.zdst >= 0) base[(size_t)h.zdst * N_ + r] = z;
+        if (h.dst1 >= 0) base[(size_t)h.dst1 * N_ + r] = o1;
+        else if (h.dst1 == QB_SLOT_OUT)
             E->out_states[((size_t)E->traj[slot].traj_id * E->ctl.nt + gp->out_index) * N_ + r] = o1;
         const double n1 = o1.x * o1.x + o1.y * o1.y;
         r0 = n1;
-        if (red & QB_RED_WRMS) {
+        if (h.red & QB_RED_WRMS) {
             const double q = sqrt(o2.x * o2.x + o2.y * o2.y)
                              / (E->ctl.opt.atol + E->ctl.opt.rtol * sqrt(n1));
             r1 = q * q;
         }
         r2 = z.x * z.x + z.y * z.y;
     }
-    if (red) {
+    if (h.red) {
         r0 = qb_warp_sum(r0); r1 = qb_warp_sum(r1); r2 = qb_warp_sum(r2);
         if (lane == 0) { part[0] = r0; part[1] = r1; part[2] = r2; }
     }
-  }
 #undef QB_VS
+}
+
+// Warp-autonomous pass kernel: one warp = one 32-row slice of one trajectory slot; no shared
+// memory, no block-level barrier.
+__global__ void __launch_bounds__(QB_TILE_ROWS, QB_MINB)
+qb_pass_kernel(const QbEngineDev* __restrict__ E)
+{
+    const int ntiles = E->ctl.ntiles;
+    const int slot = blockIdx.x / ntiles;
+    const int tile = blockIdx.x - slot * ntiles;
+    if (E->pass[slot].kind == QB_PASS_NONE) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sl = tile * (QB_TILE_ROWS / 32) + warp;
+    if ((long long)sl * 32 >= E->ctl.N) return;          // warp-uniform
+    QbWarpHdr h;
+    qb_load_hdr(E, slot, lane, h);
+    qb_pass_one_slice(E, slot, sl, lane, h, nullptr, nullptr, 0);
+}
+
+// Shared-operator variant for systems whose RHS is ONE SELL operator (mcsolve H_eff): the 8
+// warps of a CTA are 8 DIFFERENT trajectory slots working on the SAME slice, so the slice's
+// values and column indices are staged in shared memory once and re-used 8 times -- the
+// operator's L2->SM traffic drops 8x.  A CTA walks QB_SH_T consecutive slices so that each
+// warp's state gathers keep their L1 locality.
+__global__ void __launch_bounds__(QB_TILE_ROWS, QB_MINB)
+qb_pass_kernel_shared(const QbEngineDev* __restrict__ E)
+{
+    __shared__ double2 s_val[QB_SH_MAXW * 32];
+    __shared__ int s_col[QB_SH_MAXW * 32];
+    const int nslices = E->nslices;
+    const int nchunks = (nslices + QB_SH_T - 1) / QB_SH_T;
+    const int group = blockIdx.x / nchunks;
+    const int chunk = blockIdx.x - group * nchunks;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = group * (QB_TILE_ROWS / 32) + warp;
+    const bool slot_ok = slot < E->nslots && E->pass[slot].kind != QB_PASS_NONE;
+    if (!__syncthreads_or(slot_ok)) return;
+    QbWarpHdr h;
+    if (slot_ok) qb_load_hdr(E, slot, lane, h);
+    const QbOpDev& A = E->elem[0];
+    const double2* __restrict__ gval = reinterpret_cast<const double2*>(A.val);
+    for (int it = 0; it < QB_SH_T; it++) {
+        const int sl = chunk * QB_SH_T + it;
+        if (sl >= nslices) break;                        // CTA-uniform
+        const int s0 = A.slice_ptr[sl], w = A.slice_ptr[sl + 1] - s0;
+        const bool staged = w <= QB_SH_MAXW;
+        if (staged) {
+            for (int i = threadIdx.x; i < w * 32; i += QB_TILE_ROWS) {
+                s_val[i] = __ldg(gval + (size_t)s0 * 32 + i);
+                s_col[i] = __ldg(A.col + (size_t)s0 * 32 + i);
+            }
+        }
+        __syncthreads();
+        if (slot_ok) qb_pass_one_slice(E, slot, sl, lane, h, staged ? s_val : nullptr, s_col, w);
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------ control kernel
@@ -340,6 +414,7 @@ struct QbEngH : QbObj {
     long long last_rounds = 0;
     double last_ms = 0.0;
     int profiling = 0;
+    int no_shared = 0;          // debugging / A-B switch: never use qb_pass_kernel_shared
     double prof_pass_ms = 0.0;
     long long prof_pass_launches = 0;
     unsigned long long prof_vec_count = 0;
@@ -494,7 +569,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     }
     h.ctl.opt = e->opt;
     h.ctl.N = (int)s->N;
-    h.ctl.ntiles = (int)((s->N + QB_TILE_ROWS * QB_SPW - 1) / (QB_TILE_ROWS * QB_SPW));
+    h.ctl.ntiles = (int)((s->N + QB_TILE_ROWS - 1) / QB_TILE_ROWS);
     h.ctl.nelem = (int)s->elems.size();
     h.ctl.ncops = (int)s->cops.size();
     h.ctl.neops = (int)s->eops.size();
@@ -584,6 +659,10 @@ static int qb_drive(QbEngH* e, int nslots_used) {
     const long long grid1 = (long long)nslots_used * ntiles;
     const int grid2 = (nslots_used * 32 + 127) / 128;
     if (grid1 > 0x7fffffffLL) QB_FAIL(QB_E_ARG, "grid too large");
+    // one SELL operator shared by >= 8 trajectory slots: stage it per CTA (qb_pass_kernel_shared)
+    const bool use_shared = e->h.ctl.nelem == 1 && e->h.elem[0].fmt == QB_FMT_SELL && !e->h.zbuf &&
+                            nslots_used >= 8 && !e->no_shared;
+    const long long grid_sh = (long long)((nslots_used + 7) / 8) * ((e->h.nslices + QB_SH_T - 1) / QB_SH_T);
     int chunk = 8;
     long long rounds = 0;
     QB_CUDA(cudaMemsetAsync(e->h.vec_count, 0, sizeof(unsigned long long), e->stream));
@@ -606,7 +685,8 @@ static int qb_drive(QbEngH* e, int nslots_used) {
                                               nslots_used);
                 if (rcg) return rcg;
             }
-            qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d);
+            if (use_shared) qb_pass_kernel_shared<<<(unsigned)grid_sh, QB_TILE_ROWS, 0, e->stream>>>(e->d);
+            else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d);
             QB_LAUNCH_CHECK();
             if (e->profiling) cudaEventRecord(pb, e->stream);
             qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
