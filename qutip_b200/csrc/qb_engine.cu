@@ -6,11 +6,10 @@
 //       k[0..S-1] (RK stage derivatives), y_prev, y_front, y_interp, tmpA, tmpB.
 //       "y_prev <- y_front" etc. are slot relabels in QbTraj, never copies.
 //   pass[nslots], traj[nslots]    : the next vector instruction and the controller state
-//   partials[nslots][ntiles][red_stride] : per-CTA partial reductions, summed in a fixed order
+//   partials[nslots][nslices][red_stride] : per-warp partial reductions, summed in a fixed order
 // A "round" = pass kernel + control kernel; the host enqueues rounds back to back and only
 // looks at a device counter every chunk, so there is no host synchronisation per step.
 #include <algorithm>
-#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "qb_host.h"
@@ -68,6 +67,10 @@ __device__ __forceinline__ const double2* qb_vsrc(const QbEngineDev* E, int slot
 #ifndef QB_MINB
 #define QB_MINB 4
 #endif
+#define QB_SH_MAXW 40   // widest SELL slice the shared kernel stages (40*32*20 B = 25.6 KB)
+#ifndef QB_SH_T
+#define QB_SH_T 4       // consecutive slices one CTA of the shared kernel walks through
+#endif
 
 // per-warp view of a slot's pass descriptor (read straight from L1/L2-resident global memory)
 struct QbWarpHdr {
@@ -98,7 +101,7 @@ __device__ __forceinline__ void qb_load_hdr(const QbEngineDev* __restrict__ E, i
 // memory by the caller and shared by the CTA's warps (= 8 trajectories).
 __device__ __forceinline__ void qb_pass_one_slice(
     const QbEngineDev* __restrict__ E, int slot, int sl, int lane, const QbWarpHdr& h,
-    const double2* __restrict__ sval, const int* __restrict__ scol, int sw, double* part)
+    const double2* __restrict__ sval, const int* __restrict__ scol, int sw)
 {
     const QbPass* __restrict__ gp = &E->pass[slot];
     const int N = E->ctl.N;
@@ -107,6 +110,8 @@ __device__ __forceinline__ void qb_pass_one_slice(
     const bool active = r < N;
     const int kind = h.kind, nsrc = h.nsrc;
 #define QB_VS(idx) ((idx) >= 0 ? h.slot_base + (long long)(idx) * N : h.init_ptr)
+    double* __restrict__ part = E->partials + ((size_t)slot * E->nslices + sl) * E->red_stride;
+
     if (kind == QB_PASS_EXPECT) {
         const int opset = gp->opset, op_lo = gp->op_lo, nops = gp->op_hi - gp->op_lo;
         const QbOpDev* ops = (opset == QB_OPSET_EOPS) ? E->eops : E->nops;
@@ -232,28 +237,51 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
     const int ntiles = E->ctl.ntiles;
     const int slot = blockIdx.x / ntiles;
     const int tile = blockIdx.x - slot * ntiles;
-    const QbPass* __restrict__ gp = &E->pass[slot];
-    const int kind = gp->kind;
-    if (kind == QB_PASS_NONE) return;
-    __shared__ double sred[QB_TILE_ROWS / 32][QB_MAXRED];
+    if (E->pass[slot].kind == QB_PASS_NONE) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sl = tile * (QB_TILE_ROWS / 32) + warp;
-    const int nred = (kind == QB_PASS_EXPECT) ? 2 * (gp->op_hi - gp->op_lo) : (gp->red ? 3 : 0);
-    if ((long long)sl * 32 < E->ctl.N) {             // warp-uniform
-        QbWarpHdr h;
-        qb_load_hdr(E, slot, lane, h);
-        qb_pass_one_slice(E, slot, sl, lane, h, nullptr, nullptr, 0, sred[warp]);
-    } else {
-        for (int k = lane; k < nred; k += 32) sred[warp][k] = 0.0;
-    }
-    // the only block-level barrier: combine the 8 warps' partial reductions in a fixed order
-    if (nred) {
-        __syncthreads();
-        if (threadIdx.x < nred) {
-            double s_ = 0.0;
-            for (int w = 0; w < QB_TILE_ROWS / 32; w++) s_ += sred[w][threadIdx.x];
-            E->partials[((size_t)slot * ntiles + tile) * E->red_stride + threadIdx.x] = s_;
+    if ((long long)sl * 32 >= E->ctl.N) return;          // warp-uniform
+    QbWarpHdr h;
+    qb_load_hdr(E, slot, lane, h);
+    qb_pass_one_slice(E, slot, sl, lane, h, nullptr, nullptr, 0);
+}
+
+// Shared-operator variant for systems whose RHS is ONE SELL operator (mcsolve H_eff): the 8
+// warps of a CTA are 8 DIFFERENT trajectory slots working on the SAME slice, so the slice's
+// values and column indices are staged in shared memory once and re-used 8 times -- the
+// operator's L2->SM traffic drops 8x.  A CTA walks QB_SH_T consecutive slices so that each
+// warp's state gathers keep their L1 locality.
+__global__ void __launch_bounds__(QB_TILE_ROWS, QB_MINB)
+qb_pass_kernel_shared(const QbEngineDev* __restrict__ E)
+{
+    __shared__ double2 s_val[QB_SH_MAXW * 32];
+    __shared__ int s_col[QB_SH_MAXW * 32];
+    const int nslices = E->nslices;
+    const int nchunks = (nslices + QB_SH_T - 1) / QB_SH_T;
+    const int group = blockIdx.x / nchunks;
+    const int chunk = blockIdx.x - group * nchunks;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = group * (QB_TILE_ROWS / 32) + warp;
+    const bool slot_ok = slot < E->nslots && E->pass[slot].kind != QB_PASS_NONE;
+    if (!__syncthreads_or(slot_ok)) return;
+    QbWarpHdr h;
+    if (slot_ok) qb_load_hdr(E, slot, lane, h);
+    const QbOpDev& A = E->elem[0];
+    const double2* __restrict__ gval = reinterpret_cast<const double2*>(A.val);
+    for (int it = 0; it < QB_SH_T; it++) {
+        const int sl = chunk * QB_SH_T + it;
+        if (sl >= nslices) break;                        // CTA-uniform
+        const int s0 = A.slice_ptr[sl], w = A.slice_ptr[sl + 1] - s0;
+        const bool staged = w <= QB_SH_MAXW;
+        if (staged) {
+            for (int i = threadIdx.x; i < w * 32; i += QB_TILE_ROWS) {
+                s_val[i] = __ldg(gval + (size_t)s0 * 32 + i);
+                s_col[i] = __ldg(A.col + (size_t)s0 * 32 + i);
+            }
         }
+        __syncthreads();
+        if (slot_ok) qb_pass_one_slice(E, slot, sl, lane, h, staged ? s_val : nullptr, s_col, w);
+        __syncthreads();
     }
 }
 
@@ -284,11 +312,11 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
     int nred = 0;
     if (kind == QB_PASS_EXPECT) nred = 2 * (gp->op_hi - gp->op_lo);
     else if (kind != QB_PASS_NONE && gp->red) nred = 3;
-    const int ntiles = E->ctl.ntiles, stride = E->red_stride;
-    const double* __restrict__ part = E->partials + (size_t)slot * ntiles * stride;
+    const int nslices = E->nslices, stride = E->red_stride;
+    const double* __restrict__ part = E->partials + (size_t)slot * nslices * stride;
     for (int k = 0; k < nred; k++) {
         double s = 0.0;
-        for (int i = lane; i < ntiles; i += 32) s += part[(size_t)i * stride + k];
+        for (int i = lane; i < nslices; i += 32) s += part[(size_t)i * stride + k];
         s = qb_warp_sum(s);
         if (lane == 0) sred[w][k] = s;
     }
@@ -386,6 +414,7 @@ struct QbEngH : QbObj {
     long long last_rounds = 0;
     double last_ms = 0.0;
     int profiling = 0;
+    int no_shared = 0;          // debugging / A-B switch: never use qb_pass_kernel_shared
     double prof_pass_ms = 0.0;
     long long prof_pass_launches = 0;
     unsigned long long prof_vec_count = 0;
@@ -592,7 +621,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         const int nops = std::max(h.ctl.ncops, h.ctl.neops);
         h.red_stride = std::max(4, 2 * std::min(QB_MAXRED / 2, nops));
     }
-    QB_TRY(qb_dev_alloc(e, (size_t)nslots * h.ctl.ntiles * h.red_stride, &h.partials));
+    QB_TRY(qb_dev_alloc(e, (size_t)nslots * h.nslices * h.red_stride, &h.partials));
     QB_TRY(qb_dev_alloc(e, 1, &h.queue_head));
     QB_TRY(qb_dev_alloc(e, 1, &h.n_active));
     QB_TRY(qb_dev_alloc(e, 1, &h.vec_count));
@@ -630,6 +659,10 @@ static int qb_drive(QbEngH* e, int nslots_used) {
     const long long grid1 = (long long)nslots_used * ntiles;
     const int grid2 = (nslots_used * 32 + 127) / 128;
     if (grid1 > 0x7fffffffLL) QB_FAIL(QB_E_ARG, "grid too large");
+    // one SELL operator shared by >= 8 trajectory slots: stage it per CTA (qb_pass_kernel_shared)
+    const bool use_shared = e->h.ctl.nelem == 1 && e->h.elem[0].fmt == QB_FMT_SELL && !e->h.zbuf &&
+                            nslots_used >= 8 && !e->no_shared;
+    const long long grid_sh = (long long)((nslots_used + 7) / 8) * ((e->h.nslices + QB_SH_T - 1) / QB_SH_T);
     int chunk = 8;
     long long rounds = 0;
     QB_CUDA(cudaMemsetAsync(e->h.vec_count, 0, sizeof(unsigned long long), e->stream));
@@ -652,7 +685,8 @@ static int qb_drive(QbEngH* e, int nslots_used) {
                                               nslots_used);
                 if (rcg) return rcg;
             }
-            qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d);
+            if (use_shared) qb_pass_kernel_shared<<<(unsigned)grid_sh, QB_TILE_ROWS, 0, e->stream>>>(e->d);
+            else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d);
             QB_LAUNCH_CHECK();
             if (e->profiling) cudaEventRecord(pb, e->stream);
             qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
