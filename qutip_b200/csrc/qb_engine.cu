@@ -45,6 +45,7 @@ struct QbEngineDev {
     int* out_stats;
     unsigned long long* vec_count;   // state-sized vector accesses issued (algorithmic traffic)
     int nslices, red_stride;
+    double* red_final;          // [nslots][QB_MAXRED]: pre-reduced partials (large systems) or null
     // dense batched path (qb_dense.cu): z of every slot precomputed by one DMMA ZGEMM
     double2* zbuf;              // [nslots][N] or null
     const double2** xcols;      // [nslots] column pointers of the GEMM's right operand
@@ -285,6 +286,36 @@ qb_pass_kernel_shared(const QbEngineDev* __restrict__ E)
     }
 }
 
+// Large single systems (N/32 > 2048 slices): one CTA per slot sums the per-warp partials in
+// a fixed order so that the control kernel's single warp does not walk them serially.
+__global__ void __launch_bounds__(256)
+qb_partials_reduce_kernel(const QbEngineDev* __restrict__ E)
+{
+    const int slot = blockIdx.x;
+    const QbPass* gp = &E->pass[slot];
+    const int kind = gp->kind;
+    int nred = 0;
+    if (kind == QB_PASS_EXPECT) nred = 2 * (gp->op_hi - gp->op_lo);
+    else if (kind != QB_PASS_NONE && gp->red) nred = 3;
+    if (nred == 0) return;
+    __shared__ double sh[8];
+    const int nslices = E->nslices, stride = E->red_stride;
+    const double* __restrict__ part = E->partials + (size_t)slot * nslices * stride;
+    for (int k = 0; k < nred; k++) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nslices; i += 256) s += part[(size_t)i * stride + k];
+        s = qb_warp_sum(s);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t += sh[w];
+            E->red_final[(size_t)slot * QB_MAXRED + k] = t;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ control kernel
 __device__ void qb_start_traj(QbEngineDev* E, QbTraj& c, int traj_id) {
     const int S = E->ctl.tab.S;
@@ -314,6 +345,12 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
     else if (kind != QB_PASS_NONE && gp->red) nred = 3;
     const int nslices = E->nslices, stride = E->red_stride;
     const double* __restrict__ part = E->partials + (size_t)slot * nslices * stride;
+    if (E->red_final) {
+        for (int k = lane; k < nred; k += 32) sred[w][k] = E->red_final[(size_t)slot * QB_MAXRED + k];
+    } else
+    if (E->red_final) {
+        for (int k = lane; k < nred; k += 32) sred[w][k] = E->red_final[(size_t)slot * QB_MAXRED + k];
+    } else
     for (int k = 0; k < nred; k++) {
         double s = 0.0;
         for (int i = lane; i < nslices; i += 32) s += part[(size_t)i * stride + k];
@@ -626,6 +663,8 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     QB_TRY(qb_dev_alloc(e, 1, &h.n_active));
     QB_TRY(qb_dev_alloc(e, 1, &h.vec_count));
     h.zbuf = nullptr; h.xcols = nullptr; h.zcols = nullptr;
+    h.red_final = nullptr;
+    if (h.nslices > 2048) QB_TRY(qb_dev_alloc(e, (size_t)nslots * QB_MAXRED, &h.red_final));
     if (s->elems.size() == 1 && s->elems[0].fmt == QB_FMT_DENSE && nslots >= 8) {
         QB_TRY(qb_dev_alloc(e, (size_t)nslots * N, &h.zbuf));
         QB_TRY(qb_dev_alloc(e, (size_t)nslots, &h.xcols));
@@ -689,6 +728,10 @@ static int qb_drive(QbEngH* e, int nslots_used) {
             else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d);
             QB_LAUNCH_CHECK();
             if (e->profiling) cudaEventRecord(pb, e->stream);
+            if (e->h.red_final) {
+                qb_partials_reduce_kernel<<<nslots_used, 256, 0, e->stream>>>(e->d);
+                QB_LAUNCH_CHECK();
+            }
             qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
             QB_LAUNCH_CHECK();
         }
