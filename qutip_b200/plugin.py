@@ -630,10 +630,20 @@ def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, m
     ``(seed, Result, weight)`` triple ``McResult.add`` expects
     (solver/multitrajresult.py:402-434)."""
     solver = getattr(task, "__self__", None)
-    if not isinstance(solver, MCSolver) or task_kwargs:
-        raise TypeError("the 'b200' map runs MCSolver trajectories on the device; other tasks "
-                        "(or improved_sampling / mixed initial states) need a stock map")
+    task_kwargs = dict(task_kwargs or {})
+    floor = float(task_kwargs.pop("jump_prob_floor", 0.0))      # improved sampling
+    no_jump = bool(task_kwargs.pop("no_jump", False))
+    if (not isinstance(solver, MCSolver) or task_kwargs or no_jump
+            or getattr(task, "__name__", "") != "_run_one_traj"):
+        raise TypeError("the 'b200' map runs MCSolver trajectories of one pure initial state on "
+                        "the device; other tasks (mixed initial states) need a stock map")
     state0, tlist, e_ops = task_args
+    if floor >= 1 - solver.options["norm_tol"]:
+        # dark initial state under improved sampling: the reference returns all-zero
+        # trajectories without integrating (mcsolve.py:543-556); nothing to run on the device
+        for seed in values:
+            reduce_func(task(seed, *task_args, jump_prob_floor=floor))
+        return None
     seeds = list(values)
     ntraj = len(seeds)
     opts = solver.options
@@ -663,7 +673,7 @@ def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, m
         interpolate=int(bool(iopt['interpolate'])), norm_steps=int(opts['norm_steps']),
         norm_t_tol=opts['norm_t_tol'], norm_tol=opts['norm_tol'],
         norm_min_step=opts['norm_min_step'], mc_corr_eps=opts['mc_corr_eps'],
-        store_states=int(want_states or want_final))
+        store_states=int(want_states or want_final), jump_prob_floor=floor)
     ndraws = 64
     gens = [s if hasattr(s, "random") else solver._get_generator(s) for s in seeds]
     draws = np.stack([g.random(ndraws) for g in gens])
@@ -704,7 +714,7 @@ def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, m
         res.collapse = [(float(r.col_t[j, i]), int(r.col_which[j, i]))
                         for i in range(r.ncol[j])]
         if reduce_func is not None:
-            remaining = reduce_func((seeds[j], res, 1))
+            remaining = reduce_func((seeds[j], res, 1 - floor))     # weight, mcsolve.py:565
             if remaining is not None and remaining <= 0:
                 break
     return None

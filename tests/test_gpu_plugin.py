@@ -317,3 +317,17 @@ def test_matrix_valued_state_unitary_evolution():
     out = qutip.sesolve(H, U0, tl, options=dict(OPT, method="b200_vern7"))
     for a, b in zip(out.states, ref.states):
         np.testing.assert_allclose(a.full(), b.full(), rtol=RTOL, atol=ATOL)
+
+
+def test_b200_map_improved_sampling():
+    """options['improved_sampling']: thresholds floored at the no-jump probability
+    (mcsolve.py:276-279) and trajectories weighted by 1 - p_nojump."""
+    H, c_ops, sz = tfim(4, gamma=0.05)
+    psi0 = basis([2] * 4, [0] * 4)
+    tl = np.linspace(0, 1.5, 7)
+    o = dict(OPT, method="vern7", improved_sampling=True, keep_runs_results=True)
+    ref = mcsolve(H, psi0, tl, c_ops, e_ops=[sz[0]], ntraj=10, seeds=9, options=o)
+    out = mcsolve(H, psi0, tl, c_ops, e_ops=[sz[0]], ntraj=10, seeds=9, options=dict(o, map="b200"))
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    np.testing.assert_allclose(np.array(out.average_expect), np.array(ref.average_expect),
+                               rtol=RTOL, atol=ATOL)
