@@ -123,7 +123,8 @@ typedef struct {
 } qb_options;
 int qb_options_default(qb_options* opt);
 
-/* tableau: 0 vern7, 1 vern9 (solver/integrator/verner{7,9}efficient.py) */
+/* tableau: 0 vern7, 1 vern9 (solver/integrator/verner{7,9}efficient.py), 2 tsit5 (FSAL,
+ * solver/integrator/tsit5.py) */
 int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb_options* opt,
                      qb_handle* out);
 

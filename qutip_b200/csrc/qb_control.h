@@ -83,6 +83,11 @@ QB_HD int qb_eval_rhs_coefs(const QbCtl& g, QbTraj& c, double t, qb_c128* coef) 
         if (rcq_ > 0) { qb_pass_clear(p); c.pc = QB_PC_IDLE; c.hc_resume = (label); \
                         c.done = 2; return 0; }                                     \
     }
+// slot index of k[j]: for FSAL tableaux k[0] and k[s-1] exchange their buffers every step
+QB_HD int qb_ks(const QbTraj& c, int j, int s) {
+    if (c.kswap) { if (j == 0) return s - 1; if (j == s - 1) return 0; }
+    return j;
+}
 QB_HD int qb_stage_x(const QbTraj& c, int i, int first) {
     // stage `first` reads sTA (or y_prev for stage 0); then TB, TA, ... alternate
     return ((i - first) & 1) ? c.sTB : c.sTA;
@@ -151,15 +156,16 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             c.dt_int = 0.0;
             if (c.set_x == c.sF) { int tmp = c.sP; c.sP = c.sF; c.sF = tmp; }
             c.sY = c.sF;
+            c.fsal_pending = 0;                      // k[0] will hold k_fsal = f(t, y0) (:222-225)
             qb_pass_clear(p);
-            if (g.opt.first_step != 0.0) {          // :227-230, no estimate
+            if (g.opt.first_step != 0.0 && !T.fsal) {   // :227-230, no estimate
                 c.dt_safe = g.opt.first_step;
                 p.kind = QB_PASS_COMBINE; p.dst1 = c.sF; p.red = QB_RED_NORM2_O1;
                 qb_pass_src(p, c.set_x, c.set_scale, 0.0);
                 c.pc = QB_PC_SET_DONE; return 1;
             }
             // _estimate_first_step (:232-276), first RHS evaluation k0 = f(t, y0)
-            p.kind = QB_PASS_RHS; p.x = c.set_x; p.zscale = c.set_scale; p.zdst = 0;
+            p.kind = QB_PASS_RHS; p.x = c.set_x; p.zscale = c.set_scale; p.zdst = qb_ks(c, 0, s);
             p.dst1 = c.sF; p.red = QB_RED_NORM2_O1 | QB_RED_NORM2_Z;
             qb_pass_src(p, c.set_x, c.set_scale, 0.0);
             QB_COEFS_OR_PAUSE(set_t, QL_SET_BEGIN)
@@ -172,6 +178,10 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
         case QB_PC_EST0_DONE: {     // :237-256
             double norm = sqrt(red[0]);
             c.norm2_y = red[0];
+            if (g.opt.first_step != 0.0) {           // FSAL with a given first step: k_fsal only
+                c.dt_safe = g.opt.first_step;
+                L = QL_SET_DONE; break;
+            }
             double tol = g.opt.atol + norm * g.opt.rtol;
             if (norm <= g.opt.atol) norm = 1.0;
             double tmp_norm = sqrt(red[2]);
@@ -187,12 +197,12 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             qb_pass_clear(p);
             p.kind = QB_PASS_COMBINE; p.dst1 = c.sTB;
             qb_pass_src(p, c.sF, 1.0, 0.0);
-            qb_pass_src(p, 0, dt1 / 100, 0.0);
+            qb_pass_src(p, qb_ks(c, 0, s), dt1 / 100, 0.0);
             c.pc = QB_PC_EST1IN_DONE; return 1;
         }
         case QB_PC_EST1IN_DONE: {   // k1 = f(t + dt1/100, y_temp)   (:262-263)
             qb_pass_clear(p);
-            p.kind = QB_PASS_RHS; p.x = c.sTB; p.zdst = 1; p.red = QB_RED_NORM2_Z;
+            p.kind = QB_PASS_RHS; p.x = c.sTB; p.zdst = qb_ks(c, 1, s); p.red = QB_RED_NORM2_Z;
             QB_COEFS_OR_PAUSE(c.t + c.est_dt1 / 100, QB_PC_EST1IN_DONE)
             c.n_rhs++;
             c.pc = QB_PC_EST1_DONE; return 1;
@@ -240,6 +250,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
         case QL_RK_LOOP:            // while self._t_front < t and self._status >= 0   (:312)
             if (c.t_front < c.int_t && c.status >= 0) {
                 int tmp = c.sP; c.sP = c.sF; c.sF = tmp;     // y_prev <- y_front (:313), by relabel
+                if (T.fsal && c.fsal_pending) { c.kswap ^= 1; c.fsal_pending = 0; }   // k[0] <- k_fsal
                 c.t_prev = c.t_front;
                 c.step_n = 0;
                 L = QL_STEP_ATTEMPT; break;
@@ -258,18 +269,26 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             const int i = stage_i;
             const double dt = c.dt_cur;
             qb_pass_clear(p);
+            if (i == 0 && T.fsal) {
+                // k[0] = k_fsal is already there (:365-366): only build the stage-1 input
+                p.kind = QB_PASS_COMBINE; p.dst1 = qb_stage_x(c, 1, 1);
+                qb_pass_src(p, c.sP, 1.0, 0.0);
+                qb_pass_src(p, qb_ks(c, 0, s), dt * T.a[1][0], 0.0);
+                c.stage = 0;
+                c.pc = QB_PC_STAGE_DONE; return 1;
+            }
             p.kind = QB_PASS_RHS;
             p.x = (i == 0) ? c.sP : qb_stage_x(c, i, 1);
-            p.zdst = i;
+            p.zdst = qb_ks(c, i, s);
             qb_pass_src(p, c.sP, 1.0, 0.0);
             if (i < s - 1) {        // epilogue builds the next stage input (:374-375)
                 const int n = i + 1;
                 p.dst1 = qb_stage_x(c, n, 1);
-                for (int j = 0; j < i; j++) qb_pass_src(p, j, dt * T.a[n][j], 0.0);
+                for (int j = 0; j < i; j++) qb_pass_src(p, qb_ks(c, j, s), dt * T.a[n][j], 0.0);
                 p.w1z = dt * T.a[n][i];
             } else {                // y_front, error vector (:380-397)
                 p.dst1 = c.sF;
-                for (int j = 0; j < i; j++) qb_pass_src(p, j, dt * T.b[j], dt * T.e[j]);
+                for (int j = 0; j < i; j++) qb_pass_src(p, qb_ks(c, j, s), dt * T.b[j], dt * T.e[j]);
                 p.w1z = dt * T.b[i]; p.w2z = dt * T.e[i];
                 p.red = QB_RED_NORM2_O1 | QB_RED_WRMS;
             }
@@ -306,6 +325,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
                 if (c.step_n > c.nsteps_left) { c.status = QB_ST_TOO_MUCH_WORK; stop = true; }
             }
             if (!stop && err >= 1.0) { L = QL_STEP_ATTEMPT; break; }   // while error >= 1
+            if (T.fsal) c.fsal_pending = 1;                             // k_fsal <- k[s-1] (:354-355)
             c.nsteps_left -= c.step_n;                                  // :315
             L = c.int_step ? QL_AFTER_LOOP : QL_RK_LOOP;                // :317-318
             break;
@@ -324,7 +344,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             qb_pass_clear(p);
             p.kind = QB_PASS_COMBINE; p.dst1 = c.sTA;
             qb_pass_src(p, c.sP, 1.0, 0.0);
-            for (int j = 0; j < s; j++) qb_pass_src(p, j, dt * T.a[s][j], 0.0);
+            for (int j = 0; j < s; j++) qb_pass_src(p, qb_ks(c, j, s), dt * T.a[s][j], 0.0);
             c.pc = QB_PC_DENSEIN_DONE; return 1;
         }
         case QB_PC_DENSEIN_DONE: dense_i = s; L = QL_DENSE_ISSUE; break;
@@ -332,12 +352,12 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             const int i = dense_i;
             const double dt = c.dt_int;
             qb_pass_clear(p);
-            p.kind = QB_PASS_RHS; p.x = qb_stage_x(c, i, s); p.zdst = i;
+            p.kind = QB_PASS_RHS; p.x = qb_stage_x(c, i, s); p.zdst = qb_ks(c, i, s);
             qb_pass_src(p, c.sP, 1.0, 0.0);
             if (i < S - 1) {
                 const int n = i + 1;
                 p.dst1 = qb_stage_x(c, n, s);
-                for (int j = 0; j < i; j++) qb_pass_src(p, j, dt * T.a[n][j], 0.0);
+                for (int j = 0; j < i; j++) qb_pass_src(p, qb_ks(c, j, s), dt * T.a[n][j], 0.0);
                 p.w1z = dt * T.a[n][i];
             } else {                // last extra stage: fuse _interpolate_step(int_t) (:412-430)
                 const double tau = (c.int_t - c.t_prev) / dt;
@@ -345,7 +365,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
                 for (int j = 0; j < S; j++) {
                     double bf = 0.0;
                     for (int q = T.dense_order - 1; q >= 0; q--) { bf += T.bi[j][q]; bf *= tau; }
-                    if (j < i) qb_pass_src(p, j, dt * bf, 0.0); else p.w1z = dt * bf;
+                    if (j < i) qb_pass_src(p, qb_ks(c, j, s), dt * bf, 0.0); else p.w1z = dt * bf;
                 }
             }
             c.stage_arg = i;
@@ -367,7 +387,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             for (int j = 0; j < S; j++) {
                 double bf = 0.0;
                 for (int q = T.dense_order - 1; q >= 0; q--) { bf += T.bi[j][q]; bf *= tau; }
-                qb_pass_src(p, j, dt * bf, 0.0);
+                qb_pass_src(p, qb_ks(c, j, s), dt * bf, 0.0);
             }
             c.pc = QB_PC_INTERP_DONE; return 1;
         }

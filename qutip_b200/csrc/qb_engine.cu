@@ -18,7 +18,7 @@
 
 // both tableaux live in constant memory: the controller's single active lane reads them
 // through the constant cache instead of serial global loads
-__constant__ QbTableau c_tabs[2];
+__constant__ QbTableau c_tabs[3];
 
 struct QbEngineDev {
     QbCtl ctl;
@@ -584,7 +584,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
                                 qb_handle* out) {
     QbSysH* s = qb_cast<QbSysH>(sys, QB_TAG_SYS);
     if (!s) QB_FAIL(QB_E_TYPE, "not a system handle");
-    if (tableau < 0 || tableau > 1) QB_FAIL(QB_E_ARG, "unknown tableau id %d (0 vern7, 1 vern9)", tableau);
+    if (tableau < 0 || tableau > 2) QB_FAIL(QB_E_ARG, "unknown tableau id %d (0 vern7, 1 vern9, 2 tsit5)", tableau);
     if (nslots < 1 || !out || !opt) QB_FAIL(QB_E_ARG, "bad engine arguments");
     if (s->elems.empty()) QB_FAIL(QB_E_STATE, "system has no elements");
     QbEngH* e = new QbEngH();
@@ -598,7 +598,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     {
         static bool tabs_uploaded = false;
         if (!tabs_uploaded) {
-            QbTableau both[2] = {*QB_TABLEAUX[0], *QB_TABLEAUX[1]};
+            QbTableau both[3] = {*QB_TABLEAUX[0], *QB_TABLEAUX[1], *QB_TABLEAUX[2]};
             cudaError_t ce = cudaMemcpyToSymbol(c_tabs, both, sizeof(both));
             if (ce != cudaSuccess) { delete e; QB_FAIL(QB_E_CUDA, "tableau upload: %s", cudaGetErrorString(ce)); }
             tabs_uploaded = true;

@@ -152,6 +152,9 @@ struct QbTraj {
     //      the slot's coefficient buffer, sets hc_valid and resumes at pc = hc_resume ----
     double hc_t;
     int hc_valid, hc_resume, stage_arg;
+    // ---- FSAL tableaux (tsit5): k[0] of a step is k[s-1] of the previous accepted step;
+    //      done by exchanging the two slot labels at the start of the next step ----
+    int kswap, fsal_pending;
     // ---- statistics ----
     int n_rhs, n_accept, n_reject, n_pass;
 };

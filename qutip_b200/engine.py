@@ -13,7 +13,7 @@ from .coeffs import Program
 
 FMT_AUTO, FMT_CSR, FMT_DIAM, FMT_SELL = 0, 1, 2, 3
 FMT_NAMES = {0: "csr", 1: "diam", 2: "dense", 3: "sell"}
-TABLEAUX = {"vern7": 0, "vern9": 1}
+TABLEAUX = {"vern7": 0, "vern9": 1, "tsit5": 2}
 
 STATUS_MESSAGES = {
     # texts of explicit_rk.pyx:476-492 so callers can raise the reference's messages

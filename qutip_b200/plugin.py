@@ -39,7 +39,7 @@ import qutip.solver.integrator.scipy_integrator  # noqa: F401
 from . import coeffs, engine as E
 from .solve import make_thresholds  # noqa: F401
 
-__all__ = ["B200Dense", "B200Operator", "B200Vern7", "B200Vern9", "B200Adams", "bind_qobjevo", "b200_map",
+__all__ = ["B200Dense", "B200Operator", "B200Vern7", "B200Vern9", "B200Tsit5", "B200Adams", "bind_qobjevo", "b200_map",
            "register"]
 
 
@@ -345,6 +345,12 @@ class B200Vern9(_B200Integrator):
     method = "b200_vern9"
 
 
+class B200Tsit5(_B200Integrator):
+    """Tsitouras 5(4) pair (first-same-as-last), fused on the B200.  ``method="b200_tsit5"``."""
+    _tableau = "tsit5"
+    method = "b200_tsit5"
+
+
 class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
     """``method="b200_adams"``: the reference's Adams integrator (SciPy zvode, variable-order
     Adams-Moulton; solver/integrator/scipy_integrator.py:20-196) with the RHS callback
@@ -607,6 +613,7 @@ def register():
     for solver in (MESolver, SESolver, MCSolver):
         solver.add_integrator(B200Vern7, "b200_vern7")
         solver.add_integrator(B200Vern9, "b200_vern9")
+        solver.add_integrator(B200Tsit5, "b200_tsit5")
         solver.add_integrator(B200Adams, "b200_adams")
     _qparallel._maps["b200"] = b200_map
     _registered = True
@@ -618,6 +625,8 @@ def _device_method(method):
         return "vern7"
     if method in ("b200_vern9", "vern9"):
         return "vern9"
+    if method in ("b200_tsit5", "tsit5"):
+        return "tsit5"
     raise TypeError("the b200 map runs vern7 / vern9 on the device, not method=%r" % (method,))
 
 

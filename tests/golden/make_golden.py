@@ -212,7 +212,7 @@ def main():
     c_ops = [np.sqrt(0.1) * a, np.sqrt(0.05) * sm]
     psi0 = tensor(basis(N, 3), basis(2, 0))
     golden_mesolve("c1_jc", H, psi0, np.linspace(0, 10, 101), c_ops,
-                   [a.dag() * a, tensor(qeye(N), sigmaz())])
+                   [a.dag() * a, tensor(qeye(N), sigmaz())], methods=("vern7", "vern9", "tsit5"))
 
     # C2 reduced: dissipative TFIM, 4 spins (L 256^2), CSR from the reference ctor
     H, c_ops, sz = tfim(4)
@@ -228,6 +228,8 @@ def main():
     psi0 = basis([2] * 4, [0] * 4)
     golden_mcsolve("c3_tfim4_mc_strong", H, c_ops, psi0, np.linspace(0, 3, 16),
                    [sz[0], sz[1]], 16, 11, method="vern9")
+    golden_mcsolve("c3_tfim4_mc_tsit5", H, c_ops, psi0, np.linspace(0, 3, 16),
+                   [sz[0], sz[1]], 12, 13, method="tsit5")
 
     # C4 reduced: cos-driven cavity 8 (x) transmon 3, string coefficient
     Nc = 8

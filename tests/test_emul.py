@@ -46,7 +46,7 @@ def test_diam_duplicate_entries():
     np.testing.assert_allclose(s.matvec(0, x), [30.0, 3.0, 400.0])
 
 
-@pytest.mark.parametrize("name,method", [("c1_jc", "vern7"), ("c1_jc", "vern9"),
+@pytest.mark.parametrize("name,method", [("c1_jc", "vern7"), ("c1_jc", "vern9"), ("c1_jc", "tsit5"),
                                          ("c2_tfim4", "vern7"), ("c2_tfim4", "vern9"),
                                          ("c4_driven", "vern7"), ("c5_kerr_0", "vern7")])
 @pytest.mark.parametrize("fmt", [FMT_DIAM, FMT_CSR, FMT_SELL])
@@ -60,7 +60,7 @@ def test_mesolve_state_machine(name, method, fmt):
     for i in range(int(g["n_eops"])):
         s.add_eop(*_sp_arrays(functional_of(g["eop%d" % i])))
     s.set_functional(1)
-    r = s.run(0, 0 if method == "vern7" else 1, g["y0"], g["tlist"],
+    r = s.run(0, {"vern7": 0, "vern9": 1, "tsit5": 2}[method], g["y0"], g["tlist"],
               opt=default_options(store_states=1))
     assert r["status"][0] == 1
     assert np.abs(r["states"][0] - g["states_" + method]).max() < 1e-10
@@ -82,7 +82,8 @@ def test_mesolve_counts_match_oracle():
 
 @pytest.mark.parametrize("name,method,nslots", [("c3_tfim6_mc", "vern7", 24),
                                                ("c3_tfim6_mc", "vern7", 5),
-                                               ("c3_tfim4_mc_strong", "vern9", 7)])
+                                               ("c3_tfim4_mc_strong", "vern9", 7),
+                                               ("c3_tfim4_mc_tsit5", "tsit5", 5)])
 def test_mcsolve_state_machine(name, method, nslots):
     g = load(name)
     s = EmulSystem(len(g["psi0"]), 0, FMT_DIAM)
@@ -92,7 +93,7 @@ def test_mcsolve_state_machine(name, method, nslots):
     for i in range(int(g["n_eops"])):
         s.add_eop(*op_arrays(g, "eop%d" % i))
     ntraj = int(g["ntraj"])
-    r = s.run(1, 0 if method == "vern7" else 1, g["psi0"], g["tlist"], ntraj=ntraj,
+    r = s.run(1, {"vern7": 0, "vern9": 1, "tsit5": 2}[method], g["psi0"], g["tlist"], ntraj=ntraj,
               nslots=nslots, draws=g["draws"], opt=default_options(store_states=1))
     assert (r["status"] == 1).all()
     cc = np.concatenate([[0], np.cumsum(g["col_count"])])

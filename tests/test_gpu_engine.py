@@ -95,7 +95,7 @@ def test_expect_ops():
 
 
 # ------------------------------------------------------------------ mesolve
-ME_CASES = [("c1_jc", "vern7"), ("c1_jc", "vern9"), ("c2_tfim4", "vern7"),
+ME_CASES = [("c1_jc", "vern7"), ("c1_jc", "vern9"), ("c1_jc", "tsit5"), ("c2_tfim4", "vern7"),
             ("c2_tfim4", "vern9"), ("c4_driven", "vern7"), ("c5_kerr_0", "vern7")]
 
 
@@ -168,7 +168,8 @@ def test_integrator_protocol():
 # ------------------------------------------------------------------ mcsolve
 @pytest.mark.parametrize("name,method,nslots", [("c3_tfim6_mc", "vern7", 24),
                                                ("c3_tfim6_mc", "vern7", 5),
-                                               ("c3_tfim4_mc_strong", "vern9", 7)])
+                                               ("c3_tfim4_mc_strong", "vern9", 7),
+                                               ("c3_tfim4_mc_tsit5", "tsit5", 5)])
 @pytest.mark.parametrize("fmt", [qb.FMT_AUTO, qb.FMT_CSR, qb.FMT_DIAM, qb.FMT_SELL])
 def test_mcsolve_vs_reference(name, method, nslots, fmt):
     g = load(name)

@@ -58,7 +58,7 @@ def test_registered():
     assert qutip.solver.parallel._maps["b200"] is plugin.b200_map
 
 
-@pytest.mark.parametrize("method", ["vern7", "vern9"])
+@pytest.mark.parametrize("method", ["vern7", "vern9", "tsit5"])
 def test_mesolve_c1_jc(method):
     H, c_ops, psi0, e_ops = jc()
     tl = np.linspace(0, 10, 101)
@@ -167,7 +167,7 @@ def test_mcsolve_with_registered_integrator_python_driver():
     np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=RTOL, atol=ATOL)
 
 
-@pytest.mark.parametrize("method", ["vern7", "vern9"])
+@pytest.mark.parametrize("method", ["vern7", "vern9", "tsit5"])
 def test_mcsolve_b200_map_matches_reference(method):
     """Whole batch on the device through options['map']='b200': identical collapse records
     (TestSeeds-style determinism, reference tests/solver/test_mcsolve.py:326-404)."""

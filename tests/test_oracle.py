@@ -19,7 +19,7 @@ def test_matvec_matches_reference(kind):
 
 
 @pytest.mark.parametrize("name,method,tol", [
-    ("c1_jc", "vern7", 1e-11), ("c1_jc", "vern9", 1e-10),
+    ("c1_jc", "vern7", 1e-11), ("c1_jc", "vern9", 1e-10), ("c1_jc", "tsit5", 1e-10),
     ("c2_tfim4", "vern7", 1e-12), ("c2_tfim4", "vern9", 1e-10),
     ("c4_driven", "vern7", 1e-11),
     ("c5_kerr_0", "vern7", 1e-11),
@@ -52,7 +52,8 @@ def test_mesolve_kerr_stability_limited(k):
 
 
 @pytest.mark.parametrize("name,method", [("c3_tfim6_mc", "vern7"),
-                                         ("c3_tfim4_mc_strong", "vern9")])
+                                         ("c3_tfim4_mc_strong", "vern9"),
+                                         ("c3_tfim4_mc_tsit5", "tsit5")])
 def test_mcsolve_matches_reference(name, method):
     g = load(name)
     rhs = orc_rhs(g)
