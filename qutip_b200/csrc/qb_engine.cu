@@ -62,6 +62,9 @@ __device__ __forceinline__ const double2* qb_vsrc(const QbEngineDev* E, int slot
     return E->init_states + (size_t)init_idx * (size_t)E->ctl.N;
 }
 
+#ifndef QB_GRAPH_ROUNDS
+#define QB_GRAPH_ROUNDS 16   // rounds per captured CUDA graph
+#endif
 #ifndef QB_PF
 #define QB_PF 4      // epilogue source vectors prefetched before the operator sweep
 #endif
@@ -451,6 +454,9 @@ struct QbEngH : QbObj {
     long long last_rounds = 0;
     double last_ms = 0.0;
     int profiling = 0;
+    cudaGraphExec_t graph = nullptr;
+    int graph_slots = 0;
+    cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
     int no_shared = 0;          // debugging / A-B switch: never use qb_pass_kernel_shared
     double prof_pass_ms = 0.0;
     long long prof_pass_launches = 0;
@@ -466,6 +472,8 @@ struct QbEngH : QbObj {
         if (h_active) cudaFreeHost(h_active);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (graph) cudaGraphExecDestroy(graph);
+        for (auto ev : ev_chunk) if (ev) cudaEventDestroy(ev);
         for (auto ev : prof_events) cudaEventDestroy(ev);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -684,7 +692,8 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     }
     if (cudaStreamCreate(&e->stream) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess ||
         cudaEventCreate(&e->ev1) != cudaSuccess ||
-        cudaMallocHost((void**)&e->h_active, sizeof(int)) != cudaSuccess) {
+        cudaEventCreate(&e->ev_chunk[0]) != cudaSuccess || cudaEventCreate(&e->ev_chunk[1]) != cudaSuccess ||
+        cudaMallocHost((void**)&e->h_active, 2 * sizeof(int)) != cudaSuccess) {
         delete e; QB_FAIL(QB_E_CUDA, "stream/event creation failed");
     }
 #undef QB_TRY
@@ -702,45 +711,87 @@ static int qb_drive(QbEngH* e, int nslots_used) {
     const bool use_shared = e->h.ctl.nelem == 1 && e->h.elem[0].fmt == QB_FMT_SELL && !e->h.zbuf &&
                             nslots_used >= 8 && !e->no_shared;
     const long long grid_sh = (long long)((nslots_used + 7) / 8) * ((e->h.nslices + QB_SH_T - 1) / QB_SH_T);
-    int chunk = 8;
     long long rounds = 0;
     QB_CUDA(cudaMemsetAsync(e->h.vec_count, 0, sizeof(unsigned long long), e->stream));
     QB_CUDA(cudaEventRecord(e->ev0, e->stream));
     // the very first control launch turns the *_BEGIN entry points into passes
     qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
     QB_LAUNCH_CHECK();
-    for (;;) {
-        for (int i = 0; i < chunk; i++) {
-            cudaEvent_t pa = nullptr, pb = nullptr;
-            if (e->profiling) {
-                if (cudaEventCreate(&pa) != cudaSuccess || cudaEventCreate(&pb) != cudaSuccess)
-                    QB_FAIL(QB_E_CUDA, "event creation failed");
-                e->prof_events.push_back(pa); e->prof_events.push_back(pb);
-                cudaEventRecord(pa, e->stream);
-            }
-            if (e->h.zbuf) {
-                int rcg = qb_launch_dense_rhs(e->stream, e->h.elem[0].dense, e->h.ctl.N,
-                                              (const void* const*)e->h.xcols, (void* const*)e->h.zcols,
-                                              nslots_used);
-                if (rcg) return rcg;
-            }
-            if (use_shared) qb_pass_kernel_shared<<<(unsigned)grid_sh, QB_TILE_ROWS, 0, e->stream>>>(e->d);
-            else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d);
-            QB_LAUNCH_CHECK();
-            if (e->profiling) cudaEventRecord(pb, e->stream);
-            if (e->h.red_final) {
-                qb_partials_reduce_kernel<<<nslots_used, 256, 0, e->stream>>>(e->d);
-                QB_LAUNCH_CHECK();
-            }
-            qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
+    auto enqueue_round = [&](bool timed) -> int {
+        cudaEvent_t pa = nullptr, pb = nullptr;
+        if (timed) {
+            if (cudaEventCreate(&pa) != cudaSuccess || cudaEventCreate(&pb) != cudaSuccess)
+                QB_FAIL(QB_E_CUDA, "event creation failed");
+            e->prof_events.push_back(pa); e->prof_events.push_back(pb);
+            cudaEventRecord(pa, e->stream);
+        }
+        if (e->h.zbuf) {
+            int rcg = qb_launch_dense_rhs(e->stream, e->h.elem[0].dense, e->h.ctl.N,
+                                          (const void* const*)e->h.xcols, (void* const*)e->h.zcols,
+                                          nslots_used);
+            if (rcg) return rcg;
+        }
+        if (use_shared) qb_pass_kernel_shared<<<(unsigned)grid_sh, QB_TILE_ROWS, 0, e->stream>>>(e->d);
+        else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d);
+        QB_LAUNCH_CHECK();
+        if (timed) cudaEventRecord(pb, e->stream);
+        if (e->h.red_final) {
+            qb_partials_reduce_kernel<<<nslots_used, 256, 0, e->stream>>>(e->d);
             QB_LAUNCH_CHECK();
         }
-        rounds += chunk;
-        QB_CUDA(cudaMemcpyAsync(e->h_active, e->h.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
+        QB_LAUNCH_CHECK();
+        return QB_OK;
+    };
+    if (e->profiling) {
+        // per-pass CUDA-event timing: plain launches, one host look at the counter per chunk
+        int chunk = 8;
+        for (;;) {
+            for (int i = 0; i < chunk; i++) { int rc = enqueue_round(true); if (rc) return rc; }
+            rounds += chunk;
+            QB_CUDA(cudaMemcpyAsync(e->h_active, e->h.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+            QB_CUDA(cudaStreamSynchronize(e->stream));
+            if (*e->h_active <= 0) break;
+            if (chunk < 64) chunk *= 2;
+            if (rounds > 2000000000LL) QB_FAIL(QB_E_STATE, "engine did not terminate");
+        }
+    } else {
+        // CUDA graph of QB_GRAPH_ROUNDS rounds (all state lives in device memory, so the
+        // launch parameters never change), re-launched with a depth-2 pipeline: chunk k+1 is
+        // enqueued before the host looks at chunk k's counter, so the GPU never idles on the
+        // host round trip and the CPU pays one launch per QB_GRAPH_ROUNDS rounds.
+        if (!e->graph || e->graph_slots != nslots_used) {
+            if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            QB_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+            int rcc = QB_OK;
+            for (int i = 0; i < QB_GRAPH_ROUNDS && !rcc; i++) rcc = enqueue_round(false);
+            cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+            if (rcc) { if (g) cudaGraphDestroy(g); return rcc; }
+            if (ce != cudaSuccess) QB_FAIL(QB_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&e->graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) { e->graph = nullptr; QB_FAIL(QB_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)); }
+            e->graph_slots = nslots_used;
+            g_qb_launches -= (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + (e->h.red_final ? 1 : 0));
+        }
+        int pending = 0;              // chunks enqueued whose counter has not been read
+        for (;;) {
+            const int buf = (int)((rounds / QB_GRAPH_ROUNDS) & 1);
+            QB_CUDA(cudaGraphLaunch(e->graph, e->stream));
+            g_qb_launches += (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + (e->h.red_final ? 1 : 0));
+            QB_CUDA(cudaMemcpyAsync(e->h_active + buf, e->h.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+            QB_CUDA(cudaEventRecord(e->ev_chunk[buf], e->stream));
+            rounds += QB_GRAPH_ROUNDS;
+            pending++;
+            if (pending == 2) {      // wait for the older chunk only
+                QB_CUDA(cudaEventSynchronize(e->ev_chunk[buf ^ 1]));
+                pending--;
+                if (e->h_active[buf ^ 1] <= 0) break;
+            }
+            if (rounds > 2000000000LL) QB_FAIL(QB_E_STATE, "engine did not terminate");
+        }
         QB_CUDA(cudaStreamSynchronize(e->stream));
-        if (*e->h_active <= 0) break;
-        if (chunk < 64) chunk *= 2;
-        if (rounds > 2000000000LL) QB_FAIL(QB_E_STATE, "engine did not terminate");
     }
     QB_CUDA(cudaEventRecord(e->ev1, e->stream));
     QB_CUDA(cudaEventSynchronize(e->ev1));
