@@ -32,6 +32,12 @@ C3 = dict(n_spins=14, gamma=0.1, t_end=2.0, nt=21, seed=7, method="vern7")
 C2 = dict(n_spins=10, gamma=0.1, t_end=1.0, nt=11, method="vern7")
 
 
+def ncu_traffic():
+    """DRAM bytes per launch from the committed ncu --set full captures (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -191,7 +197,9 @@ def mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=False):
         "expect_sz0_final": float(r.expect[0][0][-1].real),
         "host_build_s": t_build, "upload_and_convert_s": t_upload,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": gbs / hbm_peak, "traffic": None,
+                     "frac": gbs / hbm_peak,
+                     "traffic": (ncu_traffic().get("c2_rhs_kernel_dram_bytes_per_launch")
+                                 if not quick else None),
                      "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                      "kernel": "qb_rhs_kernel (DIAM SpMV)"},
     }
@@ -393,8 +401,14 @@ def run_ours(args):
     op_alg = models.csr_algorithmic_bytes(heff.nnz, N, N) - 32 * N   # operator part only
     alg_bytes = vec_acc * 16.0 * N + pass_launches * op_alg
     achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms else 0.0
+    tr = ncu_traffic()
+    traffic = None
+    if tr.get("c3_pass_kernel_4096_slots_dram_bytes_per_launch") and n == C3["n_spins"]:
+        # the capture was taken with 4096 resident slots; scale to the slots of this run
+        traffic = tr["c3_pass_kernel_4096_slots_dram_bytes_per_launch"] * nslots / tr["c3_slots"]
     roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+            "traffic_source": "profiles/r01_traffic.json (ncu dram bytes per launch, full slots)",
             "kernel": "qb_pass_kernel",
             "algorithmic_bytes_per_launch": alg_bytes / max(1, pass_launches),
             "avg_launch_ms": pass_ms / max(1, pass_launches),
