@@ -195,6 +195,32 @@ def system_from_qobjevo(qevo, c_ops=(), n_ops=(), e_ops=(), functional=False, al
     return system
 
 
+def _device_qevo(qevo):
+    """The QobjEvo the device integrates.  ``options["matrix_form"]`` hands the integrator a
+    LindbladMatrixForm (core/cy/lindblad_matrix_form.pyx:27-203), whose RHS
+    ``-i(H_nh rho - rho H_nh^dag) + sum c rho c^dag`` acts on the un-vectorised n x n rho.
+    On the device the same linear map is applied to the column-stacked rho as the
+    superoperator ``-i(spre(H_nh) - spost(H_nh^dag)) + sum sprepost(c, c^dag)``: identical
+    result, one fused SpMV per stage instead of 2 + 2*len(c_ops) sparse-dense products."""
+    if type(qevo).__name__ != "LindbladMatrixForm":
+        return qevo
+    H_nh = qevo.H_nh
+    sup = -1j * (qutip.spre(H_nh) - qutip.spost(H_nh.dag()))
+    for c in qevo.c_ops:
+        sup = sup + qutip.sprepost(c, c.dag())
+    return QobjEvo(sup)
+
+
+def _state_columns(arr_shape, base_n):
+    """1 when the state is the (possibly n x n, to be stacked) vector the system acts on;
+    k for an N x k matrix-valued state evolved column by column."""
+    if arr_shape[0] * arr_shape[1] == base_n:
+        return 1
+    if arr_shape[0] == base_n:
+        return arr_shape[1]
+    raise TypeError("incompatible dimensions %s for a system of size %d" % (arr_shape, base_n))
+
+
 # ------------------------------------------------------------------ integrators
 class _B200Integrator(Integrator):
     """Device-resident adaptive Runge-Kutta (restates Explicit_RungeKutta,
@@ -229,7 +255,9 @@ class _B200Integrator(Integrator):
 
     def _build(self):
         o = self._options
-        self._system = system_from_qobjevo(self._qevo, allow_host=True, ncols=self._ncols)
+        dev_qevo = _device_qevo(self._qevo)
+        self._base_n = dev_qevo.shape[0]
+        self._system = system_from_qobjevo(dev_qevo, allow_host=True, ncols=self._ncols)
         self._engine = E.Engine(
             self._system, self._tableau, nslots=1, atol=o['atol'], rtol=o['rtol'],
             nsteps=int(o['nsteps']), first_step=float(o['first_step'] or 0),
@@ -255,8 +283,9 @@ class _B200Integrator(Integrator):
 
     def set_state(self, t, state):
         arr = _data.to(_data.Dense, state).to_array()
-        if arr.shape[1] != self._ncols:          # matrix-valued state: re-bind block-diagonal
-            self._ncols = arr.shape[1]
+        ncols = _state_columns(arr.shape, self._base_n)
+        if ncols != self._ncols:                 # matrix-valued state: re-bind block-diagonal
+            self._ncols = ncols
             self._build()
         self._shape = arr.shape
         self._engine.set_state(t, np.ascontiguousarray(arr.reshape(-1, order="F")))
@@ -364,7 +393,9 @@ class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
     _ncols = 1
 
     def _bind(self):
-        self._system = system_from_qobjevo(self._qevo, allow_host=True, ncols=self._ncols)
+        dev_qevo = _device_qevo(self._qevo)
+        self._base_n = dev_qevo.shape[0]
+        self._system = system_from_qobjevo(dev_qevo, allow_host=True, ncols=self._ncols)
         self._engine = E.Engine(self._system, "vern7", nslots=1)
         n = self._system.N
         self._dx = E.DeviceDense.zeros(n, 1)
@@ -397,8 +428,9 @@ class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
         return self._dout.read_into(self._hout)
 
     def set_state(self, t, state0):
-        if state0.shape[1] != self._ncols:       # matrix-valued state: block-diagonal binding
-            self._ncols = state0.shape[1]
+        ncols = _state_columns(state0.shape, self._base_n)
+        if ncols != self._ncols:                 # matrix-valued state: block-diagonal binding
+            self._ncols = ncols
             self._bind()
         super().set_state(t, _data.to(_data.Dense, state0))
 

@@ -331,3 +331,18 @@ def test_b200_map_improved_sampling():
     assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
     np.testing.assert_allclose(np.array(out.average_expect), np.array(ref.average_expect),
                                rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("method", ["b200_vern7", "b200_adams"])
+def test_matrix_form_option(method):
+    """options['matrix_form']=True (LindbladMatrixForm RHS on the un-vectorised rho) through
+    the device integrators, against the reference's matrix-form and superoperator results."""
+    H, c_ops, psi0, e_ops = jc()
+    tl = np.linspace(0, 3, 13)
+    ref = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="vern7", matrix_form=True,
+                                                               store_states=True))
+    out = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method=method, matrix_form=True,
+                                                               store_states=True))
+    tol = dict(rtol=RTOL, atol=ATOL) if method == "b200_vern7" else dict(rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), **tol)
+    np.testing.assert_allclose(out.states[-1].full(), ref.states[-1].full(), **tol)

@@ -1,8 +1,7 @@
 """Acceptance gate: the reference's OWN solver tests, parametrised over
 every registered integrator, run against the plug-in's `b200_*` methods.  The only tolerated
-failures are the forms DESIGN.md declares out of scope for the device (operator-valued
-python functions `_FuncElement`, and the `matrix_form` Lindblad RHS), which raise TypeError
-by design."""
+failures are the form DESIGN.md declares out of scope for the device (operator-valued
+python functions `_FuncElement`), which raises TypeError by design."""
 import os
 import re
 import subprocess
@@ -23,12 +22,13 @@ def test_reference_solver_tests_with_b200_methods():
     env = dict(os.environ, PYTHONPATH=ref + os.pathsep + ROOT)
     files = [os.path.join(ref, "qutip", "tests", "solver", f)
              for f in ("test_mesolve.py", "test_sesolve.py", "test_mcsolve.py", "test_integrator.py")]
-    out = subprocess.run([sys.executable, "-m", "pytest", "-p", "qutip_b200.plugin", "-q", "-k", "b200",
+    files += [os.path.join(ref, "qutip", "tests", "core", "data", f)
+              for f in ("test_convert.py", "test_dispatch.py")]
+    out = subprocess.run([sys.executable, "-m", "pytest", "-p", "qutip_b200.plugin", "-q", "-k", "b200 or convert or dispatch or Dispatch or build",
                           "-p", "no:cacheprovider"] + files, env=env, capture_output=True, text=True,
                          timeout=1500).stdout
     failed = re.findall(r"^FAILED (\S+)", out, flags=re.M)
     m = re.search(r"(\d+) passed", out)
     assert m and int(m.group(1)) >= 30, out[-2000:]
-    unexpected = [f for f in failed
-                  if not ("TDDecay[func-" in f or "matrix_form" in f)]
+    unexpected = [f for f in failed if "TDDecay[func-" not in f]
     assert not unexpected, unexpected
