@@ -33,6 +33,10 @@ struct Sys {
     int eop_functional = 0;
 };
 Sys g_sys;
+// optional log of the pass classes each trajectory issues (scheduler studies): per pass one
+// 64-bit key built from roles (P, F, I, TA, TB, k_j, INIT), not physical slot numbers
+std::vector<std::vector<uint64_t>> g_class_log;
+bool g_log_classes = false;
 
 static int popc(unsigned x) { return __builtin_popcount(x); }
 
@@ -120,6 +124,9 @@ void emul_matvec(int which, const void* x, void* y) {
     const HostOp& o = g_sys.elems[which];
     for (int64_t r = 0; r < g_sys.N; r++) ((qb_c128*)y)[r] = rowdot(o, r, (const qb_c128*)x);
 }
+void emul_log_classes(int on) { g_log_classes = on != 0; g_class_log.clear(); }
+int64_t emul_class_log_len(int traj) { return traj < (int)g_class_log.size() ? (int64_t)g_class_log[traj].size() : 0; }
+void emul_class_log_get(int traj, uint64_t* out) { for (size_t i = 0; i < g_class_log[traj].size(); i++) out[i] = g_class_log[traj][i]; }
 int emul_eval_prog(const QbInstr* p, int np, double t, const void* args, double out[2]) {
     qb_c128 r; int rc = qb_eval_prog(p, np, t, (const qb_c128*)args, nullptr, nullptr, &r);
     out[0] = r.re; out[1] = r.im; return rc;
@@ -180,7 +187,27 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
                 int issued = qb_advance(g, g.tab, c, pass[slot], red.data() + (size_t)slot * QB_MAXRED,
                                         coef.data() + (size_t)slot * g.maxcoef,
                                         probs.data() + (size_t)slot * std::max(1, g.ncops));
-                if (issued) { c.n_pass++; break; }
+                if (issued) {
+                    c.n_pass++;
+                    if (g_log_classes) {
+                        const QbPass& q = pass[slot];
+                        auto role = [&](int sidx) -> uint64_t {
+                            if (sidx < 0) return 40 + (uint64_t)(-sidx);
+                            if (sidx == c.sP) return 30; if (sidx == c.sF) return 31; if (sidx == c.sI) return 32;
+                            if (sidx == c.sTA) return 33; if (sidx == c.sTB) return 34;
+                            return (uint64_t)sidx;
+                        };
+                        uint64_t h = 1469598103934665603ull;
+                        auto mix = [&](uint64_t v) { h ^= v; h *= 1099511628211ull; };
+                        mix(q.kind); mix(q.opset); mix(q.op_lo); mix(q.op_hi);
+                        mix(role(q.x)); mix(role(q.zdst)); mix(role(q.dst1)); mix(q.nsrc);
+                        for (int i = 0; i < q.nsrc; i++) mix(role(q.src[i]));
+                        if (q.kind == QB_PASS_RHS && q.zdst == 0 && q.x == c.sP) h = 1;   // stage 0 of a step
+                        if ((int)g_class_log.size() <= c.traj_id) g_class_log.resize(c.traj_id + 1);
+                        g_class_log[c.traj_id].push_back(h);
+                    }
+                    break;
+                }
                 if (status) status[c.traj_id] = c.done;
                 if (stats) { int* st = stats + (size_t)c.traj_id * 4; st[0] = c.n_rhs; st[1] = c.n_accept; st[2] = c.n_reject; st[3] = c.n_pass; }
                 if (head >= ntraj) { active--; break; }
