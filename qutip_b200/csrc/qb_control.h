@@ -29,6 +29,10 @@ struct QbCtl {
     int nelem, ncops, neops, nargs;
     int eop_functional;         // e_ops are linear functionals (mesolve tr(E rho))
     int has_host_coef;          // some RHS element's coefficient is evaluated by the host
+    int tile_mode;              // trajectory-interleaved tiles: slot labels stay fixed (copies,
+                                // not relabels) so that lanes in the same phase issue identical
+                                // slot patterns and can execute one pass together
+    int exp_chunk;              // operators per EXPECT pass (<= QB_MAXRED / 2)
     int maxcoef;
     int nt, ndraws;
     const QbProgRef* elem_prog;  // [nelem]
@@ -154,7 +158,16 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             set_t = c.set_t;
             c.t = c.t_prev = c.t_front = set_t;
             c.dt_int = 0.0;
-            if (c.set_x == c.sF) { int tmp = c.sP; c.sP = c.sF; c.sF = tmp; }
+            if (c.set_x == c.sF) {
+                if (g.tile_mode) {                   // fixed labels: move the source out of the way
+                    qb_pass_clear(p);
+                    p.kind = QB_PASS_COMBINE; p.dst1 = c.sTA;
+                    qb_pass_src(p, c.sF, 1.0, 0.0);
+                    c.set_x = c.sTA;
+                    c.pc = QB_PC_SETCOPY_DONE; return 1;
+                }
+                int tmp = c.sP; c.sP = c.sF; c.sF = tmp;
+            }
             c.sY = c.sF;
             c.fsal_pending = 0;                      // k[0] will hold k_fsal = f(t, y0) (:222-225)
             qb_pass_clear(p);
@@ -172,6 +185,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             c.n_rhs++;
             c.pc = QB_PC_EST0_DONE; return 1;
         }
+        case QB_PC_SETCOPY_DONE: L = QL_SET_BEGIN; break;
         case QB_PC_SET_DONE:
             c.norm2_y = red[0];
             L = QL_SET_DONE; break;
@@ -249,6 +263,12 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
         }
         case QL_RK_LOOP:            // while self._t_front < t and self._status >= 0   (:312)
             if (c.t_front < c.int_t && c.status >= 0) {
+                if (g.tile_mode) {                   // y_prev <- y_front (:313) as a real copy
+                    qb_pass_clear(p);
+                    p.kind = QB_PASS_COMBINE; p.dst1 = c.sP;
+                    qb_pass_src(p, c.sF, 1.0, 0.0);
+                    c.pc = QB_PC_COPY_DONE; return 1;
+                }
                 int tmp = c.sP; c.sP = c.sF; c.sF = tmp;     // y_prev <- y_front (:313), by relabel
                 if (T.fsal && c.fsal_pending) { c.kswap ^= 1; c.fsal_pending = 0; }   // k[0] <- k_fsal
                 c.t_prev = c.t_front;
@@ -256,6 +276,10 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
                 L = QL_STEP_ATTEMPT; break;
             }
             L = QL_AFTER_LOOP; break;
+        case QB_PC_COPY_DONE:
+            c.t_prev = c.t_front;
+            c.step_n = 0;
+            L = QL_STEP_ATTEMPT; break;
         case QL_STEP_ATTEMPT: {     // _step_in_err body (:339-343) + _get_timestep (:440-449)
             double dt_needed = c.int_t - c.t_prev, dt;
             if (g.opt.interpolate) dt = c.dt_safe;
@@ -440,13 +464,15 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             qb_pass_clear(p);
             p.kind = QB_PASS_EXPECT; p.opset = c.exp_set; p.x = c.sY;
             p.op_lo = c.exp_lo;
-            p.op_hi = (c.exp_lo + QB_MAXRED / 2 < nops) ? c.exp_lo + QB_MAXRED / 2 : nops;
+            const int chunk = (g.exp_chunk > 0 && g.exp_chunk < QB_MAXRED / 2) ? g.exp_chunk : QB_MAXRED / 2;
+            p.op_hi = (c.exp_lo + chunk < nops) ? c.exp_lo + chunk : nops;
             c.pc = QB_PC_EXPECT_DONE; return 1;
         }
         case QB_PC_EXPECT_DONE: {
             const int nops = (c.exp_set == QB_OPSET_EOPS) ? g.neops : g.ncops;
             const int lo = c.exp_lo;
-            const int hi = (lo + QB_MAXRED / 2 < nops) ? lo + QB_MAXRED / 2 : nops;
+            const int chunk = (g.exp_chunk > 0 && g.exp_chunk < QB_MAXRED / 2) ? g.exp_chunk : QB_MAXRED / 2;
+            const int hi = (lo + chunk < nops) ? lo + chunk : nops;
             bool bad = false;
             for (int m = lo; m < hi; m++) {
                 qb_c128 v, cf; v.re = red[2 * (m - lo)]; v.im = red[2 * (m - lo) + 1];

@@ -105,7 +105,8 @@ enum {
     QB_PC_STEP_ENTRY,                        // Integrator.mcstep from the host
     QB_PC_SET_DONE, QB_PC_EST0_DONE, QB_PC_EST1IN_DONE, QB_PC_EST1_DONE,
     QB_PC_STAGE_DONE, QB_PC_DENSEIN_DONE, QB_PC_DENSE_DONE, QB_PC_INTERP_DONE,
-    QB_PC_EXPECT_DONE, QB_PC_STORE_DONE, QB_PC_PROBS_DONE, QB_PC_APPLY_DONE
+    QB_PC_EXPECT_DONE, QB_PC_STORE_DONE, QB_PC_PROBS_DONE, QB_PC_APPLY_DONE,
+    QB_PC_COPY_DONE, QB_PC_SETCOPY_DONE      // tile mode: explicit y_prev <- y_front copies
 };
 // continuations
 enum {

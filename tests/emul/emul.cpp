@@ -37,6 +37,7 @@ Sys g_sys;
 // 64-bit key built from roles (P, F, I, TA, TB, k_j, INIT), not physical slot numbers
 std::vector<std::vector<uint64_t>> g_class_log;
 bool g_log_classes = false;
+int g_tile_mode = 0, g_exp_chunk = 0;
 
 static int popc(unsigned x) { return __builtin_popcount(x); }
 
@@ -124,6 +125,7 @@ void emul_matvec(int which, const void* x, void* y) {
     const HostOp& o = g_sys.elems[which];
     for (int64_t r = 0; r < g_sys.N; r++) ((qb_c128*)y)[r] = rowdot(o, r, (const qb_c128*)x);
 }
+void emul_set_tile_mode(int on, int exp_chunk) { g_tile_mode = on; g_exp_chunk = exp_chunk; }
 void emul_log_classes(int on) { g_log_classes = on != 0; g_class_log.clear(); }
 int64_t emul_class_log_len(int traj) { return traj < (int)g_class_log.size() ? (int64_t)g_class_log[traj].size() : 0; }
 void emul_class_log_get(int traj, uint64_t* out) { for (size_t i = 0; i < g_class_log[traj].size(); i++) out[i] = g_class_log[traj][i]; }
@@ -148,6 +150,7 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
     g.nargs = s.nargs; g.eop_functional = s.eop_functional;
     g.maxcoef = std::max(1, g.nelem);
     g.nt = nt; g.ndraws = ndraws;
+    g.tile_mode = g_tile_mode; g.exp_chunk = g_exp_chunk;
     std::vector<QbInstr> instr;
     auto pack = [&](const std::vector<std::vector<QbInstr>>& ps) {
         std::vector<QbProgRef> refs;

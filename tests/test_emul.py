@@ -136,3 +136,33 @@ def test_coefficient_bytecode():
         coeffs.compile_expr("__import__('os').system('x')")
     with pytest.raises(TypeError):
         coeffs.compile_expr("foo(t)")
+
+
+@pytest.mark.parametrize("name,method,nslots", [("c3_tfim6_mc", "vern7", 24),
+                                               ("c3_tfim4_mc_strong", "vern9", 7)])
+def test_mcsolve_state_machine_tile_mode(name, method, nslots):
+    """Fixed slot labels (explicit y_prev <- y_front copies, chunked expectation passes) as
+    used by the trajectory-interleaved tile engine: same results as the relabelling mode."""
+    from _emul import lib
+    g = load(name)
+    lib().emul_set_tile_mode(1, 3)
+    try:
+        s = EmulSystem(len(g["psi0"]), 0, FMT_CSR)
+        s.add_element(*_sp_arrays(merged_constant_rhs(g)))
+        for i in range(int(g["n_cops"])):
+            s.add_collapse(op_arrays(g, "cop%d" % i), op_arrays(g, "nop%d" % i))
+        for i in range(int(g["n_eops"])):
+            s.add_eop(*op_arrays(g, "eop%d" % i))
+        ntraj = int(g["ntraj"])
+        r = s.run(1, {"vern7": 0, "vern9": 1}[method], g["psi0"], g["tlist"], ntraj=ntraj,
+                  nslots=nslots, draws=g["draws"], opt=default_options(store_states=1))
+    finally:
+        lib().emul_set_tile_mode(0, 0)
+    assert (r["status"] == 1).all()
+    assert np.array_equal(r["ncol"], g["col_count"])
+    cc = np.concatenate([[0], np.cumsum(g["col_count"])])
+    for j in range(ntraj):
+        n = r["ncol"][j]
+        assert np.array_equal(r["col_which"][j, :n], g["col_which"][cc[j]:cc[j + 1]])
+    assert np.abs(np.transpose(r["expect"], (1, 0, 2)) - g["runs_expect"]).max() < 1e-9
+    assert np.abs(r["states"][:, -1, :] - g["final_states"]).max() < 1e-9

@@ -346,3 +346,20 @@ def test_matrix_form_option(method):
     tol = dict(rtol=RTOL, atol=ATOL) if method == "b200_vern7" else dict(rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), **tol)
     np.testing.assert_allclose(out.states[-1].full(), ref.states[-1].full(), **tol)
+
+
+def test_propagator_and_nm_mcsolve_reuse_the_device_integrator():
+    """Callers that reuse the same integrators: propagator() drives
+    MESolver with a matrix-valued state; NonMarkovianMCSolver subclasses MCIntegrator."""
+    a = destroy(5)
+    H = a.dag() * a + 0.3 * (a + a.dag())
+    U_ref = qutip.propagator(H, 1.5, c_ops=[0.2 * a], options=dict(OPT, method="vern7"))
+    U_out = qutip.propagator(H, 1.5, c_ops=[0.2 * a], options=dict(OPT, method="b200_vern7"))
+    np.testing.assert_allclose(U_out.full(), U_ref.full(), rtol=1e-5, atol=1e-7)
+    ops_and_rates = [(a, "0.3 + 0.2 * sin(t)")]
+    kw = dict(e_ops=[a.dag() * a], ntraj=6, seeds=4)
+    ref = qutip.nm_mcsolve(H, basis(5, 3), np.linspace(0, 2, 9), ops_and_rates,
+                           options=dict(OPT, method="vern7", keep_runs_results=True), **kw)
+    out = qutip.nm_mcsolve(H, basis(5, 3), np.linspace(0, 2, 9), ops_and_rates,
+                           options=dict(OPT, method="b200_vern7", keep_runs_results=True), **kw)
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=1e-5, atol=1e-7)
