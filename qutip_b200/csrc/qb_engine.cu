@@ -747,11 +747,13 @@ static int qb_drive(QbEngH* e, int nslots_used) {
         QB_LAUNCH_CHECK();
         return QB_OK;
     };
-    if (e->profiling) {
-        // per-pass CUDA-event timing: plain launches, one host look at the counter per chunk
-        int chunk = 8;
+    if (e->profiling || nslots_used == 1) {
+        // plain launches, one host look at the counter per chunk.  Used for per-pass
+        // CUDA-event timing and for the single-slot Integrator protocol, whose calls often
+        // need only one or two rounds (an interpolation) -- a 16-round graph would be waste.
+        int chunk = e->profiling ? 8 : 2;
         for (;;) {
-            for (int i = 0; i < chunk; i++) { int rc = enqueue_round(true); if (rc) return rc; }
+            for (int i = 0; i < chunk; i++) { int rc = enqueue_round(e->profiling != 0); if (rc) return rc; }
             rounds += chunk;
             QB_CUDA(cudaMemcpyAsync(e->h_active, e->h.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
             QB_CUDA(cudaStreamSynchronize(e->stream));
