@@ -66,6 +66,15 @@ __device__ __forceinline__ const double2* qb_vsrc(const QbEngineDev* E, int slot
 #ifndef QB_GRAPH_ROUNDS
 #define QB_GRAPH_ROUNDS 16   // rounds per captured CUDA graph
 #endif
+#ifndef QB_NO_STREAM_VEC
+// epilogue sources are read once and k / y outputs are written once per pass: streaming
+// cache policy keeps them from evicting the operator and the gathered state in L1/L2
+#define QB_LDV(p) __ldcs(p)
+#define QB_STV(p, v) __stcs((p), (v))
+#else
+#define QB_LDV(p) (*(p))
+#define QB_STV(p, v) (*(p) = (v))
+#endif
 #ifndef QB_PF
 #define QB_PF 4      // epilogue source vectors prefetched before the operator sweep
 #endif
@@ -142,7 +151,7 @@ __device__ __forceinline__ void qb_pass_one_slice(
     for (int u = 0; u < QB_PF; u++) {
         const int sidx = __shfl_sync(0xffffffffu, h.my_src, u);
         const double2* p = QB_VS(sidx);
-        pv[u] = (u < nsrc && active) ? p[r] : make_double2(0.0, 0.0);
+        pv[u] = (u < nsrc && active) ? QB_LDV(p + r) : make_double2(0.0, 0.0);
     }
 
     // ---- operator application ----
@@ -199,7 +208,7 @@ __device__ __forceinline__ void qb_pass_one_slice(
         for (int u = 0; u < 4; u++) {
             const int sidx = __shfl_sync(0xffffffffu, h.my_src, (i + u) & 31);
             const double2* p = QB_VS(sidx);
-            v[u] = (i + u < nsrc && active) ? p[r] : make_double2(0.0, 0.0);
+            v[u] = (i + u < nsrc && active) ? QB_LDV(p + r) : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -214,8 +223,8 @@ __device__ __forceinline__ void qb_pass_one_slice(
     double r0 = 0.0, r1 = 0.0, r2 = 0.0;
     if (active) {
         double2* base = const_cast<double2*>(h.slot_base);
-        if (h.zdst >= 0) base[(size_t)h.zdst * N_ + r] = z;
-        if (h.dst1 >= 0) base[(size_t)h.dst1 * N_ + r] = o1;
+        if (h.zdst >= 0) QB_STV(base + (size_t)h.zdst * N_ + r, z);
+        if (h.dst1 >= 0) QB_STV(base + (size_t)h.dst1 * N_ + r, o1);
         else if (h.dst1 == QB_SLOT_OUT)
             E->out_states[((size_t)E->traj[slot].traj_id * E->ctl.nt + gp->out_index) * N_ + r] = o1;
         const double n1 = o1.x * o1.x + o1.y * o1.y;
@@ -240,8 +249,16 @@ __global__ void __launch_bounds__(QB_TILE_ROWS, QB_MINB)
 qb_pass_kernel(const QbEngineDev* __restrict__ E)
 {
     const int ntiles = E->ctl.ntiles;
+#ifdef QB_TILE_MAJOR
+    // consecutive blocks = the same 256-row tile of consecutive slots: the CTAs resident on
+    // an SM at one time read the same slices of the (shared) operator, which then hit in L1
+    const int nsl = gridDim.x / ntiles;
+    const int tile = blockIdx.x / nsl;
+    const int slot = blockIdx.x - tile * nsl;
+#else
     const int slot = blockIdx.x / ntiles;
     const int tile = blockIdx.x - slot * ntiles;
+#endif
     if (E->pass[slot].kind == QB_PASS_NONE) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sl = tile * (QB_TILE_ROWS / 32) + warp;
