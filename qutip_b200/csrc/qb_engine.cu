@@ -46,6 +46,7 @@ struct QbEngineDev {
     int* out_stats;
     unsigned long long* vec_count;   // state-sized vector accesses issued (algorithmic traffic)
     int nslices, red_stride;
+    int all_sell, pad1_;        // every RHS element is SELL and there is no dense pre-pass
     double* red_final;          // [nslots][QB_MAXRED]: pre-reduced partials (large systems) or null
     // dense batched path (qb_dense.cu): z of every slot precomputed by one DMMA ZGEMM
     double2* zbuf;              // [nslots][N] or null
@@ -146,6 +147,7 @@ __device__ __forceinline__ void qb_pass_one_slice(
     }
 
     // ---- epilogue sources: lane i holds (slot, w1, w2) of source i; prefetch the first QB_PF
+#if QB_PF > 0
     double2 pv[QB_PF];
 #pragma unroll
     for (int u = 0; u < QB_PF; u++) {
@@ -153,6 +155,7 @@ __device__ __forceinline__ void qb_pass_one_slice(
         const double2* p = QB_VS(sidx);
         pv[u] = (u < nsrc && active) ? QB_LDV(p + r) : make_double2(0.0, 0.0);
     }
+#endif
 
     // ---- operator application ----
     double2 z = make_double2(0.0, 0.0);
@@ -196,12 +199,14 @@ __device__ __forceinline__ void qb_pass_one_slice(
 
     // ---- fused linear combinations (sources in order, z last), stores, reductions ----
     double2 o1 = make_double2(0.0, 0.0), o2 = make_double2(0.0, 0.0);
+#if QB_PF > 0
 #pragma unroll
     for (int u = 0; u < QB_PF; u++) {
         const double a = __shfl_sync(0xffffffffu, h.my_w1, u), b = __shfl_sync(0xffffffffu, h.my_w2, u);
         o1.x = fma(a, pv[u].x, o1.x); o1.y = fma(a, pv[u].y, o1.y);
         o2.x = fma(b, pv[u].x, o2.x); o2.y = fma(b, pv[u].y, o2.y);
     }
+#endif
     for (int i = QB_PF; i < nsrc; i += 4) {            // rarely taken (dense-output rows)
         double2 v[4];
 #pragma unroll
@@ -243,6 +248,96 @@ __device__ __forceinline__ void qb_pass_one_slice(
 #undef QB_VS
 }
 
+// The common case -- COMBINE passes and RHS passes whose elements are all SELL -- as a lean
+// separate body: nothing but the operand pointer is fetched before the operator sweep, the
+// pass descriptor is read after it (it is L1/L2 resident), so no value other than the
+// accumulator lives across the sweep and the 64-register budget holds without spilling.
+// Everything else (EXPECT, APPLY, DIAM / CSR / dense elements) takes qb_pass_slice_generic.
+__device__ __forceinline__ void qb_pass_slice_hot(const QbEngineDev* __restrict__ E, int slot,
+                                                  int sl, int lane, int kind)
+{
+    const QbPass* __restrict__ gp = &E->pass[slot];
+    const int N = E->ctl.N;
+    const long long r = (long long)sl * 32 + lane;
+    const bool active = r < N;
+    double2 z = make_double2(0.0, 0.0);
+    if (kind == QB_PASS_RHS) {
+        const int xs = gp->x;
+        const double2* x = xs >= 0
+            ? E->pool + ((size_t)slot * E->V + xs) * (size_t)N
+            : E->init_states + (size_t)E->traj[slot].init_idx * (size_t)N;
+        const int nelem = E->ctl.nelem;
+        for (int e = 0; e < nelem; e++) {
+            const double2 q = qb_rowdot_sell(E->elem[e], sl, lane, x);
+            const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef + e];
+            z.x += c.re * q.x - c.im * q.y;
+            z.y += c.re * q.y + c.im * q.x;
+        }
+        const double zs = gp->zscale;
+        z.x *= zs; z.y *= zs;
+    }
+    // ---- fused linear combinations (sources in order, z last), stores, reductions ----
+    const int nsrc = gp->nsrc;
+    double2* slot_base = E->pool + (size_t)slot * E->V * (size_t)N;
+    const double2* init_ptr = E->init_states + (size_t)E->traj[slot].init_idx * (size_t)N;
+    int my_src = 0; double my_w1 = 0.0, my_w2 = 0.0;
+    if (lane < nsrc) { my_src = gp->src[lane]; my_w1 = gp->w1[lane]; my_w2 = gp->w2[lane]; }
+    double2 o1 = make_double2(0.0, 0.0), o2 = make_double2(0.0, 0.0);
+    for (int i = 0; i < nsrc; i += 4) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int sidx = __shfl_sync(0xffffffffu, my_src, (i + u) & 31);
+            const double2* p = sidx >= 0 ? slot_base + (long long)sidx * N : init_ptr;
+            v[u] = (i + u < nsrc && active) ? QB_LDV(p + r) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const double a = __shfl_sync(0xffffffffu, my_w1, (i + u) & 31);
+            const double b = __shfl_sync(0xffffffffu, my_w2, (i + u) & 31);
+            o1.x = fma(a, v[u].x, o1.x); o1.y = fma(a, v[u].y, o1.y);
+            o2.x = fma(b, v[u].x, o2.x); o2.y = fma(b, v[u].y, o2.y);
+        }
+    }
+    {
+        const double w1z = gp->w1z, w2z = gp->w2z;
+        o1.x = fma(w1z, z.x, o1.x); o1.y = fma(w1z, z.y, o1.y);
+        o2.x = fma(w2z, z.x, o2.x); o2.y = fma(w2z, z.y, o2.y);
+    }
+    const int red = gp->red;
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    if (active) {
+        const int zdst = gp->zdst, dst1 = gp->dst1;
+        if (zdst >= 0) QB_STV(slot_base + (size_t)zdst * N + r, z);
+        if (dst1 >= 0) QB_STV(slot_base + (size_t)dst1 * N + r, o1);
+        else if (dst1 == QB_SLOT_OUT)
+            E->out_states[((size_t)E->traj[slot].traj_id * E->ctl.nt + gp->out_index) * (size_t)N + r] = o1;
+        const double n1 = o1.x * o1.x + o1.y * o1.y;
+        r0 = n1;
+        if (red & QB_RED_WRMS) {
+            const double q = sqrt(o2.x * o2.x + o2.y * o2.y)
+                             / (E->ctl.opt.atol + E->ctl.opt.rtol * sqrt(n1));
+            r1 = q * q;
+        }
+        r2 = z.x * z.x + z.y * z.y;
+    }
+    if (red) {
+        r0 = qb_warp_sum(r0); r1 = qb_warp_sum(r1); r2 = qb_warp_sum(r2);
+        if (lane == 0) {
+            double* __restrict__ part = E->partials + ((size_t)slot * E->nslices + sl) * E->red_stride;
+            part[0] = r0; part[1] = r1; part[2] = r2;
+        }
+    }
+}
+
+static __device__ __noinline__ void qb_pass_slice_generic(const QbEngineDev* E, int slot, int sl,
+                                                          int lane)
+{
+    QbWarpHdr h;
+    qb_load_hdr(E, slot, lane, h);
+    qb_pass_one_slice(E, slot, sl, lane, h, nullptr, nullptr, 0);
+}
+
 // Warp-autonomous pass kernel: one warp = one 32-row slice of one trajectory slot; no shared
 // memory, no block-level barrier.
 __global__ void __launch_bounds__(QB_TILE_ROWS, QB_MINB)
@@ -259,13 +354,16 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E)
     const int slot = blockIdx.x / ntiles;
     const int tile = blockIdx.x - slot * ntiles;
 #endif
-    if (E->pass[slot].kind == QB_PASS_NONE) return;
+    const int kind = E->pass[slot].kind;
+    if (kind == QB_PASS_NONE) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sl = tile * (QB_TILE_ROWS / 32) + warp;
     if ((long long)sl * 32 >= E->ctl.N) return;          // warp-uniform
-    QbWarpHdr h;
-    qb_load_hdr(E, slot, lane, h);
-    qb_pass_one_slice(E, slot, sl, lane, h, nullptr, nullptr, 0);
+    if (kind == QB_PASS_COMBINE || (kind == QB_PASS_RHS && E->all_sell)) {
+        qb_pass_slice_hot(E, slot, sl, lane, kind);
+    } else {
+        qb_pass_slice_generic(E, slot, sl, lane);
+    }
 }
 
 // Shared-operator variant for systems whose RHS is ONE SELL operator (mcsolve H_eff): the 8
@@ -693,6 +791,8 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     QB_TRY(qb_dev_alloc(e, 1, &h.vec_count));
     h.zbuf = nullptr; h.xcols = nullptr; h.zcols = nullptr;
     h.red_final = nullptr;
+    h.all_sell = getenv("QB_NO_HOT") ? 0 : 1;
+    for (auto& el : s->elems) if (el.fmt != QB_FMT_SELL) h.all_sell = 0;
     if (h.nslices > 2048) QB_TRY(qb_dev_alloc(e, (size_t)nslots * QB_MAXRED, &h.red_final));
     if (s->elems.size() == 1 && s->elems[0].fmt == QB_FMT_DENSE && nslots >= 8) {
         QB_TRY(qb_dev_alloc(e, (size_t)nslots * N, &h.zbuf));

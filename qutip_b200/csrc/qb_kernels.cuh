@@ -144,6 +144,35 @@ __device__ __forceinline__ double2 qb_rowdot(const QbOpDev& A, int sl, int lane,
     return acc;
 }
 
+// SELL-only row product (hot body of the fused pass kernel), U slots in flight
+#ifndef QB_HOT_U
+#define QB_HOT_U 4
+#endif
+template <int U = QB_HOT_U>
+__device__ __forceinline__ double2 qb_rowdot_sell(const QbOpDev& A, int sl, int lane,
+                                                  const double2* __restrict__ x)
+{
+    double2 acc = make_double2(0.0, 0.0);
+    const int s0 = A.slice_ptr[sl], w = A.slice_ptr[sl + 1] - s0;
+    const double2* __restrict__ v = reinterpret_cast<const double2*>(A.val) + ((size_t)s0 * 32 + lane);
+    const int* __restrict__ c = A.col + ((size_t)s0 * 32 + lane);
+    int k = 0;
+    for (; k + U <= w; k += U) {
+        int cc[U];
+        double2 vv[U], xx[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) cc[u] = __ldg(c + (k + u) * 32);
+#pragma unroll
+        for (int u = 0; u < U; u++) vv[u] = __ldg(v + (k + u) * 32);
+#pragma unroll
+        for (int u = 0; u < U; u++) xx[u] = x[cc[u]];
+#pragma unroll
+        for (int u = 0; u < U; u++) qb_fma(acc, vv[u], xx[u]);
+    }
+    for (; k < w; k++) qb_fma(acc, __ldg(v + k * 32), x[__ldg(c + k * 32)]);
+    return acc;
+}
+
 // butterfly sum: every lane ends with the same value, order fixed -> deterministic
 __device__ __forceinline__ double qb_warp_sum(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
