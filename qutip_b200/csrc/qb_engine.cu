@@ -253,50 +253,47 @@ __device__ __forceinline__ void qb_pass_one_slice(
 // pass descriptor is read after it (it is L1/L2 resident), so no value other than the
 // accumulator lives across the sweep and the 64-register budget holds without spilling.
 // Everything else (EXPECT, APPLY, DIAM / CSR / dense elements) takes qb_pass_slice_generic.
-__device__ __forceinline__ void qb_pass_slice_hot(const QbEngineDev* __restrict__ E, int slot,
-                                                  int sl, int lane, int kind)
+__device__ __forceinline__ const double2* qb_hot_x(const QbEngineDev* __restrict__ E, int slot)
+{
+    const int xs = E->pass[slot].x;
+    return xs >= 0 ? E->pool + ((size_t)slot * E->V + xs) * (size_t)E->ctl.N
+                   : E->init_states + (size_t)E->traj[slot].init_idx * (size_t)E->ctl.N;
+}
+
+// fused linear combinations (sources in order, z last), stores, reductions of one slot
+__device__ __forceinline__ void qb_hot_epilogue(const QbEngineDev* __restrict__ E, int slot,
+                                                int sl, int lane, double2 z)
 {
     const QbPass* __restrict__ gp = &E->pass[slot];
     const int N = E->ctl.N;
     const long long r = (long long)sl * 32 + lane;
     const bool active = r < N;
-    double2 z = make_double2(0.0, 0.0);
-    if (kind == QB_PASS_RHS) {
-        const int xs = gp->x;
-        const double2* x = xs >= 0
-            ? E->pool + ((size_t)slot * E->V + xs) * (size_t)N
-            : E->init_states + (size_t)E->traj[slot].init_idx * (size_t)N;
-        const int nelem = E->ctl.nelem;
-        for (int e = 0; e < nelem; e++) {
-            const double2 q = qb_rowdot_sell(E->elem[e], sl, lane, x);
-            const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef + e];
-            z.x += c.re * q.x - c.im * q.y;
-            z.y += c.re * q.y + c.im * q.x;
-        }
-        const double zs = gp->zscale;
-        z.x *= zs; z.y *= zs;
-    }
-    // ---- fused linear combinations (sources in order, z last), stores, reductions ----
     const int nsrc = gp->nsrc;
-    double2* slot_base = E->pool + (size_t)slot * E->V * (size_t)N;
+    const int red = gp->red;
+    const bool werr = (red & QB_RED_WRMS) != 0;      // o2 (the error combination) is only
+    double2* slot_base = E->pool + (size_t)slot * E->V * (size_t)N;   // consumed by WRMS
     const double2* init_ptr = E->init_states + (size_t)E->traj[slot].init_idx * (size_t)N;
-    int my_src = 0; double my_w1 = 0.0, my_w2 = 0.0;
-    if (lane < nsrc) { my_src = gp->src[lane]; my_w1 = gp->w1[lane]; my_w2 = gp->w2[lane]; }
     double2 o1 = make_double2(0.0, 0.0), o2 = make_double2(0.0, 0.0);
+    // source slots and weights are read with warp-uniform loads (one L1 wavefront each)
     for (int i = 0; i < nsrc; i += 4) {
         double2 v[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const int sidx = __shfl_sync(0xffffffffu, my_src, (i + u) & 31);
+            const int sidx = gp->src[min(i + u, QB_MAXSRC - 1)];
             const double2* p = sidx >= 0 ? slot_base + (long long)sidx * N : init_ptr;
             v[u] = (i + u < nsrc && active) ? QB_LDV(p + r) : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const double a = __shfl_sync(0xffffffffu, my_w1, (i + u) & 31);
-            const double b = __shfl_sync(0xffffffffu, my_w2, (i + u) & 31);
+            const double a = gp->w1[min(i + u, QB_MAXSRC - 1)];
             o1.x = fma(a, v[u].x, o1.x); o1.y = fma(a, v[u].y, o1.y);
-            o2.x = fma(b, v[u].x, o2.x); o2.y = fma(b, v[u].y, o2.y);
+        }
+        if (werr) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const double b = gp->w2[min(i + u, QB_MAXSRC - 1)];
+                o2.x = fma(b, v[u].x, o2.x); o2.y = fma(b, v[u].y, o2.y);
+            }
         }
     }
     {
@@ -304,7 +301,6 @@ __device__ __forceinline__ void qb_pass_slice_hot(const QbEngineDev* __restrict_
         o1.x = fma(w1z, z.x, o1.x); o1.y = fma(w1z, z.y, o1.y);
         o2.x = fma(w2z, z.x, o2.x); o2.y = fma(w2z, z.y, o2.y);
     }
-    const int red = gp->red;
     double r0 = 0.0, r1 = 0.0, r2 = 0.0;
     if (active) {
         const int zdst = gp->zdst, dst1 = gp->dst1;
@@ -330,6 +326,55 @@ __device__ __forceinline__ void qb_pass_slice_hot(const QbEngineDev* __restrict_
     }
 }
 
+__device__ __forceinline__ void qb_pass_slice_hot(const QbEngineDev* __restrict__ E, int slot,
+                                                  int sl, int lane, int kind)
+{
+    double2 z = make_double2(0.0, 0.0);
+    if (kind == QB_PASS_RHS) {
+        const double2* x = qb_hot_x(E, slot);
+        const int nelem = E->ctl.nelem;
+        for (int e = 0; e < nelem; e++) {
+            const double2 q = qb_rowdot_sell(E->elem[e], sl, lane, x);
+            const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef + e];
+            z.x += c.re * q.x - c.im * q.y;
+            z.y += c.re * q.y + c.im * q.x;
+        }
+        const double zs = E->pass[slot].zscale;
+        z.x *= zs; z.y *= zs;
+    }
+    qb_hot_epilogue(E, slot, sl, lane, z);
+}
+
+// QB_G consecutive slots whose passes are all SELL RHS passes: one warp sweeps the slice ONCE
+// for all of them (operator values / columns loaded once, G gathered states), then runs each
+// slot's own epilogue.
+template <int G>
+__device__ __forceinline__ void qb_pass_slice_hot_multi(const QbEngineDev* __restrict__ E, int slot0,
+                                                        int sl, int lane)
+{
+    const double2* x[G];
+    double2 z[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) { x[g] = qb_hot_x(E, slot0 + g); z[g] = make_double2(0.0, 0.0); }
+    const int nelem = E->ctl.nelem;
+    for (int e = 0; e < nelem; e++) {
+        double2 q[G];
+        qb_rowdot_sell_multi<G>(E->elem[e], sl, lane, x, q);
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const qb_c128 c = E->coef[(size_t)(slot0 + g) * E->ctl.maxcoef + e];
+            z[g].x += c.re * q[g].x - c.im * q[g].y;
+            z[g].y += c.re * q[g].y + c.im * q[g].x;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const double zs = E->pass[slot0 + g].zscale;
+        z[g].x *= zs; z[g].y *= zs;
+        qb_hot_epilogue(E, slot0 + g, sl, lane, z[g]);
+    }
+}
+
 static __device__ __noinline__ void qb_pass_slice_generic(const QbEngineDev* E, int slot, int sl,
                                                           int lane)
 {
@@ -338,31 +383,50 @@ static __device__ __noinline__ void qb_pass_slice_generic(const QbEngineDev* E, 
     qb_pass_one_slice(E, slot, sl, lane, h, nullptr, nullptr, 0);
 }
 
-// Warp-autonomous pass kernel: one warp = one 32-row slice of one trajectory slot; no shared
-// memory, no block-level barrier.
+#ifndef QB_G
+#define QB_G 4       // trajectory slots sharing one operator sweep (register blocking)
+#endif
+
+// Warp-autonomous pass kernel: one warp = one 32-row slice of QB_G consecutive trajectory
+// slots; no shared memory, no block-level barrier.
 __global__ void __launch_bounds__(QB_TILE_ROWS, QB_MINB)
-qb_pass_kernel(const QbEngineDev* __restrict__ E)
+qb_pass_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
 {
     const int ntiles = E->ctl.ntiles;
-#ifdef QB_TILE_MAJOR
-    // consecutive blocks = the same 256-row tile of consecutive slots: the CTAs resident on
-    // an SM at one time read the same slices of the (shared) operator, which then hit in L1
-    const int nsl = gridDim.x / ntiles;
-    const int tile = blockIdx.x / nsl;
-    const int slot = blockIdx.x - tile * nsl;
-#else
-    const int slot = blockIdx.x / ntiles;
-    const int tile = blockIdx.x - slot * ntiles;
-#endif
-    const int kind = E->pass[slot].kind;
-    if (kind == QB_PASS_NONE) return;
+    const int grp = blockIdx.x / ntiles;
+    const int tile = blockIdx.x - grp * ntiles;
+    const int slot0 = grp * QB_G;
+    int kinds[QB_G];
+    bool any = false, all_rhs = E->all_sell != 0;
+#pragma unroll
+    for (int g = 0; g < QB_G; g++) {
+        kinds[g] = (slot0 + g < nslots_used) ? E->pass[slot0 + g].kind : QB_PASS_NONE;
+        any |= kinds[g] != QB_PASS_NONE;
+        all_rhs &= kinds[g] == QB_PASS_RHS;
+    }
+    if (!any) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sl = tile * (QB_TILE_ROWS / 32) + warp;
     if ((long long)sl * 32 >= E->ctl.N) return;          // warp-uniform
-    if (kind == QB_PASS_COMBINE || (kind == QB_PASS_RHS && E->all_sell)) {
-        qb_pass_slice_hot(E, slot, sl, lane, kind);
-    } else {
-        qb_pass_slice_generic(E, slot, sl, lane);
+    if (QB_G > 1 && all_rhs) {
+        qb_pass_slice_hot_multi<QB_G>(E, slot0, sl, lane);
+        return;
+    }
+#if QB_G == 4
+    // not all four in an RHS pass: still share the sweep inside each pair that is
+    const bool p0 = E->all_sell && kinds[0] == QB_PASS_RHS && kinds[1] == QB_PASS_RHS;
+    const bool p1 = E->all_sell && kinds[2] == QB_PASS_RHS && kinds[3] == QB_PASS_RHS;
+    if (p0) { qb_pass_slice_hot_multi<2>(E, slot0, sl, lane); kinds[0] = kinds[1] = QB_PASS_NONE; }
+    if (p1) { qb_pass_slice_hot_multi<2>(E, slot0 + 2, sl, lane); kinds[2] = kinds[3] = QB_PASS_NONE; }
+#endif
+#pragma unroll
+    for (int g = 0; g < QB_G; g++) {
+        const int kind = kinds[g];
+        if (kind == QB_PASS_NONE) continue;
+        if (kind == QB_PASS_COMBINE || (kind == QB_PASS_RHS && E->all_sell))
+            qb_pass_slice_hot(E, slot0 + g, sl, lane, kind);
+        else
+            qb_pass_slice_generic(E, slot0 + g, sl, lane);
     }
 }
 
@@ -825,7 +889,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
 // enqueue rounds until every slot is idle; one host sync per chunk
 static int qb_drive(QbEngH* e, int nslots_used) {
     const int ntiles = e->h.ctl.ntiles;
-    const long long grid1 = (long long)nslots_used * ntiles;
+    const long long grid1 = (long long)((nslots_used + QB_G - 1) / QB_G) * ntiles;
     const int grid2 = (nslots_used * 32 + 127) / 128;
     if (grid1 > 0x7fffffffLL) QB_FAIL(QB_E_ARG, "grid too large");
     // one SELL operator shared by >= 8 trajectory slots: stage it per CTA (qb_pass_kernel_shared)
@@ -853,7 +917,7 @@ static int qb_drive(QbEngH* e, int nslots_used) {
             if (rcg) return rcg;
         }
         if (use_shared) qb_pass_kernel_shared<<<(unsigned)grid_sh, QB_TILE_ROWS, 0, e->stream>>>(e->d);
-        else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d);
+        else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d, nslots_used);
         QB_LAUNCH_CHECK();
         if (timed) cudaEventRecord(pb, e->stream);
         if (e->h.red_final) {

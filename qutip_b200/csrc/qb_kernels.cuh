@@ -173,6 +173,45 @@ __device__ __forceinline__ double2 qb_rowdot_sell(const QbOpDev& A, int sl, int 
     return acc;
 }
 
+// the same sweep for G states at once: every operator slot is loaded once and applied to G
+// gathered vectors (register blocking over trajectories)
+#ifndef QB_HOT_UG
+#define QB_HOT_UG 2
+#endif
+template <int G, int U = QB_HOT_UG>
+__device__ __forceinline__ void qb_rowdot_sell_multi(const QbOpDev& A, int sl, int lane,
+                                                     const double2* const (&x)[G], double2 (&acc)[G])
+{
+#pragma unroll
+    for (int g = 0; g < G; g++) acc[g] = make_double2(0.0, 0.0);
+    const int s0 = A.slice_ptr[sl], w = A.slice_ptr[sl + 1] - s0;
+    const double2* __restrict__ v = reinterpret_cast<const double2*>(A.val) + ((size_t)s0 * 32 + lane);
+    const int* __restrict__ c = A.col + ((size_t)s0 * 32 + lane);
+    int k = 0;
+    for (; k + U <= w; k += U) {
+        int cc[U];
+        double2 vv[U], xx[U][G];
+#pragma unroll
+        for (int u = 0; u < U; u++) cc[u] = __ldg(c + (k + u) * 32);
+#pragma unroll
+        for (int u = 0; u < U; u++) vv[u] = __ldg(v + (k + u) * 32);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int g = 0; g < G; g++) xx[u][g] = x[g][cc[u]];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int g = 0; g < G; g++) qb_fma(acc[g], vv[u], xx[u][g]);
+    }
+    for (; k < w; k++) {
+        const int c0 = __ldg(c + k * 32);
+        const double2 v0 = __ldg(v + k * 32);
+#pragma unroll
+        for (int g = 0; g < G; g++) qb_fma(acc[g], v0, x[g][c0]);
+    }
+}
+
 // butterfly sum: every lane ends with the same value, order fixed -> deterministic
 __device__ __forceinline__ double qb_warp_sum(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
