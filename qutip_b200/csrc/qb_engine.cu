@@ -46,7 +46,7 @@ struct QbEngineDev {
     int* out_stats;
     unsigned long long* vec_count;   // state-sized vector accesses issued (algorithmic traffic)
     int nslices, red_stride;
-    int all_sell, pad1_;        // every RHS element is SELL and there is no dense pre-pass
+    int all_sell, all_lean;     // every RHS element is SELL / is SELL or DIAM (lean pass body)
     double* red_final;          // [nslots][QB_MAXRED]: pre-reduced partials (large systems) or null
     // dense batched path (qb_dense.cu): z of every slot precomputed by one DMMA ZGEMM
     double2* zbuf;              // [nslots][N] or null
@@ -78,6 +78,9 @@ __device__ __forceinline__ const double2* qb_vsrc(const QbEngineDev* E, int slot
 #endif
 #ifndef QB_PF
 #define QB_PF 4      // epilogue source vectors prefetched before the operator sweep
+#endif
+#ifndef QB_UL
+#define QB_UL 4      // DIAM entries in flight per warp in the lean body (HBM streaming)
 #endif
 #ifndef QB_MINB
 #define QB_MINB 4
@@ -334,7 +337,15 @@ __device__ __forceinline__ void qb_pass_slice_hot(const QbEngineDev* __restrict_
         const double2* x = qb_hot_x(E, slot);
         const int nelem = E->ctl.nelem;
         for (int e = 0; e < nelem; e++) {
-            const double2 q = qb_rowdot_sell(E->elem[e], sl, lane, x);
+            double2 q;
+            if (E->elem[e].fmt == QB_FMT_SELL) {
+                q = qb_rowdot_sell(E->elem[e], sl, lane, x);
+            } else {                       // DIAM (HBM-streamed operators)
+                const double2* xs1[1] = {x};
+                double2 a1[1] = {make_double2(0.0, 0.0)};
+                qb_rowdot_diam<1, QB_UL>(E->elem[e], sl, lane, (long long)sl * 32 + lane, xs1, a1);
+                q = a1[0];
+            }
             const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef + e];
             z.x += c.re * q.x - c.im * q.y;
             z.y += c.re * q.y + c.im * q.x;
@@ -423,7 +434,7 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
     for (int g = 0; g < QB_G; g++) {
         const int kind = kinds[g];
         if (kind == QB_PASS_NONE) continue;
-        if (kind == QB_PASS_COMBINE || (kind == QB_PASS_RHS && E->all_sell))
+        if (kind == QB_PASS_COMBINE || (kind == QB_PASS_RHS && E->all_lean))
             qb_pass_slice_hot(E, slot0 + g, sl, lane, kind);
         else
             qb_pass_slice_generic(E, slot0 + g, sl, lane);
@@ -856,7 +867,11 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     h.zbuf = nullptr; h.xcols = nullptr; h.zcols = nullptr;
     h.red_final = nullptr;
     h.all_sell = getenv("QB_NO_HOT") ? 0 : 1;
-    for (auto& el : s->elems) if (el.fmt != QB_FMT_SELL) h.all_sell = 0;
+    h.all_lean = h.all_sell;
+    for (auto& el : s->elems) {
+        if (el.fmt != QB_FMT_SELL) h.all_sell = 0;
+        if (el.fmt != QB_FMT_SELL && el.fmt != QB_FMT_DIAM) h.all_lean = 0;
+    }
     if (h.nslices > 2048) QB_TRY(qb_dev_alloc(e, (size_t)nslots * QB_MAXRED, &h.red_final));
     if (s->elems.size() == 1 && s->elems[0].fmt == QB_FMT_DENSE && nslots >= 8) {
         QB_TRY(qb_dev_alloc(e, (size_t)nslots * N, &h.zbuf));
@@ -887,7 +902,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
 }
 
 // enqueue rounds until every slot is idle; one host sync per chunk
-static int qb_drive(QbEngH* e, int nslots_used) {
+static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
     const int ntiles = e->h.ctl.ntiles;
     const long long grid1 = (long long)((nslots_used + QB_G - 1) / QB_G) * ntiles;
     const int grid2 = (nslots_used * 32 + 127) / 128;
@@ -928,9 +943,9 @@ static int qb_drive(QbEngH* e, int nslots_used) {
         QB_LAUNCH_CHECK();
         return QB_OK;
     };
-    if (e->profiling || nslots_used == 1) {
+    if (e->profiling || short_call) {
         // plain launches, one host look at the counter per chunk.  Used for per-pass
-        // CUDA-event timing and for the single-slot Integrator protocol, whose calls often
+        // CUDA-event timing and for the Integrator protocol (qb_integ_*), whose calls often
         // need only one or two rounds (an interpolation) -- a 16-round graph would be waste.
         int chunk = e->profiling ? 8 : 2;
         for (;;) {
@@ -1182,7 +1197,7 @@ static int qb_integ_launch(QbEngH* e, QbTraj& c) {
     QB_CUDA(cudaMemcpyAsync(h.n_active, &act, sizeof(int), cudaMemcpyHostToDevice, e->stream));
     QB_CUDA(cudaMemcpyAsync(e->d, &h, sizeof(QbEngineDev), cudaMemcpyHostToDevice, e->stream));
     QB_CUDA(cudaStreamSynchronize(e->stream));
-    int rc = qb_drive(e, 1);
+    int rc = qb_drive(e, 1, true);
     if (rc) return rc;
     QB_CUDA(cudaMemcpy(&c, h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
     return QB_OK;

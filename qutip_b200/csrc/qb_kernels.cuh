@@ -25,7 +25,7 @@
 // occupancy beats deeper unrolling -- U=3 at 64 registers (32 warps/SM) gives the best
 // stand-alone SpMV, U=2 the best fused pass kernel.
 #ifndef QB_U1
-#define QB_U1 3     // stand-alone SpMV / matmul / expect kernels
+#define QB_U1 4     // stand-alone SpMV / matmul / expect kernels
 #endif
 #ifndef QB_UP
 #define QB_UP 2     // inside the fused pass kernel

@@ -7,7 +7,7 @@ libs=$(ls qutip_b200/lib_*.so 2>/dev/null)
 for pass in 1 2; do
 for lib in $libs; do
   echo "== $lib"
-  QB_REPS=${QB_REPS:-4} QUTIP_B200_LIB=$PWD/$lib python tools/prof_run.py c3 ${QB_AB_NTRAJ:-1024} 2>&1 | tail -1
-  [ -n "$QB_AB_C2" ] && QUTIP_B200_LIB=$PWD/$lib python tools/prof_run.py c2 2>&1 | tail -2
+  [ -z "$QB_AB_NOC3" ] && QB_REPS=${QB_REPS:-4} QUTIP_B200_LIB=$PWD/$lib python tools/prof_run.py c3 ${QB_AB_NTRAJ:-1024} 2>&1 | tail -1
+  [ -n "$QB_AB_C2" ] && QB_REPS=${QB_REPS:-4} QUTIP_B200_LIB=$PWD/$lib python tools/prof_run.py c2 2>&1 | tail -2
 done
 done

@@ -39,5 +39,16 @@ else:
     out = qb.DeviceDense.zeros(N, 1)
     print("spmv ms", eng.rhs_bench(0.0, x, out, iters=5) / 5)
     rho0 = np.zeros(N, dtype=complex); rho0[0] = 1
-    r = eng.run_mesolve(rho0, np.linspace(0, 0.2, 3))
-    print("c2 mesolve", r.stats[0], r.gpu_ms, "ms")
+    reps = int(os.environ.get("QB_REPS", "1"))
+    ms = []
+    for _ in range(reps):
+        r = eng.run_mesolve(rho0, np.linspace(0, 0.2, 3))
+        ms.append(r.gpu_ms)
+    line = "c2 mesolve %s min %.2f ms (%s), %d rounds" % (r.stats[0], min(ms), " ".join("%.1f" % m for m in ms), r.rounds)
+    if reps > 1:
+        eng.set_profiling(True)
+        r = eng.run_mesolve(rho0, np.linspace(0, 0.2, 3))
+        pr = eng.profile()
+        line += "; profiled: pass kernel %.1f us avg over %d launches, total %.2f ms" % (
+            1e3 * pr["pass_ms"] / max(1, pr["pass_launches"]), pr["pass_launches"], r.gpu_ms)
+    print(line)
