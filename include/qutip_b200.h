@@ -54,6 +54,13 @@ int qb_csr_upload(const void* data, const int32_t* col, const int32_t* rowptr,
                   int64_t rows, int64_t cols, int64_t nnz, int format, qb_handle* out);
 int qb_dia_upload(const void* data, const int32_t* offsets, int64_t ndiag,
                   int64_t rows, int64_t cols, int format, qb_handle* out);
+/* Matrix-free superoperator of an n x n CSR operator A on the column-stacked n x n state:
+ * side 0 = I (x) A (rho -> A rho), side 1 = conj(A) (x) I (rho -> rho A^dagger) -- the two
+ * products LindbladMatrixForm.matmul_data is made of (core/cy/lindblad_matrix_form.pyx:105-203,
+ * imatmul_data_dense / imatmul_dag_dense_data core/data/matmul.pyx:1218-1248).  The handle is
+ * an operator of shape (n^2, n^2) usable wherever a CSR/Dia upload is. */
+int qb_kron_upload(const void* data, const int32_t* col, const int32_t* rowptr, int64_t n,
+                   int64_t nnz, int side, qb_handle* out);
 int qb_op_info(qb_handle h, int* fmt, int64_t* rows, int64_t* cols, int64_t* nnz,
                int64_t* device_bytes);
 int qb_free(qb_handle h);

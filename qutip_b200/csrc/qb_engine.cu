@@ -46,7 +46,7 @@ struct QbEngineDev {
     int* out_stats;
     unsigned long long* vec_count;   // state-sized vector accesses issued (algorithmic traffic)
     int nslices, red_stride;
-    int all_sell, all_lean;     // every RHS element is SELL / is SELL or DIAM (lean pass body)
+    int all_sell, all_lean;     // every RHS element is SELL / is SELL, DIAM or KRON (lean pass body)
     double* red_final;          // [nslots][QB_MAXRED]: pre-reduced partials (large systems) or null
     // dense batched path (qb_dense.cu): z of every slot precomputed by one DMMA ZGEMM
     double2* zbuf;              // [nslots][N] or null
@@ -340,6 +340,9 @@ __device__ __forceinline__ void qb_pass_slice_hot(const QbEngineDev* __restrict_
             double2 q;
             if (E->elem[e].fmt == QB_FMT_SELL) {
                 q = qb_rowdot_sell(E->elem[e], sl, lane, x);
+            } else if (E->elem[e].fmt == QB_FMT_KRON) {   // matrix-free Lindblad products
+                const long long rr = (long long)sl * 32 + lane;
+                q = qb_rowdot_kron(E->elem[e], sl, lane, rr, rr < E->ctl.N, x);
             } else {                       // DIAM (HBM-streamed operators)
                 const double2* xs1[1] = {x};
                 double2 a1[1] = {make_double2(0.0, 0.0)};
@@ -870,7 +873,8 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     h.all_lean = h.all_sell;
     for (auto& el : s->elems) {
         if (el.fmt != QB_FMT_SELL) h.all_sell = 0;
-        if (el.fmt != QB_FMT_SELL && el.fmt != QB_FMT_DIAM) h.all_lean = 0;
+        if (el.fmt != QB_FMT_SELL && el.fmt != QB_FMT_DIAM && el.fmt != QB_FMT_KRON) h.all_lean = 0;
+        if (el.fmt == QB_FMT_KRON && getenv("QB_KRON_GENERIC")) h.all_lean = 0;
     }
     if (h.nslices > 2048) QB_TRY(qb_dev_alloc(e, (size_t)nslots * QB_MAXRED, &h.red_final));
     if (s->elems.size() == 1 && s->elems[0].fmt == QB_FMT_DENSE && nslots >= 8) {

@@ -96,6 +96,71 @@ __device__ __forceinline__ void qb_rowdot_diam(const QbOpDev& A, int sl, int lan
     }
 }
 
+#ifndef QB_KU
+#define QB_KU 6      // entries of A's row j in flight in the right product rho A^dagger
+#endif
+// Matrix-free Kronecker operators on the column-stacked n x n state (row r = i + j n):
+//   kside 0:  z[i,j] = sum_k A[i,k] x[k,j]            (I (x) A,        rho -> A rho)
+//   kside 1:  z[i,j] = sum_k conj(A[j,k]) x[i,k]      (conj(A) (x) I,  rho -> rho A^dagger)
+// The right product reads row j of A, which is the same for all lanes of a warp when n is a
+// multiple of 32 (uniform loads) and gathers x[i + k n] -- consecutive lanes, coalesced.
+__device__ __forceinline__ double2 qb_rowdot_kron(const QbOpDev& A, int sl, int lane, long long r,
+                                                  bool active, const double2* __restrict__ x)
+{
+    double2 acc = make_double2(0.0, 0.0);
+    const int n = A.kn;
+    const double2* __restrict__ val = reinterpret_cast<const double2*>(A.val);
+    if (A.kside == 0) {
+        if (A.kval) {                       // n % 32 == 0: SELL sweep of A on column j of the state
+            const int spc = n >> 5;         // slices per column
+            const int j = sl / spc, isl = sl - j * spc;
+            const double2* __restrict__ xc = x + (long long)j * n;
+            const int s0 = A.slice_ptr[isl], w = A.slice_ptr[isl + 1] - s0;
+            const double2* __restrict__ v = reinterpret_cast<const double2*>(A.kval) + ((size_t)s0 * 32 + lane);
+            const int* __restrict__ c = A.kcol + ((size_t)s0 * 32 + lane);
+            for (int k = 0; k < w; k += 4) {       // full predicated batches, no serial tail
+                int cc[4];
+                double2 vv[4], xx[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) cc[u] = (k + u < w) ? __ldg(c + (k + u) * 32) : 0;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    vv[u] = (k + u < w) ? __ldg(v + (k + u) * 32) : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int u = 0; u < 4; u++) xx[u] = xc[cc[u]];
+#pragma unroll
+                for (int u = 0; u < 4; u++) qb_fma(acc, vv[u], xx[u]);
+            }
+        } else if (active) {
+            const int j = (int)(r / n), i = (int)(r - (long long)j * n);
+            const double2* __restrict__ xc = x + (long long)j * n;
+            const int p1 = A.rowptr[i + 1];
+            for (int p = A.rowptr[i]; p < p1; p++) qb_fma(acc, val[p], xc[A.col[p]]);
+        }
+    } else if (active) {
+        const int j = (int)(r / n), i = (int)(r - (long long)j * n);
+        const double2* __restrict__ xr = x + i;
+        const int p1 = __ldg(A.rowptr + j + 1);
+        // full predicated batches of QB_KU entries: the (warp-uniform, L1-resident) column
+        // indices first, then all gathers in flight, the values only when they are consumed
+        for (int p = __ldg(A.rowptr + j); p < p1; p += QB_KU) {
+            int cc[QB_KU];
+            double2 xv[QB_KU];
+#pragma unroll
+            for (int u = 0; u < QB_KU; u++) cc[u] = (p + u < p1) ? __ldg(A.col + p + u) : 0;
+#pragma unroll
+            for (int u = 0; u < QB_KU; u++) xv[u] = xr[(long long)cc[u] * n];
+#pragma unroll
+            for (int u = 0; u < QB_KU; u++) {
+                double2 a = (p + u < p1) ? __ldg(val + p + u) : make_double2(0.0, 0.0);
+                a.y = -a.y;
+                qb_fma(acc, a, xv[u]);
+            }
+        }
+    }
+    return acc;
+}
+
 // (A x)[r] for the lane's row r of slice sl, any format.  `active` lanes have r < nrows.
 template <int U = QB_U1>
 __device__ __forceinline__ double2 qb_rowdot(const QbOpDev& A, int sl, int lane, long long r,
@@ -127,6 +192,8 @@ __device__ __forceinline__ double2 qb_rowdot(const QbOpDev& A, int sl, int lane,
             const int p1 = A.rowptr[r + 1];
             for (int p = A.rowptr[r]; p < p1; p++) qb_fma(acc, val[p], x[A.col[p]]);
         }
+    } else if (A.fmt == QB_FMT_KRON) {
+        acc = qb_rowdot_kron(A, sl, lane, r, active, x);
     } else {
         if (active) {
             const double2* __restrict__ a = reinterpret_cast<const double2*>(A.dense) + r;

@@ -181,6 +181,40 @@ extern "C" int qb_csr_upload(const void* data, const int32_t* col, const int32_t
     return QB_OK;
 }
 
+extern "C" int qb_kron_upload(const void* data, const int32_t* col, const int32_t* rowptr, int64_t n,
+                              int64_t nnz, int side, qb_handle* out) {
+    if (!rowptr || n <= 0 || nnz < 0 || !out || (nnz > 0 && (!data || !col)) || (side != 0 && side != 1))
+        QB_FAIL(QB_E_ARG, "bad Kronecker operator arguments");
+    if (n > 46340) QB_FAIL(QB_E_ARG, "n*n exceeds int32 row indices");
+    if (rowptr[n] != nnz) QB_FAIL(QB_E_ARG, "row_index[n] != nnz");
+    const qb_c128* v = static_cast<const qb_c128*>(data);
+    for (int64_t p = 0; p < nnz; p++)
+        if (col[p] < 0 || col[p] >= n) QB_FAIL(QB_E_ARG, "column index out of range");
+    QbOpH* h = new QbOpH();
+    h->dev.fmt = QB_FMT_KRON; h->dev.nrows = (int)(n * n); h->dev.ncols = (int)(n * n);
+    h->dev.nnz = nnz * n;                 // non-zeros of the equivalent superoperator
+    h->dev.kn = (int)n; h->dev.kside = side;
+    std::vector<qb_c128> vv(v, v + nnz);
+    std::vector<int> cc(col, col + nnz), rp(rowptr, rowptr + n + 1);
+    int rc;
+    if (!(rc = to_device(h, vv, &h->dev.val)) && !(rc = to_device(h, cc, &h->dev.col)))
+        rc = to_device(h, rp, &h->dev.rowptr);
+    if (!rc && side == 0 && n % 32 == 0 && nnz > 0) {
+        SellHost sh;
+        build_sell(n, n, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o) {
+            for (int p = rowptr[r]; p < rowptr[r + 1]; p++) o.push_back({col[p], v[p]});
+        }, sh);
+        if ((double)sh.val.size() <= 2.0 * (double)nnz) {
+            if (!(rc = to_device(h, sh.slice_ptr, &h->dev.slice_ptr)) &&
+                !(rc = to_device(h, sh.val, &h->dev.kval)))
+                rc = to_device(h, sh.col, &h->dev.kcol);
+        }
+    }
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return QB_OK;
+}
+
 extern "C" int qb_dia_upload(const void* data, const int32_t* offsets, int64_t ndiag,
                              int64_t rows, int64_t cols, int format, qb_handle* out) {
     if (rows < 0 || cols < 0 || ndiag < 0 || !out || (ndiag > 0 && (!data || !offsets)))
@@ -484,6 +518,8 @@ extern "C" int qb_matmul(qb_handle op, qb_handle xh, double sre, double sim, qb_
     if (A.nrows == 0 || x->cols == 0) return QB_OK;
     const long long xs_r = x->fortran || x->cols == 1 ? 1 : x->cols, xs_c = x->fortran || x->cols == 1 ? x->rows : 1;
     const long long os_r = o->fortran || o->cols == 1 ? 1 : o->cols, os_c = o->fortran || o->cols == 1 ? o->rows : 1;
+    if (A.fmt == QB_FMT_KRON && xs_r != 1)
+        QB_FAIL(QB_E_ARG, "Kronecker operators need a column-major (or single-column) right operand");
     dim3 grid((unsigned)((A.nrows + 255) / 256), (unsigned)std::min<int64_t>(x->cols, 65535));
     qb_matmul_kernel<<<grid, 256>>>(A, x->d, xs_r, xs_c, o->d, os_r, os_c, (int)x->cols, make_double2(sre, sim));
     QB_LAUNCH_CHECK();

@@ -30,7 +30,7 @@ struct QbTableau {
 };
 
 // ---- operator storage on the device ----
-enum { QB_FMT_CSR = 0, QB_FMT_DIAM = 1, QB_FMT_DENSE = 2, QB_FMT_SELL = 3 };
+enum { QB_FMT_CSR = 0, QB_FMT_DIAM = 1, QB_FMT_DENSE = 2, QB_FMT_SELL = 3, QB_FMT_KRON = 4 };
 
 struct QbOpDev {
     int fmt, nrows, ncols, pad_;
@@ -50,6 +50,13 @@ struct QbOpDev {
     // slot k of slice s holds val/col[(slice_ptr[s] + k) * 32 + lane]; padding has val = 0
     // DENSE: column-major A[nrows x ncols]
     const qb_c128* dense;
+    // KRON (matrix-free superoperator of an n x n operator A acting on the column-stacked
+    // n x n state, core/cy/lindblad_matrix_form.pyx:105-203): kside 0 = I (x) A  (rho -> A rho),
+    // kside 1 = conj(A) (x) I  (rho -> rho A^dagger).  A is kept as CSR in val/col/rowptr and,
+    // when n is a multiple of 32, also as SELL in kval/kcol/slice_ptr for the left product.
+    int kn, kside;
+    const qb_c128* kval;
+    const int* kcol;
 };
 
 // ---- coefficient byte-code (qb_coeff.h) ----

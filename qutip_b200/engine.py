@@ -12,7 +12,8 @@ from ._lib import QbOptions, as_c128, check, ptr
 from .coeffs import Program
 
 FMT_AUTO, FMT_CSR, FMT_DIAM, FMT_SELL = 0, 1, 2, 3
-FMT_NAMES = {0: "csr", 1: "diam", 2: "dense", 3: "sell"}
+FMT_KRON = 4      # reported by DeviceOp.info() for matrix-free Kronecker operators
+FMT_NAMES = {0: "csr", 1: "diam", 2: "dense", 3: "sell", 4: "kron"}
 TABLEAUX = {"vern7": 0, "vern9": 1, "tsit5": 2}
 
 STATUS_MESSAGES = {
@@ -136,6 +137,25 @@ class DeviceOp(_Handle):
         return cls(h, shape)
 
     @classmethod
+    def kron(cls, m, side):
+        """Matrix-free superoperator of the n x n operator ``m`` on a column-stacked n x n
+        state: ``side=0`` is ``I (x) m`` (rho -> m rho), ``side=1`` is ``conj(m) (x) I``
+        (rho -> rho m^dagger).  Nothing of size n^2 x n^2 is built."""
+        import scipy.sparse as sp
+        m = sp.csr_matrix(m)
+        m.sort_indices()
+        n = m.shape[0]
+        if m.shape[0] != m.shape[1]:
+            raise ValueError("Kronecker operator needs a square matrix")
+        data = as_c128(m.data)
+        col = np.ascontiguousarray(m.indices, dtype=np.int32)
+        rowptr = np.ascontiguousarray(m.indptr, dtype=np.int32)
+        h = C.c_void_p()
+        check(_lib.load().qb_kron_upload(ptr(data), ptr(col), ptr(rowptr), n, int(rowptr[-1]),
+                                         int(side), C.byref(h)))
+        return cls(h, (n * n, n * n))
+
+    @classmethod
     def from_scipy(cls, m, fmt=FMT_AUTO):
         import scipy.sparse as sp
         if isinstance(m, (sp.dia_matrix, sp.dia_array)):
@@ -148,7 +168,7 @@ class DeviceOp(_Handle):
         nnz, nbytes = C.c_int64(), C.c_int64()
         check(_lib.load().qb_op_info(self.handle, C.byref(fmt), C.byref(rows), C.byref(cols),
                                      C.byref(nnz), C.byref(nbytes)))
-        return dict(format=FMT_NAMES[fmt.value], rows=rows.value, cols=cols.value,
+        return dict(format=FMT_NAMES[fmt.value], fmt=fmt.value, rows=rows.value, cols=cols.value,
                     nnz=nnz.value, device_bytes=nbytes.value)
 
 
@@ -237,11 +257,13 @@ class System(_Handle):
         self.nelem = self.ncops = self.neops = 0
         self.functional = False
         self._keep = []     # operators must outlive the system
+        self.element_ops = []
 
     def add_element(self, op, prog=None):
         p, n = _prog_args(prog)
         check(_lib.load().qb_system_add_element(self.handle, op.handle, p, n))
         self._keep.append(op)
+        self.element_ops.append(op)
         self.nelem += 1
 
     def add_collapse(self, c_op, n_op, cprog=None, nprog=None):

@@ -211,6 +211,70 @@ def _device_qevo(qevo):
     return QobjEvo(sup)
 
 
+# n (operator dimension) from which LindbladMatrixForm is bound matrix-free instead of as
+# the fused n^2 x n^2 superoperator; QUTIP_B200_MATRIX_FREE=0/1 forces either
+MATRIX_FREE_MIN_DIM = 256
+
+
+def matrix_free_system(lmf, ncols=1):
+    """Device system for a LindbladMatrixForm without materialising any n^2 x n^2 Hamiltonian
+    part (core/cy/lindblad_matrix_form.pyx:105-203): for every term ``f(t) A`` of ``H_nh`` the
+    matrix-free Kronecker operators ``-i f (I (x) A)`` and ``+i conj(f) (conj(A) (x) I)``
+    (rho -> A rho, rho -> rho A^dagger), plus the jump part ``sum |g|^2 conj(C) (x) C`` as an
+    explicit sparse superoperator (nnz = sum nnz(C)^2, small for local collapse operators).
+    Raises TypeError when a collapse operator has several terms or a python coefficient."""
+    if ncols != 1:
+        raise TypeError("matrix-valued states are not combined with matrix_form")
+    n = lmf.shape[0]
+    system = E.System(n * n)
+    system.coeff_objects, system.programs = [], []
+
+    def add(op, prog):
+        system.add_element(op, prog)
+        system.coeff_objects.append(None)
+        system.programs.append(prog)
+
+    for h, prog in bind_qobjevo(lmf.H_nh, system, allow_host=False):
+        h = sp.csr_matrix(h)
+        if prog is None:
+            pl, pr = coeffs.constant(-1j), coeffs.constant(1j)
+        else:
+            pl, pr = prog.scaled(-1j), prog.conj().scaled(1j)
+        add(E.DeviceOp.kron(h, 0), pl)
+        add(E.DeviceOp.kron(h, 1), pr)
+    jump_const = None
+    for c in lmf.c_ops:
+        ch, cp = _single_element(c, "a collapse operator (matrix_form)")
+        ch = sp.csr_matrix(ch)
+        S = sp.kron(ch.conj(), ch, format="csr")
+        if cp is None:
+            jump_const = S if jump_const is None else jump_const + S
+        else:
+            add(E.DeviceOp.from_scipy(S), cp.norm())
+    if jump_const is not None:
+        jump_const = sp.csr_matrix(jump_const)
+        jump_const.sum_duplicates()
+        jump_const.sort_indices()
+        add(E.DeviceOp.from_scipy(jump_const), None)
+    system.has_host = False
+    return system
+
+
+def _bind_system(qevo, ncols):
+    """(device system, base dimension) for the integrators."""
+    if type(qevo).__name__ == "LindbladMatrixForm" and ncols == 1:
+        import os
+        force = os.environ.get("QUTIP_B200_MATRIX_FREE")
+        want = (qevo.shape[0] >= MATRIX_FREE_MIN_DIM) if force is None else force == "1"
+        if want:
+            try:
+                return matrix_free_system(qevo), qevo.shape[0] ** 2
+            except TypeError:
+                pass            # python coefficients / multi-term c_ops: fused superoperator
+    dev_qevo = _device_qevo(qevo)
+    return system_from_qobjevo(dev_qevo, allow_host=True, ncols=ncols), dev_qevo.shape[0]
+
+
 def _state_columns(arr_shape, base_n):
     """1 when the state is the (possibly n x n, to be stacked) vector the system acts on;
     k for an N x k matrix-valued state evolved column by column."""
@@ -255,9 +319,7 @@ class _B200Integrator(Integrator):
 
     def _build(self):
         o = self._options
-        dev_qevo = _device_qevo(self._qevo)
-        self._base_n = dev_qevo.shape[0]
-        self._system = system_from_qobjevo(dev_qevo, allow_host=True, ncols=self._ncols)
+        self._system, self._base_n = _bind_system(self._qevo, self._ncols)
         self._engine = E.Engine(
             self._system, self._tableau, nslots=1, atol=o['atol'], rtol=o['rtol'],
             nsteps=int(o['nsteps']), first_step=float(o['first_step'] or 0),
@@ -393,9 +455,7 @@ class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
     _ncols = 1
 
     def _bind(self):
-        dev_qevo = _device_qevo(self._qevo)
-        self._base_n = dev_qevo.shape[0]
-        self._system = system_from_qobjevo(dev_qevo, allow_host=True, ncols=self._ncols)
+        self._system, self._base_n = _bind_system(self._qevo, self._ncols)
         self._engine = E.Engine(self._system, "vern7", nslots=1)
         n = self._system.N
         self._dx = E.DeviceDense.zeros(n, 1)

@@ -81,6 +81,54 @@ def build_system(elements, c_ops=(), n_ops=None, e_ops=(), functional=False, nar
     return s
 
 
+def lindblad_matrix_free(H_terms, c_ops):
+    """Elements of the Lindblad right-hand side in matrix form (LindbladMatrixForm,
+    core/cy/lindblad_matrix_form.pyx:105-203) for ``build_system`` / ``mesolve``: nothing of
+    the size of the Liouvillian's Hamiltonian part is built.  ``H_terms``: operators or
+    (operator, Program) pairs summing to H; ``c_ops``: operators or (operator, Program).
+    Returns [(DeviceOp, Program|None)]: per term of ``H_nh = H - i/2 sum c^dag c`` the
+    matrix-free products ``-i f A rho`` and ``+i conj(f) rho A^dagger``, and the jump part
+    ``sum |g|^2 conj(C) (x) C`` as an explicit (small) sparse superoperator."""
+    from . import coeffs
+    const = None
+    td = []
+    for t in H_terms:
+        op, prog = t if isinstance(t, (tuple, list)) else (t, None)
+        op = sp.csr_matrix(op, dtype=complex)
+        if prog is None:
+            const = op if const is None else const + op
+        else:
+            td.append((op, prog))
+    jump_const, jumps = None, []
+    for c in c_ops:
+        op, prog = c if isinstance(c, (tuple, list)) else (c, None)
+        op = sp.csr_matrix(op, dtype=complex)
+        cdc = sp.csr_matrix(op.conj().T @ op)
+        S = sp.kron(op.conj(), op, format="csr")
+        if prog is None:
+            const = -0.5j * cdc if const is None else const - 0.5j * cdc
+            jump_const = S if jump_const is None else jump_const + S
+        else:
+            td.append((-0.5j * cdc, prog.norm()))
+            jumps.append((S, prog.norm()))
+    out = []
+    for op, prog in td:
+        out.append((E.DeviceOp.kron(op, 0), prog.scaled(-1j)))
+        out.append((E.DeviceOp.kron(op, 1), prog.conj().scaled(1j)))
+    out += [(E.DeviceOp.from_scipy(S), pg) for S, pg in jumps]
+    if const is not None:
+        const = sp.csr_matrix(const)
+        const.sum_duplicates()
+        out.append((E.DeviceOp.kron(const, 0), coeffs.constant(-1j)))
+        out.append((E.DeviceOp.kron(const, 1), coeffs.constant(1j)))
+    if jump_const is not None:
+        jump_const = sp.csr_matrix(jump_const)
+        jump_const.sum_duplicates()
+        jump_const.sort_indices()
+        out.append((E.DeviceOp.from_scipy(jump_const), None))
+    return out
+
+
 class McResult(dict):
     __getattr__ = dict.__getitem__
 

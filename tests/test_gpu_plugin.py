@@ -348,6 +348,39 @@ def test_matrix_form_option(method):
     np.testing.assert_allclose(out.states[-1].full(), ref.states[-1].full(), **tol)
 
 
+def test_matrix_form_binds_matrix_free(monkeypatch):
+    """options['matrix_form']=True with the matrix-free binding forced (Kronecker operators
+    I (x) H_nh, conj(H_nh) (x) I and the sparse jump part instead of a fused superoperator),
+    against the reference's own matrix-form run; time-dependent H term and collapse rate."""
+    from qutip_b200 import engine as E
+    monkeypatch.setenv("QUTIP_B200_MATRIX_FREE", "1")
+    n = 4
+    H, c_ops, sz = tfim(n, 0.09)
+    psi0 = basis([2] * n, [0] * n)
+    ops = [qeye(2)] * n
+    ops[0] = sigmax()
+    Ht = [H, [tensor(ops), "0.4 * sin(2 * t)"]]
+    c_all = list(c_ops) + [[sz[1], "0.2 * exp(-t)"]]
+    e_ops = [sz[0], sz[n - 1]]
+    tl = np.linspace(0, 2, 9)
+    opt = dict(OPT, atol=1e-8, rtol=1e-6, store_states=True, matrix_form=True)
+    ref = mesolve(Ht, psi0, tl, c_all, e_ops=e_ops, options=dict(opt, method="vern7"))
+    out = mesolve(Ht, psi0, tl, c_all, e_ops=e_ops, options=dict(opt, method="b200_vern7"))
+    np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out.states[-1].full(), ref.states[-1].full(), rtol=RTOL, atol=ATOL)
+    solver = qutip.MESolver(QobjEvo(Ht), [QobjEvo(c) if isinstance(c, list) else c for c in c_all],
+                            options=dict(opt, method="b200_vern7"))
+    solver.start(qutip.ket2dm(psi0), 0.0)
+    fmts = [el.info()["fmt"] for el in solver._integrator._system.element_ops]
+    # (left, right) x (drive term, |g|^2 c^dag c term of the time-dependent collapse, constant H_nh)
+    assert fmts.count(E.FMT_KRON) == 6, fmts
+    # python-callable coefficients fall back to the fused superoperator binding
+    Hf = [H, [tensor(ops), lambda t: 0.4 * np.sin(2 * t)]]
+    ref = mesolve(Hf, psi0, tl, c_ops, e_ops=e_ops, options=dict(opt, method="vern7"))
+    out = mesolve(Hf, psi0, tl, c_ops, e_ops=e_ops, options=dict(opt, method="b200_vern7"))
+    np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), rtol=RTOL, atol=ATOL)
+
+
 def test_propagator_and_nm_mcsolve_reuse_the_device_integrator():
     """Callers that reuse the same integrators: propagator() drives
     MESolver with a matrix-valued state; NonMarkovianMCSolver subclasses MCIntegrator."""

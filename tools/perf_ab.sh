@@ -8,6 +8,6 @@ for pass in 1 2; do
 for lib in $libs; do
   echo "== $lib"
   [ -z "$QB_AB_NOC3" ] && QB_REPS=${QB_REPS:-4} QUTIP_B200_LIB=$PWD/$lib python tools/prof_run.py c3 ${QB_AB_NTRAJ:-1024} 2>&1 | tail -1
-  [ -n "$QB_AB_C2" ] && QB_REPS=${QB_REPS:-4} QUTIP_B200_LIB=$PWD/$lib python tools/prof_run.py c2 2>&1 | tail -2
+  [ -n "$QB_AB_C2" ] && QB_REPS=${QB_REPS:-4} QUTIP_B200_LIB=$PWD/$lib python tools/prof_run.py ${QB_AB_C2} 2>&1 | tail -2
 done
 done

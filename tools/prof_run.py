@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small driver for ncu captures (never a source of bench numbers).
     python tools/prof_run.py c3 [ntraj]   one mcsolve batch of config C3
-    python tools/prof_run.py c2           C2 SpMV x5 + one short mesolve
+    python tools/prof_run.py c2|c2mf      C2 SpMV + one short mesolve (c2mf: matrix-free RHS)
 """
 import os
 import sys
@@ -33,11 +33,16 @@ else:
     L = models.liouvillian(H, c_ops)
     N = L.shape[0]
     system = qb.System(N)
-    system.add_element(qb.DeviceOp.from_scipy(L))
+    if what == "c2mf":                      # matrix-free Lindblad right-hand side
+        for op_k, prog_k in solve.lindblad_matrix_free([H], c_ops):
+            system.add_element(op_k, prog_k)
+    else:
+        system.add_element(qb.DeviceOp.from_scipy(L))
     eng = qb.Engine(system, "vern7", nslots=1)
     x = qb.DeviceDense.from_numpy(np.random.default_rng(0).random(N) + 0j)
     out = qb.DeviceDense.zeros(N, 1)
-    print("spmv ms", eng.rhs_bench(0.0, x, out, iters=5) / 5)
+    eng.rhs_bench(0.0, x, out, iters=3)
+    print("spmv ms", eng.rhs_bench(0.0, x, out, iters=20) / 20)
     rho0 = np.zeros(N, dtype=complex); rho0[0] = 1
     reps = int(os.environ.get("QB_REPS", "1"))
     ms = []
