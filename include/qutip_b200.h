@@ -61,6 +61,12 @@ int qb_dia_upload(const void* data, const int32_t* offsets, int64_t ndiag,
  * an operator of shape (n^2, n^2) usable wherever a CSR/Dia upload is. */
 int qb_kron_upload(const void* data, const int32_t* col, const int32_t* rowptr, int64_t n,
                    int64_t nnz, int side, qb_handle* out);
+/* Matrix-free jump part of the Lindblad equation, rho -> sum_c C_c rho C_c^dagger
+ * (= sum_c conj(C_c) (x) C_c on the column-stacked state; lindblad_matrix_form.pyx:177-181,
+ * 195-199: c_op.matmul_data then c_op.adjoint_rmatmul_data): the nstack n x n operators are
+ * passed stacked row-wise as ONE CSR matrix of shape (nstack*n, n). */
+int qb_sandwich_upload(const void* data, const int32_t* col, const int32_t* rowptr,
+                       int64_t n, int64_t nstack, int64_t nnz, qb_handle* out);
 int qb_op_info(qb_handle h, int* fmt, int64_t* rows, int64_t* cols, int64_t* nnz,
                int64_t* device_bytes);
 int qb_free(qb_handle h);

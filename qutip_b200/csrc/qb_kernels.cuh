@@ -102,6 +102,7 @@ __device__ __forceinline__ void qb_rowdot_diam(const QbOpDev& A, int sl, int lan
 // Matrix-free Kronecker operators on the column-stacked n x n state (row r = i + j n):
 //   kside 0:  z[i,j] = sum_k A[i,k] x[k,j]            (I (x) A,        rho -> A rho)
 //   kside 1:  z[i,j] = sum_k conj(A[j,k]) x[i,k]      (conj(A) (x) I,  rho -> rho A^dagger)
+//   kside 2:  z[i,j] = sum_c (C_c x C_c^dagger)[i,j]  (sum conj(C_c) (x) C_c, the jump part)
 // The right product reads row j of A, which is the same for all lanes of a warp when n is a
 // multiple of 32 (uniform loads) and gathers x[i + k n] -- consecutive lanes, coalesced.
 __device__ __forceinline__ double2 qb_rowdot_kron(const QbOpDev& A, int sl, int lane, long long r,
@@ -136,6 +137,27 @@ __device__ __forceinline__ double2 qb_rowdot_kron(const QbOpDev& A, int sl, int 
             const double2* __restrict__ xc = x + (long long)j * n;
             const int p1 = A.rowptr[i + 1];
             for (int p = A.rowptr[i]; p < p1; p++) qb_fma(acc, val[p], xc[A.col[p]]);
+        }
+    } else if (A.kside == 2) {
+        // sandwich  z[i,j] = sum_c sum_{k,l} C_c[i,k] conj(C_c[j,l]) x[k,l]  (rho -> sum C rho C^dagger);
+        // the C_c are stacked row-wise in one CSR: row c*n + i
+        if (active) {
+            const int j = (int)(r / n), i = (int)(r - (long long)j * n);
+            const int nstack = A.kstack;
+            for (int c = 0; c < nstack; c++) {
+                const int* __restrict__ rp = A.rowptr + (long long)c * n;
+                const int pi0 = __ldg(rp + i), pi1 = __ldg(rp + i + 1);
+                const int pj0 = __ldg(rp + j), pj1 = __ldg(rp + j + 1);
+                if (pi0 == pi1) continue;
+                for (int q = pj0; q < pj1; q++) {
+                    double2 b = __ldg(val + q);
+                    b.y = -b.y;
+                    const double2* __restrict__ xl = x + (long long)__ldg(A.col + q) * n;
+                    double2 t = make_double2(0.0, 0.0);
+                    for (int p = pi0; p < pi1; p++) qb_fma(t, __ldg(val + p), xl[__ldg(A.col + p)]);
+                    qb_fma(acc, b, t);
+                }
+            }
         }
     } else if (active) {
         const int j = (int)(r / n), i = (int)(r - (long long)j * n);

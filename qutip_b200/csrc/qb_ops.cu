@@ -215,6 +215,34 @@ extern "C" int qb_kron_upload(const void* data, const int32_t* col, const int32_
     return QB_OK;
 }
 
+extern "C" int qb_sandwich_upload(const void* data, const int32_t* col, const int32_t* rowptr,
+                                  int64_t n, int64_t nstack, int64_t nnz, qb_handle* out) {
+    if (!rowptr || n <= 0 || nstack <= 0 || nnz < 0 || !out || (nnz > 0 && (!data || !col)))
+        QB_FAIL(QB_E_ARG, "bad sandwich operator arguments");
+    if (n > 46340 || n * nstack > 0x7fffffff) QB_FAIL(QB_E_ARG, "sandwich operator too large for int32 indices");
+    if (rowptr[n * nstack] != nnz) QB_FAIL(QB_E_ARG, "row_index[n*nstack] != nnz");
+    const qb_c128* v = static_cast<const qb_c128*>(data);
+    for (int64_t p = 0; p < nnz; p++)
+        if (col[p] < 0 || col[p] >= n) QB_FAIL(QB_E_ARG, "column index out of range");
+    QbOpH* h = new QbOpH();
+    h->dev.fmt = QB_FMT_KRON; h->dev.nrows = (int)(n * n); h->dev.ncols = (int)(n * n);
+    h->dev.kn = (int)n; h->dev.kside = 2; h->dev.kstack = (int)nstack;
+    long long sq = 0;                     // non-zeros of the equivalent superoperator
+    for (int64_t c = 0; c < nstack; c++) {
+        const long long m = rowptr[(c + 1) * n] - rowptr[c * n];
+        sq += m * m;
+    }
+    h->dev.nnz = sq;
+    std::vector<qb_c128> vv(v, v + nnz);
+    std::vector<int> cc(col, col + nnz), rp(rowptr, rowptr + n * nstack + 1);
+    int rc;
+    if (!(rc = to_device(h, vv, &h->dev.val)) && !(rc = to_device(h, cc, &h->dev.col)))
+        rc = to_device(h, rp, &h->dev.rowptr);
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return QB_OK;
+}
+
 extern "C" int qb_dia_upload(const void* data, const int32_t* offsets, int64_t ndiag,
                              int64_t rows, int64_t cols, int format, qb_handle* out) {
     if (rows < 0 || cols < 0 || ndiag < 0 || !out || (ndiag > 0 && (!data || !offsets)))

@@ -54,7 +54,8 @@ struct QbOpDev {
     // n x n state, core/cy/lindblad_matrix_form.pyx:105-203): kside 0 = I (x) A  (rho -> A rho),
     // kside 1 = conj(A) (x) I  (rho -> rho A^dagger).  A is kept as CSR in val/col/rowptr and,
     // when n is a multiple of 32, also as SELL in kval/kcol/slice_ptr for the left product.
-    int kn, kside;
+    int kn, kside;            // kside 2: sandwich sum_c C_c rho C_c^dagger, C_c stacked row-wise
+    int kstack, kpad_;
     const qb_c128* kval;
     const int* kcol;
 };

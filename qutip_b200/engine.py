@@ -156,6 +156,25 @@ class DeviceOp(_Handle):
         return cls(h, (n * n, n * n))
 
     @classmethod
+    def sandwich(cls, ops):
+        """Matrix-free ``rho -> sum_c C_c rho C_c^dagger`` on a column-stacked n x n state for
+        the list of n x n operators ``ops`` (the jump part of the Lindblad equation)."""
+        import scipy.sparse as sp
+        ops = [sp.csr_matrix(c) for c in ops]
+        n = ops[0].shape[0]
+        if any(c.shape != (n, n) for c in ops):
+            raise ValueError("sandwich operators must all be n x n")
+        m = sp.vstack(ops, format="csr")
+        m.sort_indices()
+        data = as_c128(m.data)
+        col = np.ascontiguousarray(m.indices, dtype=np.int32)
+        rowptr = np.ascontiguousarray(m.indptr, dtype=np.int32)
+        h = C.c_void_p()
+        check(_lib.load().qb_sandwich_upload(ptr(data), ptr(col), ptr(rowptr), n, len(ops),
+                                             int(rowptr[-1]), C.byref(h)))
+        return cls(h, (n * n, n * n))
+
+    @classmethod
     def from_scipy(cls, m, fmt=FMT_AUTO):
         import scipy.sparse as sp
         if isinstance(m, (sp.dia_matrix, sp.dia_array)):

@@ -220,8 +220,9 @@ def matrix_free_system(lmf, ncols=1):
     """Device system for a LindbladMatrixForm without materialising any n^2 x n^2 Hamiltonian
     part (core/cy/lindblad_matrix_form.pyx:105-203): for every term ``f(t) A`` of ``H_nh`` the
     matrix-free Kronecker operators ``-i f (I (x) A)`` and ``+i conj(f) (conj(A) (x) I)``
-    (rho -> A rho, rho -> rho A^dagger), plus the jump part ``sum |g|^2 conj(C) (x) C`` as an
-    explicit sparse superoperator (nnz = sum nnz(C)^2, small for local collapse operators).
+    (rho -> A rho, rho -> rho A^dagger), plus the jump part ``sum |g|^2 C rho C^dagger`` -- an
+    explicit sparse superoperator ``sum conj(C) (x) C`` while nnz = sum nnz(C)^2 is small, the
+    matrix-free sandwich operator beyond (solve._jump_operator).
     Raises TypeError when a collapse operator has several terms or a python coefficient."""
     if ncols != 1:
         raise TypeError("matrix-valued states are not combined with matrix_form")
@@ -242,20 +243,17 @@ def matrix_free_system(lmf, ncols=1):
             pl, pr = prog.scaled(-1j), prog.conj().scaled(1j)
         add(E.DeviceOp.kron(h, 0), pl)
         add(E.DeviceOp.kron(h, 1), pr)
-    jump_const = None
+    from .solve import _jump_operator
+    jump_const = []
     for c in lmf.c_ops:
         ch, cp = _single_element(c, "a collapse operator (matrix_form)")
         ch = sp.csr_matrix(ch)
-        S = sp.kron(ch.conj(), ch, format="csr")
         if cp is None:
-            jump_const = S if jump_const is None else jump_const + S
+            jump_const.append(ch)
         else:
-            add(E.DeviceOp.from_scipy(S), cp.norm())
-    if jump_const is not None:
-        jump_const = sp.csr_matrix(jump_const)
-        jump_const.sum_duplicates()
-        jump_const.sort_indices()
-        add(E.DeviceOp.from_scipy(jump_const), None)
+            add(_jump_operator([ch], "auto"), cp.norm())
+    if jump_const:
+        add(_jump_operator(jump_const, "auto"), None)
     system.has_host = False
     return system
 

@@ -81,14 +81,36 @@ def build_system(elements, c_ops=(), n_ops=None, e_ops=(), functional=False, nar
     return s
 
 
-def lindblad_matrix_free(H_terms, c_ops):
+# jump part sum conj(C) (x) C: built as an explicit sparse superoperator up to this many
+# non-zeros (sum nnz(C)^2), matrix-free ("sandwich") beyond
+JUMP_EXPLICIT_MAX_NNZ = 1 << 22
+
+
+def _jump_operator(ops, jump):
+    nnz2 = sum(int(sp.csr_matrix(c).nnz) ** 2 for c in ops)
+    if jump == "explicit" or (jump == "auto" and nnz2 <= JUMP_EXPLICIT_MAX_NNZ):
+        S = None
+        for c in ops:
+            c = sp.csr_matrix(c, dtype=complex)
+            K = sp.kron(c.conj(), c, format="csr")
+            S = K if S is None else S + K
+        S = sp.csr_matrix(S)
+        S.sum_duplicates()
+        S.sort_indices()
+        return E.DeviceOp.from_scipy(S)
+    return E.DeviceOp.sandwich(ops)
+
+
+def lindblad_matrix_free(H_terms, c_ops, jump="auto"):
     """Elements of the Lindblad right-hand side in matrix form (LindbladMatrixForm,
     core/cy/lindblad_matrix_form.pyx:105-203) for ``build_system`` / ``mesolve``: nothing of
     the size of the Liouvillian's Hamiltonian part is built.  ``H_terms``: operators or
     (operator, Program) pairs summing to H; ``c_ops``: operators or (operator, Program).
     Returns [(DeviceOp, Program|None)]: per term of ``H_nh = H - i/2 sum c^dag c`` the
     matrix-free products ``-i f A rho`` and ``+i conj(f) rho A^dagger``, and the jump part
-    ``sum |g|^2 conj(C) (x) C`` as an explicit (small) sparse superoperator."""
+    ``sum |g|^2 C rho C^dagger`` -- ``jump="explicit"``: the sparse superoperator
+    ``sum conj(C) (x) C`` (nnz = sum nnz(C)^2), ``"sandwich"``: matrix-free, ``"auto"``:
+    explicit while it stays small (JUMP_EXPLICIT_MAX_NNZ)."""
     from . import coeffs
     const = None
     td = []
@@ -99,33 +121,29 @@ def lindblad_matrix_free(H_terms, c_ops):
             const = op if const is None else const + op
         else:
             td.append((op, prog))
-    jump_const, jumps = None, []
+    jump_const, jumps = [], []
     for c in c_ops:
         op, prog = c if isinstance(c, (tuple, list)) else (c, None)
         op = sp.csr_matrix(op, dtype=complex)
         cdc = sp.csr_matrix(op.conj().T @ op)
-        S = sp.kron(op.conj(), op, format="csr")
         if prog is None:
             const = -0.5j * cdc if const is None else const - 0.5j * cdc
-            jump_const = S if jump_const is None else jump_const + S
+            jump_const.append(op)
         else:
             td.append((-0.5j * cdc, prog.norm()))
-            jumps.append((S, prog.norm()))
+            jumps.append((op, prog.norm()))
     out = []
     for op, prog in td:
         out.append((E.DeviceOp.kron(op, 0), prog.scaled(-1j)))
         out.append((E.DeviceOp.kron(op, 1), prog.conj().scaled(1j)))
-    out += [(E.DeviceOp.from_scipy(S), pg) for S, pg in jumps]
+    out += [(_jump_operator([op], jump), pg) for op, pg in jumps]
     if const is not None:
         const = sp.csr_matrix(const)
         const.sum_duplicates()
         out.append((E.DeviceOp.kron(const, 0), coeffs.constant(-1j)))
         out.append((E.DeviceOp.kron(const, 1), coeffs.constant(1j)))
-    if jump_const is not None:
-        jump_const = sp.csr_matrix(jump_const)
-        jump_const.sum_duplicates()
-        jump_const.sort_indices()
-        out.append((E.DeviceOp.from_scipy(jump_const), None))
+    if jump_const:
+        out.append((_jump_operator(jump_const, jump), None))
     return out
 
 

@@ -42,6 +42,21 @@ def test_kron_matmul_vs_scipy(n, side):
     np.testing.assert_allclose((K @ x).reshape(n, n, order="F"), mat, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("n", [6, 32, 40])
+def test_sandwich_matmul_vs_scipy(n):
+    ops = [_random_op(n, 0.15, 7 * n + k) for k in range(3)]
+    ops.append(sp.csr_matrix((n, n), dtype=complex))          # an empty operator in the stack
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n * n) + 1j * rng.standard_normal(n * n)
+    op = qb.DeviceOp.sandwich(ops)
+    out = qb.DeviceDense.from_numpy(np.zeros(n * n, dtype=complex))
+    E.matmul(op, qb.DeviceDense.from_numpy(x), 1.0, out)
+    rho = x.reshape(n, n, order="F")
+    ref = sum(c.toarray() @ rho @ c.toarray().conj().T for c in ops)
+    np.testing.assert_allclose(out.to_numpy().reshape(n, n, order="F"), ref, rtol=1e-12, atol=1e-12)
+    assert op.info()["nnz"] == sum(c.nnz ** 2 for c in ops)
+
+
 def test_kron_rejects_bad_input():
     with pytest.raises(ValueError):
         qb.DeviceOp.kron(sp.csr_matrix((3, 4), dtype=complex), 0)
@@ -53,8 +68,9 @@ def test_kron_rejects_bad_input():
         E.matmul(op, x, 1.0, out)
 
 
+@pytest.mark.parametrize("jump", ["explicit", "sandwich"])
 @pytest.mark.parametrize("nspins", [3, 5, 6])
-def test_mesolve_matrix_free_vs_superoperator_tfim(nspins):
+def test_mesolve_matrix_free_vs_superoperator_tfim(nspins, jump):
     """n = 8 (per-lane CSR products), n = 32 / 64 (SELL left product, warp-uniform right)."""
     H, c_ops, sz = models.tfim(nspins)
     n = H.shape[0]
@@ -63,14 +79,16 @@ def test_mesolve_matrix_free_vs_superoperator_tfim(nspins):
     y0 = rho0.reshape(-1, order="F")
     tl = np.linspace(0, 1.5, 7)
     ref = solve.mesolve([models.liouvillian(H, c_ops)], y0, tl, e_ops=[sz[0], sz[-1]])
-    out = solve.mesolve(solve.lindblad_matrix_free([H], c_ops), y0, tl, e_ops=[sz[0], sz[-1]])
+    out = solve.mesolve(solve.lindblad_matrix_free([H], c_ops, jump=jump), y0, tl,
+                        e_ops=[sz[0], sz[-1]])
     np.testing.assert_allclose(out.expect, ref.expect, rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(out.states, ref.states, rtol=RTOL, atol=ATOL)
     # same controller decisions: the two right-hand sides differ at round-off only
     assert list(out.stats[0]) == list(ref.stats[0])
 
 
-def test_mesolve_matrix_free_time_dependent():
+@pytest.mark.parametrize("jump", ["explicit", "sandwich"])
+def test_mesolve_matrix_free_time_dependent(jump):
     """C4-like driven cavity x transmon (n = 30, not a multiple of 32) with a cos drive and a
     time-dependent collapse rate."""
     H0, H1, c_ops, a, b = models.driven_cavity_transmon(10)
@@ -90,7 +108,7 @@ def test_mesolve_matrix_free_time_dependent():
     e_ops = [sp.csr_matrix(a.conj().T @ a), sp.csr_matrix(b.conj().T @ b)]
     ref = solve.mesolve([(sp.csr_matrix(L1), drive), (sp.csr_matrix(Lc), rate.norm()), L0],
                         y0, tl, e_ops=e_ops)
-    els = solve.lindblad_matrix_free([(H1, drive), H0], [(c, rate)] + list(c_ops[1:]))
+    els = solve.lindblad_matrix_free([(H1, drive), H0], [(c, rate)] + list(c_ops[1:]), jump=jump)
     out = solve.mesolve(els, y0, tl, e_ops=e_ops)
     np.testing.assert_allclose(out.expect, ref.expect, rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(out.states, ref.states, rtol=RTOL, atol=ATOL)

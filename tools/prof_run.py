@@ -33,8 +33,8 @@ else:
     L = models.liouvillian(H, c_ops)
     N = L.shape[0]
     system = qb.System(N)
-    if what == "c2mf":                      # matrix-free Lindblad right-hand side
-        for op_k, prog_k in solve.lindblad_matrix_free([H], c_ops):
+    if what.startswith("c2mf"):             # matrix-free Lindblad right-hand side (c2mfs: sandwich jumps)
+        for op_k, prog_k in solve.lindblad_matrix_free([H], c_ops, jump="sandwich" if what == "c2mfs" else "explicit"):
             system.add_element(op_k, prog_k)
     else:
         system.add_element(qb.DeviceOp.from_scipy(L))
