@@ -133,6 +133,8 @@ typedef struct {
     int max_collapses;
     int no_jump;
     double jump_prob_floor;
+    int max_order;             /* adams: highest order (1..12; 0 = 12), scipy_integrator.py:27 */
+    int pad_;
 } qb_options;
 int qb_options_default(qb_options* opt);
 

@@ -31,7 +31,8 @@ class QbOptions(C.Structure):
                 ("norm_tol", C.c_double), ("norm_min_step", C.c_double),
                 ("mc_corr_eps", C.c_double), ("store_states", C.c_int),
                 ("max_collapses", C.c_int), ("no_jump", C.c_int),
-                ("jump_prob_floor", C.c_double)]
+                ("jump_prob_floor", C.c_double), ("max_order", C.c_int),
+                ("pad_", C.c_int)]
 
 
 # every symbol include/qutip_b200.h declares (tests check the library exports them all)

@@ -19,6 +19,7 @@
 #include <math.h>
 #include "qb_types.h"
 #include "qb_coeff.h"
+#include "qb_adams.h"
 
 struct QbProgRef { int off, len; };   // len == 0: constant coefficient 1
 
@@ -79,6 +80,9 @@ QB_HD int qb_eval_rhs_coefs(const QbCtl& g, QbTraj& c, double t, qb_c128* coef) 
     c.hc_valid = 0;
     return 0;
 }
+QB_HD int qb_ad_maxord(const QbCtl& g) {
+    return (g.opt.max_order >= 1 && g.opt.max_order < QB_AD_MAXORD) ? g.opt.max_order : QB_AD_MAXORD;
+}
 // common handling of the three outcomes at a pass-issuing label `label`
 #define QB_COEFS_OR_PAUSE(tval, label)                                              \
     {                                                                               \
@@ -103,7 +107,11 @@ enum {
     QL_STEP_ATTEMPT, QL_STAGE_ISSUE, QL_AFTER_LOOP, QL_DENSE_BEGIN, QL_DENSE_ISSUE,
     QL_INTERP_ISSUE, QL_INT_DONE, QL_ME_REACHED, QL_ME_NEXT, QL_MC_ENTRY, QL_MC_LOOP,
     QL_MC_TARGET, QL_RECORD, QL_EXPECT_ISSUE, QL_AFTER_RECORD, QL_RF_LOOP, QL_RF_END,
-    QL_COLLAPSE, QL_APPLY_ISSUE, QL_FINISH
+    QL_COLLAPSE, QL_APPLY_ISSUE, QL_FINISH,
+    // Adams (qb_adams.h)
+    QL_AD_SET, QL_AD_F0, QL_AD_INT, QL_AD_LOOP, QL_AD_STEP, QL_AD_PRED_ISSUE, QL_AD_CORR_ISSUE,
+    QL_AD_CONVFAIL, QL_AD_ERRTEST, QL_AD_UPD_ISSUE, QL_AD_O520, QL_AD_O540, QL_AD_O560,
+    QL_AD_RESCALE, QL_AD_3FAIL, QL_AD_STEP_DONE, QL_AD_AFTER, QL_AD_INTERP
 };
 
 // Run the controller until it has emitted a pass (returns 1), the trajectory finished or
@@ -155,6 +163,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
 
         // ================================================================ set_initial_value
         case QL_SET_BEGIN: {        // explicit_rk.pyx:204-230 ; y0 = set_scale * V[set_x]
+            if (T.method == 1) { L = QL_AD_SET; break; }
             set_t = c.set_t;
             c.t = c.t_prev = c.t_front = set_t;
             c.dt_int = 0.0;
@@ -249,6 +258,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
 
         // ================================================================ integrate(t, step)
         case QL_INT_BEGIN: {        // explicit_rk.pyx:278-310
+            if (T.method == 1) { L = QL_AD_INT; break; }
             double t = c.int_t;
             if (t == c.t) { L = QL_INT_DONE; break; }                       // :291
             if (t < c.t_prev) { c.status = QB_ST_OUTSIDE_RANGE; L = QL_FAIL; break; }   // :294
@@ -446,6 +456,294 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             default: L = QL_FINISH; break;
             }
             break;
+
+        // ================================================================ Adams-Moulton (qb_adams.h)
+        case QL_AD_SET: {           // set_state: YH0 = set_scale * V[set_x] (in-place safe: no gather)
+            c.t = c.t_prev = c.t_front = c.ad_tn = c.set_t;
+            c.dt_int = 0.0;
+            c.sY = QB_AD_YH(0);
+            qb_pass_clear(p);
+            p.kind = QB_PASS_COMBINE; p.dst1 = QB_AD_YH(0); p.red = QB_RED_NORM2_O1;
+            qb_pass_src(p, c.set_x, c.set_scale, 0.0);
+            c.pc = QB_PC_AD_SET0_DONE; return 1;
+        }
+        case QB_PC_AD_SET0_DONE:
+            c.norm2_y = c.norm2_front = red[0];
+            L = QL_AD_F0; break;
+        case QL_AD_F0: {            // YH1 = f(t0, y0), unscaled (ad_hyh = 1); its weighted norm
+            qb_pass_clear(p);
+            p.kind = QB_PASS_RHS; p.x = QB_AD_YH(0); p.zdst = QB_AD_YH(1); p.red = QB_RED_WRMS;
+            qb_pass_src(p, QB_AD_YH(0), 1.0, 0.0);
+            p.w2z = 1.0;
+            QB_COEFS_OR_PAUSE(c.ad_tn, QL_AD_F0)
+            c.n_rhs++;
+            c.pc = QB_PC_AD_F0_DONE; return 1;
+        }
+        case QB_PC_AD_F0_DONE:
+            c.ad_f0n2 = red[1] / (double)g.N;
+            c.ad_nq = 1; c.ad_ialth = 2; c.ad_rmax = 1e4; c.ad_crate = 0.7;
+            c.ad_kflag = 0; c.ad_ncf = 0;
+            c.ad_hyh = 1.0; c.ad_hu = 0.0;
+            c.ad_h = g.opt.first_step;               // 0: chosen when the first target is known
+            L = QL_SET_DONE; break;
+
+        case QL_AD_INT: {           // integrate(t, step) with the semantics of explicit_rk.pyx:278-331
+            const double t = c.int_t;
+            if (t == c.t) { L = QL_INT_DONE; break; }
+            if (t < c.t_prev) { c.status = QB_ST_OUTSIDE_RANGE; L = QL_FAIL; break; }
+            if (t < c.t_front) { L = QL_AD_INTERP; break; }
+            c.status = QB_ST_NORMAL;
+            if (c.int_step && c.t < c.t_front && t > c.t_front) c.int_t = c.t_front;
+            c.step_n = 0;
+            L = QL_AD_LOOP; break;
+        }
+        case QL_AD_LOOP:
+            if (c.t_front < c.int_t && c.status >= 0) {
+                if (c.ad_h == 0.0) {
+                    // initial step: h0^2 = 1 / (1/(tol w0^2) + tol ||f0||^2), not past the target
+                    double tol = g.opt.rtol;
+                    if (tol < 100.0 * 2.220446049250313e-16) tol = 100.0 * 2.220446049250313e-16;
+                    if (tol > 1e-3) tol = 1e-3;
+                    double w0 = fabs(c.ad_tn) > fabs(c.int_t) ? fabs(c.ad_tn) : fabs(c.int_t);
+                    double h0 = 1.0 / sqrt(1.0 / (tol * w0 * w0) + tol * c.ad_f0n2);
+                    if (h0 > c.int_t - c.ad_tn) h0 = c.int_t - c.ad_tn;
+                    if (g.opt.max_step != 0.0 && h0 > g.opt.max_step) h0 = g.opt.max_step;
+                    if (h0 < g.opt.min_step) h0 = g.opt.min_step;
+                    c.ad_h = h0;
+                }
+                L = QL_AD_STEP; break;
+            }
+            L = QL_AD_AFTER; break;
+        case QL_AD_STEP:            // one attempt with step ad_h at order ad_nq
+            if (c.ad_tn + c.ad_h == c.ad_tn) { c.status = QB_ST_DT_UNDERFLOW; L = QL_FAIL; break; }
+            if (++c.step_n > g.opt.nsteps) { c.status = QB_ST_TOO_MUCH_WORK; L = QL_FAIL; break; }
+            c.ad_j = 0;
+            L = QL_AD_PRED_ISSUE; break;
+        case QL_AD_PRED_ISSUE: {    // YP_j = sum_{k>=j} C(k,j) eta^k YH_k   (Pascal-triangle prediction)
+            const int j = c.ad_j, nq = c.ad_nq;
+            const double eta = c.ad_h / c.ad_hyh;
+            qb_pass_clear(p);
+            p.kind = QB_PASS_COMBINE; p.dst1 = QB_AD_YP(j);
+            double w = 1.0;
+            for (int k = 0; k < j; k++) w *= eta;
+            for (int k = j; k <= nq; k++) {
+                qb_pass_src(p, QB_AD_YH(k), w, 0.0);
+                w *= eta * (double)(k + 1) / (double)(k + 1 - j);
+            }
+            c.pc = QB_PC_AD_PRED_DONE; return 1;
+        }
+        case QB_PC_AD_PRED_DONE:
+            if (++c.ad_j <= c.ad_nq) { L = QL_AD_PRED_ISSUE; break; }
+            c.ad_m = 0; c.ad_fsel = 0; c.ad_ysel = 0; c.ad_delp = 0.0;
+            L = QL_AD_CORR_ISSUE; break;
+        case QL_AD_CORR_ISSUE: {
+            // functional iteration m:  savf = h f(t_n + h, y_m);  acor_m = savf - YP1;
+            // y_{m+1} = YP0 + l_0 acor_m;  del = || acor_m - acor_{m-1} ||  -- one fused pass
+            const int m = c.ad_m;
+            const double el0 = T.a[c.ad_nq][0];
+            const int ycur = c.ad_ysel ? c.sTB : c.sTA, ynew = c.ad_ysel ? c.sTA : c.sTB;
+            const int fcur = QB_AD_SAVF(c.ad_fsel), fnew = QB_AD_SAVF(c.ad_fsel ^ 1);
+            qb_pass_clear(p);
+            p.kind = QB_PASS_RHS; p.x = (m == 0) ? QB_AD_YP(0) : ycur;
+            p.zscale = c.ad_h; p.zdst = fnew; p.dst1 = ynew; p.red = QB_RED_WRMS;
+            qb_pass_src(p, QB_AD_YP(0), 1.0, 0.0);
+            qb_pass_src(p, QB_AD_YP(1), -el0, m == 0 ? -1.0 : 0.0);
+            if (m > 0) qb_pass_src(p, fcur, 0.0, -1.0);
+            p.w1z = el0; p.w2z = 1.0;
+            QB_COEFS_OR_PAUSE(c.ad_tn + c.ad_h, QL_AD_CORR_ISSUE)
+            c.n_rhs++;
+            c.pc = QB_PC_AD_CORR_DONE; return 1;
+        }
+        case QB_PC_AD_CORR_DONE: {
+            const int nq = c.ad_nq;
+            const double tq2 = T.bi[nq][1], conit = 0.5 / (nq + 2);
+            const double del = sqrt(red[1] / (double)g.N);
+            int m = c.ad_m;
+            c.ad_ysel ^= 1; c.ad_fsel ^= 1;          // the buffers just written are current
+            if (m != 0 && c.ad_delp > 0.0) {
+                const double r = del / c.ad_delp;
+                c.ad_crate = 0.2 * c.ad_crate > r ? 0.2 * c.ad_crate : r;
+            }
+            const double cr = 1.5 * c.ad_crate < 1.0 ? 1.5 * c.ad_crate : 1.0;
+            const double dcon = del * cr / (tq2 * conit);
+            c.ad_del = del;
+            if (dcon <= 1.0) {
+                if (m == 0) { c.ad_dsm = del / tq2; L = QL_AD_ERRTEST; break; }
+                qb_pass_clear(p);                    // dsm = || savf - YP1 || / tq2
+                p.kind = QB_PASS_COMBINE; p.red = QB_RED_WRMS;
+                qb_pass_src(p, QB_AD_YP(0), 1.0, 0.0);
+                qb_pass_src(p, QB_AD_SAVF(c.ad_fsel), 0.0, 1.0);
+                qb_pass_src(p, QB_AD_YP(1), 0.0, -1.0);
+                c.pc = QB_PC_AD_DSM_DONE; return 1;
+            }
+            m++;
+            if (m == 3 || (m >= 2 && del > 2.0 * c.ad_delp)) { L = QL_AD_CONVFAIL; break; }
+            c.ad_delp = del; c.ad_m = m;
+            L = QL_AD_CORR_ISSUE; break;
+        }
+        case QB_PC_AD_DSM_DONE:
+            c.ad_dsm = sqrt(red[1] / (double)g.N) / T.bi[c.ad_nq][1];
+            L = QL_AD_ERRTEST; break;
+        case QL_AD_CONVFAIL:        // corrector did not converge: quarter the step and retry
+            c.ad_ncf++; c.ad_rmax = 2.0;
+            if (fabs(c.ad_h) <= g.opt.min_step * 1.00001 || c.ad_ncf >= 10) {
+                c.status = QB_ST_CORRECTOR_FAILED; L = QL_FAIL; break;
+            }
+            c.ad_rh = 0.25; c.ad_iredo = 1;
+            L = QL_AD_RESCALE; break;
+        case QL_AD_ERRTEST:
+            if (c.ad_dsm > 1.0) {   // local error test failed
+                c.ad_kflag--; c.ad_rmax = 2.0; c.n_reject++;
+                if (fabs(c.ad_h) <= g.opt.min_step * 1.00001) { c.status = QB_ST_DT_UNDERFLOW; L = QL_FAIL; break; }
+                if (c.ad_kflag <= -3) { L = QL_AD_3FAIL; break; }
+                c.ad_iredo = 2; c.ad_rhup = 0.0;
+                L = QL_AD_O540; break;
+            }
+            c.n_accept++;
+            c.ad_j = 0;
+            L = QL_AD_UPD_ISSUE; break;
+        case QL_AD_UPD_ISSUE: {     // YH_j = YP_j + l_j (savf - YP1)
+            const int j = c.ad_j;
+            const double elj = T.a[c.ad_nq][j];
+            qb_pass_clear(p);
+            p.kind = QB_PASS_COMBINE; p.dst1 = QB_AD_YH(j);
+            if (j == 1) qb_pass_src(p, QB_AD_YP(1), 1.0 - elj, 0.0);
+            else { qb_pass_src(p, QB_AD_YP(j), 1.0, 0.0); qb_pass_src(p, QB_AD_YP(1), -elj, 0.0); }
+            qb_pass_src(p, QB_AD_SAVF(c.ad_fsel), elj, 0.0);
+            if (j == 0) p.red = QB_RED_NORM2_O1;
+            c.pc = QB_PC_AD_UPD_DONE; return 1;
+        }
+        case QB_PC_AD_UPD_DONE:
+            if (c.ad_j == 0) c.norm2_front = red[0];
+            if (++c.ad_j <= c.ad_nq) { L = QL_AD_UPD_ISSUE; break; }
+            // the step is accepted
+            c.ad_kflag = 0; c.ad_iredo = 0; c.ad_ncf = 0;
+            c.ad_hu = c.ad_h; c.ad_tn += c.ad_h; c.ad_hyh = c.ad_h;
+            c.t_front = c.ad_tn; c.t_prev = c.ad_tn - c.ad_hu; c.dt_int = c.ad_hu;
+            c.ad_ialth--;
+            if (c.ad_ialth == 0) { L = QL_AD_O520; break; }
+            if (c.ad_ialth == 1 && c.ad_nq < qb_ad_maxord(g)) {
+                qb_pass_clear(p);                    // keep acor for the order-increase estimate
+                p.kind = QB_PASS_COMBINE; p.dst1 = c.sP;
+                qb_pass_src(p, QB_AD_SAVF(c.ad_fsel), 1.0, 0.0);
+                qb_pass_src(p, QB_AD_YP(1), -1.0, 0.0);
+                c.pc = QB_PC_AD_SAVE_DONE; return 1;
+            }
+            L = QL_AD_STEP_DONE; break;
+        case QB_PC_AD_SAVE_DONE: L = QL_AD_STEP_DONE; break;
+
+        // ---- order / step-size selection: candidates rh at order nq-1, nq, nq+1 ----
+        case QL_AD_O520:
+            c.ad_rhup = 0.0;
+            if (c.ad_nq >= qb_ad_maxord(g)) { L = QL_AD_O540; break; }
+            qb_pass_clear(p);       // dup = || acor - acor_saved || / tq3
+            p.kind = QB_PASS_COMBINE; p.red = QB_RED_WRMS;
+            qb_pass_src(p, QB_AD_YH(0), 1.0, 0.0);
+            qb_pass_src(p, QB_AD_SAVF(c.ad_fsel), 0.0, 1.0);
+            qb_pass_src(p, QB_AD_YP(1), 0.0, -1.0);
+            qb_pass_src(p, c.sP, 0.0, -1.0);
+            c.pc = QB_PC_AD_DUP_DONE; return 1;
+        case QB_PC_AD_DUP_DONE: {
+            const int l = c.ad_nq + 1;
+            const double dup = sqrt(red[1] / (double)g.N) / T.bi[c.ad_nq][2];
+            c.ad_rhup = 1.0 / (1.4 * pow(dup, 1.0 / (l + 1)) + 0.0000014);
+            L = QL_AD_O540; break;
+        }
+        case QL_AD_O540: {
+            c.ad_rhdn = 0.0;
+            if (c.ad_nq == 1) { L = QL_AD_O560; break; }
+            double w = 1.0;         // ddn = || YH_nq (at the current step size) || / tq1
+            const double eta = c.ad_h / c.ad_hyh;
+            for (int k = 0; k < c.ad_nq; k++) w *= eta;
+            qb_pass_clear(p);
+            p.kind = QB_PASS_COMBINE; p.red = QB_RED_WRMS;
+            qb_pass_src(p, QB_AD_YH(0), 1.0, 0.0);
+            qb_pass_src(p, QB_AD_YH(c.ad_nq), 0.0, w);
+            c.pc = QB_PC_AD_DDN_DONE; return 1;
+        }
+        case QB_PC_AD_DDN_DONE: {
+            const double ddn = sqrt(red[1] / (double)g.N) / T.bi[c.ad_nq][0];
+            c.ad_rhdn = 1.0 / (1.3 * pow(ddn, 1.0 / c.ad_nq) + 0.0000013);
+            L = QL_AD_O560; break;
+        }
+        case QL_AD_O560: {
+            const int nq = c.ad_nq, l = nq + 1;
+            const double rhsm = 1.0 / (1.2 * pow(c.ad_dsm, 1.0 / l) + 0.0000012);
+            const double rhup = c.ad_rhup, rhdn = c.ad_rhdn;
+            int newq; double rh;
+            if (rhsm >= rhup) {
+                if (rhsm < rhdn) { newq = nq - 1; rh = rhdn; }
+                else { newq = nq; rh = rhsm; }
+            } else if (rhup > rhdn) { newq = l; rh = rhup; }
+            else { newq = nq - 1; rh = rhdn; }
+            if (newq == nq - 1 && c.ad_kflag < 0 && rh > 1.0) rh = 1.0;
+            if (newq == l) {        // order increase: new column YH_{nq+1} = acor l_nq / (nq+1)
+                if (rh < 1.1) { c.ad_ialth = 3; L = QL_AD_STEP_DONE; break; }
+                const double r = T.a[nq][nq] / (double)l;
+                c.ad_newq = newq; c.ad_rh = rh;
+                qb_pass_clear(p);
+                p.kind = QB_PASS_COMBINE; p.dst1 = QB_AD_YH(l);
+                qb_pass_src(p, QB_AD_SAVF(c.ad_fsel), r, 0.0);
+                qb_pass_src(p, QB_AD_YP(1), -r, 0.0);
+                c.pc = QB_PC_AD_NEWCOL_DONE; return 1;
+            }
+            if (c.ad_kflag == 0 && rh < 1.1) { c.ad_ialth = 3; L = QL_AD_STEP_DONE; break; }
+            if (c.ad_kflag <= -2 && rh > 0.2) rh = 0.2;
+            c.ad_nq = newq; c.ad_rh = rh;
+            L = QL_AD_RESCALE; break;
+        }
+        case QB_PC_AD_NEWCOL_DONE:
+            c.ad_nq = c.ad_newq;
+            L = QL_AD_RESCALE; break;
+        case QL_AD_RESCALE: {       // h <- rh h (the array keeps its scaling, see QL_AD_PRED_ISSUE)
+            double rh = c.ad_rh;
+            const double h = c.ad_h;
+            if (g.opt.min_step > 0.0 && rh < g.opt.min_step / fabs(h)) rh = g.opt.min_step / fabs(h);
+            if (rh > c.ad_rmax) rh = c.ad_rmax;
+            if (g.opt.max_step != 0.0) {
+                const double q = fabs(h) * rh / g.opt.max_step;
+                if (q > 1.0) rh /= q;
+            }
+            c.ad_h = h * rh;
+            c.ad_ialth = c.ad_nq + 1;
+            if (c.ad_iredo == 0) { c.ad_rmax = 10.0; L = QL_AD_STEP_DONE; }
+            else L = QL_AD_STEP;
+            break;
+        }
+        case QL_AD_3FAIL: {         // three error-test failures: restart at order 1 with h / 10
+            if (c.ad_kflag <= -10) { c.status = QB_ST_DT_UNDERFLOW; L = QL_FAIL; break; }
+            double rh = 0.1;
+            if (g.opt.min_step > 0.0 && rh < g.opt.min_step / fabs(c.ad_h)) rh = g.opt.min_step / fabs(c.ad_h);
+            c.ad_h *= rh;
+            qb_pass_clear(p);       // YH1 = f(t_n, YH0), unscaled
+            p.kind = QB_PASS_RHS; p.x = QB_AD_YH(0); p.zdst = QB_AD_YH(1);
+            QB_COEFS_OR_PAUSE(c.ad_tn, QL_AD_3FAIL)
+            c.n_rhs++;
+            c.pc = QB_PC_AD_REF_DONE; return 1;
+        }
+        case QB_PC_AD_REF_DONE:
+            c.ad_hyh = 1.0; c.ad_nq = 1; c.ad_ialth = 5;
+            L = QL_AD_STEP; break;
+        case QL_AD_STEP_DONE:
+            L = c.int_step ? QL_AD_AFTER : QL_AD_LOOP; break;
+        case QL_AD_AFTER:
+            if (c.status < 0) { L = QL_FAIL; break; }
+            if (c.t_front > c.int_t) { L = QL_AD_INTERP; break; }
+            c.status = QB_ST_AT_FRONT;
+            c.t = c.t_front; c.sY = QB_AD_YH(0); c.norm2_y = c.norm2_front;
+            L = QL_INT_DONE; break;
+        case QL_AD_INTERP: {        // dense output: y(t) = sum_j YH_j ((t - t_n) / h)^j
+            const double sx = (c.int_t - c.ad_tn) / c.ad_hyh;
+            qb_pass_clear(p);
+            p.kind = QB_PASS_COMBINE; p.dst1 = c.sI; p.red = QB_RED_NORM2_O1;
+            double w = 1.0;
+            for (int j = 0; j <= c.ad_nq; j++) { qb_pass_src(p, QB_AD_YH(j), w, 0.0); w *= sx; }
+            c.pc = QB_PC_AD_INTERP_DONE; return 1;
+        }
+        case QB_PC_AD_INTERP_DONE:
+            c.status = QB_ST_INTERPOLATED;
+            c.t = c.int_t; c.sY = c.sI; c.norm2_y = red[0];
+            L = QL_INT_DONE; break;
 
         // ================================================================ mesolve driver
         case QL_ME_NEXT:            // for t in tlist[1:]: integrate(t)   (integrator.py:197-212)

@@ -19,7 +19,7 @@
 
 // both tableaux live in constant memory: the controller's single active lane reads them
 // through the constant cache instead of serial global loads
-__constant__ QbTableau c_tabs[3];
+__constant__ QbTableau c_tabs[4];
 
 struct QbEngineDev {
     QbCtl ctl;
@@ -700,6 +700,7 @@ extern "C" int qb_options_default(qb_options* o) {
     o->norm_steps = 25; o->norm_t_tol = 1e-6; o->norm_tol = 1e-4; o->norm_min_step = 0.1;
     o->mc_corr_eps = 1e-10; o->store_states = 0; o->max_collapses = 64; o->no_jump = 0;
     o->jump_prob_floor = 0.0;
+    o->max_order = 0; o->pad_ = 0;
     return QB_OK;
 }
 
@@ -786,7 +787,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
                                 qb_handle* out) {
     QbSysH* s = qb_cast<QbSysH>(sys, QB_TAG_SYS);
     if (!s) QB_FAIL(QB_E_TYPE, "not a system handle");
-    if (tableau < 0 || tableau > 2) QB_FAIL(QB_E_ARG, "unknown tableau id %d (0 vern7, 1 vern9, 2 tsit5)", tableau);
+    if (tableau < 0 || tableau > 3) QB_FAIL(QB_E_ARG, "unknown tableau id %d (0 vern7, 1 vern9, 2 tsit5, 3 adams)", tableau);
     if (nslots < 1 || !out || !opt) QB_FAIL(QB_E_ARG, "bad engine arguments");
     if (s->elems.empty()) QB_FAIL(QB_E_STATE, "system has no elements");
     QbEngH* e = new QbEngH();
@@ -798,12 +799,15 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     memcpy(&e->opt, opt, sizeof(QbOptions));
     if (e->opt.max_collapses < 1) e->opt.max_collapses = 1;
     QbEngineDev& h = e->h;
-    h.ctl.tab = *QB_TABLEAUX[tableau];
+    if (tableau == 3) qb_adams_table(&h.ctl.tab);
+    else h.ctl.tab = *QB_TABLEAUX[tableau];
     h.tableau_id = tableau;
     {
         static bool tabs_uploaded = false;
         if (!tabs_uploaded) {
-            QbTableau both[3] = {*QB_TABLEAUX[0], *QB_TABLEAUX[1], *QB_TABLEAUX[2]};
+            static QbTableau both[4];
+            both[0] = *QB_TABLEAUX[0]; both[1] = *QB_TABLEAUX[1]; both[2] = *QB_TABLEAUX[2];
+            qb_adams_table(&both[3]);
             cudaError_t ce = cudaMemcpyToSymbol(c_tabs, both, sizeof(both));
             if (ce != cudaSuccess) { delete e; QB_FAIL(QB_E_CUDA, "tableau upload: %s", cudaGetErrorString(ce)); }
             tabs_uploaded = true;

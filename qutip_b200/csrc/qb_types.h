@@ -27,6 +27,10 @@ struct QbTableau {
     double c[QB_MAX_STAGES];
     double e[QB_MAX_STAGES];
     double bi[QB_MAX_STAGES][QB_MAX_DENSE_ORDER];
+    // 0: explicit Runge-Kutta (the fields above).  1: variable-order Adams-Moulton in
+    // Nordsieck form (qb_adams.h): a[nq][0..nq] = corrector coefficients l_j of order nq,
+    // bi[nq][0..2] = the three error-test constants of order nq, S = number of work vectors
+    int method;
 };
 
 // ---- operator storage on the device ----
@@ -79,7 +83,8 @@ enum {
     QB_ST_COLLAPSE_INDEX = -11,    // mcsolve.py:388-392 IndexError corner
     QB_ST_RNG_EXHAUSTED = -12,     // host must supply a longer threshold table
     QB_ST_TOO_MANY_COLLAPSES = -13,
-    QB_ST_BAD_PROGRAM = -14
+    QB_ST_BAD_PROGRAM = -14,
+    QB_ST_CORRECTOR_FAILED = -15   // Adams corrector iteration did not converge (zvode istate -5)
 };
 
 // ---- pass descriptor: one vector instruction executed by the pass kernel ----
@@ -114,7 +119,11 @@ enum {
     QB_PC_SET_DONE, QB_PC_EST0_DONE, QB_PC_EST1IN_DONE, QB_PC_EST1_DONE,
     QB_PC_STAGE_DONE, QB_PC_DENSEIN_DONE, QB_PC_DENSE_DONE, QB_PC_INTERP_DONE,
     QB_PC_EXPECT_DONE, QB_PC_STORE_DONE, QB_PC_PROBS_DONE, QB_PC_APPLY_DONE,
-    QB_PC_COPY_DONE, QB_PC_SETCOPY_DONE      // tile mode: explicit y_prev <- y_front copies
+    QB_PC_COPY_DONE, QB_PC_SETCOPY_DONE,     // tile mode: explicit y_prev <- y_front copies
+    // Adams (qb_adams.h)
+    QB_PC_AD_SET0_DONE, QB_PC_AD_F0_DONE, QB_PC_AD_PRED_DONE, QB_PC_AD_CORR_DONE,
+    QB_PC_AD_DSM_DONE, QB_PC_AD_UPD_DONE, QB_PC_AD_SAVE_DONE, QB_PC_AD_DUP_DONE,
+    QB_PC_AD_DDN_DONE, QB_PC_AD_NEWCOL_DONE, QB_PC_AD_REF_DONE, QB_PC_AD_INTERP_DONE
 };
 // continuations
 enum {
@@ -166,6 +175,13 @@ struct QbTraj {
     int kswap, fsal_pending;
     // ---- statistics ----
     int n_rhs, n_accept, n_reject, n_pass;
+    // ---- Adams-Moulton / Nordsieck integrator state (qb_adams.h) ----
+    double ad_tn;              // time of the Nordsieck array
+    double ad_h;               // step size of the running / next attempt (0: not chosen yet)
+    double ad_hyh;             // step size the stored array YH is scaled for
+    double ad_hu;              // last successful step size
+    double ad_rmax, ad_crate, ad_del, ad_delp, ad_dsm, ad_rhup, ad_rhdn, ad_rh, ad_f0n2;
+    int ad_nq, ad_ialth, ad_kflag, ad_ncf, ad_m, ad_iredo, ad_j, ad_fsel, ad_ysel, ad_newq;
 };
 
 // ---- options (defaults = reference: qutip_integrator.py:51-59, mcsolve.py:460-465) ----
@@ -180,4 +196,6 @@ struct QbOptions {
     int max_collapses;         // capacity of the per-trajectory collapse record
     int no_jump;               // mcsolve: sample the no-jump trajectory (target 0)
     double jump_prob_floor;    // improved sampling floor (mcsolve.py:276-279)
+    int max_order;             // Adams: highest order used (0 = QB_AD_MAXORD)
+    int pad_;
 };

@@ -14,7 +14,7 @@ from .coeffs import Program
 FMT_AUTO, FMT_CSR, FMT_DIAM, FMT_SELL = 0, 1, 2, 3
 FMT_KRON = 4      # reported by DeviceOp.info() for matrix-free Kronecker operators
 FMT_NAMES = {0: "csr", 1: "diam", 2: "dense", 3: "sell", 4: "kron"}
-TABLEAUX = {"vern7": 0, "vern9": 1, "tsit5": 2}
+TABLEAUX = {"vern7": 0, "vern9": 1, "tsit5": 2, "adams": 3}
 
 STATUS_MESSAGES = {
     # texts of explicit_rk.pyx:476-492 so callers can raise the reference's messages
@@ -33,6 +33,8 @@ STATUS_MESSAGES = {
     -12: "threshold table exhausted: more random draws are needed for this trajectory",
     -13: "more collapses than max_collapses in one trajectory",
     -14: "coefficient program failed on the device",
+    -15: ("Repeated convergence failures of the Adams corrector (perhaps wrong step size or "
+          "tolerances too tight)."),
 }
 
 

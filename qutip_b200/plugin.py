@@ -322,7 +322,7 @@ class _B200Integrator(Integrator):
             self._system, self._tableau, nslots=1, atol=o['atol'], rtol=o['rtol'],
             nsteps=int(o['nsteps']), first_step=float(o['first_step'] or 0),
             min_step=float(o['min_step'] or 0), max_step=float(o['max_step'] or 0),
-            interpolate=int(bool(o['interpolate'])))
+            interpolate=int(bool(o.get('interpolate', True))), max_order=int(o.get('order', 0) or 0))
         if self._system.has_host:
             objs = self._system.coeff_objects
             self._engine.host_coeffs = lambda t: [1.0 if c is None else complex(c(t)) for c in objs]
@@ -440,14 +440,67 @@ class B200Tsit5(_B200Integrator):
     method = "b200_tsit5"
 
 
-class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
-    """``method="b200_adams"``: the reference's Adams integrator (SciPy zvode, variable-order
+class B200Adams(_B200Integrator):
+    """``method="b200_adams"``: variable-order (1..12), variable-step Adams-Moulton method in
+    Nordsieck form running entirely on the device (csrc/qb_adams.h) -- the device-resident
+    counterpart of the reference's ``method="adams"`` (IntegratorScipyAdams,
+    solver/integrator/scipy_integrator.py:20-196: SciPy zvode, Adams, order 12).  Same option
+    keys and defaults as the reference integrator; results agree with it within the
+    integration tolerance (the step sequence is not zvode's -- use ``b200_zvode`` for that)."""
+    integrator_options = {
+        'atol': 1e-8,
+        'rtol': 1e-6,
+        'nsteps': 2500,
+        'order': 12,
+        'first_step': 0,
+        'max_step': 0,
+        'min_step': 0,
+    }
+    _tableau = "adams"
+    method = "b200_adams"
+
+    @property
+    def options(self):
+        """
+        Supported options by the device Adams method (keys and defaults of the stock
+        ``adams``, scipy_integrator.py:22-30):
+
+        atol : float, default: 1e-8
+            Absolute tolerance.
+
+        rtol : float, default: 1e-6
+            Relative tolerance.
+
+        order : int, default: 12
+            Highest order used (<= 12).
+
+        nsteps : int, default: 2500
+            Max. number of internal steps/call.
+
+        first_step : float, default: 0
+            Size of initial step (0 = automatic).
+
+        min_step : float, default: 0
+            Minimum step size (0 = automatic).
+
+        max_step : float, default: 0
+            Maximum step size (0 = automatic)
+        """
+        return self._options
+
+    @options.setter
+    def options(self, new_options):
+        Integrator.options.fset(self, new_options)
+
+
+class B200Zvode(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
+    """``method="b200_zvode"``: the reference's Adams integrator (SciPy zvode, variable-order
     Adams-Moulton; solver/integrator/scipy_integrator.py:20-196) with the RHS callback
     ``_mul_np_vec`` (:62-71) evaluated on the device: every ``QobjEvo.matmul_data`` call
     becomes one fused ``qb_engine_rhs`` launch.  Step control and order selection stay in
     SciPy's compiled zvode, exactly as in the reference, so the step sequence is the
-    reference's; the state crosses PCIe once per RHS evaluation (a device-resident Adams is
-    SURVEY 8f's next row)."""
+    reference's; the state crosses PCIe once per RHS evaluation (``b200_adams`` is the
+    device-resident Adams method)."""
     method = "adams"
 
     _ncols = 1
@@ -464,7 +517,7 @@ class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
     def _prepare(self):
         qevo = getattr(self.derivative, "__self__", None)
         if not isinstance(qevo, QobjEvo) or getattr(self.derivative, "__name__", "") != "matmul_data":
-            raise TypeError("b200_adams integrates QobjEvo systems on the device; use "
+            raise TypeError("b200_zvode integrates QobjEvo systems on the device; use "
                             "method='adams' for arbitrary callables")
         self._qevo = qevo
         self._bind()
@@ -500,7 +553,7 @@ class B200Adams(qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams):
         super().reset(hard)
 
     def __getstate__(self):
-        raise TypeError("b200_adams integrators hold device handles and SciPy zvode state; "
+        raise TypeError("b200_zvode integrators hold device handles and SciPy zvode state; "
                         "re-create them instead of pickling")
 
 
@@ -705,6 +758,7 @@ def register():
         solver.add_integrator(B200Vern9, "b200_vern9")
         solver.add_integrator(B200Tsit5, "b200_tsit5")
         solver.add_integrator(B200Adams, "b200_adams")
+        solver.add_integrator(B200Zvode, "b200_zvode")
     _qparallel._maps["b200"] = b200_map
     _registered = True
 
@@ -717,7 +771,10 @@ def _device_method(method):
         return "vern9"
     if method in ("b200_tsit5", "tsit5"):
         return "tsit5"
-    raise TypeError("the b200 map runs vern7 / vern9 on the device, not method=%r" % (method,))
+    if method in ("b200_adams", "adams"):
+        return "adams"
+    raise TypeError("the b200 map runs vern7 / vern9 / tsit5 / adams on the device, not method=%r"
+                    % (method,))
 
 
 def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, map_kw=None,
@@ -769,7 +826,8 @@ def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, m
         system, method, nslots=min(ntraj, 4096), atol=iopt['atol'], rtol=iopt['rtol'],
         nsteps=int(iopt['nsteps']), first_step=float(iopt['first_step'] or 0),
         min_step=float(iopt['min_step'] or 0), max_step=float(iopt['max_step'] or 0),
-        interpolate=int(bool(iopt['interpolate'])), norm_steps=int(opts['norm_steps']),
+        interpolate=int(bool(iopt.get('interpolate', True))),
+        max_order=int(iopt.get('order', 0) or 0), norm_steps=int(opts['norm_steps']),
         norm_t_tol=opts['norm_t_tol'], norm_tol=opts['norm_tol'],
         norm_min_step=opts['norm_min_step'], mc_corr_eps=opts['mc_corr_eps'],
         store_states=int(want_states or want_final), jump_prob_floor=floor)

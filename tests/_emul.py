@@ -22,11 +22,12 @@ class QbOptions(C.Structure):
                 ("norm_tol", C.c_double), ("norm_min_step", C.c_double),
                 ("mc_corr_eps", C.c_double), ("store_states", C.c_int),
                 ("max_collapses", C.c_int), ("no_jump", C.c_int),
-                ("jump_prob_floor", C.c_double)]
+                ("jump_prob_floor", C.c_double), ("max_order", C.c_int),
+                ("pad_", C.c_int)]
 
 
 def default_options(**kw):
-    o = QbOptions(1e-8, 1e-6, 1000, 0.0, 0.0, 0.0, 1, 25, 1e-6, 1e-4, 0.1, 1e-10, 0, 64, 0, 0.0)
+    o = QbOptions(1e-8, 1e-6, 1000, 0.0, 0.0, 0.0, 1, 25, 1e-6, 1e-4, 0.1, 1e-10, 0, 64, 0, 0.0, 0, 0)
     for k, v in kw.items():
         setattr(o, k, v)
     return o
@@ -39,7 +40,7 @@ def lib():
         out = os.path.join(HERE, "emul", "libemul.so")
         deps = [src] + [os.path.join(HERE, "..", "qutip_b200", "csrc", f)
                         for f in ("qb_control.h", "qb_coeff.h", "qb_types.h", "qb_diam.h",
-                                  "qb_tableaux.h")]
+                                  "qb_tableaux.h", "qb_adams.h")]
         if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out)
                                           for d in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread",

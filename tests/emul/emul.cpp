@@ -120,6 +120,13 @@ double emul_diam_avg_lanes(int which) {
     const HostOp& o = g_sys.elems[which];
     return o.dh.ent.empty() ? 0.0 : (double)o.dh.val.size() / (double)o.dh.ent.size();
 }
+// Adams corrector coefficients / error constants of order nq (qb_adams.h)
+void emul_adams_table(int nq, double* el, double* tq) {
+    static QbTableau T;
+    qb_adams_table(&T);
+    for (int j = 0; j <= nq; j++) el[j] = T.a[nq][j];
+    for (int j = 0; j < 3; j++) tq[j] = T.bi[nq][j];
+}
 // y = A x with the element `which` (format check)
 void emul_matvec(int which, const void* x, void* y) {
     const HostOp& o = g_sys.elems[which];
@@ -143,7 +150,8 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
     Sys& s = g_sys;
     const int64_t N = s.N;
     QbCtl g; memset(&g, 0, sizeof g);
-    g.tab = *QB_TABLEAUX[tableau];
+    if (tableau == 3) qb_adams_table(&g.tab);
+    else g.tab = *QB_TABLEAUX[tableau];
     g.opt = *opt;
     g.N = (int)N; g.ntiles = 1;
     g.nelem = (int)s.elems.size(); g.ncops = (int)s.cops.size(); g.neops = (int)s.eops.size();

@@ -118,8 +118,10 @@ def test_refuses_host_only_forms():
         mcsolve(Hc, basis(5, 1), [0, 1], [a], ntraj=2, options=dict(OPT, map="b200"))
 
 
-@pytest.mark.parametrize("method", ["vern7", "adams"])
-def test_python_function_coefficients_evaluated_by_host(method):
+@pytest.mark.parametrize("method,dev,rtol,atol", [("vern7", "b200_vern7", RTOL, ATOL),
+                                                  ("adams", "b200_zvode", RTOL, ATOL),
+                                                  ("adams", "b200_adams", 1e-4, 5e-5)])
+def test_python_function_coefficients_evaluated_by_host(method, dev, rtol, atol):
     """FunctionCoefficient: the scalar is evaluated on the host for each stage time while the
     matvecs, stage combinations and step control stay on the device."""
     a = destroy(8)
@@ -127,17 +129,16 @@ def test_python_function_coefficients_evaluated_by_host(method):
     c_ops = [QobjEvo([a, lambda t, k: np.sqrt(k * np.exp(-t))], args={"k": 0.5})]
     tl = np.linspace(0, 3, 16)
     ref = mesolve(H, basis(8, 3), tl, c_ops, e_ops=[a.dag() * a], options=dict(OPT, method=method))
-    out = mesolve(H, basis(8, 3), tl, c_ops, e_ops=[a.dag() * a],
-                  options=dict(OPT, method="b200_" + method))
-    np.testing.assert_allclose(out.expect[0], ref.expect[0], rtol=RTOL, atol=ATOL)
+    out = mesolve(H, basis(8, 3), tl, c_ops, e_ops=[a.dag() * a], options=dict(OPT, method=dev))
+    np.testing.assert_allclose(out.expect[0], ref.expect[0], rtol=rtol, atol=atol)
     # args updated between steps (Solver.step(t, args=...), reference test_mesolver_stepping)
     s_ref = qutip.MESolver(H, c_ops, options=dict(OPT, method=method))
-    s_out = qutip.MESolver(H, c_ops, options=dict(OPT, method="b200_" + method))
+    s_out = qutip.MESolver(H, c_ops, options=dict(OPT, method=dev))
     for s in (s_ref, s_out):
         s.start(basis(8, 3), 0)
     for t, args in ((1.0, None), (2.0, {"k": 0.0, "A": 0.1})):
         x, y = s_ref.step(t, args=args), s_out.step(t, args=args)
-        np.testing.assert_allclose(y.full(), x.full(), rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(y.full(), x.full(), rtol=max(rtol, 1e-5), atol=max(atol, 1e-7))
 
 
 def test_integrator_pickle_roundtrip():
@@ -290,12 +291,12 @@ def test_c5_sweep_members_match_reference():
         np.testing.assert_allclose(r.expect[k, 0].real, ref.expect[0], rtol=RTOL, atol=ATOL)
 
 
-def test_adams_with_device_rhs():
-    """method='b200_adams': SciPy zvode (the reference's Adams) with the RHS on the device."""
+def test_zvode_with_device_rhs():
+    """method='b200_zvode': SciPy zvode (the reference's Adams) with the RHS on the device."""
     H, c_ops, psi0, e_ops = jc()
     tl = np.linspace(0, 5, 26)
     ref = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="adams"))
-    out = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="b200_adams"))
+    out = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="b200_zvode"))
     np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), rtol=RTOL, atol=ATOL)
     # time-dependent + mcsolve driver on top of it
     a = destroy(6)
@@ -303,9 +304,49 @@ def test_adams_with_device_rhs():
     ref = mcsolve(Ht, basis(6, 2), np.linspace(0, 2, 9), [0.5 * a], e_ops=[a.dag() * a], ntraj=5,
                   seeds=3, options=dict(OPT, method="adams", keep_runs_results=True))
     out = mcsolve(Ht, basis(6, 2), np.linspace(0, 2, 9), [0.5 * a], e_ops=[a.dag() * a], ntraj=5,
-                  seeds=3, options=dict(OPT, method="b200_adams", keep_runs_results=True))
+                  seeds=3, options=dict(OPT, method="b200_zvode", keep_runs_results=True))
     assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
     np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=1e-5, atol=1e-7)
+
+
+def test_device_resident_adams():
+    """method='b200_adams': the Nordsieck Adams-Moulton method on the device against the
+    reference's zvode-based 'adams' at the accuracy the reference asks of it
+    (tests/solver/test_integrator.py:71-98, test_mesolve.py:110-123), same option keys."""
+    stock = qutip.solver.integrator.scipy_integrator.IntegratorScipyAdams.integrator_options
+    assert plugin.B200Adams.integrator_options == stock
+    H, c_ops, psi0, e_ops = jc()
+    tl = np.linspace(0, 5, 26)
+    exact = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="vern9", atol=1e-12, rtol=1e-10))
+    ref = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="adams"))
+    out = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method="b200_adams", store_states=True))
+    np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), rtol=1e-4, atol=5e-5)
+    err_out = np.abs(np.array(out.expect) - np.array(exact.expect)).max()
+    err_ref = np.abs(np.array(ref.expect) - np.array(exact.expect)).max()
+    assert err_out < 5e-5 and err_out < 50 * max(err_ref, 1e-7)
+    assert abs(out.states[-1].tr() - 1) < 1e-6
+    # tighter tolerances and a capped order are honoured
+    tight = mesolve(H, psi0, tl, c_ops, e_ops=e_ops,
+                    options=dict(OPT, method="b200_adams", atol=1e-11, rtol=1e-9, order=5, nsteps=20000))
+    assert np.abs(np.array(tight.expect) - np.array(exact.expect)).max() < 2e-7
+    with pytest.raises(Exception, match="Too much work"):
+        mesolve(H, psi0, tl, c_ops, options=dict(OPT, method="b200_adams", nsteps=3))
+    # time-dependent Hamiltonian, mcsolve driver on top of the integrator (mcstep protocol)
+    a = destroy(6)
+    Ht = QobjEvo([a.dag() * a, [a + a.dag(), "0.3*sin(2*t)"]])
+    kw = dict(e_ops=[a.dag() * a], ntraj=5, seeds=3)
+    ref = mcsolve(Ht, basis(6, 2), np.linspace(0, 2, 9), [0.5 * a],
+                  options=dict(OPT, method="adams", keep_runs_results=True), **kw)
+    out = mcsolve(Ht, basis(6, 2), np.linspace(0, 2, 9), [0.5 * a],
+                  options=dict(OPT, method="b200_adams", keep_runs_results=True), **kw)
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    np.testing.assert_allclose(np.concatenate(out.col_times), np.concatenate(ref.col_times), atol=1e-3)
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=1e-3, atol=1e-3)
+    # whole-batch mcsolve on the device with the Adams method
+    out = mcsolve(Ht, basis(6, 2), np.linspace(0, 2, 9), [0.5 * a],
+                  options=dict(OPT, method="adams", map="b200", keep_runs_results=True), **kw)
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=1e-3, atol=1e-3)
 
 
 def test_matrix_valued_state_unitary_evolution():
@@ -333,7 +374,7 @@ def test_b200_map_improved_sampling():
                                rtol=RTOL, atol=ATOL)
 
 
-@pytest.mark.parametrize("method", ["b200_vern7", "b200_adams"])
+@pytest.mark.parametrize("method", ["b200_vern7", "b200_adams", "b200_zvode"])
 def test_matrix_form_option(method):
     """options['matrix_form']=True (LindbladMatrixForm RHS on the un-vectorised rho) through
     the device integrators, against the reference's matrix-form and superoperator results."""
@@ -343,7 +384,8 @@ def test_matrix_form_option(method):
                                                                store_states=True))
     out = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(OPT, method=method, matrix_form=True,
                                                                store_states=True))
-    tol = dict(rtol=RTOL, atol=ATOL) if method == "b200_vern7" else dict(rtol=1e-4, atol=1e-6)
+    tol = {"b200_vern7": dict(rtol=RTOL, atol=ATOL), "b200_zvode": dict(rtol=1e-4, atol=1e-6),
+           "b200_adams": dict(rtol=1e-4, atol=5e-5)}[method]
     np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), **tol)
     np.testing.assert_allclose(out.states[-1].full(), ref.states[-1].full(), **tol)
 

@@ -27,7 +27,7 @@ def test_registration_surfaces():
     from qutip.core import data as _data
     for solver in (qutip.MESolver, qutip.SESolver, qutip.MCSolver):
         av = solver.avail_integrators()
-        for key in ("b200_vern7", "b200_vern9", "b200_tsit5", "b200_adams"):
+        for key in ("b200_vern7", "b200_vern9", "b200_tsit5", "b200_adams", "b200_zvode"):
             assert key in av and issubclass(av[key], qutip.solver.integrator.Integrator)
     assert plugin.B200Dense in _data.to.dtypes and plugin.B200Operator in _data.to.dtypes
     assert _data.to.parse("b200") is plugin.B200Dense
