@@ -121,8 +121,9 @@ enum {
 //           red[2]=|z|^2 ; EXPECT: red[2m], red[2m+1] = <x|O_m|x>)
 //   coef  : per-slot coefficient buffer the next pass will read
 //   probs : per-slot scratch [ncops]
+//   lm    : per-slot weight table of LINMAP passes
 QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
-                     const double* red, qb_c128* coef, double* probs)
+                     const double* red, qb_c128* coef, double* probs, QbLinMap* lm)
 {
     const int s = T.s, S = T.S;
     int L = c.pc;
@@ -517,23 +518,27 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
         case QL_AD_STEP:            // one attempt with step ad_h at order ad_nq
             if (c.ad_tn + c.ad_h == c.ad_tn) { c.status = QB_ST_DT_UNDERFLOW; L = QL_FAIL; break; }
             if (++c.step_n > g.opt.nsteps) { c.status = QB_ST_TOO_MUCH_WORK; L = QL_FAIL; break; }
-            c.ad_j = 0;
             L = QL_AD_PRED_ISSUE; break;
-        case QL_AD_PRED_ISSUE: {    // YP_j = sum_{k>=j} C(k,j) eta^k YH_k   (Pascal-triangle prediction)
-            const int j = c.ad_j, nq = c.ad_nq;
+        case QL_AD_PRED_ISSUE: {    // YP_j = sum_{k>=j} C(k,j) eta^k YH_k  (Pascal-triangle prediction,
+            const int nq = c.ad_nq;  // every history vector read once: one LINMAP pass)
             const double eta = c.ad_h / c.ad_hyh;
             qb_pass_clear(p);
-            p.kind = QB_PASS_COMBINE; p.dst1 = QB_AD_YP(j);
-            double w = 1.0;
-            for (int k = 0; k < j; k++) w *= eta;
-            for (int k = j; k <= nq; k++) {
-                qb_pass_src(p, QB_AD_YH(k), w, 0.0);
-                w *= eta * (double)(k + 1) / (double)(k + 1 - j);
+            p.kind = QB_PASS_LINMAP; p.nsrc = nq + 1;
+            for (int k = 0; k <= nq; k++) p.src[k] = QB_AD_YH(k);
+            lm->nout = nq + 1;
+            for (int jj = 0; jj <= nq; jj++) {
+                lm->dst[jj] = QB_AD_YP(jj);
+                for (int k = 0; k < QB_LM_MAXSRC; k++) lm->w[jj][k] = 0.0;
+                double w = 1.0;
+                for (int k = 0; k < jj; k++) w *= eta;
+                for (int k = jj; k <= nq; k++) {
+                    lm->w[jj][k] = w;
+                    w *= eta * (double)(k + 1) / (double)(k + 1 - jj);
+                }
             }
             c.pc = QB_PC_AD_PRED_DONE; return 1;
         }
         case QB_PC_AD_PRED_DONE:
-            if (++c.ad_j <= c.ad_nq) { L = QL_AD_PRED_ISSUE; break; }
             c.ad_m = 0; c.ad_fsel = 0; c.ad_ysel = 0; c.ad_delp = 0.0;
             L = QL_AD_CORR_ISSUE; break;
         case QL_AD_CORR_ISSUE: {
@@ -600,35 +605,39 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
                 L = QL_AD_O540; break;
             }
             c.n_accept++;
-            c.ad_j = 0;
             L = QL_AD_UPD_ISSUE; break;
-        case QL_AD_UPD_ISSUE: {     // YH_j = YP_j + l_j (savf - YP1)
-            const int j = c.ad_j;
-            const double elj = T.a[c.ad_nq][j];
+        case QL_AD_UPD_ISSUE: {     // YH_j = YP_j + l_j (savf - YP1), all columns in one LINMAP pass;
+            const int nq = c.ad_nq;  // when due, acor = savf - YP1 is kept for the order-increase estimate
             qb_pass_clear(p);
-            p.kind = QB_PASS_COMBINE; p.dst1 = QB_AD_YH(j);
-            if (j == 1) qb_pass_src(p, QB_AD_YP(1), 1.0 - elj, 0.0);
-            else { qb_pass_src(p, QB_AD_YP(j), 1.0, 0.0); qb_pass_src(p, QB_AD_YP(1), -elj, 0.0); }
-            qb_pass_src(p, QB_AD_SAVF(c.ad_fsel), elj, 0.0);
-            if (j == 0) p.red = QB_RED_NORM2_O1;
+            p.kind = QB_PASS_LINMAP; p.nsrc = nq + 2; p.red = QB_RED_NORM2_O1;
+            for (int k = 0; k <= nq; k++) p.src[k] = QB_AD_YP(k);
+            p.src[nq + 1] = QB_AD_SAVF(c.ad_fsel);
+            int nout = nq + 1;
+            for (int jj = 0; jj <= nq; jj++) {
+                const double elj = T.a[nq][jj];
+                lm->dst[jj] = QB_AD_YH(jj);
+                for (int k = 0; k < QB_LM_MAXSRC; k++) lm->w[jj][k] = 0.0;
+                lm->w[jj][jj] = 1.0;
+                lm->w[jj][1] -= elj;
+                lm->w[jj][nq + 1] = elj;
+            }
+            if (c.ad_ialth == 2 && nq < qb_ad_maxord(g)) {       // ialth will be 1 after this step
+                lm->dst[nout] = c.sP;
+                for (int k = 0; k < QB_LM_MAXSRC; k++) lm->w[nout][k] = 0.0;
+                lm->w[nout][1] = -1.0; lm->w[nout][nq + 1] = 1.0;
+                nout++;
+            }
+            lm->nout = nout;
             c.pc = QB_PC_AD_UPD_DONE; return 1;
         }
         case QB_PC_AD_UPD_DONE:
-            if (c.ad_j == 0) c.norm2_front = red[0];
-            if (++c.ad_j <= c.ad_nq) { L = QL_AD_UPD_ISSUE; break; }
+            c.norm2_front = red[0];
             // the step is accepted
             c.ad_kflag = 0; c.ad_iredo = 0; c.ad_ncf = 0;
             c.ad_hu = c.ad_h; c.ad_tn += c.ad_h; c.ad_hyh = c.ad_h;
             c.t_front = c.ad_tn; c.t_prev = c.ad_tn - c.ad_hu; c.dt_int = c.ad_hu;
             c.ad_ialth--;
             if (c.ad_ialth == 0) { L = QL_AD_O520; break; }
-            if (c.ad_ialth == 1 && c.ad_nq < qb_ad_maxord(g)) {
-                qb_pass_clear(p);                    // keep acor for the order-increase estimate
-                p.kind = QB_PASS_COMBINE; p.dst1 = c.sP;
-                qb_pass_src(p, QB_AD_SAVF(c.ad_fsel), 1.0, 0.0);
-                qb_pass_src(p, QB_AD_YP(1), -1.0, 0.0);
-                c.pc = QB_PC_AD_SAVE_DONE; return 1;
-            }
             L = QL_AD_STEP_DONE; break;
         case QB_PC_AD_SAVE_DONE: L = QL_AD_STEP_DONE; break;
 

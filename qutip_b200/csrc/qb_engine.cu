@@ -35,6 +35,7 @@ struct QbEngineDev {
     double2* out_states;
     QbTraj* traj;
     QbPass* pass;
+    QbLinMap* linmap;      // [nslots] weights of LINMAP passes (Adams prediction / update)
     qb_c128* coef;
     double* probs;
     double* partials;
@@ -415,6 +416,7 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
 #pragma unroll
     for (int g = 0; g < QB_G; g++) {
         kinds[g] = (slot0 + g < nslots_used) ? E->pass[slot0 + g].kind : QB_PASS_NONE;
+        if (kinds[g] == QB_PASS_LINMAP) kinds[g] = QB_PASS_NONE;      // qb_linmap_kernel's
         any |= kinds[g] != QB_PASS_NONE;
         all_rhs &= kinds[g] == QB_PASS_RHS;
     }
@@ -444,6 +446,66 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
     }
 }
 
+// LINMAP passes (Adams prediction / update): V[dst[j]] = sum_k w[j][k] V[src[k]] for up to 14
+// outputs of up to 15 sources.  Every source row is loaded ONCE into registers (that is the
+// point of the pass: O(q) instead of O(q^2) vector reads per step), which needs ~100
+// registers -- hence a kernel of its own, launched only by Adams engines; the weights are
+// staged in shared memory.
+__global__ void __launch_bounds__(QB_TILE_ROWS, 2)
+qb_linmap_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
+{
+    __shared__ double s_w[QB_LM_MAXOUT][QB_LM_MAXSRC];
+    __shared__ int s_dst[QB_LM_MAXOUT];
+    const int ntiles = E->ctl.ntiles;
+    const int slot = blockIdx.x / ntiles;
+    const int tile = blockIdx.x - slot * ntiles;
+    if (slot >= nslots_used) return;
+    const QbPass* __restrict__ gp = &E->pass[slot];
+    if (gp->kind != QB_PASS_LINMAP) return;               // CTA-uniform
+    const QbLinMap* __restrict__ lm = &E->linmap[slot];
+    const int nout = lm->nout, nsrc = gp->nsrc;
+    for (int i = threadIdx.x; i < nout * QB_LM_MAXSRC; i += QB_TILE_ROWS)
+        s_w[i / QB_LM_MAXSRC][i % QB_LM_MAXSRC] = lm->w[i / QB_LM_MAXSRC][i % QB_LM_MAXSRC];
+    if (threadIdx.x < nout) s_dst[threadIdx.x] = lm->dst[threadIdx.x];
+    __syncthreads();
+    const int N = E->ctl.N;
+    const size_t N_ = (size_t)N;
+    const long long r = (long long)tile * QB_TILE_ROWS + threadIdx.x;
+    const bool active = r < N;
+    double2* slot_base = E->pool + (size_t)slot * E->V * N_;
+    const double2* init_ptr = E->init_states + (size_t)E->traj[slot].init_idx * N_;
+    double2 v[QB_LM_MAXSRC];
+#pragma unroll
+    for (int k = 0; k < QB_LM_MAXSRC; k++) {
+        const int sidx = gp->src[k];
+        const double2* p = sidx >= 0 ? slot_base + (long long)sidx * N : init_ptr;
+        v[k] = (k < nsrc && active) ? QB_LDV(p + r) : make_double2(0.0, 0.0);
+    }
+    double n0 = 0.0;
+    for (int j = 0; j < nout; j++) {
+        double2 o = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < QB_LM_MAXSRC; k++) {
+            const double w = s_w[j][k];
+            o.x = fma(w, v[k].x, o.x); o.y = fma(w, v[k].y, o.y);
+        }
+        if (active) {
+            QB_STV(slot_base + (size_t)s_dst[j] * N_ + r, o);
+            if (j == 0) n0 = o.x * o.x + o.y * o.y;
+        }
+    }
+    if (gp->red) {
+        const int lane = threadIdx.x & 31, sl = (int)(((long long)tile * QB_TILE_ROWS + threadIdx.x) >> 5);
+        if ((long long)sl * 32 < N) {                      // warp-uniform
+            n0 = qb_warp_sum(n0);
+            if (lane == 0) {
+                double* __restrict__ part = E->partials + ((size_t)slot * E->nslices + sl) * E->red_stride;
+                part[0] = n0; part[1] = 0.0; part[2] = 0.0;
+            }
+        }
+    }
+}
+
 // Shared-operator variant for systems whose RHS is ONE SELL operator (mcsolve H_eff): the 8
 // warps of a CTA are 8 DIFFERENT trajectory slots working on the SAME slice, so the slice's
 // values and column indices are staged in shared memory once and re-used 8 times -- the
@@ -460,7 +522,8 @@ qb_pass_kernel_shared(const QbEngineDev* __restrict__ E)
     const int chunk = blockIdx.x - group * nchunks;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = group * (QB_TILE_ROWS / 32) + warp;
-    const bool slot_ok = slot < E->nslots && E->pass[slot].kind != QB_PASS_NONE;
+    const bool slot_ok = slot < E->nslots && E->pass[slot].kind != QB_PASS_NONE &&
+                         E->pass[slot].kind != QB_PASS_LINMAP;
     if (!__syncthreads_or(slot_ok)) return;
     QbWarpHdr h;
     if (slot_ok) qb_load_hdr(E, slot, lane, h);
@@ -483,12 +546,14 @@ qb_pass_kernel_shared(const QbEngineDev* __restrict__ E)
     }
 }
 
-// Large single systems (N/32 > 2048 slices): one CTA per slot sums the per-warp partials in
-// a fixed order so that the control kernel's single warp does not walk them serially.
+// Large systems (N/32 > 2048 slices): QB_RED_CTAS CTAs per slot sum the per-warp partials in
+// a fixed order (the control kernel's warp then adds the QB_RED_CTAS sub-sums), so that the
+// control kernel's single warp does not walk tens of thousands of partials serially.
+#define QB_RED_CTAS 32
 __global__ void __launch_bounds__(256)
 qb_partials_reduce_kernel(const QbEngineDev* __restrict__ E)
 {
-    const int slot = blockIdx.x;
+    const int slot = blockIdx.x / QB_RED_CTAS, c = blockIdx.x - slot * QB_RED_CTAS;
     const QbPass* gp = &E->pass[slot];
     const int kind = gp->kind;
     int nred = 0;
@@ -497,17 +562,19 @@ qb_partials_reduce_kernel(const QbEngineDev* __restrict__ E)
     if (nred == 0) return;
     __shared__ double sh[8];
     const int nslices = E->nslices, stride = E->red_stride;
+    const int chunk = (nslices + QB_RED_CTAS - 1) / QB_RED_CTAS;
+    const int i0 = c * chunk, i1 = min(nslices, i0 + chunk);
     const double* __restrict__ part = E->partials + (size_t)slot * nslices * stride;
     for (int k = 0; k < nred; k++) {
         double s = 0.0;
-        for (int i = threadIdx.x; i < nslices; i += 256) s += part[(size_t)i * stride + k];
+        for (int i = i0 + threadIdx.x; i < i1; i += 256) s += part[(size_t)i * stride + k];
         s = qb_warp_sum(s);
         if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
         __syncthreads();
         if (threadIdx.x == 0) {
             double t = 0.0;
             for (int w = 0; w < 8; w++) t += sh[w];
-            E->red_final[(size_t)slot * QB_MAXRED + k] = t;
+            E->red_final[((size_t)slot * QB_RED_CTAS + c) * QB_MAXRED + k] = t;
         }
         __syncthreads();
     }
@@ -543,10 +610,11 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
     const int nslices = E->nslices, stride = E->red_stride;
     const double* __restrict__ part = E->partials + (size_t)slot * nslices * stride;
     if (E->red_final) {
-        for (int k = lane; k < nred; k += 32) sred[w][k] = E->red_final[(size_t)slot * QB_MAXRED + k];
-    } else
-    if (E->red_final) {
-        for (int k = lane; k < nred; k += 32) sred[w][k] = E->red_final[(size_t)slot * QB_MAXRED + k];
+        for (int k = 0; k < nred; k++) {      // lane c holds CTA c's sub-sum
+            double sv = E->red_final[((size_t)slot * QB_RED_CTAS + lane) * QB_MAXRED + k];
+            sv = qb_warp_sum(sv);
+            if (lane == 0) sred[w][k] = sv;
+        }
     } else
     for (int k = 0; k < nred; k++) {
         double s = 0.0;
@@ -562,13 +630,15 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
     qb_c128* coef = E->coef + (size_t)slot * E->ctl.maxcoef;
     double* probs = E->probs + (size_t)slot * (E->ctl.ncops > 0 ? E->ctl.ncops : 1);
     for (;;) {
-        const int issued = qb_advance(E->ctl, c_tabs[E->tableau_id], c, p, sred[w], coef, probs);
+        const int issued = qb_advance(E->ctl, c_tabs[E->tableau_id], c, p, sred[w], coef, probs,
+                                      &E->linmap[slot]);
         if (issued) {
             c.n_pass++;
             if (E->vec_count) {
                 // algorithmic state traffic of the pass: x once, every source once, stores
                 unsigned long long nv = (unsigned long long)p.nsrc + (p.zdst >= 0) + (p.dst1 != -1)
                                         + (p.kind != QB_PASS_COMBINE ? 1 : 0);
+                if (p.kind == QB_PASS_LINMAP) nv = (unsigned long long)p.nsrc + E->linmap[slot].nout;
                 atomicAdd(E->vec_count, nv);
             }
             break;
@@ -868,6 +938,8 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         h.red_stride = std::max(4, 2 * std::min(QB_MAXRED / 2, nops));
     }
     QB_TRY(qb_dev_alloc(e, (size_t)nslots * h.nslices * h.red_stride, &h.partials));
+    h.linmap = nullptr;
+    if (h.ctl.tab.method == 1) QB_TRY(qb_dev_alloc(e, (size_t)nslots, &h.linmap));
     QB_TRY(qb_dev_alloc(e, 1, &h.queue_head));
     QB_TRY(qb_dev_alloc(e, 1, &h.n_active));
     QB_TRY(qb_dev_alloc(e, 1, &h.vec_count));
@@ -880,7 +952,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         if (el.fmt != QB_FMT_SELL && el.fmt != QB_FMT_DIAM && el.fmt != QB_FMT_KRON) h.all_lean = 0;
         if (el.fmt == QB_FMT_KRON && getenv("QB_KRON_GENERIC")) h.all_lean = 0;
     }
-    if (h.nslices > 2048) QB_TRY(qb_dev_alloc(e, (size_t)nslots * QB_MAXRED, &h.red_final));
+    if (h.nslices > 2048) QB_TRY(qb_dev_alloc(e, (size_t)nslots * QB_RED_CTAS * QB_MAXRED, &h.red_final));
     if (s->elems.size() == 1 && s->elems[0].fmt == QB_FMT_DENSE && nslots >= 8) {
         QB_TRY(qb_dev_alloc(e, (size_t)nslots * N, &h.zbuf));
         QB_TRY(qb_dev_alloc(e, (size_t)nslots, &h.xcols));
@@ -942,9 +1014,13 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
         if (use_shared) qb_pass_kernel_shared<<<(unsigned)grid_sh, QB_TILE_ROWS, 0, e->stream>>>(e->d);
         else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d, nslots_used);
         QB_LAUNCH_CHECK();
+        if (e->h.linmap) {
+            qb_linmap_kernel<<<(unsigned)((long long)nslots_used * ntiles), QB_TILE_ROWS, 0, e->stream>>>(e->d, nslots_used);
+            QB_LAUNCH_CHECK();
+        }
         if (timed) cudaEventRecord(pb, e->stream);
         if (e->h.red_final) {
-            qb_partials_reduce_kernel<<<nslots_used, 256, 0, e->stream>>>(e->d);
+            qb_partials_reduce_kernel<<<nslots_used * QB_RED_CTAS, 256, 0, e->stream>>>(e->d);
             QB_LAUNCH_CHECK();
         }
         qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
@@ -983,13 +1059,13 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
             cudaGraphDestroy(g);
             if (ce != cudaSuccess) { e->graph = nullptr; QB_FAIL(QB_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)); }
             e->graph_slots = nslots_used;
-            g_qb_launches -= (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + (e->h.red_final ? 1 : 0));
+            g_qb_launches -= (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + (e->h.red_final ? 1 : 0) + (e->h.linmap ? 1 : 0));
         }
         int pending = 0;              // chunks enqueued whose counter has not been read
         for (;;) {
             const int buf = (int)((rounds / QB_GRAPH_ROUNDS) & 1);
             QB_CUDA(cudaGraphLaunch(e->graph, e->stream));
-            g_qb_launches += (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + (e->h.red_final ? 1 : 0));
+            g_qb_launches += (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + (e->h.red_final ? 1 : 0) + (e->h.linmap ? 1 : 0));
             QB_CUDA(cudaMemcpyAsync(e->h_active + buf, e->h.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
             QB_CUDA(cudaEventRecord(e->ev_chunk[buf], e->stream));
             rounds += QB_GRAPH_ROUNDS;

@@ -88,7 +88,8 @@ enum {
 };
 
 // ---- pass descriptor: one vector instruction executed by the pass kernel ----
-enum { QB_PASS_NONE = 0, QB_PASS_RHS, QB_PASS_APPLY, QB_PASS_EXPECT, QB_PASS_COMBINE };
+enum { QB_PASS_NONE = 0, QB_PASS_RHS, QB_PASS_APPLY, QB_PASS_EXPECT, QB_PASS_COMBINE,
+       QB_PASS_LINMAP };   // LINMAP: several outputs, each a linear combination of src[0..nsrc)
 enum { QB_RED_NORM2_O1 = 1, QB_RED_WRMS = 2, QB_RED_NORM2_Z = 4 };
 enum { QB_OPSET_EOPS = 0, QB_OPSET_NOPS = 1, QB_OPSET_COPS = 2 };
 #define QB_SLOT_INIT (-2)     // source vector = the trajectory's initial state buffer
@@ -108,6 +109,17 @@ struct QbPass {
     int src[QB_MAXSRC];
     double w1[QB_MAXSRC];
     double w2[QB_MAXSRC];
+};
+
+// weights / destinations of a LINMAP pass (one per trajectory slot, next to the QbPass):
+// V[dst[j]] = sum_k w[j][k] V[src[k]]; used by the Adams integrator for the Nordsieck
+// prediction and update, which touch every history vector once
+#define QB_LM_MAXSRC 15
+#define QB_LM_MAXOUT 14
+struct QbLinMap {
+    int nout, pad_;
+    int dst[QB_LM_MAXOUT];
+    double w[QB_LM_MAXOUT][QB_LM_MAXSRC];
 };
 
 // ---- program counter of the per-trajectory controller (qb_control.h) ----

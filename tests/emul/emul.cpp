@@ -173,6 +173,7 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
     const int S = g.tab.S, V = S + 5;
     std::vector<qb_c128> pool((size_t)nslots * V * N);
     std::vector<QbTraj> traj(nslots); std::vector<QbPass> pass(nslots);
+    std::vector<QbLinMap> linmap(nslots);
     std::vector<qb_c128> coef((size_t)nslots * g.maxcoef);
     std::vector<double> probs((size_t)nslots * std::max(1, g.ncops));
     std::vector<double> red((size_t)nslots * QB_MAXRED);
@@ -197,7 +198,8 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
             for (;;) {
                 int issued = qb_advance(g, g.tab, c, pass[slot], red.data() + (size_t)slot * QB_MAXRED,
                                         coef.data() + (size_t)slot * g.maxcoef,
-                                        probs.data() + (size_t)slot * std::max(1, g.ncops));
+                                        probs.data() + (size_t)slot * std::max(1, g.ncops),
+                                        &linmap[slot]);
                 if (issued) {
                     c.n_pass++;
                     if (g_log_classes) {
@@ -249,6 +251,25 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
                     }
                     rd[2 * (m - p.op_lo)] = sre; rd[2 * (m - p.op_lo) + 1] = sim;
                 }
+                continue;
+            }
+            if (p.kind == QB_PASS_LINMAP) {
+                const QbLinMap& lm = linmap[slot];
+                qb_c128* base = pool.data() + (size_t)slot * V * N;
+                std::vector<std::vector<qb_c128>> outs(lm.nout, std::vector<qb_c128>(N));
+                for (int j = 0; j < lm.nout; j++)
+                    for (int64_t r = 0; r < N; r++) {
+                        qb_c128 o = {0, 0};
+                        for (int k = 0; k < p.nsrc; k++) {
+                            const qb_c128 v = vsrc(slot, p.src[k])[r];
+                            o.re += lm.w[j][k] * v.re; o.im += lm.w[j][k] * v.im;
+                        }
+                        outs[j][r] = o;
+                    }
+                double n0 = 0;
+                for (int64_t r = 0; r < N; r++) n0 += outs[0][r].re * outs[0][r].re + outs[0][r].im * outs[0][r].im;
+                for (int j = 0; j < lm.nout; j++) memcpy(base + (size_t)lm.dst[j] * N, outs[j].data(), N * sizeof(qb_c128));
+                rd[0] = n0; rd[1] = 0; rd[2] = 0;
                 continue;
             }
             // operator application into zbuf (x must not alias any destination)

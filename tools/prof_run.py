@@ -38,7 +38,7 @@ else:
             system.add_element(op_k, prog_k)
     else:
         system.add_element(qb.DeviceOp.from_scipy(L))
-    eng = qb.Engine(system, "vern7", nslots=1)
+    eng = qb.Engine(system, os.environ.get("QB_METHOD", "vern7"), nslots=1, nsteps=100000)
     x = qb.DeviceDense.from_numpy(np.random.default_rng(0).random(N) + 0j)
     out = qb.DeviceDense.zeros(N, 1)
     eng.rhs_bench(0.0, x, out, iters=3)
@@ -47,7 +47,7 @@ else:
     reps = int(os.environ.get("QB_REPS", "1"))
     ms = []
     for _ in range(reps):
-        r = eng.run_mesolve(rho0, np.linspace(0, 0.2, 3))
+        r = eng.run_mesolve(rho0, np.linspace(0, float(os.environ.get("QB_TEND", "0.2")), 3))
         ms.append(r.gpu_ms)
     line = "c2 mesolve %s min %.2f ms (%s), %d rounds" % (r.stats[0], min(ms), " ".join("%.1f" % m for m in ms), r.rounds)
     if reps > 1:
