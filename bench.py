@@ -209,8 +209,15 @@ def mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=False):
         "host_build_s": t_mf_build,
         "max_abs_diff_expect_vs_liouvillian": float(np.max(np.abs(rm.expect - r.expect))),
     }
+    # device-resident Adams (the reference's default method for mesolve) on the same system
+    aeng = qb.Engine(system, "adams", nslots=1, nsteps=100000)
+    aeng.run_mesolve(rho0, tlist[:2])
+    ra = aeng.run_mesolve(rho0, tlist)
+    adams = {"mesolve_rhs_evals": int(ra.stats[0][0]), "steps": int(ra.stats[0][1] + ra.stats[0][2]),
+             "mesolve_gpu_ms": ra.gpu_ms,
+             "max_abs_diff_expect_vs_vern7": float(np.max(np.abs(ra.expect - r.expect)))}
     return {
-        "matrix_free": matrix_free,
+        "matrix_free": matrix_free, "adams": adams,
         "workload": "C2 mesolve dissipative TFIM %d spins, Liouvillian %d^2, nnz %d, vern7, tlist linspace(0,1,11)"
                     % (n, N, L.nnz),
         "operator_format": info["format"], "operator_device_bytes": info["device_bytes"],

@@ -139,7 +139,9 @@ typedef struct {
 int qb_options_default(qb_options* opt);
 
 /* tableau: 0 vern7, 1 vern9 (solver/integrator/verner{7,9}efficient.py), 2 tsit5 (FSAL,
- * solver/integrator/tsit5.py) */
+ * solver/integrator/tsit5.py), 3 adams: variable-order Adams-Moulton in Nordsieck form on the
+ * device (counterpart of IntegratorScipyAdams, solver/integrator/scipy_integrator.py:20-196;
+ * options: nsteps, max_order, first_step, min_step, max_step, atol, rtol) */
 int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb_options* opt,
                      qb_handle* out);
 
