@@ -780,27 +780,72 @@ def _device_method(method):
 def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, map_kw=None,
              progress_bar=None, progress_bar_kwargs={}):
     """Map function for ``MCSolver.run(..., options={"map": "b200"})`` (protocol of
-    solver/parallel.py:49-132).  ``task`` is ``MCSolver._run_one_traj`` bound to the solver,
-    ``values`` the per-trajectory seeds, ``task_args = (state0, tlist, e_ops)``.  All
-    trajectories run as one device batch; each one is handed to ``reduce_func`` as the
+    solver/parallel.py:49-132).  Trajectory tasks -- ``MCSolver._run_one_traj`` (one pure
+    initial state, ``values`` = seeds, ``task_args = (state0, tlist, e_ops)``) and
+    ``_run_one_traj_mixed`` (mixed initial states, ``values`` = trajectory ids or
+    ``(id, jump_prob_floor)`` pairs, multitraj.py:285-352, mcsolve.py:752-792) -- run as device
+    batches, one per initial state; each trajectory is handed to ``reduce_func`` as the
     ``(seed, Result, weight)`` triple ``McResult.add`` expects
-    (solver/multitrajresult.py:402-434)."""
-    solver = getattr(task, "__self__", None)
+    (solver/multitrajresult.py:402-434).  Any other task (the no-jump simulations of
+    improved sampling) is executed in the calling process like ``serial_map``."""
+    task_args = tuple(task_args or ())
     task_kwargs = dict(task_kwargs or {})
-    floor = float(task_kwargs.pop("jump_prob_floor", 0.0))      # improved sampling
-    no_jump = bool(task_kwargs.pop("no_jump", False))
-    if (not isinstance(solver, MCSolver) or task_kwargs or no_jump
-            or getattr(task, "__name__", "") != "_run_one_traj"):
-        raise TypeError("the 'b200' map runs MCSolver trajectories of one pure initial state on "
-                        "the device; other tasks (mixed initial states) need a stock map")
-    state0, tlist, e_ops = task_args
+    inner = getattr(task, "func", task)                   # mcsolve._unpack_arguments wrapper
+    solver = getattr(inner, "__self__", None)
+    name = getattr(inner, "__name__", "")
+    if not isinstance(solver, MCSolver) or name not in ("_run_one_traj", "_run_one_traj_mixed"):
+        results = []
+        for v in values:
+            out = task(v, *task_args, **task_kwargs)
+            if reduce_func is not None:
+                remaining = reduce_func(out)
+                if remaining is not None and remaining <= 0:
+                    break
+            else:
+                results.append(out)
+        return None if reduce_func is not None else results
+    if bool(task_kwargs.pop("no_jump", False)):
+        raise TypeError("the 'b200' map does not run forced no-jump trajectories")
+    if name == "_run_one_traj":
+        floor = float(task_kwargs.pop("jump_prob_floor", 0.0))      # improved sampling
+        if task_kwargs:
+            raise TypeError("unsupported trajectory arguments %s for the 'b200' map" % list(task_kwargs))
+        state0, tlist, e_ops = task_args
+        _b200_batch(solver, state0, tlist, e_ops, list(values), floor, 1.0, reduce_func, task)
+        return None
+    # mixed initial states: group the trajectory ids by initial state, one batch per group
+    if inner is task:                 # values = ids, task_args = (seeds, ics, tlist, e_ops)
+        seeds, ics, tlist, e_ops = task_args
+        items = [(int(v), float(task_kwargs.get("jump_prob_floor", 0.0))) for v in values]
+    else:                             # values = (id, jump_prob_floor), the rest by keyword
+        seeds, ics = task_kwargs["seeds"], task_kwargs["ics"]
+        tlist, e_ops = task_kwargs["tlist"], task_kwargs["e_ops"]
+        items = [(int(v[0]), float(v[1])) for v in values]
+    groups = {}
+    for tid, floor in items:
+        groups.setdefault((ics.get_state_index(tid), floor), []).append(tid)
+    for (_, floor), ids in sorted(groups.items(), key=lambda kv: kv[1][0]):
+        state, weight = ics.get_state_and_weight(ids[0])
+        stop = _b200_batch(solver, state, tlist, e_ops, [seeds[t] for t in ids], floor, weight,
+                           reduce_func, solver._run_one_traj)
+        if stop:
+            break
+    return None
+
+
+def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func, task):
+    """One device batch: all trajectories of one initial state.  Returns True when
+    ``reduce_func`` asked to stop."""
     if floor >= 1 - solver.options["norm_tol"]:
         # dark initial state under improved sampling: the reference returns all-zero
         # trajectories without integrating (mcsolve.py:543-556); nothing to run on the device
-        for seed in values:
-            reduce_func(task(seed, *task_args, jump_prob_floor=floor))
-        return None
-    seeds = list(values)
+        for seed in seeds:
+            sd, res, w = solver._run_one_traj(seed, state0, tlist, e_ops, jump_prob_floor=floor)
+            if reduce_func is not None:
+                remaining = reduce_func((sd, res, w * weight))
+                if remaining is not None and remaining <= 0:
+                    return True
+        return False
     ntraj = len(seeds)
     opts = solver.options
     method = _device_method(opts["method"])
@@ -871,10 +916,10 @@ def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, m
         res.collapse = [(float(r.col_t[j, i]), int(r.col_which[j, i]))
                         for i in range(r.ncol[j])]
         if reduce_func is not None:
-            remaining = reduce_func((seeds[j], res, 1 - floor))     # weight, mcsolve.py:565
+            remaining = reduce_func((seeds[j], res, (1 - floor) * weight))     # mcsolve.py:565
             if remaining is not None and remaining <= 0:
-                break
-    return None
+                return True
+    return False
 
 
 register()

@@ -423,6 +423,32 @@ def test_matrix_form_binds_matrix_free(monkeypatch):
     np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("improved", [False, True])
+def test_b200_map_mixed_initial_states(improved):
+    """mcsolve from a statistical mixture (density matrix or [(ket, weight)] list,
+    multitraj.py:285-352, mcsolve.py:752-792): one device batch per initial state, weights
+    and the per-state no-jump floors of improved sampling as in the reference."""
+    a = destroy(6)
+    H = a.dag() * a + 0.3 * (a + a.dag())
+    c_ops = [0.5 * a, 0.2 * a.dag() * a]
+    ics = [(basis(6, 3), 0.5), (basis(6, 1), 0.3), ((basis(6, 0) + basis(6, 2)).unit(), 0.2)]
+    tl = np.linspace(0, 2, 9)
+    kw = dict(e_ops=[a.dag() * a, a + a.dag()], ntraj=[6, 4, 3], seeds=11)
+    o = dict(OPT, keep_runs_results=True, improved_sampling=improved)
+    ref = qutip.MCSolver(H, c_ops, options=dict(o, method="vern7")).run(ics, tl, **kw)
+    out = qutip.MCSolver(H, c_ops, options=dict(o, method="vern7", map="b200")).run(ics, tl, **kw)
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(np.array(out.average_expect), np.array(ref.average_expect), rtol=RTOL, atol=ATOL)
+    assert list(out.ntraj_per_initial_state) == list(ref.ntraj_per_initial_state)
+    # a density matrix as initial state is decomposed by the reference into its eigenstates
+    rho0 = 0.6 * qutip.ket2dm(basis(6, 2)) + 0.4 * qutip.ket2dm(basis(6, 4))
+    kw2 = dict(e_ops=[a.dag() * a], ntraj=8, seeds=5)
+    ref = mcsolve(H, rho0, tl, c_ops, options=dict(o, method="vern7"), **kw2)
+    out = mcsolve(H, rho0, tl, c_ops, options=dict(o, method="vern7", map="b200"), **kw2)
+    np.testing.assert_allclose(np.array(out.average_expect), np.array(ref.average_expect), rtol=RTOL, atol=ATOL)
+
+
 def test_propagator_and_nm_mcsolve_reuse_the_device_integrator():
     """Callers that reuse the same integrators: propagator() drives
     MESolver with a matrix-valued state; NonMarkovianMCSolver subclasses MCIntegrator."""
