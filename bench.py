@@ -190,7 +190,7 @@ def mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=False):
     # device: I (x) H_nh, conj(H_nh) (x) I as Kronecker operators + the sparse jump part)
     solve = __import__("qutip_b200.solve", fromlist=["x"])
     t0 = time.perf_counter()
-    els = solve.lindblad_matrix_free([H], c_ops)
+    els = solve.lindblad_matrix_free([H], c_ops, jump="explicit")
     t_mf_build = time.perf_counter() - t0
     msys = qb.System(N)
     for op_k, prog_k in els:
@@ -234,6 +234,19 @@ def mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=False):
                      "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                      "kernel": "qb_rhs_kernel (DIAM SpMV)"},
     }
+
+
+def plugin_figures(quick=False):
+    """The same C2 system through QuTiP's own mesolve with the plug-in (matrix_form): wall time
+    a QuTiP user sees, including QuTiP's host-side preparation and the binding."""
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "plugin_c2_matrix_form.py"),
+           "6" if quick else str(C2["n_spins"]), "ref"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600).stdout.strip().splitlines()
+        return json.loads(out[-1])
+    except Exception as exc:          # missing reference build etc.: the figure is optional
+        return {"unavailable": repr(exc)[:200]}
 
 
 def extra_figures(qb, models, quick=False):
@@ -471,6 +484,7 @@ def run_ours(args):
             line.update(extra_figures(qb, models, quick=args.quick))
         except Exception as exc:
             line["extra_figures_error"] = repr(exc)[:300]
+        line["plugin_matrix_form_c2"] = plugin_figures(quick=args.quick)
     if world == 1 and not args.no_cpu:
         # reference CPU arm on a bounded sample, in a subprocess (it forks worker processes)
         try:

@@ -146,8 +146,11 @@ __device__ __forceinline__ double2 qb_rowdot_kron(const QbOpDev& A, int sl, int 
             const int nstack = A.kstack;
             for (int c = 0; c < nstack; c++) {
                 const int* __restrict__ rp = A.rowptr + (long long)c * n;
-                const int pi0 = __ldg(rp + i), pi1 = __ldg(rp + i + 1);
+                // row j is the same for the whole warp when n is a multiple of 32: an operator
+                // with an empty row j is skipped before any per-lane load
                 const int pj0 = __ldg(rp + j), pj1 = __ldg(rp + j + 1);
+                if (pj0 == pj1) continue;
+                const int pi0 = __ldg(rp + i), pi1 = __ldg(rp + i + 1);
                 if (pi0 == pi1) continue;
                 for (int q = pj0; q < pj1; q++) {
                     double2 b = __ldg(val + q);

@@ -127,7 +127,7 @@ def test_matrix_free_mesolve_12_spins():
     n = H.shape[0]
     N = n * n
     els = solve.lindblad_matrix_free([H], c_ops)
-    assert [o.info()["format"] for o, _ in els] == ["kron", "kron", "kron"]   # sandwich jumps
+    assert [o.info()["format"] for o, _ in els] == ["kron", "kron", "kron"]   # sandwich jumps (auto)
     assert sum(o.info()["device_bytes"] for o, _ in els) < 8e6
     system = qb.System(N)
     for op, prog in els:
