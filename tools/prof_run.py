@@ -18,7 +18,7 @@ if what == "c3":
     n = 14
     H, c_ops, sz = models.tfim(n)
     system = solve.build_system([models.heff(H, c_ops)], c_ops, e_ops=[sz[0]])
-    eng = qb.Engine(system, "vern7", nslots=ntraj)
+    eng = qb.Engine(system, os.environ.get("QB_METHOD", "vern7"), nslots=ntraj, nsteps=100000)
     draws = solve.make_thresholds(7, ntraj, 64)
     reps = int(os.environ.get("QB_REPS", "1"))
     ms = []
