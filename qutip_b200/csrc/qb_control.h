@@ -61,7 +61,7 @@ QB_HD void qb_pass_clear(QbPass& p) {
 // reference iadd_data skips exact-zero factors (explicit_rk.pyx:38-39)
 QB_HD void qb_pass_src(QbPass& p, int slot, double w1, double w2) {
     if (w1 == 0.0 && w2 == 0.0) return;
-    p.src[p.nsrc] = slot; p.w1[p.nsrc] = w1; p.w2[p.nsrc] = w2; p.nsrc++;
+    p.sw[p.nsrc].src = slot; p.sw[p.nsrc].w1 = w1; p.w2[p.nsrc] = w2; p.nsrc++;
 }
 QB_HD int qb_eval_ref(const QbCtl& g, const QbTraj& c, QbProgRef pr, double t, qb_c128* out) {
     if (pr.len == 0) { out->re = 1.0; out->im = 0.0; return 0; }
@@ -524,7 +524,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             const double eta = c.ad_h / c.ad_hyh;
             qb_pass_clear(p);
             p.kind = QB_PASS_LINMAP; p.nsrc = nq + 1;
-            for (int k = 0; k <= nq; k++) p.src[k] = QB_AD_YH(k);
+            for (int k = 0; k <= nq; k++) p.sw[k].src = QB_AD_YH(k);
             lm->nout = nq + 1;
             for (int jj = 0; jj <= nq; jj++) {
                 lm->dst[jj] = QB_AD_YP(jj);
@@ -610,8 +610,8 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             const int nq = c.ad_nq;  // when due, acor = savf - YP1 is kept for the order-increase estimate
             qb_pass_clear(p);
             p.kind = QB_PASS_LINMAP; p.nsrc = nq + 2; p.red = QB_RED_NORM2_O1;
-            for (int k = 0; k <= nq; k++) p.src[k] = QB_AD_YP(k);
-            p.src[nq + 1] = QB_AD_SAVF(c.ad_fsel);
+            for (int k = 0; k <= nq; k++) p.sw[k].src = QB_AD_YP(k);
+            p.sw[nq + 1].src = QB_AD_SAVF(c.ad_fsel);
             int nout = nq + 1;
             for (int jj = 0; jj <= nq; jj++) {
                 const double elj = T.a[nq][jj];

@@ -107,7 +107,7 @@ __device__ __forceinline__ void qb_load_hdr(const QbEngineDev* __restrict__ E, i
     h.kind = gp->kind; h.nsrc = gp->nsrc; h.zdst = gp->zdst; h.dst1 = gp->dst1; h.red = gp->red;
     h.xslot = gp->x;
     h.my_src = 0; h.my_w1 = 0.0; h.my_w2 = 0.0;
-    if (lane < h.nsrc) { h.my_src = gp->src[lane]; h.my_w1 = gp->w1[lane]; h.my_w2 = gp->w2[lane]; }
+    if (lane < h.nsrc) { h.my_src = gp->sw[lane].src; h.my_w1 = gp->sw[lane].w1; h.my_w2 = gp->w2[lane]; }
     h.zscale = gp->zscale; h.w1z = gp->w1z; h.w2z = gp->w2z;
     h.slot_base = E->pool + (size_t)slot * E->V * N_;
     h.init_ptr = E->init_states + (size_t)E->traj[slot].init_idx * N_;
@@ -278,20 +278,19 @@ __device__ __forceinline__ void qb_hot_epilogue(const QbEngineDev* __restrict__ 
     double2* slot_base = E->pool + (size_t)slot * E->V * (size_t)N;   // consumed by WRMS
     const double2* init_ptr = E->init_states + (size_t)E->traj[slot].init_idx * (size_t)N;
     double2 o1 = make_double2(0.0, 0.0), o2 = make_double2(0.0, 0.0);
-    // source slots and weights are read with warp-uniform loads (one L1 wavefront each)
     for (int i = 0; i < nsrc; i += 4) {
         double2 v[4];
+        double a[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const int sidx = gp->src[min(i + u, QB_MAXSRC - 1)];
-            const double2* p = sidx >= 0 ? slot_base + (long long)sidx * N : init_ptr;
+            // (slot, weight) of source i + u in one uniform 16-byte load
+            const int4 sw = *reinterpret_cast<const int4*>(&gp->sw[min(i + u, QB_MAXSRC - 1)]);
+            a[u] = __hiloint2double(sw.w, sw.z);
+            const double2* p = sw.x >= 0 ? slot_base + (long long)sw.x * N : init_ptr;
             v[u] = (i + u < nsrc && active) ? QB_LDV(p + r) : make_double2(0.0, 0.0);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const double a = gp->w1[min(i + u, QB_MAXSRC - 1)];
-            o1.x = fma(a, v[u].x, o1.x); o1.y = fma(a, v[u].y, o1.y);
-        }
+        for (int u = 0; u < 4; u++) { o1.x = fma(a[u], v[u].x, o1.x); o1.y = fma(a[u], v[u].y, o1.y); }
         if (werr) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -301,9 +300,9 @@ __device__ __forceinline__ void qb_hot_epilogue(const QbEngineDev* __restrict__ 
         }
     }
     {
-        const double w1z = gp->w1z, w2z = gp->w2z;
-        o1.x = fma(w1z, z.x, o1.x); o1.y = fma(w1z, z.y, o1.y);
-        o2.x = fma(w2z, z.x, o2.x); o2.y = fma(w2z, z.y, o2.y);
+        const double2 hz = *reinterpret_cast<const double2*>(&gp->w1z);  // w1z, w2z
+        o1.x = fma(hz.x, z.x, o1.x); o1.y = fma(hz.x, z.y, o1.y);
+        o2.x = fma(hz.y, z.x, o2.x); o2.y = fma(hz.y, z.y, o2.y);
     }
     double r0 = 0.0, r1 = 0.0, r2 = 0.0;
     if (active) {
@@ -477,7 +476,7 @@ qb_linmap_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
     double2 v[QB_LM_MAXSRC];
 #pragma unroll
     for (int k = 0; k < QB_LM_MAXSRC; k++) {
-        const int sidx = gp->src[k];
+        const int sidx = gp->sw[k].src;
         const double2* p = sidx >= 0 ? slot_base + (long long)sidx * N : init_ptr;
         v[k] = (k < nsrc && active) ? QB_LDV(p + r) : make_double2(0.0, 0.0);
     }

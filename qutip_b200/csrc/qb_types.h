@@ -1,6 +1,7 @@
 // qb_types.h -- plain-old-data shared by the host API, the CUDA kernels and the
 // host-side unit-test harness of the step controller (tests/emul).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __CUDACC__
@@ -95,7 +96,10 @@ enum { QB_OPSET_EOPS = 0, QB_OPSET_NOPS = 1, QB_OPSET_COPS = 2 };
 #define QB_SLOT_INIT (-2)     // source vector = the trajectory's initial state buffer
 #define QB_SLOT_OUT (-3)      // destination = the stored-states output buffer
 
-struct QbPass {
+// Laid out for 16-byte warp-uniform loads in the hot epilogue: (x, zdst, dst1, nsrc),
+// (red, out_index, zscale), (w1z, w2z) and one (slot, weight) pair per source.
+struct QbSrcW { int src; int pad_; double w1; };
+struct alignas(16) QbPass {
     int kind;
     int opset, op_lo, op_hi;   // EXPECT: ops [lo,hi) of opset ; APPLY: c_ops[op_lo]
     int x;                     // operator input slot
@@ -106,10 +110,12 @@ struct QbPass {
     int out_index;             // tlist index for QB_SLOT_OUT / expectation records
     double zscale;
     double w1z, w2z;           // weight of z in o1 / o2
-    int src[QB_MAXSRC];
-    double w1[QB_MAXSRC];
-    double w2[QB_MAXSRC];
+    QbSrcW sw[QB_MAXSRC];      // source slot and its weight in o1
+    double w2[QB_MAXSRC];      // weight of the source in o2
 };
+static_assert(offsetof(QbPass, x) == 16 && offsetof(QbPass, red) == 32 && offsetof(QbPass, w1z) == 48 &&
+              offsetof(QbPass, sw) == 64 && sizeof(QbSrcW) == 16 && sizeof(QbPass) % 16 == 0,
+              "QbPass layout is read with 16-byte loads");
 
 // weights / destinations of a LINMAP pass (one per trajectory slot, next to the QbPass):
 // V[dst[j]] = sum_k w[j][k] V[src[k]]; used by the Adams integrator for the Nordsieck

@@ -214,7 +214,7 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
                         auto mix = [&](uint64_t v) { h ^= v; h *= 1099511628211ull; };
                         mix(q.kind); mix(q.opset); mix(q.op_lo); mix(q.op_hi);
                         mix(role(q.x)); mix(role(q.zdst)); mix(role(q.dst1)); mix(q.nsrc);
-                        for (int i = 0; i < q.nsrc; i++) mix(role(q.src[i]));
+                        for (int i = 0; i < q.nsrc; i++) mix(role(q.sw[i].src));
                         if (q.kind == QB_PASS_RHS && q.zdst == 0 && q.x == c.sP) h = 1;   // stage 0 of a step
                         if ((int)g_class_log.size() <= c.traj_id) g_class_log.resize(c.traj_id + 1);
                         g_class_log[c.traj_id].push_back(h);
@@ -261,7 +261,7 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
                     for (int64_t r = 0; r < N; r++) {
                         qb_c128 o = {0, 0};
                         for (int k = 0; k < p.nsrc; k++) {
-                            const qb_c128 v = vsrc(slot, p.src[k])[r];
+                            const qb_c128 v = vsrc(slot, p.sw[k].src)[r];
                             o.re += lm.w[j][k] * v.re; o.im += lm.w[j][k] * v.im;
                         }
                         outs[j][r] = o;
@@ -298,8 +298,8 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
                 const qb_c128 z = zbuf[r];
                 qb_c128 o1 = {0, 0}, o2 = {0, 0};
                 for (int i = 0; i < p.nsrc; i++) {
-                    const qb_c128 v = vsrc(slot, p.src[i])[r];
-                    o1.re += p.w1[i] * v.re; o1.im += p.w1[i] * v.im;
+                    const qb_c128 v = vsrc(slot, p.sw[i].src)[r];
+                    o1.re += p.sw[i].w1 * v.re; o1.im += p.sw[i].w1 * v.im;
                     o2.re += p.w2[i] * v.re; o2.im += p.w2[i] * v.im;
                 }
                 o1.re += p.w1z * z.re; o1.im += p.w1z * z.im;
