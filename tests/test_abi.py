@@ -47,3 +47,28 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle-free", ""), f
+
+
+def test_options_struct_matches_header_and_defaults():
+    """qb_options as declared in the header, the ctypes mirrors (package and test emulator)
+    and the defaults of the reference (qutip_integrator.py:51-59, mcsolve.py:460-465)."""
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built")
+    text = open(os.path.join(ROOT, "include", "qutip_b200.h")).read()
+    body = re.search(r"typedef struct \{([^}]*)\} qb_options;", text).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
+    from engine_fields import package_fields, emulator_fields
+    assert names == package_fields() == emulator_fields()
+    from qutip_b200.engine import make_options
+    o = make_options()
+    assert (o.atol, o.rtol, o.nsteps, o.first_step, o.min_step, o.max_step) == (1e-8, 1e-6, 1000, 0, 0, 0)
+    assert (o.interpolate, o.norm_steps, o.norm_t_tol, o.norm_tol, o.norm_min_step, o.mc_corr_eps) == \
+        (1, 25, 1e-6, 1e-4, 0.1, 1e-10)
+    assert o.max_order == 0 and o.jump_prob_floor == 0.0 and o.no_jump == 0
+    with pytest.raises(KeyError):
+        make_options(bogus=1)
