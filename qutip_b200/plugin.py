@@ -793,7 +793,9 @@ def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, m
     inner = getattr(task, "func", task)                   # mcsolve._unpack_arguments wrapper
     solver = getattr(inner, "__self__", None)
     name = getattr(inner, "__name__", "")
-    if not isinstance(solver, MCSolver) or name not in ("_run_one_traj", "_run_one_traj_mixed"):
+    # subclasses (NonMarkovianMCSolver: martingale weights per trajectory, nm_mcsolve.py:305-324)
+    # override the trajectory function; they run through their own code, one trajectory at a time
+    if type(solver) is not MCSolver or name not in ("_run_one_traj", "_run_one_traj_mixed"):
         results = []
         for v in values:
             out = task(v, *task_args, **task_kwargs)

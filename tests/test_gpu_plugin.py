@@ -464,3 +464,8 @@ def test_propagator_and_nm_mcsolve_reuse_the_device_integrator():
     out = qutip.nm_mcsolve(H, basis(5, 3), np.linspace(0, 2, 9), ops_and_rates,
                            options=dict(OPT, method="b200_vern7", keep_runs_results=True), **kw)
     np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=1e-5, atol=1e-7)
+    # the 'b200' map does not take over subclasses of MCSolver: nm_mcsolve keeps its own
+    # trajectory function (martingale weights), run in-process with the device integrator
+    out = qutip.nm_mcsolve(H, basis(5, 3), np.linspace(0, 2, 9), ops_and_rates,
+                           options=dict(OPT, method="b200_vern7", map="b200", keep_runs_results=True), **kw)
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=1e-5, atol=1e-7)
