@@ -706,6 +706,9 @@ struct QbEngH : QbObj {
     QbOptions opt;
     QbEngineDev h;                 // host mirror of the device descriptor
     QbEngineDev* d = nullptr;
+    // Integrator protocol (slot 0): host mirrors that save a blocking copy per call
+    QbTraj traj0; bool traj0_valid = false;          // slot 0's controller state after the last call
+    QbEngineDev d_copy; bool d_copy_valid = false;   // what *d currently holds
     std::vector<void*> owned;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1029,7 +1032,9 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
     if (e->profiling || short_call) {
         // plain launches, one host look at the counter per chunk.  Used for per-pass
         // CUDA-event timing and for the Integrator protocol (qb_integ_*), whose calls often
-        // need only one or two rounds (an interpolation) -- a 16-round graph would be waste.
+        // need only one or two rounds (an interpolation) -- a 16-round graph would be waste
+        // (measured: continuing on the graph after the first chunk costs more in idle rounds
+        // than it saves in launches).
         int chunk = e->profiling ? 8 : 2;
         for (;;) {
             for (int i = 0; i < chunk; i++) { int rc = enqueue_round(e->profiling != 0); if (rc) return rc; }
@@ -1105,6 +1110,7 @@ static int qb_run_common(QbEngH* e, int mode, int64_t ntraj,
                          void* d_expect, int32_t* d_status, int32_t* d_ncol, double* d_col_t,
                          int32_t* d_col_which, int32_t* d_stats, void* d_states) {
     QbEngineDev& h = e->h;
+    e->traj0_valid = false; e->d_copy_valid = false;
     if (h.ctl.has_host_coef) QB_FAIL(QB_E_STATE, "host-evaluated (python) coefficients are only supported by the integrator protocol, not by batched runs");
     if (mode == 1 && h.ctl.ncops == 0) QB_FAIL(QB_E_STATE, "mcsolve mode needs collapse operators");
     if (mode == 1 && !d_draws && !e->opt.no_jump) QB_FAIL(QB_E_ARG, "mcsolve mode needs the threshold table");
@@ -1252,6 +1258,14 @@ extern "C" int qb_engine_last_run_info(qb_handle eng, int64_t* rounds, double* g
 }
 
 // ---- Integrator protocol on slot 0 ----
+static int qb_integ_traj(QbEngH* e, QbTraj* c) {
+    if (!e->traj0_valid) {
+        QB_CUDA(cudaMemcpy(&e->traj0, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+        e->traj0_valid = true;
+    }
+    *c = e->traj0;
+    return QB_OK;
+}
 static int qb_integ_prepare(QbEngH* e) {
     QbEngineDev& h = e->h;
     if (!e->d_tlist) { QB_CUDA(cudaMalloc(&e->d_tlist, 8)); }
@@ -1278,11 +1292,17 @@ static int qb_integ_launch(QbEngH* e, QbTraj& c) {
     QB_CUDA(cudaMemsetAsync(h.pass, 0, sizeof(QbPass), e->stream));
     QB_CUDA(cudaMemcpyAsync(h.queue_head, &head, sizeof(int), cudaMemcpyHostToDevice, e->stream));
     QB_CUDA(cudaMemcpyAsync(h.n_active, &act, sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    QB_CUDA(cudaMemcpyAsync(e->d, &h, sizeof(QbEngineDev), cudaMemcpyHostToDevice, e->stream));
-    QB_CUDA(cudaStreamSynchronize(e->stream));
+    if (!e->d_copy_valid || memcmp(&e->d_copy, &h, sizeof(QbEngineDev)) != 0) {
+        QB_CUDA(cudaMemcpyAsync(e->d, &h, sizeof(QbEngineDev), cudaMemcpyHostToDevice, e->stream));
+        QB_CUDA(cudaStreamSynchronize(e->stream));      // &h must stay intact until copied
+        memcpy(&e->d_copy, &h, sizeof(QbEngineDev));
+        e->d_copy_valid = true;
+    }
+    e->traj0_valid = false;
     int rc = qb_drive(e, 1, true);
     if (rc) return rc;
     QB_CUDA(cudaMemcpy(&c, h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    e->traj0 = c; e->traj0_valid = true;
     return QB_OK;
 }
 
@@ -1321,7 +1341,7 @@ extern "C" int qb_integ_integrate(qb_handle eng, double t, int step, double* t_o
     if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
     int rc = qb_integ_prepare(e); if (rc) return rc;
     QbTraj c;
-    QB_CUDA(cudaMemcpy(&c, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    { int rct = qb_integ_traj(e, &c); if (rct) return rct; }
     if (c.sP == 0 && c.sF == 0) { if (status) *status = QB_ST_NOT_INITIATED; return QB_OK; }
     QB_CUDA(cudaMemcpy(e->d_tlist, &t, 8, cudaMemcpyHostToDevice));
     c.tl_idx = 0; c.tl_end = 1; c.done = 0;
@@ -1340,7 +1360,7 @@ extern "C" int qb_integ_pending_coef(qb_handle eng, double* t) {
     QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
     if (!e || !t) QB_FAIL(QB_E_TYPE, "not an engine handle");
     QbTraj c;
-    QB_CUDA(cudaMemcpy(&c, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    { int rct = qb_integ_traj(e, &c); if (rct) return rct; }
     if (c.done != 2) QB_FAIL(QB_E_STATE, "no coefficient request pending");
     *t = c.hc_t;
     return QB_OK;
@@ -1349,7 +1369,7 @@ extern "C" int qb_integ_resume(qb_handle eng, const void* vals, double* t_out, i
     QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
     if (!e || !vals) QB_FAIL(QB_E_TYPE, "not an engine handle");
     QbTraj c;
-    QB_CUDA(cudaMemcpy(&c, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    { int rct = qb_integ_traj(e, &c); if (rct) return rct; }
     if (c.done != 2) QB_FAIL(QB_E_STATE, "no coefficient request pending");
     // values of ALL elements are accepted; the controller overwrites the device-evaluated ones
     QB_CUDA(cudaMemcpy(e->h.coef, vals, (size_t)e->h.ctl.nelem * 16, cudaMemcpyHostToDevice));
@@ -1364,7 +1384,7 @@ extern "C" int qb_integ_get_state(qb_handle eng, double* t, void* y) {
     QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
     if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
     QbTraj c;
-    QB_CUDA(cudaMemcpy(&c, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    { int rct = qb_integ_traj(e, &c); if (rct) return rct; }
     if (t) *t = c.t;
     if (y) {
         const size_t N = (size_t)e->sys->N;
@@ -1377,7 +1397,7 @@ extern "C" int qb_integ_stats(qb_handle eng, int64_t stats[4]) {
     QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
     if (!e || !stats) QB_FAIL(QB_E_TYPE, "not an engine handle");
     QbTraj c;
-    QB_CUDA(cudaMemcpy(&c, e->h.traj, sizeof(QbTraj), cudaMemcpyDeviceToHost));
+    { int rct = qb_integ_traj(e, &c); if (rct) return rct; }
     stats[0] = c.n_rhs; stats[1] = c.n_accept; stats[2] = c.n_reject; stats[3] = c.n_pass;
     return QB_OK;
 }
@@ -1391,6 +1411,7 @@ extern "C" int qb_engine_rhs_coef(qb_handle eng, const void* vals, qb_handle xh,
     if (!e || !x || !o || !vals) QB_FAIL(QB_E_TYPE, "bad handles");
     if (x->size() != e->sys->N || o->size() != e->sys->N) QB_FAIL(QB_E_SHAPE, "incompatible shapes");
     QB_CUDA(cudaMemcpyAsync(e->h.coef, vals, (size_t)e->h.ctl.nelem * 16, cudaMemcpyHostToDevice, e->stream));
+    e->d_copy_valid = false;
     QB_CUDA(cudaMemcpyAsync(e->d, &e->h, sizeof(QbEngineDev), cudaMemcpyHostToDevice, e->stream));
     qb_rhs_kernel<<<(e->h.ctl.N + QB_TILE_ROWS - 1) / QB_TILE_ROWS, QB_TILE_ROWS, 0, e->stream>>>(e->d, x->d, o->d, e->h.coef);
     QB_LAUNCH_CHECK();
@@ -1417,6 +1438,7 @@ extern "C" int qb_engine_rhs(qb_handle eng, double t, qb_handle xh, qb_handle ou
             QB_FAIL(QB_E_STATE, "coefficient program failed");
     }
     QB_CUDA(cudaMemcpyAsync(e->h.coef, coef.data(), coef.size() * 16, cudaMemcpyHostToDevice, e->stream));
+    e->d_copy_valid = false;
     QB_CUDA(cudaMemcpyAsync(e->d, &e->h, sizeof(QbEngineDev), cudaMemcpyHostToDevice, e->stream));
     qb_rhs_kernel<<<(e->h.ctl.N + QB_TILE_ROWS - 1) / QB_TILE_ROWS, QB_TILE_ROWS, 0, e->stream>>>(e->d, x->d, o->d, e->h.coef);
     QB_LAUNCH_CHECK();
