@@ -177,6 +177,8 @@ def mcsolve(heff_elements, c_ops, psi0, tlist, ntraj, seeds=None, e_ops=(), meth
         r2 = engine.run_mcsolve(psi0, tlist, full[todo], ntraj=len(todo))
         for k in ("expect", "status", "ncol", "stats"):
             r[k][todo] = r2[k]
+        if r.states is not None:
+            r.states[todo] = r2.states
         w = r2.col_t.shape[1]
         r.col_t[todo, :w] = r2.col_t
         r.col_which[todo, :w] = r2.col_which
@@ -193,7 +195,7 @@ def mcsolve(heff_elements, c_ops, psi0, tlist, ntraj, seeds=None, e_ops=(), meth
     col_which = [r.col_which[j, :r.ncol[j]].copy() for j in range(ntraj)]
     return McResult(runs_expect=runs, average_expect=avg, std_expect=std, col_times=col_times,
                     col_which=col_which, ncol=r.ncol, stats=r.stats, rounds=r.rounds,
-                    gpu_ms=r.gpu_ms, engine=engine)
+                    states=r.states, gpu_ms=r.gpu_ms, engine=engine)
 
 
 def mesolve(elements, y0, tlist, e_ops=(), method="vern7", args=None, nargs=0,
