@@ -484,7 +484,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             c.ad_f0n2 = red[1] / (double)g.N;
             c.ad_nq = 1; c.ad_ialth = 2; c.ad_rmax = 1e4; c.ad_crate = 0.7;
             c.ad_kflag = 0; c.ad_ncf = 0;
-            c.ad_hyh = 1.0; c.ad_hu = 0.0;
+            c.ad_hyh = 1.0; c.ad_hu = 0.0; c.ad_pred_nq = -1;
             c.ad_h = g.opt.first_step;               // 0: chosen when the first target is known
             L = QL_SET_DONE; break;
 
@@ -521,6 +521,11 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             L = QL_AD_PRED_ISSUE; break;
         case QL_AD_PRED_ISSUE: {    // YP_j = sum_{k>=j} C(k,j) eta^k YH_k  (Pascal-triangle prediction,
             const int nq = c.ad_nq;  // every history vector read once: one LINMAP pass)
+            if (c.ad_pred_nq == nq && c.ad_pred_h == c.ad_h && c.ad_hyh == c.ad_h) {
+                c.ad_pred_nq = -1;   // already written by the previous step's update pass
+                L = QB_PC_AD_PRED_DONE; break;
+            }
+            c.ad_pred_nq = -1;
             const double eta = c.ad_h / c.ad_hyh;
             qb_pass_clear(p);
             p.kind = QB_PASS_LINMAP; p.nsrc = nq + 1;
@@ -627,6 +632,24 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
                 lm->w[nout][1] = -1.0; lm->w[nout][nq + 1] = 1.0;
                 nout++;
             }
+            // Unless an order / step-size decision follows this step (it reads savf and YP1),
+            // the same pass also writes the NEXT step's prediction YP'_j = sum_{k>=j} C(k,j) YH_k
+            // (same h): one round per step less, and the new YH is not re-read.
+            c.ad_pred_nq = -1;
+            if (c.ad_ialth != 1 && nout + nq + 1 <= QB_LM_MAXOUT) {
+                for (int jj = 0; jj <= nq; jj++) {
+                    double* wr = lm->w[nout + jj];
+                    for (int k = 0; k < QB_LM_MAXSRC; k++) wr[k] = 0.0;
+                    double cb = 1.0;                         // C(k, jj)
+                    for (int k = jj; k <= nq; k++) {
+                        for (int m2 = 0; m2 <= nq + 1; m2++) wr[m2] += cb * lm->w[k][m2];
+                        cb *= (double)(k + 1) / (double)(k + 1 - jj);
+                    }
+                    lm->dst[nout + jj] = QB_AD_YP(jj);
+                }
+                nout += nq + 1;
+                c.ad_pred_h = c.ad_h; c.ad_pred_nq = nq;
+            }
             lm->nout = nout;
             c.pc = QB_PC_AD_UPD_DONE; return 1;
         }
@@ -731,7 +754,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             c.pc = QB_PC_AD_REF_DONE; return 1;
         }
         case QB_PC_AD_REF_DONE:
-            c.ad_hyh = 1.0; c.ad_nq = 1; c.ad_ialth = 5;
+            c.ad_hyh = 1.0; c.ad_nq = 1; c.ad_ialth = 5; c.ad_pred_nq = -1;
             L = QL_AD_STEP; break;
         case QL_AD_STEP_DONE:
             L = c.int_step ? QL_AD_AFTER : QL_AD_LOOP; break;

@@ -121,7 +121,7 @@ static_assert(offsetof(QbPass, x) == 16 && offsetof(QbPass, red) == 32 && offset
 // V[dst[j]] = sum_k w[j][k] V[src[k]]; used by the Adams integrator for the Nordsieck
 // prediction and update, which touch every history vector once
 #define QB_LM_MAXSRC 15
-#define QB_LM_MAXOUT 14
+#define QB_LM_MAXOUT 28
 struct QbLinMap {
     int nout, pad_;
     int dst[QB_LM_MAXOUT];
@@ -200,6 +200,10 @@ struct QbTraj {
     double ad_hu;              // last successful step size
     double ad_rmax, ad_crate, ad_del, ad_delp, ad_dsm, ad_rhup, ad_rhdn, ad_rh, ad_f0n2;
     int ad_nq, ad_ialth, ad_kflag, ad_ncf, ad_m, ad_iredo, ad_j, ad_fsel, ad_ysel, ad_newq;
+    // the update pass of an accepted step also wrote the prediction of the next one, valid
+    // for step size ad_pred_h at order ad_pred_nq (-1: none)
+    double ad_pred_h;
+    int ad_pred_nq, ad_pad_;
 };
 
 // ---- options (defaults = reference: qutip_integrator.py:51-59, mcsolve.py:460-465) ----
