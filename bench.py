@@ -510,7 +510,9 @@ def main():
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ntraj", type=int, default=10000, help="trajectories per GPU per step")
-    ap.add_argument("--slots", type=int, default=4096, help="concurrent trajectory slots")
+    ap.add_argument("--slots", type=int, default=10000,
+                    help="concurrent trajectory slots (10^4 = the whole step resident: 55 GB of the 180 GB HBM; "
+                         "fewer slots are refilled by continuous batching, measured 3 % slower)")
     ap.add_argument("--spins", type=int, default=0, help="override C3's 14 spins (debug)")
     ap.add_argument("--ref-spins", type=int, default=0)
     ap.add_argument("--ref-sample", type=int, default=0)
