@@ -259,9 +259,11 @@ __device__ __forceinline__ void qb_pass_one_slice(
 // Everything else (EXPECT, APPLY, DIAM / CSR / dense elements) takes qb_pass_slice_generic.
 __device__ __forceinline__ const double2* qb_hot_x(const QbEngineDev* __restrict__ E, int slot)
 {
+    // (slot * V + vector) fits 32 bits: ONE widening multiply per address instead of 64-bit
+    // multiply chains (address arithmetic was a quarter of the epilogue's instructions)
     const int xs = E->pass[slot].x;
-    return xs >= 0 ? E->pool + ((size_t)slot * E->V + xs) * (size_t)E->ctl.N
-                   : E->init_states + (size_t)E->traj[slot].init_idx * (size_t)E->ctl.N;
+    if (xs >= 0) return E->pool + (long long)(slot * E->V + xs) * E->ctl.N;
+    return E->init_states + (long long)E->traj[slot].init_idx * E->ctl.N;
 }
 
 // fused linear combinations (sources in order, z last), stores, reductions of one slot
@@ -275,8 +277,8 @@ __device__ __forceinline__ void qb_hot_epilogue(const QbEngineDev* __restrict__ 
     const int nsrc = gp->nsrc;
     const int red = gp->red;
     const bool werr = (red & QB_RED_WRMS) != 0;      // o2 (the error combination) is only
-    double2* slot_base = E->pool + (size_t)slot * E->V * (size_t)N;   // consumed by WRMS
-    const double2* init_ptr = E->init_states + (size_t)E->traj[slot].init_idx * (size_t)N;
+    double2* const pool_r = E->pool + r;             // consumed by WRMS
+    const int vbase = slot * E->V;
     double2 o1 = make_double2(0.0, 0.0), o2 = make_double2(0.0, 0.0);
     for (int i = 0; i < nsrc; i += 4) {
         double2 v[4];
@@ -286,8 +288,10 @@ __device__ __forceinline__ void qb_hot_epilogue(const QbEngineDev* __restrict__ 
             // (slot, weight) of source i + u in one uniform 16-byte load
             const int4 sw = *reinterpret_cast<const int4*>(&gp->sw[min(i + u, QB_MAXSRC - 1)]);
             a[u] = __hiloint2double(sw.w, sw.z);
-            const double2* p = sw.x >= 0 ? slot_base + (long long)sw.x * N : init_ptr;
-            v[u] = (i + u < nsrc && active) ? QB_LDV(p + r) : make_double2(0.0, 0.0);
+            const double2* p = pool_r + (long long)(vbase + max(sw.x, 0)) * N;
+            if (sw.x < 0)                                 // the initial-state buffer (first pass)
+                p = E->init_states + ((long long)E->traj[slot].init_idx * N + r);
+            v[u] = (i + u < nsrc && active) ? QB_LDV(p) : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) { o1.x = fma(a[u], v[u].x, o1.x); o1.y = fma(a[u], v[u].y, o1.y); }
@@ -307,8 +311,8 @@ __device__ __forceinline__ void qb_hot_epilogue(const QbEngineDev* __restrict__ 
     double r0 = 0.0, r1 = 0.0, r2 = 0.0;
     if (active) {
         const int zdst = gp->zdst, dst1 = gp->dst1;
-        if (zdst >= 0) QB_STV(slot_base + (size_t)zdst * N + r, z);
-        if (dst1 >= 0) QB_STV(slot_base + (size_t)dst1 * N + r, o1);
+        if (zdst >= 0) QB_STV(pool_r + (long long)(vbase + zdst) * N, z);
+        if (dst1 >= 0) QB_STV(pool_r + (long long)(vbase + dst1) * N, o1);
         else if (dst1 == QB_SLOT_OUT)
             E->out_states[((size_t)E->traj[slot].traj_id * E->ctl.nt + gp->out_index) * (size_t)N + r] = o1;
         const double n1 = o1.x * o1.x + o1.y * o1.y;
@@ -323,7 +327,7 @@ __device__ __forceinline__ void qb_hot_epilogue(const QbEngineDev* __restrict__ 
     if (red) {
         r0 = qb_warp_sum(r0); r1 = qb_warp_sum(r1); r2 = qb_warp_sum(r2);
         if (lane == 0) {
-            double* __restrict__ part = E->partials + ((size_t)slot * E->nslices + sl) * E->red_stride;
+            double* __restrict__ part = E->partials + (long long)(slot * E->nslices + sl) * E->red_stride;
             part[0] = r0; part[1] = r1; part[2] = r2;
         }
     }
