@@ -1,8 +1,9 @@
 """qutip_b200 -- B200-native (sm_100a) accelerator for QuTiP's time-evolution hot path.
 
 Scope: the complex128 Liouvillian / effective-Hamiltonian matvec (QobjEvo.matmul_data over
-CSR, Dia and Dense operators) inside every explicit Runge-Kutta step (vern7 / vern9) of
-mesolve and mcsolve, including mcsolve's norm-threshold jump detection and
+CSR, Dia and Dense operators, or matrix-free Kronecker operators for the Lindblad matrix
+form) inside every explicit Runge-Kutta step (vern7 / vern9 / tsit5) and a device-resident
+Adams method of mesolve and mcsolve, including mcsolve's norm-threshold jump detection and
 collapse-operator selection.  All compute runs in hand-written CUDA kernels behind the C
 ABI of ``libqutip_b200.so`` (include/qutip_b200.h); there is no CPU fallback.
 

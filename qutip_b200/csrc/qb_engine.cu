@@ -7,8 +7,10 @@
 //       "y_prev <- y_front" etc. are slot relabels in QbTraj, never copies.
 //   pass[nslots], traj[nslots]    : the next vector instruction and the controller state
 //   partials[nslots][nslices][red_stride] : per-warp partial reductions, summed in a fixed order
-// A "round" = pass kernel + control kernel; the host enqueues rounds back to back and only
-// looks at a device counter every chunk, so there is no host synchronisation per step.
+//   linmap[nslots]                : weights of multi-output passes (Adams prediction / update)
+// A "round" = pass kernel (+ qb_linmap_kernel for Adams engines, + the partial-sum reduction
+// for N > 65536) + control kernel; the host enqueues rounds back to back (CUDA graphs of 16
+// rounds) and only looks at a device counter every chunk: no host synchronisation per step.
 #include <algorithm>
 #include <stdlib.h>
 #include <string.h>
@@ -17,7 +19,7 @@
 #include "qb_kernels.cuh"
 #include "qb_tableaux.h"
 
-// both tableaux live in constant memory: the controller's single active lane reads them
+// the tableaux (and the generated Adams coefficient table) live in constant memory: the controller's single active lane reads them
 // through the constant cache instead of serial global loads
 __constant__ QbTableau c_tabs[4];
 

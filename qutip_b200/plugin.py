@@ -8,15 +8,19 @@
   for the operations the stock RK loop and solvers call on a state: matmul, add, mul,
   imul, neg, zeros-like copies, norm.l2 / norm.frobenius, ode.wrmn_error, expect,
   expect_super, trace_oper_ket, inner;
-* integrators ``"b200_vern7"`` / ``"b200_vern9"`` with ``MESolver.add_integrator``,
-  ``SESolver.add_integrator`` and ``MCSolver.add_integrator``
+* integrators ``"b200_vern7"`` / ``"b200_vern9"`` / ``"b200_tsit5"`` with
+  ``MESolver.add_integrator``, ``SESolver.add_integrator`` and ``MCSolver.add_integrator``
   (solver/solver_base.py:475-492): the whole adaptive RK stepping of
   ``Explicit_RungeKutta`` runs fused on the device, same ``integrator_options`` keys and
   defaults as ``IntegratorVern7`` (solver/integrator/qutip_integrator.py:51-59);
+  ``"b200_adams"`` (Nordsieck Adams-Moulton on the device, option keys of the stock
+  ``adams``) and ``"b200_zvode"`` (SciPy zvode with the right-hand side on the device);
+  ``options["matrix_form"]`` is bound matrix-free (Kronecker / sandwich operators);
 * the map ``options["map"] = "b200"`` in ``qutip.solver.parallel._maps``
   (solver/parallel.py:541-559): ``MCSolver.run`` hands all seeds to the device engine,
   which runs every trajectory (RK steps, jump detection, collapse selection) without
-  host round trips and feeds per-trajectory ``Result`` objects to ``McResult.add``.
+  host round trips and feeds per-trajectory ``Result`` objects to ``McResult.add``
+  (pure and mixed initial states, improved sampling).
 
 Anything that cannot run on the device (python-function coefficients or operators,
 feedback arguments, non-Qobj e_ops in the batched map) raises ``TypeError`` naming the
