@@ -712,6 +712,7 @@ struct QbEngH : QbObj {
     QbOptions opt;
     QbEngineDev h;                 // host mirror of the device descriptor
     QbEngineDev* d = nullptr;
+    void* io_p[12] = {nullptr}; size_t io_cap[12] = {0};   // staging buffers of qb_engine_run
     // Integrator protocol (slot 0): host mirrors that save a blocking copy per call
     QbTraj traj0; bool traj0_valid = false;          // slot 0's controller state after the last call
     QbEngineDev d_copy; bool d_copy_valid = false;   // what *d currently holds
@@ -738,6 +739,7 @@ struct QbEngH : QbObj {
     QbEngH() : QbObj(QB_TAG_ENG) { memset(&h, 0, sizeof h); }
     ~QbEngH() override {
         for (void* p : owned) cudaFree(p);
+        for (void* p : io_p) if (p) cudaFree(p);
         if (d_tlist) cudaFree(d_tlist);
         if (d_init) cudaFree(d_init);
         if (d_args) cudaFree(d_args);
@@ -1177,10 +1179,20 @@ extern "C" int qb_engine_run_device(qb_handle eng, int mode, int64_t ntraj,
 }
 
 namespace {
+// input / output staging of qb_engine_run: owned by the engine and only ever grown, so that
+// repeated runs do not pay a dozen (synchronising) cudaMalloc / cudaFree pairs each
 struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) { if (bytes == 0) bytes = 16; return cudaMalloc(&p, bytes) == cudaSuccess ? 0 : -1; }
+    void*& p;
+    size_t& cap;
+    DevBuf(void*& p_, size_t& cap_) : p(p_), cap(cap_) {}
+    int alloc(size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        if (bytes <= cap) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return -1; }
+        cap = bytes;
+        return 0;
+    }
 };
 }
 
@@ -1197,7 +1209,10 @@ extern "C" int qb_engine_run(qb_handle eng, int mode, int64_t ntraj,
     const int neops = e->h.ctl.neops, nargs = e->sys->nargs, maxcol = e->opt.max_collapses;
     if (nargs > 0 && !args) QB_FAIL(QB_E_ARG, "system has args but none were given");
     if (final_states && ntraj > e->nslots) QB_FAIL(QB_E_ARG, "final_states needs nslots >= ntraj");
-    DevBuf b_init, b_map, b_tl, b_args, b_draws, b_exp, b_st, b_ncol, b_ct, b_cw, b_stats, b_states;
+    DevBuf b_init(e->io_p[0], e->io_cap[0]), b_map(e->io_p[1], e->io_cap[1]), b_tl(e->io_p[2], e->io_cap[2]),
+        b_args(e->io_p[3], e->io_cap[3]), b_draws(e->io_p[4], e->io_cap[4]), b_exp(e->io_p[5], e->io_cap[5]),
+        b_st(e->io_p[6], e->io_cap[6]), b_ncol(e->io_p[7], e->io_cap[7]), b_ct(e->io_p[8], e->io_cap[8]),
+        b_cw(e->io_p[9], e->io_cap[9]), b_stats(e->io_p[10], e->io_cap[10]), b_states(e->io_p[11], e->io_cap[11]);
 #define QB_A(buf, bytes) do { if (buf.alloc(bytes)) QB_FAIL(QB_E_ALLOC, "device allocation of %zu bytes failed", (size_t)(bytes)); } while (0)
     QB_A(b_init, (size_t)ninit * N * 16);
     QB_CUDA(cudaMemcpy(b_init.p, init_states, (size_t)ninit * N * 16, cudaMemcpyHostToDevice));
@@ -1219,12 +1234,13 @@ extern "C" int qb_engine_run(qb_handle eng, int mode, int64_t ntraj,
         QB_A(b_states, (size_t)ntraj * nt * N * 16);
     }
 #undef QB_A
-    int rc = qb_run_common(e, mode, ntraj, b_init.p, static_cast<int32_t*>(b_map.p),
-                           static_cast<double*>(b_tl.p), nt, b_args.p,
-                           static_cast<double*>(b_draws.p), ndraws, b_exp.p,
+    // the staging buffers are cached: a buffer this run did not fill must not be passed on
+    int rc = qb_run_common(e, mode, ntraj, b_init.p, init_map ? static_cast<int32_t*>(b_map.p) : nullptr,
+                           static_cast<double*>(b_tl.p), nt, nargs > 0 ? b_args.p : nullptr,
+                           (draws && ndraws > 0) ? static_cast<double*>(b_draws.p) : nullptr, ndraws, b_exp.p,
                            static_cast<int32_t*>(b_st.p), static_cast<int32_t*>(b_ncol.p),
                            static_cast<double*>(b_ct.p), static_cast<int32_t*>(b_cw.p),
-                           static_cast<int32_t*>(b_stats.p), b_states.p);
+                           static_cast<int32_t*>(b_stats.p), e->opt.store_states ? b_states.p : nullptr);
     if (rc) return rc;
     if (expect && neops > 0) QB_CUDA(cudaMemcpy(expect, b_exp.p, (size_t)ntraj * neops * nt * 16, cudaMemcpyDeviceToHost));
     if (status) QB_CUDA(cudaMemcpy(status, b_st.p, ntraj * 4, cudaMemcpyDeviceToHost));
