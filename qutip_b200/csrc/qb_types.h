@@ -16,7 +16,9 @@
 #define QB_MAXSRC 28          // sources of one linear combination (y_prev + all k)
 #define QB_MAXRED 64          // reduction outputs per pass (32 complex expectations)
 #define QB_SLICE 32           // rows per DIAM slice == warp size
+#ifndef QB_TILE_ROWS
 #define QB_TILE_ROWS 256      // rows per CTA of the pass kernel (8 warps)
+#endif
 
 struct qb_c128 { double re, im; };
 
