@@ -236,6 +236,17 @@ def mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=False):
     }
 
 
+def reference_spmv(quick=False):
+    """Metric (2) on the reference's CPU path: its own CSR x Dense matmul on the C2 Liouvillian."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_spmv.py"),
+           "6" if quick else str(C2["n_spins"]), "10"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600).stdout.strip().splitlines()
+        return json.loads(out[-1])
+    except Exception as exc:
+        return {"unavailable": repr(exc)[:200]}
+
+
 def plugin_figures(quick=False):
     """The same C2 system through QuTiP's own mesolve with the plug-in (matrix_form): wall time
     a QuTiP user sees, including QuTiP's host-side preparation and the binding."""
@@ -485,6 +496,7 @@ def run_ours(args):
         except Exception as exc:
             line["extra_figures_error"] = repr(exc)[:300]
         line["plugin_matrix_form_c2"] = plugin_figures(quick=args.quick)
+        line["mesolve"]["cpu_spmv_reference"] = reference_spmv(quick=args.quick)
     if world == 1 and not args.no_cpu:
         # reference CPU arm on a bounded sample, in a subprocess (it forks worker processes)
         try:
