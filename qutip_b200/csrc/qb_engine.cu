@@ -456,7 +456,10 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
 // point of the pass: O(q) instead of O(q^2) vector reads per step), which needs ~100
 // registers -- hence a kernel of its own, launched only by Adams engines; the weights are
 // staged in shared memory.
-__global__ void __launch_bounds__(QB_TILE_ROWS, 2)
+#ifndef QB_LM_MINB
+#define QB_LM_MINB 2
+#endif
+__global__ void __launch_bounds__(QB_TILE_ROWS, QB_LM_MINB)
 qb_linmap_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
 {
     __shared__ double s_w[QB_LM_MAXOUT][QB_LM_MAXSRC];
