@@ -31,6 +31,7 @@ int qb_version(void);
 const char* qb_last_error(void);
 int qb_device_count(int* n);
 int qb_set_device(int dev);
+int qb_device_mem_info(int64_t* free_bytes, int64_t* total_bytes);   /* current device */
 int qb_synchronize(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t qb_launch_count(void);
@@ -47,9 +48,11 @@ int qb_dense_download(qb_handle h, void* host);
 int qb_dense_write(qb_handle h, const void* host);      /* overwrite from host memory */
 int qb_dense_copy(qb_handle h, qb_handle* out);
 int qb_dense_info(qb_handle h, int64_t* rows, int64_t* cols, int* fortran, void** devptr);
-/* operator formats: 0 auto (sliced ELLPACK for small L2-resident operators with little
- * padding, diagonal-masked slices when the matrix is diagonal structured, CSR otherwise),
- * 1 force CSR, 2 force DIAM, 3 force SELL */
+/* operator formats: 0 auto (rule-compressed sliced ELLPACK for small L2-resident operators
+ * whose 32-row slices are diagonal structured -- no per-element column index, one constant per
+ * constant diagonal --, plain sliced ELLPACK for other small operators with little padding,
+ * diagonal-masked slices for large diagonal-structured operators, CSR otherwise),
+ * 1 force CSR, 2 force DIAM, 3 force SELL, 5 force RSELL */
 int qb_csr_upload(const void* data, const int32_t* col, const int32_t* rowptr,
                   int64_t rows, int64_t cols, int64_t nnz, int format, qb_handle* out);
 int qb_dia_upload(const void* data, const int32_t* offsets, int64_t ndiag,
@@ -210,6 +213,31 @@ int qb_engine_rhs_bench(qb_handle eng, double t, qb_handle x, qb_handle out, int
 int qb_engine_set_profiling(qb_handle eng, int on);
 int qb_engine_profile(qb_handle eng, double* pass_ms, int64_t* pass_launches,
                       double* state_vector_accesses);
+
+/* ---- multi-GPU: the one collective of the sharded workloads -----------------------------
+ * mcsolve trajectories (and sweep members) are independent given their seeds
+ * (solver/multitraj.py:250-256; map dispatch solver/parallel.py:541-559); the only exchange
+ * is the sum _TrajectorySum.reduce_expect accumulates (solver/multitrajresult.py:1116-1124).
+ * A communicator is an NCCL group (bound at run time, libnccl.so.2):
+ *   qb_comm_init_all  : one process drives ndev devices (ncclCommInitAll); local member i
+ *                       lives on devs[i].
+ *   qb_comm_unique_id / qb_comm_init_rank : one process per device (ncclCommInitRank on the
+ *                       current device); the 128-byte id of rank 0 is passed to the other
+ *                       ranks by the launcher.
+ *   qb_comm_allreduce_sum : bufs[i] = count doubles in host memory of local member i, summed
+ *                       over the whole group in place with ONE ncclAllReduce.
+ *   qb_comm_reduce_expect : engines[i] (on member i's device, NULL if that member ran
+ *                       nothing) has just finished qb_engine_run; the per-trajectory expectation
+ *                       values still on the devices are reduced to [2][n_e][n_t] complex sums
+ *                       (sum e, sum (re^2, im^2)) per member, summed with ONE ncclAllReduce over
+ *                       NVLink and returned in sums (host, 4 * n_e * n_t doubles). */
+int qb_comm_nccl_version(int* version);
+int qb_comm_init_all(int ndev, const int* devs, qb_handle* out);
+int qb_comm_unique_id(void* id, int nbytes);
+int qb_comm_init_rank(int nranks, int rank, const void* id, qb_handle* out);
+int qb_comm_info(qb_handle comm, int* nranks, int* nlocal);
+int qb_comm_allreduce_sum(qb_handle comm, double* const* bufs, int64_t count);
+int qb_comm_reduce_expect(qb_handle comm, const qb_handle* engines, int neops, int nt, void* sums);
 
 #ifdef __cplusplus
 }

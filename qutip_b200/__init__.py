@@ -16,7 +16,7 @@ Layers
 """
 from ._lib import QbError, LIB_PATH, device_count, launch_count  # noqa: F401
 from .engine import (DeviceDense, DeviceOp, Engine, System, FMT_AUTO, FMT_CSR,  # noqa: F401
-                     FMT_DIAM, FMT_SELL, STATUS_MESSAGES, make_options)
+                     FMT_DIAM, FMT_SELL, FMT_RSELL, STATUS_MESSAGES, make_options)
 from . import coeffs  # noqa: F401
 
 __version__ = "0.1.0"

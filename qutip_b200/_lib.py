@@ -38,7 +38,7 @@ class QbOptions(C.Structure):
 # every symbol include/qutip_b200.h declares (tests check the library exports them all)
 SYMBOLS = [
     "qb_version", "qb_last_error", "qb_device_count", "qb_set_device", "qb_synchronize",
-    "qb_launch_count",
+    "qb_launch_count", "qb_device_mem_info",
     "qb_dense_upload", "qb_dense_zeros", "qb_dense_download", "qb_dense_write", "qb_dense_copy", "qb_dense_info",
     "qb_csr_upload", "qb_dia_upload", "qb_kron_upload", "qb_sandwich_upload", "qb_op_info", "qb_free",
     "qb_matmul", "qb_axpy", "qb_scal", "qb_copy", "qb_zero", "qb_nrm2", "qb_wrms_error",
@@ -51,6 +51,8 @@ SYMBOLS = [
     "qb_engine_rhs_bench", "qb_engine_set_profiling", "qb_engine_profile",
     "qb_zgemm", "qb_zgemm_bench", "qb_integ_pending_coef", "qb_integ_resume",
     "qb_engine_rhs_coef",
+    "qb_comm_nccl_version", "qb_comm_init_all", "qb_comm_unique_id", "qb_comm_init_rank",
+    "qb_comm_info", "qb_comm_allreduce_sum", "qb_comm_reduce_expect",
 ]
 
 _lib = None
@@ -126,6 +128,14 @@ def load():
         "qb_engine_profile": [vp, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)],
         "qb_device_count": [C.POINTER(i32)],
         "qb_set_device": [i32],
+        "qb_device_mem_info": [C.POINTER(i64), C.POINTER(i64)],
+        "qb_comm_nccl_version": [C.POINTER(i32)],
+        "qb_comm_init_all": [i32, C.POINTER(i32), pp],
+        "qb_comm_unique_id": [vp, i32],
+        "qb_comm_init_rank": [i32, i32, vp, pp],
+        "qb_comm_info": [vp, C.POINTER(i32), C.POINTER(i32)],
+        "qb_comm_allreduce_sum": [vp, pp, i64],
+        "qb_comm_reduce_expect": [vp, pp, i32, i32, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

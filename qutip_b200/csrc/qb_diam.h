@@ -7,6 +7,7 @@
 // the reference's CSR (core/data/csr.pyx) -- become extra entries with the same offset.
 #pragma once
 #include <algorithm>
+#include <string.h>
 #include <thread>
 #include <vector>
 #include "qb_types.h"
@@ -142,5 +143,149 @@ inline void build_sell(int64_t nrows, int64_t ncols, RowFn row_fn, SellHost& out
             }
         out.slice_ptr.push_back(out.slice_ptr.back() + width);
     }
+}
+
+// ---- RSELL: SELL with per-slot rule descriptors (qb_types.h) ----
+// One slot of a slice = one "diagonal" of the slice under the better of two keys:
+// col - row (banded operators: ladder operators, hopping terms) or col ^ row (operators of
+// tensor products of two-level systems flip bits of the row index).  Slots whose lanes all
+// follow the rule need no column block; slots whose 32 values are bitwise equal need no
+// value block.  Slices that are not diagonal structured under either key fall back to plain
+// ELLPACK slots (explicit columns and values, row order) -- the format is a superset of SELL.
+struct RsellHost {
+    std::vector<int> slice_ptr;          // [nslices + 1], in slots
+    std::vector<QbSlotDesc> desc;
+    std::vector<qb_c128> val;            // explicit value blocks, 32 per block
+    std::vector<int> col;                // explicit column blocks, 32 per block
+    long long nnz = 0;
+    long long stored() const { return (long long)desc.size(); }
+    long long bytes() const {
+        return (long long)desc.size() * 32 + (long long)val.size() * 16 + (long long)col.size() * 4 +
+               (long long)slice_ptr.size() * 4;
+    }
+};
+
+template <class RowFn>
+inline void build_rsell(int64_t nrows, int64_t ncols, RowFn row_fn, RsellHost& out) {
+    const int64_t nslices = (nrows + 31) / 32;
+    out.slice_ptr.assign(1, 0);
+    std::vector<std::vector<std::pair<int, qb_c128>>> rows(32);
+    struct Key { long long key; int occ; };
+    auto emit = [&](int rule, int delta, const int* cols, const qb_c128* vals, const bool* have,
+                    int64_t r0) {
+        // column rule usable only if every lane's implied column is a valid index
+        bool rule_ok = rule != QB_RS_COL_EXPL;
+        if (rule_ok)
+            for (int l = 0; l < 32; l++) {
+                const long long r = r0 + l;
+                const long long c = rule == QB_RS_COL_ADD ? r + delta : (r ^ (long long)delta);
+                if (c < 0 || c >= ncols) { rule_ok = false; break; }
+            }
+        bool konst = true;
+        for (int l = 0; l < 32; l++)
+            if (!have[l] || memcmp(&vals[l], &vals[0], sizeof(qb_c128)) != 0) { konst = false; break; }
+        QbSlotDesc d;
+        d.rule = rule_ok ? rule : QB_RS_COL_EXPL; d.delta = rule_ok ? delta : 0;
+        d.cpos = 0; d.vpos = 0; d.vre = 0.0; d.vim = 0.0;
+        if (!rule_ok) {
+            d.cpos = (int)(out.col.size() / 32);
+            for (int l = 0; l < 32; l++) {
+                long long c = have[l] ? cols[l] : std::min<long long>(r0 + l, ncols - 1);
+                if (c < 0) c = 0;
+                out.col.push_back((int)c);
+            }
+        }
+        if (konst) { d.rule |= QB_RS_VAL_CONST; d.vre = vals[0].re; d.vim = vals[0].im; }
+        else {
+            d.vpos = (int)(out.val.size() / 32);
+            for (int l = 0; l < 32; l++) out.val.push_back(have[l] ? vals[l] : qb_c128{0.0, 0.0});
+        }
+        out.desc.push_back(d);
+    };
+    for (int64_t sl = 0; sl < nslices; sl++) {
+        const int64_t r0 = sl * 32;
+        int width = 0; long long cnt = 0;
+        for (int l = 0; l < 32; l++) {
+            rows[l].clear();
+            if (r0 + l < nrows) {
+                row_fn(r0 + l, rows[l]);
+                std::stable_sort(rows[l].begin(), rows[l].end(),
+                                 [](const std::pair<int, qb_c128>& a, const std::pair<int, qb_c128>& b) {
+                                     return a.first < b.first; });
+            }
+            width = std::max(width, (int)rows[l].size());
+            cnt += (long long)rows[l].size();
+        }
+        out.nnz += cnt;
+        // distinct (key, occurrence) pairs under both keys; occurrence > 0 only for duplicate
+        // (row, col) pairs, which the reference's CSR allows (core/data/csr.pyx)
+        std::vector<std::pair<long long, int>> kadd, kxor;
+        for (int l = 0; l < 32; l++) {
+            int occ = 0;
+            for (size_t k = 0; k < rows[l].size(); k++) {
+                occ = (k > 0 && rows[l][k].first == rows[l][k - 1].first) ? occ + 1 : 0;
+                const long long r = r0 + l, c = rows[l][k].first;
+                kadd.push_back({c - r, occ}); kxor.push_back({c ^ r, occ});
+            }
+        }
+        auto uniq = [](std::vector<std::pair<long long, int>>& v) {
+            std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
+        uniq(kadd); uniq(kxor);
+        const bool use_xor = kxor.size() < kadd.size();
+        const auto& keys = use_xor ? kxor : kadd;
+        const int rule = use_xor ? QB_RS_COL_XOR : QB_RS_COL_ADD;
+        int cols[32]; qb_c128 vals[32]; bool have[32];
+        if (cnt > 0 && (long long)keys.size() * 32 <= 2 * cnt + 64) {
+            for (const auto& kk : keys) {
+                for (int l = 0; l < 32; l++) {
+                    have[l] = false; vals[l] = qb_c128{0.0, 0.0}; cols[l] = 0;
+                    const long long r = r0 + l;
+                    int occ = 0;
+                    for (size_t k = 0; k < rows[l].size(); k++) {
+                        occ = (k > 0 && rows[l][k].first == rows[l][k - 1].first) ? occ + 1 : 0;
+                        const long long c = rows[l][k].first;
+                        const long long key = use_xor ? (c ^ r) : (c - r);
+                        if (key == kk.first && occ == kk.second) {
+                            have[l] = true; vals[l] = rows[l][k].second; cols[l] = (int)c; break;
+                        }
+                    }
+                }
+                emit(rule, (int)kk.first, cols, vals, have, r0);
+            }
+            out.slice_ptr.push_back(out.slice_ptr.back() + (int)keys.size());
+        } else {
+            for (int k = 0; k < width; k++) {
+                for (int l = 0; l < 32; l++) {
+                    have[l] = k < (int)rows[l].size();
+                    vals[l] = have[l] ? rows[l][k].second : qb_c128{0.0, 0.0};
+                    cols[l] = have[l] ? rows[l][k].first : 0;
+                }
+                emit(QB_RS_COL_EXPL, 0, cols, vals, have, r0);
+            }
+            out.slice_ptr.push_back(out.slice_ptr.back() + width);
+        }
+    }
+}
+
+// y = A x on the host (format unit tests; never used by the product path)
+inline void rsell_matvec_host(const RsellHost& A, int64_t nrows, const qb_c128* x, qb_c128* y) {
+    const int64_t nslices = (nrows + 31) / 32;
+    for (int64_t sl = 0; sl < nslices; sl++)
+        for (int l = 0; l < 32; l++) {
+            const int64_t r = sl * 32 + l;
+            if (r >= nrows) continue;
+            double re = 0.0, im = 0.0;
+            for (int k = A.slice_ptr[sl]; k < A.slice_ptr[sl + 1]; k++) {
+                const QbSlotDesc& d = A.desc[k];
+                const int cr = d.rule & QB_RS_COL_MASK;
+                const long long c = cr == QB_RS_COL_ADD ? r + d.delta : cr == QB_RS_COL_XOR ? (r ^ (long long)d.delta)
+                                                                       : A.col[(size_t)d.cpos * 32 + l];
+                qb_c128 v = {d.vre, d.vim};
+                if (!(d.rule & QB_RS_VAL_CONST)) v = A.val[(size_t)d.vpos * 32 + l];
+                re += v.re * x[c].re - v.im * x[c].im;
+                im += v.re * x[c].im + v.im * x[c].re;
+            }
+            y[r].re = re; y[r].im = im;
+        }
 }
 }  // namespace qbdiam

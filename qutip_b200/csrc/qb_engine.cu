@@ -50,6 +50,7 @@ struct QbEngineDev {
     unsigned long long* vec_count;   // state-sized vector accesses issued (algorithmic traffic)
     int nslices, red_stride;
     int all_sell, all_lean;     // every RHS element is SELL / is SELL, DIAM or KRON (lean pass body)
+    int all_rsell, pad1_;       // every RHS element is RSELL: tile-staged pass kernel
     double* red_final;          // [nslots][QB_MAXRED]: pre-reduced partials (large systems) or null
     // dense batched path (qb_dense.cu): z of every slot precomputed by one DMMA ZGEMM
     double2* zbuf;              // [nslots][N] or null
@@ -451,6 +452,166 @@ qb_pass_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
     }
 }
 
+// ------------------------------------------------------------------ tile-staged pass kernel
+// For systems whose RHS elements are all RSELL.  One CTA = one tile of `trows` consecutive
+// rows of ONE trajectory slot; its 8 warps walk the tile's 32-row slices.
+//  * The tile's rows of the operand state x are staged in shared memory by ONE TMA bulk copy
+//    (cp.async.bulk + mbarrier, issued by thread 0): every gather whose column falls inside
+//    the tile is a conflict-free LDS.128 instead of an L1 lookup (the warp-autonomous kernel
+//    above is bound by L1 wavefronts: 4 per gathered 512 bytes, replayed); columns outside
+//    the tile are gathered from global memory (L2 hits: the slot's other tiles run at the
+//    same time).  The operator costs two warp-uniform loads per slot (RSELL descriptors).
+//  * The first QB_TP epilogue sources of a slice are requested BEFORE the sweep and held in
+//    registers (the shared-memory sweep needs few), so their HBM latency overlaps the sweep
+//    instead of following it in dependent batches -- the latency chain per slice is
+//    max(HBM, sweep) instead of their sum, which is what bounded the old kernel's bytes in
+//    flight.
+// Partial reductions, stores and every other pass kind are the same as in qb_pass_kernel.
+#ifndef QB_TT_MINB
+#define QB_TT_MINB 3
+#endif
+#ifndef QB_TP
+#define QB_TP 6      // epilogue sources prefetched into registers before the sweep
+#endif
+__device__ __forceinline__ unsigned qb_smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ bool qb_mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__global__ void __launch_bounds__(256, QB_TT_MINB)
+qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trows)
+{
+    extern __shared__ __align__(128) unsigned char qb_tile_smem[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const double2* const sx = reinterpret_cast<const double2*>(qb_tile_smem);
+    const int N = E->ctl.N;
+    const int ntiles = (N + trows - 1) / trows;
+    const int slot = blockIdx.x / ntiles;
+    const int tile = blockIdx.x - slot * ntiles;
+    if (slot >= nslots_used) return;
+    const QbPass* __restrict__ gp = &E->pass[slot];
+    const int kind = gp->kind;
+    if (kind == QB_PASS_NONE || kind == QB_PASS_LINMAP) return;       // CTA-uniform
+    const int lo = tile * trows;
+    const int rows = min(trows, N - lo);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int sl1 = (lo + rows + 31) >> 5;
+    if (kind != QB_PASS_RHS && kind != QB_PASS_COMBINE) {             // EXPECT / APPLY: rare
+        for (int sl = (lo >> 5) + warp; sl < sl1; sl += nw) qb_pass_slice_generic(E, slot, sl, lane);
+        return;
+    }
+    const int vbase = slot * E->V;
+    const double2* const initp = E->init_states + (long long)E->traj[slot].init_idx * N;
+    const double2* gx1[1] = {nullptr};
+    const double2* sx1[1] = {sx};
+    const unsigned bar = qb_smem_u32(&mbar);
+    if (kind == QB_PASS_RHS) {
+        const int xs = gp->x;
+        gx1[0] = xs >= 0 ? E->pool + (long long)(vbase + xs) * N : initp;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const unsigned bytes = (unsigned)rows * 16u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(qb_smem_u32(qb_tile_smem)), "l"(gx1[0] + lo), "r"(bytes), "r"(bar) : "memory");
+        }
+        __syncthreads();          // the barrier object is initialised before anybody polls it
+    }
+    const int nsrc = gp->nsrc;
+    const int red = gp->red;
+    const bool werr = (red & QB_RED_WRMS) != 0;
+    const int nelem = E->ctl.nelem;
+    bool staged = false;
+    for (int sl = (lo >> 5) + warp; sl < sl1; sl += nw) {
+        const int r = sl * 32 + lane;
+        const bool active = r < N;
+        double2* const pool_r = E->pool + r;
+        // ---- request the first QB_TP sources
+        double2 pv[QB_TP];
+#pragma unroll
+        for (int u = 0; u < QB_TP; u++) {
+            const int s = gp->sw[u].src;
+            const double2* p = s >= 0 ? pool_r + (long long)(vbase + max(s, 0)) * N : initp + r;
+            pv[u] = (u < nsrc && active) ? QB_LDV(p) : make_double2(0.0, 0.0);
+        }
+        // ---- operator sweep (x from the staged tile / global memory)
+        double2 z = make_double2(0.0, 0.0);
+        if (kind == QB_PASS_RHS) {
+            if (!staged) { while (!qb_mbar_try_wait(bar, 0u)) { } staged = true; }
+            for (int e = 0; e < nelem; e++) {
+                double2 q[1];
+                qb_rowdot_rsell<1, true>(E->elem[e], sl, lane, r, gx1, sx1, lo, rows, q);
+                const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef + e];
+                z.x += c.re * q[0].x - c.im * q[0].y;
+                z.y += c.re * q[0].y + c.im * q[0].x;
+            }
+            const double zs = gp->zscale;
+            z.x *= zs; z.y *= zs;
+        }
+        // ---- fused linear combinations (sources in order, z last), stores, reductions
+        double2 o1 = make_double2(0.0, 0.0), o2 = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < QB_TP; u++) {
+            const double a = gp->sw[u].w1;
+            o1.x = fma(a, pv[u].x, o1.x); o1.y = fma(a, pv[u].y, o1.y);
+            if (werr) { const double b = gp->w2[u]; o2.x = fma(b, pv[u].x, o2.x); o2.y = fma(b, pv[u].y, o2.y); }
+        }
+        for (int i = QB_TP; i < nsrc; i += 4) {
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int s = gp->sw[min(i + u, QB_MAXSRC - 1)].src;
+                const double2* p = s >= 0 ? pool_r + (long long)(vbase + max(s, 0)) * N : initp + r;
+                v[u] = (i + u < nsrc && active) ? QB_LDV(p) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const double a = gp->sw[min(i + u, QB_MAXSRC - 1)].w1;
+                o1.x = fma(a, v[u].x, o1.x); o1.y = fma(a, v[u].y, o1.y);
+                if (werr) {
+                    const double b = gp->w2[min(i + u, QB_MAXSRC - 1)];
+                    o2.x = fma(b, v[u].x, o2.x); o2.y = fma(b, v[u].y, o2.y);
+                }
+            }
+        }
+        {
+            const double2 hz = *reinterpret_cast<const double2*>(&gp->w1z);  // w1z, w2z
+            o1.x = fma(hz.x, z.x, o1.x); o1.y = fma(hz.x, z.y, o1.y);
+            o2.x = fma(hz.y, z.x, o2.x); o2.y = fma(hz.y, z.y, o2.y);
+        }
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+        if (active) {
+            const int zdst = gp->zdst, dst1 = gp->dst1;
+            if (zdst >= 0) QB_STV(pool_r + (long long)(vbase + zdst) * N, z);
+            if (dst1 >= 0) QB_STV(pool_r + (long long)(vbase + dst1) * N, o1);
+            else if (dst1 == QB_SLOT_OUT)
+                E->out_states[((size_t)E->traj[slot].traj_id * E->ctl.nt + gp->out_index) * (size_t)N + r] = o1;
+            const double n1 = o1.x * o1.x + o1.y * o1.y;
+            r0 = n1;
+            if (werr) {
+                const double q = sqrt(o2.x * o2.x + o2.y * o2.y) / (E->ctl.opt.atol + E->ctl.opt.rtol * sqrt(n1));
+                r1 = q * q;
+            }
+            r2 = z.x * z.x + z.y * z.y;
+        }
+        if (red) {
+            r0 = qb_warp_sum(r0); r1 = qb_warp_sum(r1); r2 = qb_warp_sum(r2);
+            if (lane == 0) {
+                double* __restrict__ part = E->partials + (long long)(slot * E->nslices + sl) * E->red_stride;
+                part[0] = r0; part[1] = r1; part[2] = r2;
+            }
+        }
+    }
+}
+
 // LINMAP passes (Adams prediction / update): V[dst[j]] = sum_k w[j][k] V[src[k]] for up to 14
 // outputs of up to 15 sources.  Every source row is loaded ONCE into registers (that is the
 // point of the pass: O(q) instead of O(q^2) vector reads per step), which needs ~100
@@ -734,11 +895,14 @@ struct QbEngH : QbObj {
     int graph_slots = 0;
     cudaEvent_t ev_chunk[2] = {nullptr, nullptr};
     int no_shared = 1;          // qb_pass_kernel_shared only when QB_SHARED is set
+    int tile_g = 0, tile_rows = 0, tile_xw = 0, tile_ns = 0, tile_threads = 256;   // TMA-staged kernel (tile_g == 0: off)
+    size_t tile_smem = 0;
     double prof_pass_ms = 0.0;
     long long prof_pass_launches = 0;
     unsigned long long prof_vec_count = 0;
     std::vector<cudaEvent_t> prof_events;
     int maxcoef = 1;
+    int64_t last_ntraj = 0; int last_nt = 0;     // shape of the expectation values of the last qb_engine_run
     QbEngH() : QbObj(QB_TAG_ENG) { memset(&h, 0, sizeof h); }
     ~QbEngH() override {
         for (void* p : owned) cudaFree(p);
@@ -886,7 +1050,8 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     else h.ctl.tab = *QB_TABLEAUX[tableau];
     h.tableau_id = tableau;
     {
-        static bool tabs_uploaded = false;
+        static bool tabs_uploaded_dev[64] = {false};     // constant memory is per device
+        bool& tabs_uploaded = tabs_uploaded_dev[(e->device >= 0 && e->device < 64) ? e->device : 0];
         if (!tabs_uploaded) {
             static QbTableau both[4];
             both[0] = *QB_TABLEAUX[0]; both[1] = *QB_TABLEAUX[1]; both[2] = *QB_TABLEAUX[2];
@@ -965,6 +1130,21 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         if (el.fmt != QB_FMT_SELL && el.fmt != QB_FMT_DIAM && el.fmt != QB_FMT_KRON) h.all_lean = 0;
         if (el.fmt == QB_FMT_KRON && getenv("QB_KRON_GENERIC")) h.all_lean = 0;
     }
+    h.all_rsell = 1;
+    for (auto& el : s->elems) if (el.fmt != QB_FMT_RSELL) h.all_rsell = 0;
+    if (h.all_rsell && !getenv("QB_NO_TILE")) {
+        // tile geometry: QB_TILE_ROWS rows of one slot per CTA (x tile = rows * 16 B of smem)
+        const char* er = getenv("QB_TILE_ROWS"); const char* et = getenv("QB_TILE_THREADS");
+        int rows = er ? atoi(er) : 1024, thr = et ? atoi(et) : 256;
+        const int nround = (int)((s->N + 31) / 32 * 32);
+        rows = std::max(32, std::min(rows, 8192)) & ~31;
+        if (rows > nround) rows = nround;
+        thr = std::max(32, std::min(256, thr)) & ~31;
+        if (thr > rows) thr = rows;
+        e->tile_g = 1; e->tile_rows = rows; e->tile_threads = thr; e->tile_smem = (size_t)rows * 16;
+        cudaError_t ce = cudaFuncSetAttribute(qb_pass_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
+        if (ce != cudaSuccess) { delete e; QB_FAIL(QB_E_CUDA, "tile kernel shared memory: %s", cudaGetErrorString(ce)); }
+    }
     if (h.nslices > 2048) QB_TRY(qb_dev_alloc(e, (size_t)nslots * QB_RED_CTAS * QB_MAXRED, &h.red_final));
     if (s->elems.size() == 1 && s->elems[0].fmt == QB_FMT_DENSE && nslots >= 8) {
         QB_TRY(qb_dev_alloc(e, (size_t)nslots * N, &h.zbuf));
@@ -1024,7 +1204,12 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
                                           nslots_used);
             if (rcg) return rcg;
         }
-        if (use_shared) qb_pass_kernel_shared<<<(unsigned)grid_sh, QB_TILE_ROWS, 0, e->stream>>>(e->d);
+        if (e->tile_g) {
+            const int nt = (e->h.ctl.N + e->tile_rows - 1) / e->tile_rows;
+            qb_pass_tile_kernel<<<(unsigned)(nslots_used * nt), e->tile_threads, e->tile_smem, e->stream>>>(
+                e->d, nslots_used, e->tile_rows);
+        }
+        else if (use_shared) qb_pass_kernel_shared<<<(unsigned)grid_sh, QB_TILE_ROWS, 0, e->stream>>>(e->d);
         else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d, nslots_used);
         QB_LAUNCH_CHECK();
         if (e->h.linmap) {
@@ -1176,6 +1361,7 @@ extern "C" int qb_engine_run_device(qb_handle eng, int mode, int64_t ntraj,
     QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
     if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
     if (ntraj < 1 || nt < 1 || !d_init_states || !d_tlist || ninit < 1) QB_FAIL(QB_E_ARG, "bad run arguments");
+    if (e->device >= 0) QB_CUDA(cudaSetDevice(e->device));
     if (e->sys->nargs > 0 && !d_args) QB_FAIL(QB_E_ARG, "system has args but none were given");
     return qb_run_common(e, mode, ntraj, d_init_states, d_init_map, d_tlist, nt, d_args, d_draws,
                          ndraws, d_expect, d_status, d_ncol, d_col_t, d_col_which, d_stats, d_states);
@@ -1208,8 +1394,11 @@ extern "C" int qb_engine_run(qb_handle eng, int mode, int64_t ntraj,
     QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
     if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
     if (ntraj < 1 || nt < 1 || !init_states || !tlist || ninit < 1) QB_FAIL(QB_E_ARG, "bad run arguments");
+    if (e->device >= 0) QB_CUDA(cudaSetDevice(e->device));
     const size_t N = (size_t)e->sys->N;
-    const int neops = e->h.ctl.neops, nargs = e->sys->nargs, maxcol = e->opt.max_collapses;
+    // (the Integrator protocol zeroes h.ctl.neops; the system's own count is authoritative)
+    const int neops = (int)e->sys->eops.size(), nargs = e->sys->nargs, maxcol = e->opt.max_collapses;
+    e->last_ntraj = 0; e->last_nt = 0;
     if (nargs > 0 && !args) QB_FAIL(QB_E_ARG, "system has args but none were given");
     if (final_states && ntraj > e->nslots) QB_FAIL(QB_E_ARG, "final_states needs nslots >= ntraj");
     DevBuf b_init(e->io_p[0], e->io_cap[0]), b_map(e->io_p[1], e->io_cap[1]), b_tl(e->io_p[2], e->io_cap[2]),
@@ -1245,6 +1434,7 @@ extern "C" int qb_engine_run(qb_handle eng, int mode, int64_t ntraj,
                            static_cast<double*>(b_ct.p), static_cast<int32_t*>(b_cw.p),
                            static_cast<int32_t*>(b_stats.p), e->opt.store_states ? b_states.p : nullptr);
     if (rc) return rc;
+    e->last_ntraj = ntraj; e->last_nt = nt;
     if (expect && neops > 0) QB_CUDA(cudaMemcpy(expect, b_exp.p, (size_t)ntraj * neops * nt * 16, cudaMemcpyDeviceToHost));
     if (status) QB_CUDA(cudaMemcpy(status, b_st.p, ntraj * 4, cudaMemcpyDeviceToHost));
     if (ncol) QB_CUDA(cudaMemcpy(ncol, b_ncol.p, ntraj * 4, cudaMemcpyDeviceToHost));
@@ -1265,12 +1455,24 @@ extern "C" int qb_engine_run(qb_handle eng, int mode, int64_t ntraj,
     return QB_OK;
 }
 
-extern "C" int qb_reduce_expect(const void* d_expect, int64_t ntraj, int neops, int nt, void* d_sums) {
+int qb_reduce_expect_on(cudaStream_t stream, const void* d_expect, int64_t ntraj, int neops, int nt, void* d_sums) {
     const int n = neops * nt;
     if (n <= 0 || ntraj < 0 || !d_expect || !d_sums) QB_FAIL(QB_E_ARG, "bad reduce arguments");
-    qb_reduce_expect_kernel<<<(n + 127) / 128, 128>>>(static_cast<const double2*>(d_expect), ntraj, n,
-                                                       static_cast<double2*>(d_sums));
+    qb_reduce_expect_kernel<<<(n + 127) / 128, 128, 0, stream>>>(static_cast<const double2*>(d_expect), ntraj, n,
+                                                                  static_cast<double2*>(d_sums));
     QB_LAUNCH_CHECK();
+    return QB_OK;
+}
+extern "C" int qb_reduce_expect(const void* d_expect, int64_t ntraj, int neops, int nt, void* d_sums) {
+    return qb_reduce_expect_on(nullptr, d_expect, ntraj, neops, nt, d_sums);
+}
+// where the per-trajectory expectation values of the last qb_engine_run live (qb_comm.cu)
+int qb_engine_expect_view(qb_handle eng, const void** d_expect, int* neops, int* device, int64_t* ntraj, int* nt) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    if (e->last_ntraj < 1 || !e->io_p[5]) QB_FAIL(QB_E_STATE, "engine has no finished batched run");
+    *d_expect = e->io_p[5]; *neops = (int)e->sys->eops.size(); *device = e->device;
+    *ntraj = e->last_ntraj; *nt = e->last_nt;
     return QB_OK;
 }
 
@@ -1293,6 +1495,7 @@ static int qb_integ_traj(QbEngH* e, QbTraj* c) {
 }
 static int qb_integ_prepare(QbEngH* e) {
     QbEngineDev& h = e->h;
+    if (e->device >= 0) QB_CUDA(cudaSetDevice(e->device));
     if (!e->d_tlist) { QB_CUDA(cudaMalloc(&e->d_tlist, 8)); }
     if (!e->d_init) { QB_CUDA(cudaMalloc(&e->d_init, (size_t)e->sys->N * 16)); }
     if (e->sys->nargs > 0 && !e->d_args) {

@@ -11,7 +11,8 @@
 #include "../../include/qutip_b200.h"
 
 extern thread_local std::string g_qb_err;
-extern long long g_qb_launches;
+#include <atomic>
+extern std::atomic<long long> g_qb_launches;
 
 #define QB_FAIL(code, ...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); \
     g_qb_err = _b; return (code); } while (0)
@@ -23,11 +24,12 @@ extern long long g_qb_launches;
     cudaGetErrorString(_e), __FILE__, __LINE__); g_qb_err = _b; return QB_E_CUDA; } } while (0)
 
 enum { QB_TAG_DENSE = 0x51420001, QB_TAG_OP = 0x51420002, QB_TAG_SYS = 0x51420003,
-       QB_TAG_ENG = 0x51420004 };
+       QB_TAG_ENG = 0x51420004, QB_TAG_COMM = 0x51420005 };
 
 struct QbObj {
     uint32_t tag;
-    explicit QbObj(uint32_t t) : tag(t) {}
+    int device = -1;          // device that was current when the object was created
+    explicit QbObj(uint32_t t) : tag(t) { if (cudaGetDevice(&device) != cudaSuccess) { device = -1; cudaGetLastError(); } }
     virtual ~QbObj() { tag = 0; }
 };
 

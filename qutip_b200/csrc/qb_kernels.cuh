@@ -186,6 +186,67 @@ __device__ __forceinline__ double2 qb_rowdot_kron(const QbOpDev& A, int sl, int 
     return acc;
 }
 
+// RSELL sweep (qb_types.h): acc[g] = (A x_g)[r] for the lane's row r of slice sl, g < G.
+// Per slot two warp-uniform 16-byte loads fetch the descriptor; columns follow the slot's
+// rule (row + delta, row ^ delta, or an explicit block) and values are the slot's constant
+// or an explicit block -- diagonal-structured operators issue no per-element index loads.
+// STAGED: rows [lo, lo + trows) of every x_g were staged in shared memory (sx[g], by a TMA
+// bulk copy); columns inside that window are gathered from shared memory (conflict-free
+// LDS.128, no L1 tag stage / replays), the others from global memory.
+#ifndef QB_RS_U
+#define QB_RS_U 2
+#endif
+template <int G, bool STAGED, int U = QB_RS_U>
+__device__ __forceinline__ void qb_rowdot_rsell(const QbOpDev& A, int sl, int lane, int r,
+                                                const double2* const (&x)[G],
+                                                const double2* const (&sx)[G], int lo, int trows,
+                                                double2 (&acc)[G])
+{
+#pragma unroll
+    for (int g = 0; g < G; g++) acc[g] = make_double2(0.0, 0.0);
+    const int s0 = __ldg(A.slice_ptr + sl), s1 = __ldg(A.slice_ptr + sl + 1);
+    const int4* __restrict__ dsc = reinterpret_cast<const int4*>(A.sdesc);
+    const double2* __restrict__ val = reinterpret_cast<const double2*>(A.val) + lane;
+    const int* __restrict__ col = A.col + lane;
+    auto slot = [&](int k, int& c, double2& v) {
+        const int4 d = __ldg(dsc + 2 * k);
+        const int cr = d.x & QB_RS_COL_MASK;
+        c = r + d.y;
+        if (cr == QB_RS_COL_XOR) c = r ^ d.y;
+        if (cr == QB_RS_COL_EXPL) c = __ldg(col + d.z * 32);
+        if (d.x & QB_RS_VAL_CONST) v = __ldg(reinterpret_cast<const double2*>(dsc + 2 * k + 1));
+        else v = __ldg(val + (long long)d.w * 32);
+    };
+    auto gather = [&](int g, int c) -> double2 {
+        if (STAGED) {
+            const unsigned o = (unsigned)(c - lo);
+            if (o < (unsigned)trows) return sx[g][o];
+        }
+        return x[g][c];
+    };
+    int k = s0;
+    for (; k + U <= s1; k += U) {
+        int cc[U];
+        double2 vv[U], xx[U][G];
+#pragma unroll
+        for (int u = 0; u < U; u++) slot(k + u, cc[u], vv[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int g = 0; g < G; g++) xx[u][g] = gather(g, cc[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int g = 0; g < G; g++) qb_fma(acc[g], vv[u], xx[u][g]);
+    }
+    for (; k < s1; k++) {
+        int c; double2 v;
+        slot(k, c, v);
+#pragma unroll
+        for (int g = 0; g < G; g++) qb_fma(acc[g], v, gather(g, c));
+    }
+}
+
 // (A x)[r] for the lane's row r of slice sl, any format.  `active` lanes have r < nrows.
 template <int U = QB_U1>
 __device__ __forceinline__ double2 qb_rowdot(const QbOpDev& A, int sl, int lane, long long r,
@@ -219,6 +280,11 @@ __device__ __forceinline__ double2 qb_rowdot(const QbOpDev& A, int sl, int lane,
         }
     } else if (A.fmt == QB_FMT_KRON) {
         acc = qb_rowdot_kron(A, sl, lane, r, active, x);
+    } else if (A.fmt == QB_FMT_RSELL) {
+        const double2* xs1[1] = {x};
+        double2 a1[1];
+        qb_rowdot_rsell<1, false>(A, sl, lane, (int)r, xs1, xs1, 0, 0, a1);
+        acc = a1[0];
     } else {
         if (active) {
             const double2* __restrict__ a = reinterpret_cast<const double2*>(A.dense) + r;

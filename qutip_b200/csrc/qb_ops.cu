@@ -11,7 +11,7 @@
 #include "qb_diam.h"
 
 thread_local std::string g_qb_err;
-long long g_qb_launches = 0;
+std::atomic<long long> g_qb_launches{0};
 
 extern "C" int qb_version(void) { return 100; }
 extern "C" const char* qb_last_error(void) { return g_qb_err.c_str(); }
@@ -23,6 +23,13 @@ extern "C" int qb_device_count(int* n) {
     return QB_OK;
 }
 extern "C" int qb_set_device(int dev) { QB_CUDA(cudaSetDevice(dev)); return QB_OK; }
+extern "C" int qb_device_mem_info(int64_t* free_bytes, int64_t* total_bytes) {
+    size_t f = 0, t = 0;
+    QB_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return QB_OK;
+}
 extern "C" int qb_synchronize(void) { QB_CUDA(cudaDeviceSynchronize()); return QB_OK; }
 
 // ------------------------------------------------------------------ dense
@@ -123,6 +130,24 @@ static int finish_sell(QbOpH* h, SellHost& sh, int64_t rows, int64_t cols) {
     if ((rc = to_device(h, sh.col, &h->dev.col))) return rc;
     return QB_OK;
 }
+static int finish_rsell(QbOpH* h, RsellHost& rs, int64_t rows, int64_t cols) {
+    h->dev.fmt = QB_FMT_RSELL; h->dev.nrows = (int)rows; h->dev.ncols = (int)cols;
+    h->dev.nnz = rs.nnz;
+    int rc;
+    if ((rc = to_device(h, rs.slice_ptr, &h->dev.slice_ptr))) return rc;
+    if ((rc = to_device(h, rs.desc, &h->dev.sdesc))) return rc;
+    if ((rc = to_device(h, rs.val, &h->dev.val))) return rc;
+    if ((rc = to_device(h, rs.col, &h->dev.col))) return rc;
+    return QB_OK;
+}
+// RSELL replaces SELL when the slices are diagonal structured: at most 1.75 stored lanes per
+// non-zero (every slot costs one gather for all 32 lanes) and L2-resident
+static bool want_rsell(const RsellHost& rs, int64_t rows, long long sell_padded) {
+    if (getenv("QB_NO_RSELL") || rs.nnz == 0 || rows < 32) return false;
+    const long long stored = rs.stored() * 32;
+    return rs.bytes() <= (48ll << 20) && (double)stored <= 1.75 * (double)rs.nnz &&
+           stored <= sell_padded + sell_padded / 4;
+}
 // operators up to this size stay L2-resident when many trajectories re-read them: prefer
 // the instruction-lean SELL sweep; larger ones are HBM streams: prefer the compact DIAM
 static const long long QB_SELL_MAX_BYTES = 48ll << 20;
@@ -167,7 +192,16 @@ extern "C" int qb_csr_upload(const void* data, const int32_t* col, const int32_t
             use_sell = nnz > 0 && rows >= 32 && padded * 20 <= QB_SELL_MAX_BYTES &&
                        (double)padded <= 1.5 * (double)nnz;
     }
-    if (use_sell) rc = finish_sell(h, sh, rows, cols);
+    RsellHost rs;
+    bool use_rsell = (format == 5);
+    if (format == 5 || (format == 0 && use_sell)) {
+        build_rsell(rows, cols, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o) {
+            for (int p = rowptr[r]; p < rowptr[r + 1]; p++) o.push_back({col[p], v[p]});
+        }, rs);
+        if (format == 0) use_rsell = want_rsell(rs, rows, (long long)sh.val.size());
+    }
+    if (use_rsell) rc = finish_rsell(h, rs, rows, cols);
+    else if (use_sell) rc = finish_sell(h, sh, rows, cols);
     else if (use_diam) rc = finish_diam(h, dh, rows, cols);
     else {
         h->dev.fmt = QB_FMT_CSR; h->dev.nrows = (int)rows; h->dev.ncols = (int)cols; h->dev.nnz = nnz;
@@ -292,7 +326,23 @@ extern "C" int qb_dia_upload(const void* data, const int32_t* offsets, int64_t n
             use_sell = sh.nnz > 0 && rows >= 32 && padded * 20 <= QB_SELL_MAX_BYTES &&
                        (double)padded <= 1.5 * (double)sh.nnz;
     }
-    if (use_sell) rc = finish_sell(h, sh, rows, cols);
+    RsellHost rs;
+    bool use_rsell = (format == 5);
+    if (format == 5 || (format == 0 && use_sell)) {
+        build_rsell(rows, cols, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o) {
+            for (int k = 0; k < ndiag; k++) {
+                const int d = order[k];
+                const int64_t c = r + offsets[d];
+                if (c < 0 || c >= cols) continue;
+                const qb_c128 x = v[(size_t)d * cols + c];
+                if (x.re == 0.0 && x.im == 0.0) continue;
+                o.push_back({(int)c, x});
+            }
+        }, rs);
+        if (format == 0) use_rsell = want_rsell(rs, rows, (long long)sh.val.size());
+    }
+    if (use_rsell) rc = finish_rsell(h, rs, rows, cols);
+    else if (use_sell) rc = finish_sell(h, sh, rows, cols);
     else if (use_diam) rc = finish_diam(h, dh, rows, cols);
     else {
         // sparse diagonals: fall back to CSR built from the slices
@@ -364,6 +414,18 @@ qb_matmul_kernel(QbOpDev A, const double2* __restrict__ X, long long xs_r, long 
                     const int* col = A.col + ((size_t)s0 * 32 + lane);
                     for (int k = 0; k < w; k++)
                         qb_fma(q, val[k * 32], X[(long long)col[k * 32] * xs_r + c * xs_c]);
+                } else if (A.fmt == QB_FMT_RSELL) {
+                    const double2* val = reinterpret_cast<const double2*>(A.val);
+                    for (int k = A.slice_ptr[sl]; k < A.slice_ptr[sl + 1]; k++) {
+                        const QbSlotDesc d = A.sdesc[k];
+                        const int cr = d.rule & QB_RS_COL_MASK;
+                        const long long cc = cr == QB_RS_COL_ADD ? r + d.delta
+                                           : cr == QB_RS_COL_XOR ? (r ^ (long long)d.delta)
+                                                                 : A.col[(size_t)d.cpos * 32 + lane];
+                        const double2 vv = (d.rule & QB_RS_VAL_CONST) ? make_double2(d.vre, d.vim)
+                                                                      : val[(size_t)d.vpos * 32 + lane];
+                        qb_fma(q, vv, X[cc * xs_r + c * xs_c]);
+                    }
                 }
             }
             if (A.fmt == QB_FMT_DIAM) {

@@ -37,7 +37,25 @@ struct QbTableau {
 };
 
 // ---- operator storage on the device ----
-enum { QB_FMT_CSR = 0, QB_FMT_DIAM = 1, QB_FMT_DENSE = 2, QB_FMT_SELL = 3, QB_FMT_KRON = 4 };
+enum { QB_FMT_CSR = 0, QB_FMT_DIAM = 1, QB_FMT_DENSE = 2, QB_FMT_SELL = 3, QB_FMT_KRON = 4,
+       QB_FMT_RSELL = 5 };
+
+// RSELL ("rule" sliced ELLPACK): SELL whose slots carry a 32-byte descriptor read with two
+// warp-uniform loads.  A slot of a 32-row slice is one diagonal of the slice: its column is
+// given by a rule -- row + delta, row ^ delta (tensor-product / spin operators flip one bit
+// of the row index) -- or by an explicit 32-lane column block, and its value is one constant
+// for the whole slot or an explicit 32-lane value block.  Diagonal-structured operators
+// shrink from 20 B per stored element to 32 B per (slice, diagonal) + the non-constant
+// diagonals, and the sweep needs no per-element index loads.
+enum { QB_RS_COL_EXPL = 0, QB_RS_COL_ADD = 1, QB_RS_COL_XOR = 2, QB_RS_COL_MASK = 3,
+       QB_RS_VAL_CONST = 4 };
+struct alignas(16) QbSlotDesc {
+    int rule;        // QB_RS_COL_* | QB_RS_VAL_CONST
+    int delta;       // operand of the column rule
+    int cpos;        // explicit columns: col[cpos * 32 + lane]
+    int vpos;        // explicit values:  val[vpos * 32 + lane]
+    double vre, vim; // constant value
+};
 
 struct QbOpDev {
     int fmt, nrows, ncols, pad_;
@@ -65,6 +83,8 @@ struct QbOpDev {
     int kstack, kpad_;
     const qb_c128* kval;
     const int* kcol;
+    // RSELL: slice_ptr[nslices+1] indexes sdesc[]; explicit blocks live in val / col
+    const QbSlotDesc* sdesc;
 };
 
 // ---- coefficient byte-code (qb_coeff.h) ----

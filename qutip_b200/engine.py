@@ -12,8 +12,9 @@ from ._lib import QbOptions, as_c128, check, ptr
 from .coeffs import Program
 
 FMT_AUTO, FMT_CSR, FMT_DIAM, FMT_SELL = 0, 1, 2, 3
+FMT_RSELL = 5     # rule-compressed sliced ELLPACK (qb_types.h); same code as upload format and as reported format
 FMT_KRON = 4      # reported by DeviceOp.info() for matrix-free Kronecker operators
-FMT_NAMES = {0: "csr", 1: "diam", 2: "dense", 3: "sell", 4: "kron"}
+FMT_NAMES = {0: "csr", 1: "diam", 2: "dense", 3: "sell", 4: "kron", 5: "rsell"}
 TABLEAUX = {"vern7": 0, "vern9": 1, "tsit5": 2, "adams": 3}
 
 STATUS_MESSAGES = {
@@ -467,3 +468,74 @@ class Engine(_Handle):
         ms, n, v = C.c_double(), C.c_int64(), C.c_double()
         check(_lib.load().qb_engine_profile(self.handle, C.byref(ms), C.byref(n), C.byref(v)))
         return dict(pass_ms=ms.value, pass_launches=n.value, state_vector_accesses=v.value)
+
+
+# --------------------------------------------------------------------- multi-GPU
+def set_device(dev):
+    """make ``dev`` the current CUDA device of the calling thread (handles created afterwards
+    live there; engine calls switch to their own device by themselves)."""
+    check(_lib.load().qb_set_device(int(dev)))
+
+
+def mem_info():
+    """(free, total) bytes of the current device"""
+    free, total = C.c_int64(), C.c_int64()
+    check(_lib.load().qb_device_mem_info(C.byref(free), C.byref(total)))
+    return free.value, total.value
+
+
+class Comm(_Handle):
+    """NCCL group for the one collective of the sharded workloads: the sum of the expectation
+    sums over the devices (solver/multitrajresult.py:1116-1124 across shards; C ABI
+    ``qb_comm_*``).  ``Comm.all(devices)``: this process drives all ``devices``
+    (ncclCommInitAll).  ``Comm.rank(nranks, rank, uid)``: one process per device; ``uid`` is
+    ``Comm.unique_id()`` of rank 0, distributed by the launcher."""
+
+    ID_BYTES = 128
+
+    def __init__(self, h, nranks, nlocal):
+        super().__init__(h)
+        self.nranks, self.nlocal = nranks, nlocal
+
+    @classmethod
+    def all(cls, devices):
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        check(_lib.load().qb_comm_init_all(len(devices), devs, C.byref(h)))
+        return cls(h, len(devices), len(devices))
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * Comm.ID_BYTES)()
+        check(_lib.load().qb_comm_unique_id(buf, Comm.ID_BYTES))
+        return bytes(buf)
+
+    @classmethod
+    def rank(cls, nranks, rank, uid):
+        buf = (C.c_ubyte * Comm.ID_BYTES).from_buffer_copy(bytes(uid))
+        h = C.c_void_p()
+        check(_lib.load().qb_comm_init_rank(int(nranks), int(rank), buf, C.byref(h)))
+        return cls(h, int(nranks), 1)
+
+    def allreduce_sum(self, arrays):
+        """in-place sum over the group of one float64 / complex128 array per local member"""
+        arrays = list(arrays)
+        if len(arrays) != self.nlocal:
+            raise ValueError("one array per local member")
+        views = [a.view(np.float64).reshape(-1) for a in arrays]
+        if any(not a.flags.c_contiguous for a in arrays) or len({v.size for v in views}) != 1:
+            raise ValueError("arrays must be contiguous and of equal size")
+        ptrs = (C.c_void_p * self.nlocal)(*[v.ctypes.data for v in views])
+        check(_lib.load().qb_comm_allreduce_sum(self.handle, ptrs, views[0].size))
+        return arrays
+
+    def reduce_expect(self, engines, neops, nt):
+        """(sum_j e_j, sum_j (re^2, im^2)) over ALL trajectories of the group, [n_e][n_t] each:
+        every engine (``None`` for a member that ran nothing) reduces the expectation values
+        its last run left on its device, then ONE ncclAllReduce."""
+        if len(engines) != self.nlocal:
+            raise ValueError("one engine per local member")
+        hs = (C.c_void_p * self.nlocal)(*[None if e is None else e.handle for e in engines])
+        out = np.zeros((2, neops, nt), dtype=np.complex128)
+        check(_lib.load().qb_comm_reduce_expect(self.handle, hs, int(neops), int(nt), ptr(out)))
+        return out[0], out[1]

@@ -26,6 +26,9 @@ Anything that cannot run on the device (python-function coefficients or operator
 feedback arguments, non-Qobj e_ops in the batched map) raises ``TypeError`` naming the
 stock method to use instead -- there is no CPU fallback in this package.
 """
+import os
+import threading
+
 import numpy as np
 import scipy.sparse as sp
 
@@ -40,11 +43,11 @@ from qutip.solver.sesolve import SESolver
 from qutip.solver import parallel as _qparallel
 import qutip.solver.integrator.scipy_integrator  # noqa: F401
 
-from . import coeffs, engine as E
+from . import _lib, coeffs, engine as E, solve
 from .solve import make_thresholds  # noqa: F401
 
 __all__ = ["B200Dense", "B200Operator", "B200Vern7", "B200Vern9", "B200Tsit5", "B200Adams", "bind_qobjevo", "b200_map",
-           "register"]
+           "register", "configure"]
 
 
 # ------------------------------------------------------------------ QobjEvo -> device system
@@ -839,6 +842,71 @@ def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, m
     return None
 
 
+# devices the "b200" map shards over (None: the current device only).  Set with
+# ``configure(devices=[0, 1, ...])`` / ``configure(devices="all")`` or QUTIP_B200_DEVICES=0,1,..
+_DEVICES = None
+
+
+def configure(devices=None):
+    """Choose the GPUs ``options={"map": "b200"}`` uses: a list of device indices, ``"all"``
+    (every device of the box) or ``None`` (the current device).  Trajectories are sharded in
+    contiguous blocks of the seed list, every device holds its own copy of the
+    operators, and the expectation sums are combined by ONE ncclAllReduce."""
+    global _DEVICES
+    if devices == "all":
+        devices = list(range(max(1, _lib.device_count())))
+    _DEVICES = None if devices is None else [int(d) for d in devices]
+    return _DEVICES
+
+
+def _map_devices():
+    if _DEVICES is not None:
+        return list(_DEVICES)
+    env = os.environ.get("QUTIP_B200_DEVICES", "").strip()
+    if env == "all":
+        return list(range(max(1, _lib.device_count())))
+    if env:
+        return [int(x) for x in env.split(",") if x.strip() != ""]
+    return None
+
+
+def _run_engine_batch(make_engine, psi0, tlist, draws, gens, max_collapses):
+    """One engine, trajectories = rows of ``draws``: run, then re-run the trajectories whose
+    threshold table (status -12) or collapse record (status -13) was too short with longer
+    ones -- the reference has neither limit (mcsolve.py:371-406 appends to python lists)."""
+    ntraj, ndraws = draws.shape
+    eng = make_engine(max_collapses)
+    r = eng.run_mcsolve(psi0, tlist, draws, ntraj=ntraj)
+    while ((r.status == -12) | (r.status == -13)).any():
+        todo = np.nonzero((r.status == -12) | (r.status == -13))[0]
+        if (r.status[todo] == -13).any():
+            max_collapses *= 4
+            eng_retry = make_engine(max_collapses)
+        else:
+            eng_retry = eng
+        if (r.status[todo] == -12).any():
+            if gens is None:
+                raise IntegratorException(E.STATUS_MESSAGES[-12])
+            more = np.stack([gens[j].random(3 * ndraws) for j in range(ntraj)])
+            draws = np.concatenate([draws, more], axis=1)
+            ndraws = draws.shape[1]
+        r2 = eng_retry.run_mcsolve(psi0, tlist, np.ascontiguousarray(draws[todo]), ntraj=len(todo))
+        if r2.col_t.shape[1] > r.col_t.shape[1]:
+            for key in ("col_t", "col_which"):
+                wide = np.zeros((ntraj, r2[key].shape[1]), dtype=r[key].dtype)
+                wide[:, :r[key].shape[1]] = r[key]
+                r[key] = wide
+        w = r2.col_t.shape[1]
+        for key in ("expect", "status", "ncol", "stats"):
+            r[key][todo] = r2[key]
+        r.col_t[todo, :w] = r2.col_t
+        r.col_which[todo, :w] = r2.col_which
+        if r.states is not None:
+            r.states[todo] = r2.states
+    r["engine"] = eng
+    return r
+
+
 def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func, task):
     """One device batch: all trajectories of one initial state.  Returns True when
     ``reduce_func`` asked to stop."""
@@ -865,49 +933,93 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
         raise TypeError("superoperator Hamiltonians are not supported by the 'b200' map")
     want_states = bool(opts["store_states"]) or (opts["store_states"] is None and not e_dict)
     want_final = bool(opts["store_final_state"])
-    system = system_from_qobjevo(rhs.rhs, rhs.c_ops, rhs.n_ops,
-                                 [QobjEvo(e) if isinstance(e, qutip.Qobj) else e
-                                  for e in e_dict.values()], allow_host=True)
-    if system.has_host:
-        raise TypeError("python-callable coefficients need a host evaluation per RHS call; the "
-                        "'b200' map runs whole batches on the device and cannot use them. Use "
-                        "string/array coefficients, or method='b200_vern7' with a stock map.")
+    e_evos = [QobjEvo(e) if isinstance(e, qutip.Qobj) else e for e in e_dict.values()]
     iopt = solver._integrator._integrator.options
-    eng = E.Engine(
-        system, method, nslots=min(ntraj, 4096), atol=iopt['atol'], rtol=iopt['rtol'],
-        nsteps=int(iopt['nsteps']), first_step=float(iopt['first_step'] or 0),
-        min_step=float(iopt['min_step'] or 0), max_step=float(iopt['max_step'] or 0),
-        interpolate=int(bool(iopt.get('interpolate', True))),
-        max_order=int(iopt.get('order', 0) or 0), norm_steps=int(opts['norm_steps']),
-        norm_t_tol=opts['norm_t_tol'], norm_tol=opts['norm_tol'],
-        norm_min_step=opts['norm_min_step'], mc_corr_eps=opts['mc_corr_eps'],
-        store_states=int(want_states or want_final), jump_prob_floor=floor)
+    psi0 = _data.to(_data.Dense, state0).to_array().reshape(-1, order="F")
+    tlist = np.asarray(tlist, dtype=float)
+    N = psi0.size
     ndraws = 64
     gens = [s if hasattr(s, "random") else solver._get_generator(s) for s in seeds]
     draws = np.stack([g.random(ndraws) for g in gens])
-    psi0 = _data.to(_data.Dense, state0).to_array().reshape(-1, order="F")
-    tlist = np.asarray(tlist, dtype=float)
-    r = eng.run_mcsolve(psi0, tlist, draws, ntraj=ntraj)
-    while (r.status == -12).any():           # threshold table too short: extend and redo those
-        todo = np.nonzero(r.status == -12)[0]
-        more = np.stack([gens[j].random(3 * ndraws) for j in todo])
-        draws_ext = np.concatenate([draws[todo], more], axis=1)
-        r2 = eng.run_mcsolve(psi0, tlist, draws_ext, ntraj=len(todo))
-        for key in ("expect", "status", "ncol", "col_t", "col_which", "stats"):
-            r[key][todo] = r2[key]
-        if r.states is not None:
-            r.states[todo] = r2.states
-        full = np.zeros((ntraj, draws_ext.shape[1]))
-        full[:, :draws.shape[1]] = draws
-        full[todo] = draws_ext
-        draws, ndraws = full, draws_ext.shape[1]
-    herm = [bool(e.isherm) if isinstance(e, qutip.Qobj) else False for e in e_dict.values()]
-    for j in range(ntraj):
-        st = int(r.status[j])
+    devices = _map_devices()
+    multi = devices is not None and len(devices) > 1 and ntraj >= 2 * len(devices)
+    store = int(want_states or want_final)
+
+    def shard(lo, hi, device):
+        if device is not None:
+            E.set_device(device)
+        system = system_from_qobjevo(rhs.rhs, rhs.c_ops, rhs.n_ops, e_evos, allow_host=True)
+        if system.has_host:
+            raise TypeError("python-callable coefficients need a host evaluation per RHS call; the "
+                            "'b200' map runs whole batches on the device and cannot use them. Use "
+                            "string/array coefficients, or method='b200_vern7' with a stock map.")
+        nslots = min(hi - lo, solve.default_nslots(N, method))
+
+        def make_engine(max_collapses):
+            return E.Engine(
+                system, method, nslots=nslots, atol=iopt['atol'], rtol=iopt['rtol'],
+                nsteps=int(iopt['nsteps']), first_step=float(iopt['first_step'] or 0),
+                min_step=float(iopt['min_step'] or 0), max_step=float(iopt['max_step'] or 0),
+                interpolate=int(bool(iopt.get('interpolate', True))),
+                max_order=int(iopt.get('order', 0) or 0), norm_steps=int(opts['norm_steps']),
+                norm_t_tol=opts['norm_t_tol'], norm_tol=opts['norm_tol'],
+                norm_min_step=opts['norm_min_step'], mc_corr_eps=opts['mc_corr_eps'],
+                store_states=store, jump_prob_floor=floor, max_collapses=max_collapses)
+
+        return _run_engine_batch(make_engine, psi0, tlist, np.ascontiguousarray(draws[lo:hi]),
+                                 gens[lo:hi], _MAX_COLLAPSES)
+
+    sums = None
+    if not multi:
+        r = shard(0, ntraj, devices[0] if devices else None)
+    else:
+        # contiguous blocks of the seed list, one host thread per device (the C ABI calls
+        # release the GIL); ONE ncclAllReduce of the device-side expectation sums
+        world = len(devices)
+        comm = E.Comm.all(devices)
+        parts, errors = [None] * world, []
+
+        def work(i):
+            try:
+                lo, hi = solve.shard_range(ntraj, i, world)
+                if hi > lo:
+                    parts[i] = shard(lo, hi, devices[i])
+            except BaseException as exc:
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        live = [q for q in parts if q is not None]
+        if e_dict:
+            sums = comm.reduce_expect([None if q is None else q.engine for q in parts],
+                                      len(e_dict), len(tlist))
+        comm.free()
+        width = max(q.col_t.shape[1] for q in live)
+
+        def cat(key, pad=False):
+            arrs = [q[key] for q in live]
+            if pad:
+                arrs = [np.pad(x, ((0, 0), (0, width - x.shape[1]))) for x in arrs]
+            return np.concatenate(arrs)
+
+        r = E.RunResult(expect=cat("expect"), status=cat("status"), ncol=cat("ncol"),
+                        col_t=cat("col_t", True), col_which=cat("col_which", True), stats=cat("stats"),
+                        states=None if live[0].states is None else cat("states"))
+    bad = np.nonzero(r.status != 1)[0]
+    if bad.size:
+        st = int(r.status[bad[0]])
         if st == -10:
             raise RuntimeError(E.STATUS_MESSAGES[-10])
-        if st != 1:
-            raise IntegratorException(E.STATUS_MESSAGES.get(st, "integration failed"))
+        raise IntegratorException(E.STATUS_MESSAGES.get(st, "integration failed"))
+    herm = [bool(e.isherm) if isinstance(e, qutip.Qobj) else False for e in e_dict.values()]
+    w_traj = (1 - floor) * weight                                        # mcsolve.py:565
+
+    def make_result(j):
         res = solver._trajectory_resultclass(e_dict, solver.options)
         res.times = list(tlist)
         for m, k in enumerate(res.e_data):
@@ -919,13 +1031,71 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
             if want_states:
                 res.states = qs
             res._final_state = qs[-1]
-        res.collapse = [(float(r.col_t[j, i]), int(r.col_which[j, i]))
-                        for i in range(r.ncol[j])]
+        res.collapse = [(float(r.col_t[j, i]), int(r.col_which[j, i])) for i in range(r.ncol[j])]
+        return res
+
+    first = 0
+    target = getattr(reduce_func, "__self__", None)
+    if _bulk_feed_ok(target, want_states, want_final) and ntraj > 1:
+        # averages only: trajectory 0 goes through McResult.add (it sizes the accumulators),
+        # the others are added to the running sums in bulk -- what _TrajectorySum.reduce_expect
+        # (multitrajresult.py:1116-1124) and _McBaseResult._add_collapse do one by one
+        remaining = reduce_func((seeds[0], make_result(0), w_traj))
+        if remaining is not None and remaining <= 0:
+            return True
+        room = ntraj - 1
+        if target._target_ntraj is not None:
+            room = min(room, int(target._target_ntraj - target.num_trajectories))
+        if room > 0:
+            sel = slice(1, 1 + room)
+            target.seeds.extend(seeds[sel])
+            target._trajectories_weight_info.extend([w_traj] * room)
+            target.num_trajectories += room
+            for m in range(len(e_dict)):
+                vals = r.expect[sel, m]
+                vals = vals.real if herm[m] else vals
+                if sums is not None and room == ntraj - 1 and not np.iscomplexobj(vals):
+                    # multi-device: the NCCL-reduced sums of ALL trajectories minus trajectory 0
+                    v0 = r.expect[0, m].real
+                    s1 = sums[0][m].real - v0
+                    s2 = sums[1][m].real - v0 * v0
+                else:
+                    s1, s2 = vals.sum(axis=0), (vals ** 2).sum(axis=0)
+                target._sum_rel.sum_expect[m] += w_traj * s1
+                target._sum_rel.sum2_expect[m] += w_traj * s2
+            ct, cw, nc = r.col_t, r.col_which, r.ncol
+            target.collapse.extend(
+                [list(zip(ct[j, :nc[j]].tolist(), cw[j, :nc[j]].tolist())) for j in range(1, 1 + room)])
+        remaining = target._early_finish_check()
+        return remaining is not None and remaining <= 0
+    for j in range(first, ntraj):
         if reduce_func is not None:
-            remaining = reduce_func((seeds[j], res, (1 - floor) * weight))     # mcsolve.py:565
+            remaining = reduce_func((seeds[j], make_result(j), w_traj))
             if remaining is not None and remaining <= 0:
                 return True
     return False
+
+
+_MAX_COLLAPSES = 64       # initial capacity of the per-trajectory collapse record (grown on demand)
+
+
+def _bulk_feed_ok(target, want_states, want_final):
+    """The vectorised feed replaces exactly the processors a plain averaging McResult runs per
+    trajectory (_increment_traj, _reduce_expect, _add_collapse); anything else -- kept
+    trajectories, averaged states, target tolerances, subclasses -- takes McResult.add."""
+    from qutip.solver.multitrajresult import McResult, MultiTrajResult, _McBaseResult
+    if type(target) is not McResult or want_states or want_final:
+        return False
+    if target.options["keep_runs_results"] or target.runs_e_data:
+        return False
+    try:
+        procs = {getattr(pr, "__func__", None) for pr in target._state_processors}
+        allowed = {MultiTrajResult._increment_traj, MultiTrajResult._reduce_expect,
+                   _McBaseResult._add_collapse}
+        check = getattr(target._early_finish_check, "__func__", None)
+        return procs <= allowed and check in (MultiTrajResult._fixed_end, MultiTrajResult._no_end)
+    except AttributeError:
+        return False
 
 
 register()

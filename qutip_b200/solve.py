@@ -7,9 +7,13 @@ records come back as arrays shaped like the reference's ``McResult`` fields
 wrappers in plugin.py translate Qobj/QobjEvo into these calls.
 
 Multi-GPU: trajectories are independent given their seed-derived thresholds
-(multitraj.py:250-256), so each rank of a torch.distributed job takes a contiguous block
-of the spawned seed list and only the expectation sums are reduced (one NCCL all-reduce).
+(multitraj.py:250-256), so each device takes a contiguous block of the spawned seed list and
+only the expectation sums are reduced -- ONE ncclAllReduce issued through the C ABI
+(engine.Comm).  ``mcsolve(..., devices=[0, 1, ...])`` drives all devices from this process
+(one host thread per device); ``mcsolve_sharded`` is the one-process-per-device form.
 """
+import threading
+
 import numpy as np
 import scipy.sparse as sp
 
@@ -153,25 +157,40 @@ class McResult(dict):
     __getattr__ = dict.__getitem__
 
 
+def default_nslots(N, method="vern7", fraction=0.6):
+    """Resident trajectory slots when the caller does not say: as many as fit in ``fraction``
+    of the free device memory (every slot owns S + 5 state-sized vectors), at most 16384."""
+    V = {"vern7": 21, "vern9": 31, "tsit5": 12, "adams": 33}.get(method, 31)
+    free, _ = E.mem_info()
+    return int(max(1, min(16384, fraction * free // (V * N * 16 + 4096))))
+
+
 def mcsolve(heff_elements, c_ops, psi0, tlist, ntraj, seeds=None, e_ops=(), method="vern7",
-            nslots=None, ndraws=64, options=None, n_ops=None, draws=None, engine=None):
+            nslots=None, ndraws=64, options=None, n_ops=None, draws=None, engine=None,
+            devices=None, first=0):
     """Monte-Carlo trajectories on the device.  ``heff_elements`` is mcsolve's rhs
     (-iH - 1/2 sum c^dag c, solver/mcsolve.py:493-496).  Returns per-trajectory
     expectation values [n_e][ntraj][nt], their average / std as the reference computes
     them (multitrajresult.py:261-279,1116-1124) and the collapse records."""
+    if devices is not None and len(devices) > 1:
+        return mcsolve_multi(heff_elements, c_ops, psi0, tlist, ntraj, seeds, devices, e_ops=e_ops,
+                             method=method, nslots=nslots, ndraws=ndraws, options=options,
+                             n_ops=n_ops, draws=draws)
+    if devices:
+        E.set_device(devices[0])
     opts = dict(options or {})
     if engine is None:
         system = build_system(heff_elements, c_ops, n_ops, e_ops)
-        nslots = min(ntraj, nslots or 4096)
+        nslots = min(ntraj, nslots or default_nslots(system.N, method))
         engine = E.Engine(system, method, nslots=nslots, **opts)
     if draws is None:
-        draws = make_thresholds(seeds, ntraj, ndraws)
+        draws = make_thresholds(seeds, ntraj, ndraws, first=first)
     r = engine.run_mcsolve(psi0, tlist, draws, ntraj=ntraj)
     # trajectories whose threshold table ran out are re-run with a longer one
     todo = np.nonzero(r.status == -12)[0]
     while todo.size:
         ndraws *= 4
-        full = make_thresholds(seeds, ntraj, ndraws) if seeds is not None else None
+        full = make_thresholds(seeds, ntraj, ndraws, first=first) if seeds is not None else None
         if full is None:
             raise QbError(-12, E.STATUS_MESSAGES[-12])
         r2 = engine.run_mcsolve(psi0, tlist, full[todo], ntraj=len(todo))
@@ -230,33 +249,95 @@ def shard_range(ntraj, rank, world):
     return lo, min(ntraj, lo + per)
 
 
-def reduce_expect_sums(runs_expect, group=None, device=None):
-    """[2][n_e][nt] = (sum_j e_j, sum_j |e_j|^2) over the local trajectories, all-reduced
-    over the ranks with ONE collective (NCCL on GPUs, gloo in the CPU tests).  This is the
-    reduce of _TrajectorySum.reduce_expect (multitrajresult.py:1116-1124)."""
-    import torch
-    import torch.distributed as dist
-    local = np.stack([runs_expect.sum(axis=1), (np.abs(runs_expect) ** 2).sum(axis=1)])
-    buf = torch.from_numpy(np.ascontiguousarray(local.view(np.float64)))
-    if device is not None:
-        buf = buf.to(device)
-    if dist.is_available() and dist.is_initialized():
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    out = buf.cpu().numpy().view(np.complex128)
-    return out[0], out[1]
+def local_expect_sums(runs_expect):
+    """[2][n_e][nt]: (sum_j e_j, sum_j (re_j^2, im_j^2)) of runs_expect[n_e][ntraj][nt] -- the
+    quantities _TrajectorySum.reduce_expect accumulates (multitrajresult.py:1116-1124), laid
+    out like the device reduction (qb_reduce_expect)."""
+    runs = np.asarray(runs_expect, dtype=np.complex128)
+    return np.stack([runs.sum(axis=1), (runs.real ** 2).sum(axis=1) + 1j * (runs.imag ** 2).sum(axis=1)])
+
+
+def finish_expect_sums(s1, s2, ntraj):
+    """average and standard deviation as multitrajresult.py:261-279 forms them"""
+    avg = s1 / ntraj
+    avg2 = (s2.real + s2.imag) / ntraj
+    return avg, np.sqrt(np.abs(avg2 - np.abs(avg) ** 2))
+
+
+def reduce_expect_sums(runs_expect, comm=None, allreduce=None):
+    """Expectation sums over all ranks with ONE collective: ``comm`` (engine.Comm, NCCL) on
+    GPUs; ``allreduce`` (callable summing a float64 array in place over the ranks) lets the
+    CPU tests exercise the same host logic over gloo."""
+    local = np.ascontiguousarray(local_expect_sums(runs_expect))
+    if comm is not None:
+        comm.allreduce_sum([local])
+    elif allreduce is not None:
+        allreduce(local.view(np.float64).reshape(-1))
+    return local[0], local[1]
 
 
 def mcsolve_sharded(heff_elements, c_ops, psi0, tlist, ntraj, seeds, e_ops=(), rank=0, world=1,
-                    device=None, **kw):
-    """Each rank runs trajectories [lo, hi) of the global seed list and the averages are
-    formed from one all-reduce of the expectation sums."""
+                    comm=None, allreduce=None, **kw):
+    """One process per device: this rank runs trajectories [lo, hi) of the global seed list;
+    the averages come from one all-reduce of the expectation sums."""
     lo, hi = shard_range(ntraj, rank, world)
     draws = make_thresholds(seeds, hi - lo, kw.pop("ndraws", 64), first=lo)
     res = mcsolve(heff_elements, c_ops, psi0, tlist, hi - lo, e_ops=e_ops, draws=draws, **kw)
-    s1, s2 = reduce_expect_sums(res.runs_expect, device=device)
-    avg = s1 / ntraj
-    std = np.sqrt(np.abs(s2 / ntraj - np.abs(avg) ** 2))
-    res["global_average_expect"] = avg
-    res["global_std_expect"] = std
+    if comm is not None and len(e_ops):
+        s1, s2 = comm.reduce_expect([res.engine], len(e_ops), len(tlist))
+    else:
+        s1, s2 = reduce_expect_sums(res.runs_expect, allreduce=allreduce)
+    res["global_average_expect"], res["global_std_expect"] = finish_expect_sums(s1, s2, ntraj)
     res["shard"] = (lo, hi)
     return res
+
+
+def mcsolve_multi(heff_elements, c_ops, psi0, tlist, ntraj, seeds, devices, e_ops=(),
+                  method="vern7", nslots=None, ndraws=64, options=None, n_ops=None, draws=None):
+    """All ``devices`` of the box from ONE process: device d gets the contiguous block
+    ``shard_range(ntraj, d, len(devices))`` of the seed list, its own copy of the operators
+    and one host thread (the C ABI calls release the GIL); per-trajectory records are
+    concatenated in seed order; the averages come from ONE ncclAllReduce of the device-side
+    expectation sums (engine.Comm.reduce_expect)."""
+    devices = list(devices)
+    world = len(devices)
+    comm = E.Comm.all(devices)
+    parts = [None] * world
+    errors = []
+
+    def work(i):
+        try:
+            lo, hi = shard_range(ntraj, i, world)
+            if hi <= lo:
+                return
+            E.set_device(devices[i])
+            d = draws[lo:hi] if draws is not None else make_thresholds(seeds, hi - lo, ndraws, first=lo)
+            parts[i] = mcsolve(heff_elements, c_ops, psi0, tlist, hi - lo, seeds=seeds, e_ops=e_ops,
+                               method=method, nslots=nslots, ndraws=ndraws, options=options,
+                               n_ops=n_ops, draws=d, first=lo)
+        except BaseException as exc:      # re-raised in the calling thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    live = [p for p in parts if p is not None]
+    out = McResult(
+        runs_expect=np.concatenate([p.runs_expect for p in live], axis=1),
+        col_times=[c for p in live for c in p.col_times],
+        col_which=[c for p in live for c in p.col_which],
+        ncol=np.concatenate([p.ncol for p in live]), stats=np.concatenate([p.stats for p in live]),
+        rounds=max(p.rounds for p in live), gpu_ms=max(p.gpu_ms for p in live),
+        states=None if live[0].states is None else np.concatenate([p.states for p in live]),
+        engine=[None if p is None else p.engine for p in parts], devices=devices)
+    if len(e_ops):
+        s1, s2 = comm.reduce_expect(out.engine, len(e_ops), len(tlist))
+        out["average_expect"], out["std_expect"] = finish_expect_sums(s1, s2, ntraj)
+    else:
+        out["average_expect"] = out["std_expect"] = np.zeros((0, len(tlist)))
+    comm.free()
+    return out

@@ -12,7 +12,7 @@ from qutip_b200.coeffs import Program, QbInstr
 HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-FMT_CSR, FMT_DIAM, FMT_SELL = 0, 1, 3
+FMT_CSR, FMT_DIAM, FMT_SELL, FMT_RSELL = 0, 1, 3, 5
 
 
 class QbOptions(C.Structure):
@@ -98,6 +98,11 @@ class EmulSystem:
 
     def set_functional(self, f):
         self.L.emul_set_functional(int(f))
+
+    def rsell_stats(self, which):
+        out = (C.c_longlong * 5)()
+        self.L.emul_rsell_stats(which, out)
+        return dict(slots=out[0], col_blocks=out[1], val_blocks=out[2], bytes=out[3], xor_slots=out[4])
 
     def matvec(self, which, x):
         x = np.ascontiguousarray(x, dtype=np.complex128)

@@ -25,6 +25,7 @@ struct HostOp {
     std::vector<qb_c128> val; std::vector<int> col, rowptr;      // CSR
     qbdiam::DiamHost dh;                                           // DIAM
     qbdiam::SellHost sh;                                           // SELL
+    qbdiam::RsellHost rs;                                          // RSELL
 };
 struct Sys {
     int64_t N = 0; int nargs = 0;
@@ -59,6 +60,19 @@ static qb_c128 rowdot(const HostOp& A, int64_t r, const qb_c128* x) {
         }
         return acc;
     }
+    if (A.fmt == QB_FMT_RSELL) {
+        for (int k = A.rs.slice_ptr[sl]; k < A.rs.slice_ptr[sl + 1]; k++) {
+            const QbSlotDesc& d = A.rs.desc[k];
+            const int cr = d.rule & QB_RS_COL_MASK;
+            const long long c = cr == QB_RS_COL_ADD ? r + d.delta : cr == QB_RS_COL_XOR ? (r ^ (long long)d.delta)
+                                                                   : A.rs.col[(size_t)d.cpos * 32 + lane];
+            qb_c128 a = {d.vre, d.vim};
+            if (!(d.rule & QB_RS_VAL_CONST)) a = A.rs.val[(size_t)d.vpos * 32 + lane];
+            const qb_c128 b = x[c];
+            acc.re += a.re * b.re - a.im * b.im; acc.im += a.re * b.im + a.im * b.re;
+        }
+        return acc;
+    }
     long long vb = A.dh.slice_vbase[sl];
     const unsigned lt = (1u << lane) - 1u;
     for (int e = A.dh.slice_ptr[sl]; e < A.dh.slice_ptr[sl + 1]; e++) {
@@ -83,6 +97,10 @@ static HostOp make_op(const qb_c128* data, const int32_t* col, const int32_t* ro
         qbdiam::build_sell(rows, cols, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o2) {
             for (int p = rowptr[r]; p < rowptr[r + 1]; p++) o2.push_back({col[p], data[p]});
         }, o.sh);
+    } else if (fmt == QB_FMT_RSELL) {
+        qbdiam::build_rsell(rows, cols, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o2) {
+            for (int p = rowptr[r]; p < rowptr[r + 1]; p++) o2.push_back({col[p], data[p]});
+        }, o.rs);
     } else {
         qbdiam::build_diam(rows, [&](int64_t sl, std::vector<qbdiam::Entry>& es) {
             const int64_t r0 = sl * 32, r1 = std::min<int64_t>(rows, r0 + 32);
@@ -119,6 +137,15 @@ void emul_set_functional(int f) { g_sys.eop_functional = f; }
 double emul_diam_avg_lanes(int which) {
     const HostOp& o = g_sys.elems[which];
     return o.dh.ent.empty() ? 0.0 : (double)o.dh.val.size() / (double)o.dh.ent.size();
+}
+// RSELL statistics of element `which`: out = {slots, explicit column blocks, explicit value
+// blocks, device bytes, xor-rule slots}
+void emul_rsell_stats(int which, long long* out) {
+    const HostOp& o = g_sys.elems[which];
+    long long nx = 0;
+    for (auto& d : o.rs.desc) nx += (d.rule & QB_RS_COL_MASK) == QB_RS_COL_XOR;
+    out[0] = o.rs.stored(); out[1] = (long long)o.rs.col.size() / 32;
+    out[2] = (long long)o.rs.val.size() / 32; out[3] = o.rs.bytes(); out[4] = nx;
 }
 // Adams corrector coefficients / error constants of order nq (qb_adams.h)
 void emul_adams_table(int nq, double* el, double* tq) {

@@ -1,7 +1,8 @@
 """Host-side logic of the multi-GPU path on CPU: world_size-2 gloo job.  Each rank owns a
 contiguous block of the global seed list; the only collective is one all-reduce of the
-expectation sums (solve.reduce_expect_sums), which must reproduce the reference's
-trajectory average / std (multitrajresult.py:261-279,1116-1124)."""
+expectation sums (solve.reduce_expect_sums; on GPUs the same sums go through
+engine.Comm = ncclAllReduce behind the C ABI, here through gloo), which must reproduce the
+reference's trajectory average / std (multitrajresult.py:261-279,1116-1124)."""
 import os
 import socket
 
@@ -33,9 +34,13 @@ def _worker(rank, world, port, q):
     d = solve.make_thresholds(int(g["seed"]), hi - lo, 64, first=lo)
     assert np.array_equal(d, g["draws"][lo:hi])
     runs = g["runs_expect"][:, lo:hi, :].astype(complex)      # stands in for the device run
-    s1, s2 = solve.reduce_expect_sums(runs)
-    avg = s1 / ntraj
-    std = np.sqrt(np.abs(s2 / ntraj - np.abs(avg) ** 2))
+    import torch
+
+    def gloo_allreduce(flat):               # sums the float64 array in place over the ranks
+        dist.all_reduce(torch.from_numpy(flat), op=dist.ReduceOp.SUM)
+
+    s1, s2 = solve.reduce_expect_sums(runs, allreduce=gloo_allreduce)
+    avg, std = solve.finish_expect_sums(s1, s2, ntraj)
     q.put((rank, lo, hi, avg.real, std))
     dist.destroy_process_group()
 

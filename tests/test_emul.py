@@ -8,7 +8,7 @@ RHS-evaluation counts and collapse records."""
 import numpy as np
 import pytest
 
-from _emul import FMT_CSR, FMT_DIAM, FMT_SELL, EmulSystem, default_options
+from _emul import FMT_CSR, FMT_DIAM, FMT_RSELL, FMT_SELL, EmulSystem, default_options
 from _golden import coeff_spec, load, op_arrays, orc_op, orc_rhs
 from _systems import functional_of, merged_constant_rhs
 from qutip_b200 import coeffs
@@ -22,7 +22,7 @@ def _sp_arrays(m):
 
 
 @pytest.mark.parametrize("kind", ["csr", "dia"])
-@pytest.mark.parametrize("fmt", [FMT_DIAM, FMT_SELL])
+@pytest.mark.parametrize("fmt", [FMT_DIAM, FMT_SELL, FMT_RSELL])
 def test_diam_format_matvec(kind, fmt):
     g = load("matmul")
     n = len(g["x"])
@@ -41,15 +41,53 @@ def test_diam_duplicate_entries():
     s.add_element("csr", (3, 3), dict(data=data, col=col, rowptr=rowptr))
     x = np.array([1.0, 10.0, 100.0], dtype=complex)
     np.testing.assert_allclose(s.matvec(0, x), [30.0, 3.0, 400.0])
-    s = EmulSystem(3, 0, FMT_SELL)
-    s.add_element("csr", (3, 3), dict(data=data, col=col, rowptr=rowptr))
-    np.testing.assert_allclose(s.matvec(0, x), [30.0, 3.0, 400.0])
+    for fmt in (FMT_SELL, FMT_RSELL):
+        s = EmulSystem(3, 0, fmt)
+        s.add_element("csr", (3, 3), dict(data=data, col=col, rowptr=rowptr))
+        np.testing.assert_allclose(s.matvec(0, x), [30.0, 3.0, 400.0])
+
+
+def test_rsell_spin_chain_is_rule_compressed():
+    # H_eff of the dissipative TFIM (C3 model, 8 spins): every slot of every slice follows the
+    # xor rule (sigma_x flips one bit of the row index) and only the diagonal needs a value
+    # block -- no column index is stored at all (qb_types.h, RSELL)
+    from qutip_b200 import models
+    H, c_ops, _ = models.tfim(8)
+    A = models.heff(H, c_ops)
+    n = A.shape[0]
+    s = EmulSystem(n, 0, FMT_RSELL)
+    s.add_element(*_sp_arrays(A))
+    st = s.rsell_stats(0)
+    assert st["slots"] == (n // 32) * 9 and st["xor_slots"] == st["slots"]
+    assert st["col_blocks"] == 0 and st["val_blocks"] == n // 32
+    assert st["bytes"] < 0.25 * (A.nnz * 20)
+    x = np.random.default_rng(1).random(n) + 1j * np.random.default_rng(2).random(n)
+    np.testing.assert_allclose(s.matvec(0, x), A @ x, rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("n", [32, 33, 63, 100, 257, 400])
+def test_rsell_banded_and_random(n):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(n)
+    a = sp.diags([np.sqrt(np.arange(1, n))], [1]).tocsr()            # destroy(n): row + 1 rule
+    band = (a + a.T + sp.diags([np.arange(n) * (1 - 0.5j)], [0])).tocsr()
+    rnd = sp.random(n, n, density=0.05, random_state=rng, dtype=float).tocsr() * (1 + 2j)
+    for m in (band, rnd, sp.csr_matrix((n, n), dtype=complex), (band + rnd).tocsr()):
+        m = sp.csr_matrix(m, dtype=complex)
+        s = EmulSystem(n, 0, FMT_RSELL)
+        s.add_element(*_sp_arrays(m))
+        x = rng.random(n) + 1j * rng.random(n)
+        np.testing.assert_allclose(s.matvec(0, x), m @ x, rtol=1e-13, atol=1e-13)
+    s = EmulSystem(n, 0, FMT_RSELL)
+    s.add_element(*_sp_arrays(band))
+    st = s.rsell_stats(0)
+    assert st["col_blocks"] <= 2 * 3          # only the first / last slice can leave the band rule
 
 
 @pytest.mark.parametrize("name,method", [("c1_jc", "vern7"), ("c1_jc", "vern9"), ("c1_jc", "tsit5"),
                                          ("c2_tfim4", "vern7"), ("c2_tfim4", "vern9"),
                                          ("c4_driven", "vern7"), ("c5_kerr_0", "vern7")])
-@pytest.mark.parametrize("fmt", [FMT_DIAM, FMT_CSR, FMT_SELL])
+@pytest.mark.parametrize("fmt", [FMT_DIAM, FMT_CSR, FMT_SELL, FMT_RSELL])
 def test_mesolve_state_machine(name, method, fmt):
     g = load(name)
     s = EmulSystem(len(g["y0"]), 0, fmt)

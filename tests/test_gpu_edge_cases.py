@@ -22,7 +22,7 @@ def test_zero_operator_keeps_the_state(method):
 
 
 @pytest.mark.parametrize("N", [1, 2, 31, 33, 255, 257])
-@pytest.mark.parametrize("fmt", [qb.FMT_AUTO, qb.FMT_CSR, qb.FMT_DIAM, qb.FMT_SELL])
+@pytest.mark.parametrize("fmt", [qb.FMT_AUTO, qb.FMT_CSR, qb.FMT_DIAM, qb.FMT_SELL, qb.FMT_RSELL])
 def test_ragged_sizes_decay(N, fmt):
     """dy/dt = -diag(k) y + coupling: sizes around the slice / tile boundaries."""
     rng = np.random.default_rng(N)
@@ -80,7 +80,7 @@ def test_unsorted_and_duplicate_csr_indices_all_formats():
     rowptr = np.array([0, 3, 4, 6], dtype=np.int32)
     dense = np.array([[2, 0, 4], [0, 4, 0], [-1, 5, 0]], dtype=complex)
     x = np.array([1.0, 10.0, 100.0], dtype=complex)
-    for fmt in (qb.FMT_AUTO, qb.FMT_CSR, qb.FMT_DIAM, qb.FMT_SELL):
+    for fmt in (qb.FMT_AUTO, qb.FMT_CSR, qb.FMT_DIAM, qb.FMT_SELL, qb.FMT_RSELL):
         op = qb.DeviceOp.from_csr(data, col, rowptr, (3, 3), fmt)
         out = E.matmul(op, qb.DeviceDense.from_numpy(x))
         np.testing.assert_allclose(out.to_numpy().ravel(), dense @ x)

@@ -17,7 +17,7 @@ ATOL, RTOL = 1e-8, 1e-6
 
 # ------------------------------------------------------------------ data layer
 @pytest.mark.parametrize("kind", ["csr", "dia", "dense"])
-@pytest.mark.parametrize("fmt", [qb.FMT_AUTO, qb.FMT_CSR, qb.FMT_DIAM, qb.FMT_SELL])
+@pytest.mark.parametrize("fmt", [qb.FMT_AUTO, qb.FMT_CSR, qb.FMT_DIAM, qb.FMT_SELL, qb.FMT_RSELL])
 def test_matmul_vs_reference(kind, fmt):
     g = load("matmul")
     if kind == "dense" and fmt != qb.FMT_AUTO:
@@ -100,7 +100,7 @@ ME_CASES = [("c1_jc", "vern7"), ("c1_jc", "vern9"), ("c1_jc", "tsit5"), ("c2_tfi
 
 
 @pytest.mark.parametrize("name,method", ME_CASES)
-@pytest.mark.parametrize("fmt", [qb.FMT_AUTO, qb.FMT_CSR, qb.FMT_DIAM, qb.FMT_SELL])
+@pytest.mark.parametrize("fmt", [qb.FMT_AUTO, qb.FMT_CSR, qb.FMT_DIAM, qb.FMT_SELL, qb.FMT_RSELL])
 def test_mesolve_vs_reference(name, method, fmt):
     g = load(name)
     system = me_system_from_golden(g, fmt)
@@ -170,7 +170,7 @@ def test_integrator_protocol():
                                                ("c3_tfim6_mc", "vern7", 5),
                                                ("c3_tfim4_mc_strong", "vern9", 7),
                                                ("c3_tfim4_mc_tsit5", "tsit5", 5)])
-@pytest.mark.parametrize("fmt", [qb.FMT_AUTO, qb.FMT_CSR, qb.FMT_DIAM, qb.FMT_SELL])
+@pytest.mark.parametrize("fmt", [qb.FMT_AUTO, qb.FMT_CSR, qb.FMT_DIAM, qb.FMT_SELL, qb.FMT_RSELL])
 def test_mcsolve_vs_reference(name, method, nslots, fmt):
     g = load(name)
     eng = qb.Engine(mc_system_from_golden(g, fmt), method, nslots=nslots)

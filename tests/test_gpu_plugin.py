@@ -469,3 +469,79 @@ def test_propagator_and_nm_mcsolve_reuse_the_device_integrator():
     out = qutip.nm_mcsolve(H, basis(5, 3), np.linspace(0, 2, 9), ops_and_rates,
                            options=dict(OPT, method="b200_vern7", map="b200", keep_runs_results=True), **kw)
     np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=1e-5, atol=1e-7)
+
+
+def test_b200_map_bulk_feed_matches_per_trajectory_add():
+    """keep_runs_results=False takes the vectorised feed (running sums of McResult updated in
+    bulk): averages, std, collapse records and counters must equal both the reference's own
+    run and the per-trajectory feed (multitrajresult.py:402-434,1116-1124)."""
+    H, c_ops, sz = tfim(6)
+    psi0 = basis([2] * 6, [0] * 6)
+    tl = np.linspace(0, 2, 21)
+    e_ops = [sz[0], sz[1] * sz[2], sigmam_like(6)]          # two Hermitian, one non-Hermitian e_op
+    kw = dict(e_ops=e_ops, ntraj=40)
+    ref = mcsolve(H, psi0, tl, c_ops, seeds=np.random.SeedSequence(11),
+                  options=dict(OPT, method="vern7"), **kw)
+    out = mcsolve(H, psi0, tl, c_ops, seeds=np.random.SeedSequence(11),
+                  options=dict(OPT, method="vern7", map="b200"), **kw)
+    assert out.num_trajectories == ref.num_trajectories == 40
+    assert len(out.seeds) == 40 and out.stats["end_condition"] == ref.stats["end_condition"]
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    for a, b in zip(out.col_times, ref.col_times):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)
+    for a, b in zip(out.average_expect, ref.average_expect):
+        np.testing.assert_allclose(a, b, rtol=RTOL, atol=ATOL)
+    for a, b in zip(out.std_expect, ref.std_expect):
+        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-7)
+    assert out.runs_weights == ref.runs_weights
+
+
+def sigmam_like(n):
+    ops = [qeye(2)] * n
+    ops[0] = sigmam()
+    return tensor(ops)
+
+
+def test_b200_map_more_collapses_than_initial_record(monkeypatch):
+    """A strongly damped oscillator jumps more often than the initial capacity of the device
+    collapse record: those trajectories are re-run with a larger record instead of failing
+    (the reference appends to a python list, mcsolve.py:371-406)."""
+    monkeypatch.setattr(plugin, "_MAX_COLLAPSES", 4)
+    a = destroy(12)
+    H = a.dag() * a
+    c_ops = [np.sqrt(2.0) * a, np.sqrt(1.5) * a.dag()]
+    psi0 = basis(12, 6)
+    tl = np.linspace(0, 3, 7)
+    o = dict(OPT, method="vern7", keep_runs_results=True)
+    ref = mcsolve(H, psi0, tl, c_ops, e_ops=[a.dag() * a], ntraj=8, seeds=2, options=o)
+    out = mcsolve(H, psi0, tl, c_ops, e_ops=[a.dag() * a], ntraj=8, seeds=2, options=dict(o, map="b200"))
+    assert max(len(w) for w in ref.col_which) > 4
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=RTOL, atol=ATOL)
+
+
+def test_b200_map_sharded_over_devices():
+    """plugin.configure(devices=[0, 1]): contiguous blocks of the seed list per device, one
+    ncclAllReduce of the expectation sums -- identical records to the single-device run."""
+    import qutip_b200 as qb
+    if qb.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    H, c_ops, sz = tfim(6)
+    psi0 = basis([2] * 6, [0] * 6)
+    tl = np.linspace(0, 2, 21)
+    kw = dict(e_ops=[sz[0], sz[3]], ntraj=31)
+    for keep in (False, True):
+        o = dict(OPT, method="vern7", map="b200", keep_runs_results=keep)
+        plugin.configure(None)
+        one = mcsolve(H, psi0, tl, c_ops, seeds=np.random.SeedSequence(5), options=o, **kw)
+        plugin.configure([0, 1])
+        try:
+            two = mcsolve(H, psi0, tl, c_ops, seeds=np.random.SeedSequence(5), options=o, **kw)
+        finally:
+            plugin.configure(None)
+        assert [list(w) for w in two.col_which] == [list(w) for w in one.col_which]
+        assert [list(t) for t in two.col_times] == [list(t) for t in one.col_times]
+        for a, b in zip(two.average_expect, one.average_expect):
+            np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-13)
+        for a, b in zip(two.std_expect, one.std_expect):
+            np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
