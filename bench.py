@@ -2,11 +2,11 @@
 """bench.py -- BASELINE.json's metric on B200:
     mcsolve trajectories/s @1/2/4/8 B200 ; mesolve Liouvillian SpMV GB/s vs HBM
 
-A "step" is one pass of the hot path over one batch: mcsolve of `--ntraj` trajectories per
-GPU of config C3 (dissipative TFIM, 14 spins, dim 16384, vern7, tlist = linspace(0,2,21),
-e_op sigma_z on spin 0, seeds SeedSequence(7)).  Ranks shard the trajectories (weak
-scaling: the per-GPU batch is fixed) and the only collective is one all-reduce of the
-expectation sums.  The JSON line also carries the mesolve/C2 figures (TFIM 10 spins,
+A "step" is one pass of the hot path over one batch: mcsolve of `--ntraj` trajectories
+of config C3 (dissipative TFIM, 14 spins, dim 16384, vern7, tlist = linspace(0,2,21),
+e_op sigma_z on spin 0, seeds SeedSequence(7)).  Ranks shard the `--ntraj` trajectories of a
+step (strong scaling, BASELINE config 3; `--scaling weak` fixes the per-GPU batch instead)
+and the only collective is one ncclAllReduce of the expectation sums (qb_comm_*).  The JSON line also carries the mesolve/C2 figures (TFIM 10 spins,
 Liouvillian 2^20, SpMV GB/s and RHS-evals/s) with their own roofline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            our arm
@@ -34,7 +34,7 @@ C2 = dict(n_spins=10, gamma=0.1, t_end=1.0, nt=11, method="vern7")
 
 def ncu_traffic():
     """DRAM bytes per launch from the committed ncu --set full captures (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     return json.load(open(p)) if os.path.exists(p) else {}
 
 
@@ -133,7 +133,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup_ref, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "C3 mcsolve dissipative TFIM %d spins (dim %d), vern7, tlist linspace(0,2,21), "
                                "e_op sz_0; %d trajectories per step" % (n, 2 ** n, sample)},
@@ -322,7 +322,33 @@ def extra_figures(qb, models, quick=False):
     return out
 
 
+def _plugin_solver(n, method):
+    """qutip.MCSolver of config C3 with the plug-in registered (the reference package comes from
+    oracle/_ref; only its host-side solver classes run, every trajectory runs on the device)."""
+    import oracle
+    ref = oracle.ref_path()
+    if ref is None:
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import warnings
+    warnings.filterwarnings("ignore")
+    import qutip
+    import qutip_b200.plugin  # noqa: F401  (registers the map)
+    from qutip_b200 import models
+    H, c_ops, sz = models.tfim(n, C3["gamma"])
+    dims = [[2] * n, [2] * n]
+    Hq = qutip.Qobj(H, dims=dims)
+    cq = [qutip.Qobj(c, dims=dims) for c in c_ops]
+    eq = [qutip.Qobj(sz[0], dims=dims)]
+    psi0 = qutip.basis([2] * n, [0] * n)
+    solver = qutip.MCSolver(Hq, cq, options={"progress_bar": False, "method": method, "map": "b200"})
+    return solver, psi0, eq
+
+
 def run_ours(args):
+    # torch is harness plumbing here (rendezvous, barrier, max over ranks, device buffers of
+    # the device-resident timing); the product's collective is its own ncclAllReduce (Comm)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -332,11 +358,17 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     import qutip_b200 as qb
+    from qutip_b200 import engine as E
     from qutip_b200 import models, solve
     from qutip_b200 import _lib
-    _lib.check(_lib.load().qb_set_device(local))
+    E.set_device(local)
     hbm_peak, peak_src = peaks()
     dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        uid = [E.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = E.Comm.rank(world, rank, uid[0])
 
     n = args.spins or C3["n_spins"]
     H, c_ops, sz = models.tfim(n, C3["gamma"])
@@ -344,18 +376,21 @@ def run_ours(args):
     N = heff.shape[0]
     tlist = np.linspace(0, C3["t_end"], C3["nt"])
     psi0 = models.basis_state(n)
-    ntraj = args.ntraj
-    nslots = min(ntraj, args.slots)
+    # strong scaling (BASELINE config 3): --ntraj trajectories in TOTAL, contiguous blocks of
+    # the seed list per rank; --scaling weak: --ntraj per GPU
+    weak = args.scaling == "weak"
+    total = args.ntraj * world if weak else args.ntraj
+    lo, hi = solve.shard_range(total, rank, world)
+    ntraj = hi - lo
+    nslots = max(1, min(ntraj, args.slots))
     system = solve.build_system([heff], c_ops, e_ops=[sz[0]])
     eng = qb.Engine(system, C3["method"], nslots=nslots)
     eng.set_profiling(True)
     ndraws = 64
-    # every rank / step uses its own block of the global seed list SeedSequence(7).spawn
     total_steps = args.warmup + args.steps
 
-    def step_draws(i):
-        first = (i * world + rank) * ntraj
-        return solve.make_thresholds(C3["seed"], ntraj, ndraws, first=first)
+    def step_draws(i):          # every step uses its own block of SeedSequence(7).spawn
+        return solve.make_thresholds(C3["seed"], ntraj, ndraws, first=i * total + lo)
 
     draws_all = [step_draws(i) for i in range(total_steps)]
 
@@ -388,13 +423,12 @@ def run_ours(args):
             eng.handle, 1, ntraj, vp(d_psi), 1, None, vp(d_tl), nt, None, vp(d_draws[i]), ndraws,
             vp(d_exp), vp(d_status), vp(d_ncol), vp(d_colt), vp(d_colw), vp(d_stats), None))
         _lib.check(lib.qb_reduce_expect(vp(d_exp), ntraj, neops, nt, vp(d_sums)))
-        if world > 1:
-            dist.all_reduce(d_sums)          # the single collective of the path
+        if comm is not None:                 # the single collective of the path (our ncclAllReduce)
+            comm.allreduce_sum_device([d_sums.data_ptr()], d_sums.numel())
         rounds, ms = C.c_int64(), C.c_double()
         lib.qb_engine_last_run_info(eng.handle, C.byref(rounds), C.byref(ms))
         return rounds.value, ms.value, eng.profile()
 
-    launches0 = qb.launch_count()
     for i in range(args.warmup):
         device_step(i)
     sampler = ClockSampler(local)
@@ -402,8 +436,6 @@ def run_ours(args):
         sampler.start()
     barrier()
     launches1 = qb.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
     t0 = time.perf_counter()
     gpu_ms = pass_ms = 0.0
     rounds = pass_launches = 0
@@ -413,7 +445,6 @@ def run_ours(args):
         rounds += r_; gpu_ms += ms_
         pass_ms += prof["pass_ms"]; pass_launches += prof["pass_launches"]
         vec_acc += prof["state_vector_accesses"]
-    ev1.record()
     barrier()
     wall = time.perf_counter() - t0
     launches2 = qb.launch_count()
@@ -425,27 +456,45 @@ def run_ours(args):
     status = d_status.cpu().numpy()
     stats = d_stats.cpu().numpy().reshape(ntraj, 4)
     ncol = d_ncol.cpu().numpy()
+    dev_sums = d_sums.cpu().numpy().view(np.complex128).reshape(2, neops, nt)
     ok = bool((status == 1).all())
-    value = world * ntraj * args.steps / t_dev
+    value = total * args.steps / t_dev
+    del d_exp, d_colt, d_colw, d_draws
+    eng.free()                        # the end-to-end arm allocates its own engine
+    torch.cuda.empty_cache()
 
-    # ---- end to end through the public API with host buffers (H2D + D2H inside) ----
-    pin_psi = torch.from_numpy(psi0.copy()).pin_memory()
-    pin_draws = [torch.from_numpy(d.copy()).pin_memory() for d in draws_all[args.warmup:]]
-    barrier()
-    t0 = time.perf_counter()
-    e2e_res = None
-    for i in range(args.steps):
-        e2e_res = eng.run_mcsolve(pin_psi.numpy(), tlist, pin_draws[i].numpy(), ntraj=ntraj)
+    # ---- end to end: the call a user makes -- qutip's MCSolver.run(..., options={"map": "b200"})
+    #      on host objects; thresholds, uploads, the whole batch, downloads and McResult inside ----
+    e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    ps = _plugin_solver(n, C3["method"])
+    if ps is not None:
+        solver, psi0_q, eq = ps
+        e2e_times = []
+        last = None
+        for i in range(1 + args.steps):            # first call: untimed warm-up (qutip's lazy imports)
+            seeds = np.random.SeedSequence(C3["seed"]).spawn((args.warmup + i) * total + hi)[-ntraj:]
+            barrier()
+            t1 = time.perf_counter()
+            last = solver.run(psi0_q, tlist, ntraj=ntraj, e_ops=eq, seeds=seeds)
+            sums = np.ascontiguousarray(np.stack([np.asarray(last.average_expect[0], dtype=np.float64) * ntraj]))
+            if comm is not None:
+                comm.allreduce_sum([sums])
+            barrier()
+            if i > 0:
+                e2e_times.append(time.perf_counter() - t1)
+        e2e_t = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
         if world > 1:
-            solve.reduce_expect_sums(np.transpose(e2e_res.expect, (1, 0, 2)), device=dev)
-    barrier()
-    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * ntraj * args.steps / float(e2e_t[0])
-    h2d = psi0.nbytes + tlist.nbytes + draws_all[0].nbytes
-    d2h = e2e_res.expect.nbytes + e2e_res.status.nbytes + e2e_res.ncol.nbytes + \
-        e2e_res.col_t.nbytes + e2e_res.col_which.nbytes + e2e_res.stats.nbytes
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        h2d = psi0.nbytes + tlist.nbytes + ntraj * ndraws * 8
+        d2h = ntraj * (neops * nt * 16 + 4 + 4 + maxcol * 12 + 16)
+        e2e = {"value": total * args.steps / float(e2e_t[0]), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "api": "qutip.MCSolver(H, c_ops, options={'map': 'b200', 'method': 'vern7'}).run(psi0, tlist, "
+                      "ntraj, e_ops, seeds) per rank on its block of the seed list + one ncclAllReduce",
+               "num_trajectories": int(last.num_trajectories),
+               "avg_sz0_final_global": float(sums[0][-1] / total)}
+    else:
+        e2e["unavailable"] = "oracle/_ref (the reference package hosting MCSolver) is not built"
 
     if rank != 0:
         if world > 1:
@@ -457,14 +506,14 @@ def run_ours(args):
     alg_bytes = vec_acc * 16.0 * N + pass_launches * op_alg
     achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms else 0.0
     tr = ncu_traffic()
-    traffic = None
-    if tr.get("c3_pass_kernel_4096_slots_dram_bytes_per_launch") and n == C3["n_spins"]:
-        # the capture was taken with 4096 resident slots; scale to the slots of this run
-        traffic = tr["c3_pass_kernel_4096_slots_dram_bytes_per_launch"] * nslots / tr["c3_slots"]
+    traffic, traffic_src = None, None
+    if tr.get("c3_pass_kernel_dram_bytes_per_launch") and n == C3["n_spins"] and tr.get("c3_slots") == nslots:
+        traffic = tr["c3_pass_kernel_dram_bytes_per_launch"]
+        traffic_src = "profiles/r02_traffic.json (ncu --set full, dram read+write of one launch at %d slots)" % nslots
     roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-            "traffic_source": "profiles/r01_traffic.json (ncu dram bytes per launch, full slots)",
-            "kernel": "qb_pass_kernel",
+            "traffic_source": traffic_src,
+            "kernel": "qb_pass_tile_kernel",
             "algorithmic_bytes_per_launch": alg_bytes / max(1, pass_launches),
             "avg_launch_ms": pass_ms / max(1, pass_launches),
             "pass_kernel_share_of_step": pass_ms / gpu_ms if gpu_ms else None}
@@ -472,14 +521,15 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C3 mcsolve dissipative TFIM %d spins (dim %d), vern7, tlist linspace(0,2,21), "
-                               "e_op sz_0, seeds SeedSequence(7); %d trajectories per GPU per step, %d slots"
-                               % (n, N, ntraj, nslots),
+                               "e_op sz_0, seeds SeedSequence(7); %d trajectories per step in total, "
+                               "%d per GPU, %d slots"
+                               % (n, N, total, ntraj, nslots),
                    "l2": "state working set %.1f GB per GPU >> 126 MB L2" % (nslots * (16 + 5) * N * 16 / 1e9),
-                   "parallelism": "trajectories sharded over %d GPU(s), one all-reduce of expectation sums" % world},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h)},
+                   "parallelism": "contiguous blocks of the seed list over %d GPU(s), one ncclAllReduce of "
+                                  "the expectation sums" % world},
+        "e2e": e2e,
         "gpu_launches": int(launches2 - launches1),
         "clocks": clocks,
         "roofline": roof,
@@ -488,6 +538,7 @@ def run_ours(args):
         "jumps_per_trajectory": float(ncol.mean()),
         "rounds_per_step": rounds / args.steps,
         "wall_s_timed_region": wall,
+        "avg_sz0_final_device_arm": float(dev_sums[0, 0, -1].real / total),
     }
     if world == 1 and not args.no_mesolve:
         line["mesolve"] = mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=args.quick)
@@ -514,6 +565,119 @@ def run_ours(args):
     return 0
 
 
+def run_side_workload(args):
+    """--workload sweep | dense: the other sharding workloads of SURVEY 8e as SCALE-able modes
+    (same launch contract: one rank per GPU, barrier + max over ranks, one JSON line).
+      sweep: C5, 4096 driven-Kerr oscillators (N = 30, Liouvillian 900^2), members sharded in
+             contiguous blocks, no data-path collective (per-system outputs) -> systems/s
+      dense: C5 dense block, H_eff of dimension --dense-dim (dense complex128) times a block of
+             --ntraj trajectories as ZGEMM on the FP64 tensor cores inside mcsolve, columns
+             (trajectories) sharded, one ncclAllReduce of the expectation sums -> trajectories/s"""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    import scipy.sparse as sp
+    import qutip_b200 as qb
+    from qutip_b200 import coeffs, models, solve
+    from qutip_b200 import engine as E
+    E.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = None
+    if world > 1 and args.workload == "dense":
+        uid = [E.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = E.Comm.rank(world, rank, uid[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "sweep":
+        Ls, sargs, a = models.kerr_sweep(30, 16)
+        total = len(sargs)
+        lo, hi = solve.shard_range(total, rank, world)
+        idx = {"U": 0, "D": 1, "F": 2}
+        elements = [(Ls[0], coeffs.compile_expr("U", arg_index=idx)),
+                    (Ls[1], coeffs.compile_expr("D", arg_index=idx)),
+                    (Ls[2], coeffs.compile_expr("F", arg_index=idx)), (Ls[3], None)]
+        n_op = (a.conj().T @ a).toarray()
+        rho0 = np.zeros(900, dtype=complex); rho0[0] = 1.0
+        tl = np.linspace(0, 10, 21)
+        mine = sargs[lo:hi]
+
+        def step(engine=None):
+            return solve.mesolve(elements, rho0, tl, e_ops=[n_op], args=mine, nargs=3, store_states=False,
+                                 engine=engine, nslots=hi - lo)
+        metric, unit = "sweep_systems_per_s", "systems/s"
+        workload = ("C5 sweep: %d driven-Kerr oscillators N=30 (Liouvillian 900^2), vern7, t in [0,10], 21 "
+                    "output times, <a^dag a>; %d members per GPU" % (total, hi - lo))
+        parallelism = "members sharded in contiguous blocks over %d GPU(s), no data-path collective" % world
+    else:
+        dim, total = args.dense_dim, args.ntraj if args.ntraj != 10000 else 4096
+        lo, hi = solve.shard_range(total, rank, world)
+        rng = np.random.default_rng(dim)
+        Hd = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+        Hd = (Hd + Hd.conj().T) / np.sqrt(dim)
+        cs = [sp.csr_matrix(sp.random(dim, dim, 4.0 / dim, random_state=dim + k, dtype=float) * 0.7).astype(complex)
+              for k in range(2)]
+        heff = -1j * Hd - 0.5 * sum((c.conj().T @ c).toarray() for c in cs)
+        psi0 = rng.standard_normal(dim) + 1j * rng.standard_normal(dim)
+        psi0 /= np.linalg.norm(psi0)
+        e_op = sp.diags(rng.random(dim)).tocsr().astype(complex)
+        tl = np.linspace(0, 1.0, 6)
+        draws = solve.make_thresholds(5, hi - lo, 64, first=lo)
+        system = solve.build_system([heff], cs, e_ops=[e_op])
+        eng0 = qb.Engine(system, "vern7", nslots=hi - lo)
+
+        def step(engine=None):
+            r = eng0.run_mcsolve(psi0, tl, draws)
+            if comm is not None:
+                comm.reduce_expect([eng0], 1, len(tl))
+            return r
+        metric, unit = "dense_heff_mcsolve_trajectories_per_s", "trajectories/s"
+        workload = ("C5 dense block: mcsolve with dense H_eff dim %d (ZGEMM on the FP64 tensor cores), %d "
+                    "trajectories in total, %d per GPU, vern7, t in [0,1]" % (dim, total, hi - lo))
+        parallelism = "trajectory columns sharded over %d GPU(s), one ncclAllReduce of the expectation sums" % world
+
+    r = step()
+    engine = r.get("engine") if isinstance(r, dict) else None
+    for _ in range(max(0, args.warmup - 1)):
+        r = step(engine)
+    barrier()
+    l0 = qb.launch_count()
+    gpu_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = step(engine)
+        gpu_ms += r.gpu_ms
+    barrier()
+    wall = time.perf_counter() - t0
+    l1 = qb.launch_count()
+    el = torch.tensor([gpu_ms * 1e-3, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        stats = r.stats
+        line = {"metric": metric, "value": total * args.steps / float(el[0]), "unit": unit, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(el[0]) / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": workload, "parallelism": parallelism},
+                "e2e": {"value": total * args.steps / float(el[1]), "unit": unit,
+                        "note": "wall clock of the host-buffer calls (uploads, run, downloads)"},
+                "gpu_launches": int(l1 - l0), "rhs_evals_per_member": float(np.mean(stats[:, 0])),
+                "all_ok": bool((r.get("status", np.ones(1)) == 1).all()) if "status" in r else True}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -521,7 +685,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ntraj", type=int, default=10000, help="trajectories per GPU per step")
+    ap.add_argument("--ntraj", type=int, default=10000,
+                    help="trajectories per step: in total, sharded over the GPUs (strong scaling, BASELINE "
+                         "config 3); per GPU with --scaling weak")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "sweep", "dense"],
+                    help="c3: the headline mcsolve metric; sweep / dense: the other sharded workloads (C5)")
+    ap.add_argument("--dense-dim", type=int, default=1024)
     ap.add_argument("--slots", type=int, default=10000,
                     help="concurrent trajectory slots (10^4 = the whole step resident: 55 GB of the 180 GB HBM; "
                          "fewer slots are refilled by continuous batching, measured 3 % slower)")
@@ -534,6 +704,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "c3":
+        return run_side_workload(args)
     return run_ours(args)
 
 

@@ -237,6 +237,7 @@ int qb_comm_unique_id(void* id, int nbytes);
 int qb_comm_init_rank(int nranks, int rank, const void* id, qb_handle* out);
 int qb_comm_info(qb_handle comm, int* nranks, int* nlocal);
 int qb_comm_allreduce_sum(qb_handle comm, double* const* bufs, int64_t count);
+int qb_comm_allreduce_sum_device(qb_handle comm, void* const* dbufs, int64_t count);   /* device buffers */
 int qb_comm_reduce_expect(qb_handle comm, const qb_handle* engines, int neops, int nt, void* sums);
 
 #ifdef __cplusplus

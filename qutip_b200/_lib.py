@@ -52,7 +52,7 @@ SYMBOLS = [
     "qb_zgemm", "qb_zgemm_bench", "qb_integ_pending_coef", "qb_integ_resume",
     "qb_engine_rhs_coef",
     "qb_comm_nccl_version", "qb_comm_init_all", "qb_comm_unique_id", "qb_comm_init_rank",
-    "qb_comm_info", "qb_comm_allreduce_sum", "qb_comm_reduce_expect",
+    "qb_comm_info", "qb_comm_allreduce_sum", "qb_comm_allreduce_sum_device", "qb_comm_reduce_expect",
 ]
 
 _lib = None
@@ -135,6 +135,7 @@ def load():
         "qb_comm_init_rank": [i32, i32, vp, pp],
         "qb_comm_info": [vp, C.POINTER(i32), C.POINTER(i32)],
         "qb_comm_allreduce_sum": [vp, pp, i64],
+        "qb_comm_allreduce_sum_device": [vp, pp, i64],
         "qb_comm_reduce_expect": [vp, pp, i32, i32, vp],
     }
     for name, args in sig.items():

@@ -205,6 +205,31 @@ extern "C" int qb_comm_allreduce_sum(qb_handle comm, double* const* bufs, int64_
     return QB_OK;
 }
 
+// same, on device buffers: dbufs[i] = `count` doubles on the device of local member i; the
+// collective is enqueued after everything already queued on the legacy default stream of each
+// device and the call returns when the sums are in place
+extern "C" int qb_comm_allreduce_sum_device(qb_handle comm, void* const* dbufs, int64_t count) {
+    QbCommH* c = qb_cast<QbCommH>(comm, QB_TAG_COMM);
+    if (!c) QB_FAIL(QB_E_TYPE, "not a communicator handle");
+    if (!dbufs || count < 1) QB_FAIL(QB_E_ARG, "bad all-reduce arguments");
+    const NcclApi* api = nccl_api();
+    if (!api) QB_FAIL(QB_E_STATE, "NCCL unavailable: %s", g_nccl.err.c_str());
+    for (size_t i = 0; i < c->devs.size(); i++) {
+        QB_CUDA(cudaSetDevice(c->devs[i]));
+        QB_CUDA(cudaDeviceSynchronize());          // producers of dbufs[i] have finished
+    }
+    QB_NCCL(api, api->GroupStart());
+    for (size_t i = 0; i < c->devs.size(); i++)
+        QB_NCCL(api, api->AllReduce(dbufs[i], dbufs[i], (size_t)count, ncclDouble, ncclSum, c->comms[i], c->streams[i]));
+    QB_NCCL(api, api->GroupEnd());
+    g_qb_launches += (long long)c->devs.size();
+    for (size_t i = 0; i < c->devs.size(); i++) {
+        QB_CUDA(cudaSetDevice(c->devs[i]));
+        QB_CUDA(cudaStreamSynchronize(c->streams[i]));
+    }
+    return QB_OK;
+}
+
 // internal accessors of qb_engine.cu
 int qb_engine_expect_view(qb_handle eng, const void** d_expect, int* neops, int* device, int64_t* ntraj, int* nt);
 int qb_reduce_expect_on(cudaStream_t stream, const void* d_expect, int64_t ntraj, int neops, int nt, void* d_sums);

@@ -111,7 +111,7 @@ enum {
     // Adams (qb_adams.h)
     QL_AD_SET, QL_AD_F0, QL_AD_INT, QL_AD_LOOP, QL_AD_STEP, QL_AD_PRED_ISSUE, QL_AD_CORR_ISSUE,
     QL_AD_CONVFAIL, QL_AD_ERRTEST, QL_AD_UPD_ISSUE, QL_AD_O520, QL_AD_O540, QL_AD_O560,
-    QL_AD_RESCALE, QL_AD_3FAIL, QL_AD_STEP_DONE, QL_AD_AFTER, QL_AD_INTERP
+    QL_AD_RESCALE, QL_AD_3FAIL, QL_AD_3FAIL_ISSUE, QL_AD_STEP_DONE, QL_AD_AFTER, QL_AD_INTERP
 };
 
 // Run the controller until it has emitted a pass (returns 1), the trajectory finished or
@@ -288,6 +288,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             }
             L = QL_AFTER_LOOP; break;
         case QB_PC_COPY_DONE:
+            if (T.fsal && c.fsal_pending) { c.kswap ^= 1; c.fsal_pending = 0; }   // k[0] <- k_fsal
             c.t_prev = c.t_front;
             c.step_n = 0;
             L = QL_STEP_ATTEMPT; break;
@@ -747,9 +748,12 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             double rh = 0.1;
             if (g.opt.min_step > 0.0 && rh < g.opt.min_step / fabs(c.ad_h)) rh = g.opt.min_step / fabs(c.ad_h);
             c.ad_h *= rh;
+            L = QL_AD_3FAIL_ISSUE; break;
+        }
+        case QL_AD_3FAIL_ISSUE: {   // resumable (host-evaluated coefficients): the step is scaled once
             qb_pass_clear(p);       // YH1 = f(t_n, YH0), unscaled
             p.kind = QB_PASS_RHS; p.x = QB_AD_YH(0); p.zdst = QB_AD_YH(1);
-            QB_COEFS_OR_PAUSE(c.ad_tn, QL_AD_3FAIL)
+            QB_COEFS_OR_PAUSE(c.ad_tn, QL_AD_3FAIL_ISSUE)
             c.n_rhs++;
             c.pc = QB_PC_AD_REF_DONE; return 1;
         }

@@ -7,6 +7,8 @@
 // the reference's CSR (core/data/csr.pyx) -- become extra entries with the same offset.
 #pragma once
 #include <algorithm>
+#include <map>
+#include <string>
 #include <string.h>
 #include <thread>
 #include <vector>
@@ -152,25 +154,33 @@ inline void build_sell(int64_t nrows, int64_t ncols, RowFn row_fn, SellHost& out
 // follow the rule need no column block; slots whose 32 values are bitwise equal need no
 // value block.  Slices that are not diagonal structured under either key fall back to plain
 // ELLPACK slots (explicit columns and values, row order) -- the format is a superset of SELL.
+// Descriptor lists are de-duplicated: explicit blocks are addressed relative to the slice's
+// own base (sinfo), so every interior slice of a structured operator shares ONE list -- small
+// enough to live in the constant bank (kernel parameters) of the fused pass kernel.
 struct RsellHost {
-    std::vector<int> slice_ptr;          // [nslices + 1], in slots
-    std::vector<QbSlotDesc> desc;
+    // [nslices][4]: first descriptor, count | fast count << 12 | xor-fast count << 24,
+    // value-block base, column-block base.  A list holds the xor-rule constant slots first,
+    // then the add-rule constant slots ("fast": no explicit block), then the rest.
+    std::vector<int> sinfo;
+    bool overflow = false;               // a slice does not fit the packed counts: use another format
+    std::vector<QbSlotDesc> desc;        // de-duplicated descriptor lists
     std::vector<qb_c128> val;            // explicit value blocks, 32 per block
     std::vector<int> col;                // explicit column blocks, 32 per block
-    long long nnz = 0;
-    long long stored() const { return (long long)desc.size(); }
+    long long nnz = 0, slots = 0;
+    long long stored() const { return slots; }
     long long bytes() const {
         return (long long)desc.size() * 32 + (long long)val.size() * 16 + (long long)col.size() * 4 +
-               (long long)slice_ptr.size() * 4;
+               (long long)sinfo.size() * 4;
     }
 };
 
 template <class RowFn>
 inline void build_rsell(int64_t nrows, int64_t ncols, RowFn row_fn, RsellHost& out) {
     const int64_t nslices = (nrows + 31) / 32;
-    out.slice_ptr.assign(1, 0);
     std::vector<std::vector<std::pair<int, qb_c128>>> rows(32);
-    struct Key { long long key; int occ; };
+    std::vector<QbSlotDesc> cur;          // descriptor list of the slice being built
+    int vbase = 0, cbase = 0;
+    std::map<std::string, int> seen;      // descriptor list (bytes) -> first descriptor
     auto emit = [&](int rule, int delta, const int* cols, const qb_c128* vals, const bool* have,
                     int64_t r0) {
         // column rule usable only if every lane's implied column is a valid index
@@ -185,10 +195,10 @@ inline void build_rsell(int64_t nrows, int64_t ncols, RowFn row_fn, RsellHost& o
         for (int l = 0; l < 32; l++)
             if (!have[l] || memcmp(&vals[l], &vals[0], sizeof(qb_c128)) != 0) { konst = false; break; }
         QbSlotDesc d;
+        memset(&d, 0, sizeof d);
         d.rule = rule_ok ? rule : QB_RS_COL_EXPL; d.delta = rule_ok ? delta : 0;
-        d.cpos = 0; d.vpos = 0; d.vre = 0.0; d.vim = 0.0;
         if (!rule_ok) {
-            d.cpos = (int)(out.col.size() / 32);
+            d.cpos = (int)(out.col.size() / 32) - cbase;
             for (int l = 0; l < 32; l++) {
                 long long c = have[l] ? cols[l] : std::min<long long>(r0 + l, ncols - 1);
                 if (c < 0) c = 0;
@@ -197,10 +207,10 @@ inline void build_rsell(int64_t nrows, int64_t ncols, RowFn row_fn, RsellHost& o
         }
         if (konst) { d.rule |= QB_RS_VAL_CONST; d.vre = vals[0].re; d.vim = vals[0].im; }
         else {
-            d.vpos = (int)(out.val.size() / 32);
+            d.vpos = (int)(out.val.size() / 32) - vbase;
             for (int l = 0; l < 32; l++) out.val.push_back(have[l] ? vals[l] : qb_c128{0.0, 0.0});
         }
-        out.desc.push_back(d);
+        cur.push_back(d);
     };
     for (int64_t sl = 0; sl < nslices; sl++) {
         const int64_t r0 = sl * 32;
@@ -217,6 +227,8 @@ inline void build_rsell(int64_t nrows, int64_t ncols, RowFn row_fn, RsellHost& o
             cnt += (long long)rows[l].size();
         }
         out.nnz += cnt;
+        cur.clear();
+        vbase = (int)(out.val.size() / 32); cbase = (int)(out.col.size() / 32);
         // distinct (key, occurrence) pairs under both keys; occurrence > 0 only for duplicate
         // (row, col) pairs, which the reference's CSR allows (core/data/csr.pyx)
         std::vector<std::pair<long long, int>> kadd, kxor;
@@ -252,7 +264,6 @@ inline void build_rsell(int64_t nrows, int64_t ncols, RowFn row_fn, RsellHost& o
                 }
                 emit(rule, (int)kk.first, cols, vals, have, r0);
             }
-            out.slice_ptr.push_back(out.slice_ptr.back() + (int)keys.size());
         } else {
             for (int k = 0; k < width; k++) {
                 for (int l = 0; l < 32; l++) {
@@ -262,8 +273,29 @@ inline void build_rsell(int64_t nrows, int64_t ncols, RowFn row_fn, RsellHost& o
                 }
                 emit(QB_RS_COL_EXPL, 0, cols, vals, have, r0);
             }
-            out.slice_ptr.push_back(out.slice_ptr.back() + width);
         }
+        // "fast" slots (column rule + constant value: no explicit block at all) first; the
+        // sweep runs them in a lean loop of their own
+        auto is_fast = [](const QbSlotDesc& d) {
+            return (d.rule & QB_RS_COL_MASK) != QB_RS_COL_EXPL && (d.rule & QB_RS_VAL_CONST); };
+        auto is_xfast = [&](const QbSlotDesc& d) { return is_fast(d) && (d.rule & QB_RS_COL_MASK) == QB_RS_COL_XOR; };
+        std::stable_partition(cur.begin(), cur.end(), is_fast);
+        std::stable_partition(cur.begin(), cur.end(), is_xfast);
+        int nfast = 0, nxor = 0;
+        for (auto& d : cur) { nfast += is_fast(d); nxor += is_xfast(d); }
+        if (cur.size() > 4095 || nxor > 255) out.overflow = true;
+        // share the descriptor list with an earlier slice that has the same one
+        int dstart = (int)out.desc.size();
+        if (!cur.empty()) {
+            std::string keyb(reinterpret_cast<const char*>(cur.data()), cur.size() * sizeof(QbSlotDesc));
+            auto it = seen.find(keyb);
+            if (it != seen.end()) dstart = it->second;
+            else { seen.emplace(std::move(keyb), dstart); out.desc.insert(out.desc.end(), cur.begin(), cur.end()); }
+        }
+        out.slots += (long long)cur.size();
+        out.sinfo.push_back(dstart);
+        out.sinfo.push_back((int)(cur.size() & 4095) | ((nfast & 4095) << 12) | ((nxor & 255) << 24));
+        out.sinfo.push_back(vbase); out.sinfo.push_back(cbase);
     }
 }
 
@@ -275,13 +307,14 @@ inline void rsell_matvec_host(const RsellHost& A, int64_t nrows, const qb_c128* 
             const int64_t r = sl * 32 + l;
             if (r >= nrows) continue;
             double re = 0.0, im = 0.0;
-            for (int k = A.slice_ptr[sl]; k < A.slice_ptr[sl + 1]; k++) {
+            const int* si = &A.sinfo[(size_t)sl * 4];
+            for (int k = si[0]; k < si[0] + (si[1] & 4095); k++) {
                 const QbSlotDesc& d = A.desc[k];
                 const int cr = d.rule & QB_RS_COL_MASK;
                 const long long c = cr == QB_RS_COL_ADD ? r + d.delta : cr == QB_RS_COL_XOR ? (r ^ (long long)d.delta)
-                                                                       : A.col[(size_t)d.cpos * 32 + l];
+                                                                       : A.col[(size_t)(si[3] + d.cpos) * 32 + l];
                 qb_c128 v = {d.vre, d.vim};
-                if (!(d.rule & QB_RS_VAL_CONST)) v = A.val[(size_t)d.vpos * 32 + l];
+                if (!(d.rule & QB_RS_VAL_CONST)) v = A.val[(size_t)(si[2] + d.vpos) * 32 + l];
                 re += v.re * x[c].re - v.im * x[c].im;
                 im += v.re * x[c].im + v.im * x[c].re;
             }

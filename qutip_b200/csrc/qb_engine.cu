@@ -485,128 +485,187 @@ __device__ __forceinline__ bool qb_mbar_try_wait(unsigned bar, unsigned parity) 
     return ok != 0;
 }
 
+// engine constants of the tile kernel as a kernel parameter (constant bank): warp-uniform
+// operands that cost neither a register nor an L1 wavefront
+struct QbTileArgs {
+    double2* pool;
+    const QbPass* pass;
+    const qb_c128* coef;
+    double* partials;
+    int N, V, nslices, red_stride, nelem, maxcoef;
+    double atol, rtol;
+    QbTileElem elem[QB_MAX_ELEMS];
+};
+
+template <bool CD>
 __global__ void __launch_bounds__(256, QB_TT_MINB)
-qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trows)
+qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trows,
+                    const __grid_constant__ QbTileArgs ta, const __grid_constant__ QbConstDesc cd)
 {
     extern __shared__ __align__(128) unsigned char qb_tile_smem[];
     __shared__ __align__(8) unsigned long long mbar;
-    const double2* const sx = reinterpret_cast<const double2*>(qb_tile_smem);
-    const int N = E->ctl.N;
+    const int N = ta.N;
     const int ntiles = (N + trows - 1) / trows;
     const int slot = blockIdx.x / ntiles;
     const int tile = blockIdx.x - slot * ntiles;
     if (slot >= nslots_used) return;
-    const QbPass* __restrict__ gp = &E->pass[slot];
+    const QbPass* __restrict__ gp = &ta.pass[slot];
     const int kind = gp->kind;
     if (kind == QB_PASS_NONE || kind == QB_PASS_LINMAP) return;       // CTA-uniform
     const int lo = tile * trows;
     const int rows = min(trows, N - lo);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    const int sl1 = (lo + rows + 31) >> 5;
+    const int sl0 = lo >> 5, sl1 = (lo + rows + 31) >> 5;
     if (kind != QB_PASS_RHS && kind != QB_PASS_COMBINE) {             // EXPECT / APPLY: rare
-        for (int sl = (lo >> 5) + warp; sl < sl1; sl += nw) qb_pass_slice_generic(E, slot, sl, lane);
+        for (int sl = sl0 + warp; sl < sl1; sl += nw) qb_pass_slice_generic(E, slot, sl, lane);
         return;
     }
-    const int vbase = slot * E->V;
+    const int vbase = slot * ta.V;
     const double2* const initp = E->init_states + (long long)E->traj[slot].init_idx * N;
-    const double2* gx1[1] = {nullptr};
-    const double2* sx1[1] = {sx};
+    const double2* gx = nullptr;
+    // shared-window address of the staged tile, computed ONCE (volatile: the compiler would
+    // otherwise re-derive it from SR_CgaCtaId in front of every LDS to save a register)
+    unsigned sxa;
+    asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}"
+                 : "=r"(sxa) : "l"(qb_tile_smem));
     const unsigned bar = qb_smem_u32(&mbar);
     if (kind == QB_PASS_RHS) {
         const int xs = gp->x;
-        gx1[0] = xs >= 0 ? E->pool + (long long)(vbase + xs) * N : initp;
+        gx = xs >= 0 ? ta.pool + (long long)(vbase + xs) * N : initp;
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             const unsigned bytes = (unsigned)rows * 16u;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(qb_smem_u32(qb_tile_smem)), "l"(gx1[0] + lo), "r"(bytes), "r"(bar) : "memory");
+                         :: "r"(sxa), "l"(gx + lo), "r"(bytes), "r"(bar) : "memory");
         }
         __syncthreads();          // the barrier object is initialised before anybody polls it
     }
     const int nsrc = gp->nsrc;
     const int red = gp->red;
     const bool werr = (red & QB_RED_WRMS) != 0;
-    const int nelem = E->ctl.nelem;
+    const int nelem = ta.nelem;
+    const bool pow2 = (trows & (trows - 1)) == 0;       // tiles are aligned power-of-two blocks
     bool staged = false;
-    for (int sl = (lo >> 5) + warp; sl < sl1; sl += nw) {
-        const int r = sl * 32 + lane;
-        const bool active = r < N;
-        double2* const pool_r = E->pool + r;
-        // ---- request the first QB_TP sources
-        double2 pv[QB_TP];
+    // a warp takes PAIRS of adjacent slices: everything warp-uniform (descriptor lists, pass
+    // descriptor, weights) is read once per pair
+    const int npairs = (sl1 - sl0 + 1) >> 1;
+    for (int pr = warp; pr < npairs; pr += nw) {
+        const int sla = sl0 + 2 * pr;
+        const bool hasb = sla + 1 < sl1;
+        const int slb = hasb ? sla + 1 : sla;
+        const int r[2] = {sla * 32 + lane, slb * 32 + lane};
+        const bool act[2] = {r[0] < N, hasb && r[1] < N};
+        // ---- request the first QB_TP sources of both rows
+        double2 pv[QB_TP][2];
 #pragma unroll
         for (int u = 0; u < QB_TP; u++) {
             const int s = gp->sw[u].src;
-            const double2* p = s >= 0 ? pool_r + (long long)(vbase + max(s, 0)) * N : initp + r;
-            pv[u] = (u < nsrc && active) ? QB_LDV(p) : make_double2(0.0, 0.0);
+            const double2* p = s >= 0 ? ta.pool + (long long)(vbase + max(s, 0)) * N : initp;
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                pv[u][j] = (u < nsrc && act[j]) ? QB_LDV(p + r[j]) : make_double2(0.0, 0.0);
         }
         // ---- operator sweep (x from the staged tile / global memory)
-        double2 z = make_double2(0.0, 0.0);
+        double2 z[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
         if (kind == QB_PASS_RHS) {
             if (!staged) { while (!qb_mbar_try_wait(bar, 0u)) { } staged = true; }
             for (int e = 0; e < nelem; e++) {
-                double2 q[1];
-                qb_rowdot_rsell<1, true>(E->elem[e], sl, lane, r, gx1, sx1, lo, rows, q);
-                const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef + e];
-                z.x += c.re * q[0].x - c.im * q[0].y;
-                z.y += c.re * q[0].y + c.im * q[0].x;
+                const QbTileElem& A = ta.elem[e];
+                const QbSlotDesc* cdp = cd.d + cd.elem_off[e];
+                const int4 sa = __ldg(reinterpret_cast<const int4*>(A.sinfo) + sla);
+                const int4 sb = __ldg(reinterpret_cast<const int4*>(A.sinfo) + slb);
+                double2 q[2];
+                if (hasb && sa.x == sb.x && sa.y == sb.y) {
+                    const int vb[2] = {sa.z, sb.z}, cb[2] = {sa.w, sb.w};
+                    qb_rowdot_rsell_tile<2, CD>(A, cdp, sa.x, sa.y, vb, cb, r, lane, gx, sxa, lo, rows, trows, pow2, q);
+                } else {
+                    double2 q1[1];
+                    const int va[1] = {sa.z}, ca[1] = {sa.w}, ra[1] = {r[0]};
+                    qb_rowdot_rsell_tile<1, CD>(A, cdp, sa.x, sa.y, va, ca, ra, lane, gx, sxa, lo, rows, trows, pow2, q1);
+                    q[0] = q1[0]; q[1] = make_double2(0.0, 0.0);
+                    if (hasb) {
+                        const int vb1[1] = {sb.z}, cb1[1] = {sb.w}, rb1[1] = {r[1]};
+                        qb_rowdot_rsell_tile<1, CD>(A, cdp, sb.x, sb.y, vb1, cb1, rb1, lane, gx, sxa, lo, rows, trows, pow2, q1);
+                        q[1] = q1[0];
+                    }
+                }
+                const qb_c128 c = ta.coef[(size_t)slot * ta.maxcoef + e];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    z[j].x += c.re * q[j].x - c.im * q[j].y;
+                    z[j].y += c.re * q[j].y + c.im * q[j].x;
+                }
             }
             const double zs = gp->zscale;
-            z.x *= zs; z.y *= zs;
+#pragma unroll
+            for (int j = 0; j < 2; j++) { z[j].x *= zs; z[j].y *= zs; }
         }
         // ---- fused linear combinations (sources in order, z last), stores, reductions
-        double2 o1 = make_double2(0.0, 0.0), o2 = make_double2(0.0, 0.0);
+        double2 o1[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+        double2 o2[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
 #pragma unroll
         for (int u = 0; u < QB_TP; u++) {
             const double a = gp->sw[u].w1;
-            o1.x = fma(a, pv[u].x, o1.x); o1.y = fma(a, pv[u].y, o1.y);
-            if (werr) { const double b = gp->w2[u]; o2.x = fma(b, pv[u].x, o2.x); o2.y = fma(b, pv[u].y, o2.y); }
-        }
-        for (int i = QB_TP; i < nsrc; i += 4) {
-            double2 v[4];
+            const double b = werr ? gp->w2[u] : 0.0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int j = 0; j < 2; j++) {
+                o1[j].x = fma(a, pv[u][j].x, o1[j].x); o1[j].y = fma(a, pv[u][j].y, o1[j].y);
+                o2[j].x = fma(b, pv[u][j].x, o2[j].x); o2[j].y = fma(b, pv[u][j].y, o2[j].y);
+            }
+        }
+        for (int i = QB_TP; i < nsrc; i += 2) {
+            double2 v[2][2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
                 const int s = gp->sw[min(i + u, QB_MAXSRC - 1)].src;
-                const double2* p = s >= 0 ? pool_r + (long long)(vbase + max(s, 0)) * N : initp + r;
-                v[u] = (i + u < nsrc && active) ? QB_LDV(p) : make_double2(0.0, 0.0);
+                const double2* p = s >= 0 ? ta.pool + (long long)(vbase + max(s, 0)) * N : initp;
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+                    v[u][j] = (i + u < nsrc && act[j]) ? QB_LDV(p + r[j]) : make_double2(0.0, 0.0);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 2; u++) {
                 const double a = gp->sw[min(i + u, QB_MAXSRC - 1)].w1;
-                o1.x = fma(a, v[u].x, o1.x); o1.y = fma(a, v[u].y, o1.y);
-                if (werr) {
-                    const double b = gp->w2[min(i + u, QB_MAXSRC - 1)];
-                    o2.x = fma(b, v[u].x, o2.x); o2.y = fma(b, v[u].y, o2.y);
+                const double b = werr ? gp->w2[min(i + u, QB_MAXSRC - 1)] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    o1[j].x = fma(a, v[u][j].x, o1[j].x); o1[j].y = fma(a, v[u][j].y, o1[j].y);
+                    o2[j].x = fma(b, v[u][j].x, o2[j].x); o2[j].y = fma(b, v[u][j].y, o2[j].y);
                 }
             }
         }
-        {
-            const double2 hz = *reinterpret_cast<const double2*>(&gp->w1z);  // w1z, w2z
-            o1.x = fma(hz.x, z.x, o1.x); o1.y = fma(hz.x, z.y, o1.y);
-            o2.x = fma(hz.y, z.x, o2.x); o2.y = fma(hz.y, z.y, o2.y);
-        }
-        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-        if (active) {
-            const int zdst = gp->zdst, dst1 = gp->dst1;
-            if (zdst >= 0) QB_STV(pool_r + (long long)(vbase + zdst) * N, z);
-            if (dst1 >= 0) QB_STV(pool_r + (long long)(vbase + dst1) * N, o1);
-            else if (dst1 == QB_SLOT_OUT)
-                E->out_states[((size_t)E->traj[slot].traj_id * E->ctl.nt + gp->out_index) * (size_t)N + r] = o1;
-            const double n1 = o1.x * o1.x + o1.y * o1.y;
-            r0 = n1;
-            if (werr) {
-                const double q = sqrt(o2.x * o2.x + o2.y * o2.y) / (E->ctl.opt.atol + E->ctl.opt.rtol * sqrt(n1));
-                r1 = q * q;
+        const double2 hz = *reinterpret_cast<const double2*>(&gp->w1z);  // w1z, w2z
+        const int zdst = gp->zdst, dst1 = gp->dst1;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            if (j == 1 && !hasb) break;                                  // warp-uniform
+            o1[j].x = fma(hz.x, z[j].x, o1[j].x); o1[j].y = fma(hz.x, z[j].y, o1[j].y);
+            o2[j].x = fma(hz.y, z[j].x, o2[j].x); o2[j].y = fma(hz.y, z[j].y, o2[j].y);
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+            if (act[j]) {
+                double2* const pool_r = ta.pool + r[j];
+                if (zdst >= 0) QB_STV(pool_r + (long long)(vbase + zdst) * N, z[j]);
+                if (dst1 >= 0) QB_STV(pool_r + (long long)(vbase + dst1) * N, o1[j]);
+                else if (dst1 == QB_SLOT_OUT)
+                    E->out_states[((size_t)E->traj[slot].traj_id * E->ctl.nt + gp->out_index) * (size_t)N + r[j]] = o1[j];
+                const double n1 = o1[j].x * o1[j].x + o1[j].y * o1[j].y;
+                r0 = n1;
+                if (werr) {
+                    const double q = sqrt(o2[j].x * o2[j].x + o2[j].y * o2[j].y) /
+                                     (ta.atol + ta.rtol * sqrt(n1));
+                    r1 = q * q;
+                }
+                r2 = z[j].x * z[j].x + z[j].y * z[j].y;
             }
-            r2 = z.x * z.x + z.y * z.y;
-        }
-        if (red) {
-            r0 = qb_warp_sum(r0); r1 = qb_warp_sum(r1); r2 = qb_warp_sum(r2);
-            if (lane == 0) {
-                double* __restrict__ part = E->partials + (long long)(slot * E->nslices + sl) * E->red_stride;
-                part[0] = r0; part[1] = r1; part[2] = r2;
+            if (red) {
+                r0 = qb_warp_sum(r0); r1 = qb_warp_sum(r1); r2 = qb_warp_sum(r2);
+                if (lane == 0) {
+                    double* __restrict__ part = ta.partials +
+                        (long long)(slot * ta.nslices + (j ? slb : sla)) * ta.red_stride;
+                    part[0] = r0; part[1] = r1; part[2] = r2;
+                }
             }
         }
     }
@@ -897,6 +956,8 @@ struct QbEngH : QbObj {
     int no_shared = 1;          // qb_pass_kernel_shared only when QB_SHARED is set
     int tile_g = 0, tile_rows = 0, tile_xw = 0, tile_ns = 0, tile_threads = 256;   // TMA-staged kernel (tile_g == 0: off)
     size_t tile_smem = 0;
+    QbConstDesc cdesc;          // descriptor lists in the constant bank (n == 0: read from global memory)
+    QbTileArgs targs;
     double prof_pass_ms = 0.0;
     long long prof_pass_launches = 0;
     unsigned long long prof_vec_count = 0;
@@ -1142,8 +1203,33 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         thr = std::max(32, std::min(256, thr)) & ~31;
         if (thr > rows) thr = rows;
         e->tile_g = 1; e->tile_rows = rows; e->tile_threads = thr; e->tile_smem = (size_t)rows * 16;
-        cudaError_t ce = cudaFuncSetAttribute(qb_pass_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
+        cudaError_t ce = cudaFuncSetAttribute(qb_pass_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qb_pass_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
         if (ce != cudaSuccess) { delete e; QB_FAIL(QB_E_CUDA, "tile kernel shared memory: %s", cudaGetErrorString(ce)); }
+        memset(&e->targs, 0, sizeof e->targs);
+        e->targs.pool = h.pool; e->targs.pass = h.pass; e->targs.coef = h.coef; e->targs.partials = h.partials;
+        e->targs.N = h.ctl.N; e->targs.V = h.V; e->targs.nslices = h.nslices; e->targs.red_stride = h.red_stride;
+        e->targs.nelem = h.ctl.nelem; e->targs.maxcoef = h.ctl.maxcoef;
+        e->targs.atol = e->opt.atol; e->targs.rtol = e->opt.rtol;
+        for (size_t i = 0; i < s->elems.size(); i++) {
+            e->targs.elem[i].sinfo = s->elems[i].sinfo; e->targs.elem[i].val = s->elems[i].val;
+            e->targs.elem[i].col = s->elems[i].col; e->targs.elem[i].sdesc = s->elems[i].sdesc;
+        }
+        // descriptor lists of all elements into the constant-bank table when they fit
+        memset(&e->cdesc, 0, sizeof e->cdesc);
+        int total = 0;
+        for (auto& el : s->elems) total += el.ndesc;
+        if (total <= QB_CD_MAX && !getenv("QB_NO_CDESC")) {
+            int off = 0;
+            for (size_t i = 0; i < s->elems.size(); i++) {
+                e->cdesc.elem_off[i] = off;
+                if (s->elems[i].ndesc > 0 &&
+                    cudaMemcpy(&e->cdesc.d[off], s->elems[i].sdesc, (size_t)s->elems[i].ndesc * sizeof(QbSlotDesc),
+                               cudaMemcpyDeviceToHost) != cudaSuccess) { delete e; QB_FAIL(QB_E_CUDA, "descriptor read-back failed"); }
+                off += s->elems[i].ndesc;
+            }
+            e->cdesc.n = total > 0 ? total : 0;
+        }
     }
     if (h.nslices > 2048) QB_TRY(qb_dev_alloc(e, (size_t)nslots * QB_RED_CTAS * QB_MAXRED, &h.red_final));
     if (s->elems.size() == 1 && s->elems[0].fmt == QB_FMT_DENSE && nslots >= 8) {
@@ -1206,8 +1292,12 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
         }
         if (e->tile_g) {
             const int nt = (e->h.ctl.N + e->tile_rows - 1) / e->tile_rows;
-            qb_pass_tile_kernel<<<(unsigned)(nslots_used * nt), e->tile_threads, e->tile_smem, e->stream>>>(
-                e->d, nslots_used, e->tile_rows);
+            if (e->cdesc.n > 0)
+                qb_pass_tile_kernel<true><<<(unsigned)(nslots_used * nt), e->tile_threads, e->tile_smem, e->stream>>>(
+                    e->d, nslots_used, e->tile_rows, e->targs, e->cdesc);
+            else
+                qb_pass_tile_kernel<false><<<(unsigned)(nslots_used * nt), e->tile_threads, e->tile_smem, e->stream>>>(
+                    e->d, nslots_used, e->tile_rows, e->targs, e->cdesc);
         }
         else if (use_shared) qb_pass_kernel_shared<<<(unsigned)grid_sh, QB_TILE_ROWS, 0, e->stream>>>(e->d);
         else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d, nslots_used);

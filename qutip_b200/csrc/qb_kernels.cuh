@@ -186,64 +186,144 @@ __device__ __forceinline__ double2 qb_rowdot_kron(const QbOpDev& A, int sl, int 
     return acc;
 }
 
-// RSELL sweep (qb_types.h): acc[g] = (A x_g)[r] for the lane's row r of slice sl, g < G.
-// Per slot two warp-uniform 16-byte loads fetch the descriptor; columns follow the slot's
-// rule (row + delta, row ^ delta, or an explicit block) and values are the slot's constant
-// or an explicit block -- diagonal-structured operators issue no per-element index loads.
-// STAGED: rows [lo, lo + trows) of every x_g were staged in shared memory (sx[g], by a TMA
-// bulk copy); columns inside that window are gathered from shared memory (conflict-free
-// LDS.128, no L1 tag stage / replays), the others from global memory.
+// RSELL sweep (qb_types.h).  Per slot the descriptor gives the column rule (row + delta,
+// row ^ delta, or an explicit block) and the value (one constant or an explicit block), so
+// diagonal-structured operators issue no per-element index loads.
 #ifndef QB_RS_U
 #define QB_RS_U 2
 #endif
-template <int G, bool STAGED, int U = QB_RS_U>
-__device__ __forceinline__ void qb_rowdot_rsell(const QbOpDev& A, int sl, int lane, int r,
-                                                const double2* const (&x)[G],
-                                                const double2* const (&sx)[G], int lo, int trows,
-                                                double2 (&acc)[G])
+__device__ __forceinline__ double2 qb_lds128(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+// generic form (stand-alone kernels, rare passes): (A x)[r] for the lane's row r of slice sl,
+// descriptors and x from global memory
+template <int U = QB_RS_U>
+__device__ __forceinline__ double2 qb_rowdot_rsell(const QbOpDev& A, int sl, int lane, int r,
+                                                   const double2* __restrict__ x)
 {
-#pragma unroll
-    for (int g = 0; g < G; g++) acc[g] = make_double2(0.0, 0.0);
-    const int s0 = __ldg(A.slice_ptr + sl), s1 = __ldg(A.slice_ptr + sl + 1);
+    double2 acc = make_double2(0.0, 0.0);
+    const int4 si = __ldg(reinterpret_cast<const int4*>(A.sinfo) + sl);
     const int4* __restrict__ dsc = reinterpret_cast<const int4*>(A.sdesc);
-    const double2* __restrict__ val = reinterpret_cast<const double2*>(A.val) + lane;
-    const int* __restrict__ col = A.col + lane;
+    const double2* __restrict__ val = reinterpret_cast<const double2*>(A.val) + ((long long)si.z * 32 + lane);
+    const int* __restrict__ col = A.col + ((long long)si.w * 32 + lane);
+    const int s1 = si.x + (si.y & 4095);
     auto slot = [&](int k, int& c, double2& v) {
         const int4 d = __ldg(dsc + 2 * k);
         const int cr = d.x & QB_RS_COL_MASK;
-        c = r + d.y;
-        if (cr == QB_RS_COL_XOR) c = r ^ d.y;
+        c = (cr == QB_RS_COL_XOR) ? (r ^ d.y) : (r + d.y);
         if (cr == QB_RS_COL_EXPL) c = __ldg(col + d.z * 32);
-        if (d.x & QB_RS_VAL_CONST) v = __ldg(reinterpret_cast<const double2*>(dsc + 2 * k + 1));
-        else v = __ldg(val + (long long)d.w * 32);
+        v = __ldg(reinterpret_cast<const double2*>(dsc + 2 * k + 1));
+        if (!(d.x & QB_RS_VAL_CONST)) v = __ldg(val + d.w * 32);
     };
-    auto gather = [&](int g, int c) -> double2 {
-        if (STAGED) {
-            const unsigned o = (unsigned)(c - lo);
-            if (o < (unsigned)trows) return sx[g][o];
-        }
-        return x[g][c];
-    };
-    int k = s0;
+    int k = si.x;
     for (; k + U <= s1; k += U) {
         int cc[U];
-        double2 vv[U], xx[U][G];
+        double2 vv[U], xx[U];
 #pragma unroll
         for (int u = 0; u < U; u++) slot(k + u, cc[u], vv[u]);
 #pragma unroll
-        for (int u = 0; u < U; u++)
+        for (int u = 0; u < U; u++) xx[u] = __ldg(x + cc[u]);
 #pragma unroll
-            for (int g = 0; g < G; g++) xx[u][g] = gather(g, cc[u]);
-#pragma unroll
-        for (int u = 0; u < U; u++)
-#pragma unroll
-            for (int g = 0; g < G; g++) qb_fma(acc[g], vv[u], xx[u][g]);
+        for (int u = 0; u < U; u++) qb_fma(acc, vv[u], xx[u]);
     }
     for (; k < s1; k++) {
         int c; double2 v;
         slot(k, c, v);
+        qb_fma(acc, v, __ldg(x + c));
+    }
+    return acc;
+}
+
+// Fused-pass form: RB slices that SHARE one descriptor list (same first descriptor and
+// count; base[j] = the slice's explicit value / column block bases), descriptors from the
+// constant bank (CD, kernel parameter) or global memory.  Rows [lo, lo + trows) of x were
+// staged in shared memory (shared-window address sxa, by a TMA bulk copy): columns inside
+// that window are gathered with conflict-free LDS.128 (no L1 tag stage / replays), the
+// others from global memory.
+struct QbTileElem { const int* sinfo; const qb_c128* val; const int* col; const QbSlotDesc* sdesc; };
+template <int RB, bool CD>
+__device__ __forceinline__ void qb_rowdot_rsell_tile(const QbTileElem& A, const QbSlotDesc* __restrict__ cdesc,
+                                                     int dstart, int dcount, const int (&vb)[RB],
+                                                     const int (&cb)[RB], const int (&r)[RB], int lane,
+                                                     const double2* __restrict__ x, unsigned sxa,
+                                                     int lo, int trows, int tnom, bool pow2, double2 (&acc)[RB])
+{
 #pragma unroll
-        for (int g = 0; g < G; g++) qb_fma(acc[g], v, gather(g, c));
+    for (int j = 0; j < RB; j++) acc[j] = make_double2(0.0, 0.0);
+    const QbSlotDesc* __restrict__ dsc = CD ? cdesc + dstart : A.sdesc + dstart;
+    const int ntot = dcount & 4095, nfast = (dcount >> 12) & 4095;
+    const int nxor = pow2 ? (dcount >> 24) & 255 : 0;
+    auto fetch = [&](int k, int& rule, int& delta, int& cpos, int& vpos, double2& cv) {
+        if (CD) {
+            rule = dsc[k].rule; delta = dsc[k].delta; cpos = dsc[k].cpos; vpos = dsc[k].vpos;
+            cv = make_double2(dsc[k].vre, dsc[k].vim);
+        } else {
+            const int4 d = __ldg(reinterpret_cast<const int4*>(dsc + k));
+            cv = __ldg(reinterpret_cast<const double2*>(dsc + k) + 1);
+            rule = d.x; delta = d.y; cpos = d.z; vpos = d.w;
+        }
+    };
+    auto gather = [&](int c) -> double2 {
+        const unsigned o = (unsigned)(c - lo);
+        if (o < (unsigned)trows) return qb_lds128(sxa + o * 16u);
+        return __ldg(x + c);
+    };
+    // xor slots with a constant value on a power-of-two tile: the partner row is at the own
+    // tile offset ^ (delta * 16) when delta < tile rows (warp-uniform branch), else in global
+    // memory -- no per-lane bounds test, no select between two loads
+    unsigned sa[RB];
+#pragma unroll
+    for (int j = 0; j < RB; j++) sa[j] = (unsigned)(r[j] - lo) * 16u;
+    int k = 0;
+    for (; k < nxor; k++) {
+        int delta;
+        double2 cv, xv[RB];
+        if (CD) { delta = dsc[k].delta; cv = make_double2(dsc[k].vre, dsc[k].vim); }
+        else {
+            delta = __ldg(&dsc[k].delta);
+            cv = __ldg(reinterpret_cast<const double2*>(dsc + k) + 1);
+        }
+        if (delta < tnom) {        // tnom: nominal (power-of-two) tile rows
+#pragma unroll
+            for (int j = 0; j < RB; j++) xv[j] = qb_lds128(sxa + (sa[j] ^ ((unsigned)delta << 4)));
+        } else {
+#pragma unroll
+            for (int j = 0; j < RB; j++) xv[j] = __ldg(x + (r[j] ^ delta));
+        }
+#pragma unroll
+        for (int j = 0; j < RB; j++) qb_fma(acc[j], cv, xv[j]);
+    }
+    // other fast slots: column = (row ^ xd) + ad, one constant value
+    for (; k < nfast; k++) {
+        int ru, de, cp, vp;
+        double2 cv;
+        fetch(k, ru, de, cp, vp, cv);
+        const bool isx = (ru & QB_RS_COL_MASK) == QB_RS_COL_XOR;
+        const int xd = isx ? de : 0, ad = isx ? 0 : de;
+#pragma unroll
+        for (int j = 0; j < RB; j++) qb_fma(acc[j], cv, gather((r[j] ^ xd) + ad));
+    }
+    // general slots: explicit column and / or value blocks
+    const double2* __restrict__ val = reinterpret_cast<const double2*>(A.val) + lane;
+    const int* __restrict__ col = A.col + lane;
+    for (; k < ntot; k++) {
+        int rule, delta, cpos, vpos;
+        double2 cv;
+        fetch(k, rule, delta, cpos, vpos, cv);
+        const int cr = rule & QB_RS_COL_MASK;
+        int c[RB];
+        double2 v[RB];
+#pragma unroll
+        for (int j = 0; j < RB; j++) {
+            c[j] = (cr == QB_RS_COL_XOR) ? (r[j] ^ delta) : (r[j] + delta);
+            if (cr == QB_RS_COL_EXPL) c[j] = __ldg(col + (long long)(cb[j] + cpos) * 32);
+            v[j] = cv;
+            if (!(rule & QB_RS_VAL_CONST)) v[j] = __ldg(val + (long long)(vb[j] + vpos) * 32);
+        }
+#pragma unroll
+        for (int j = 0; j < RB; j++) qb_fma(acc[j], v[j], gather(c[j]));
     }
 }
 
@@ -281,10 +361,7 @@ __device__ __forceinline__ double2 qb_rowdot(const QbOpDev& A, int sl, int lane,
     } else if (A.fmt == QB_FMT_KRON) {
         acc = qb_rowdot_kron(A, sl, lane, r, active, x);
     } else if (A.fmt == QB_FMT_RSELL) {
-        const double2* xs1[1] = {x};
-        double2 a1[1];
-        qb_rowdot_rsell<1, false>(A, sl, lane, (int)r, xs1, xs1, 0, 0, a1);
-        acc = a1[0];
+        acc = qb_rowdot_rsell(A, sl, lane, (int)r, x);
     } else {
         if (active) {
             const double2* __restrict__ a = reinterpret_cast<const double2*>(A.dense) + r;

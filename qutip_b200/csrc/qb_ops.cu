@@ -134,7 +134,8 @@ static int finish_rsell(QbOpH* h, RsellHost& rs, int64_t rows, int64_t cols) {
     h->dev.fmt = QB_FMT_RSELL; h->dev.nrows = (int)rows; h->dev.ncols = (int)cols;
     h->dev.nnz = rs.nnz;
     int rc;
-    if ((rc = to_device(h, rs.slice_ptr, &h->dev.slice_ptr))) return rc;
+    h->dev.ndesc = (int)rs.desc.size();
+    if ((rc = to_device(h, rs.sinfo, &h->dev.sinfo))) return rc;
     if ((rc = to_device(h, rs.desc, &h->dev.sdesc))) return rc;
     if ((rc = to_device(h, rs.val, &h->dev.val))) return rc;
     if ((rc = to_device(h, rs.col, &h->dev.col))) return rc;
@@ -143,7 +144,7 @@ static int finish_rsell(QbOpH* h, RsellHost& rs, int64_t rows, int64_t cols) {
 // RSELL replaces SELL when the slices are diagonal structured: at most 1.75 stored lanes per
 // non-zero (every slot costs one gather for all 32 lanes) and L2-resident
 static bool want_rsell(const RsellHost& rs, int64_t rows, long long sell_padded) {
-    if (getenv("QB_NO_RSELL") || rs.nnz == 0 || rows < 32) return false;
+    if (getenv("QB_NO_RSELL") || rs.nnz == 0 || rows < 32 || rs.overflow) return false;
     const long long stored = rs.stored() * 32;
     return rs.bytes() <= (48ll << 20) && (double)stored <= 1.75 * (double)rs.nnz &&
            stored <= sell_padded + sell_padded / 4;
@@ -416,14 +417,15 @@ qb_matmul_kernel(QbOpDev A, const double2* __restrict__ X, long long xs_r, long 
                         qb_fma(q, val[k * 32], X[(long long)col[k * 32] * xs_r + c * xs_c]);
                 } else if (A.fmt == QB_FMT_RSELL) {
                     const double2* val = reinterpret_cast<const double2*>(A.val);
-                    for (int k = A.slice_ptr[sl]; k < A.slice_ptr[sl + 1]; k++) {
+                    const int4 si = reinterpret_cast<const int4*>(A.sinfo)[sl];
+                    for (int k = si.x; k < si.x + (si.y & 4095); k++) {
                         const QbSlotDesc d = A.sdesc[k];
                         const int cr = d.rule & QB_RS_COL_MASK;
                         const long long cc = cr == QB_RS_COL_ADD ? r + d.delta
                                            : cr == QB_RS_COL_XOR ? (r ^ (long long)d.delta)
-                                                                 : A.col[(size_t)d.cpos * 32 + lane];
+                                                                 : A.col[(size_t)(si.w + d.cpos) * 32 + lane];
                         const double2 vv = (d.rule & QB_RS_VAL_CONST) ? make_double2(d.vre, d.vim)
-                                                                      : val[(size_t)d.vpos * 32 + lane];
+                                                                      : val[(size_t)(si.z + d.vpos) * 32 + lane];
                         qb_fma(q, vv, X[cc * xs_r + c * xs_c]);
                     }
                 }

@@ -52,8 +52,8 @@ enum { QB_RS_COL_EXPL = 0, QB_RS_COL_ADD = 1, QB_RS_COL_XOR = 2, QB_RS_COL_MASK 
 struct alignas(16) QbSlotDesc {
     int rule;        // QB_RS_COL_* | QB_RS_VAL_CONST
     int delta;       // operand of the column rule
-    int cpos;        // explicit columns: col[cpos * 32 + lane]
-    int vpos;        // explicit values:  val[vpos * 32 + lane]
+    int cpos;        // explicit columns: col[(slice column base + cpos) * 32 + lane]
+    int vpos;        // explicit values:  val[(slice value base + vpos) * 32 + lane]
     double vre, vim; // constant value
 };
 
@@ -83,8 +83,23 @@ struct QbOpDev {
     int kstack, kpad_;
     const qb_c128* kval;
     const int* kcol;
-    // RSELL: slice_ptr[nslices+1] indexes sdesc[]; explicit blocks live in val / col
+    // RSELL: sinfo[nslices][4] = (first descriptor, count | fast count << 12 | xor-fast count
+    // << 24, value-block base, column-block base) of every slice -- a list holds the xor-rule
+    // constant-value slots first, then the add-rule ones ("fast": no explicit block), then the rest; sdesc[ndesc] the de-duplicated descriptor lists; explicit blocks
+    // live in val / col
     const QbSlotDesc* sdesc;
+    const int* sinfo;
+    int ndesc, rpad_;
+};
+
+// descriptor lists of a system's RSELL elements in the constant bank (kernel parameter of the
+// fused pass kernel): warp-uniform reads that do not touch the L1 data pipe
+#define QB_CD_MAX 80
+struct QbConstDesc {
+    int n;                          // 0: lists are read from global memory
+    int elem_off[QB_MAX_ELEMS];     // first descriptor of element e in d[]
+    int cpad_[3];
+    QbSlotDesc d[QB_CD_MAX];
 };
 
 // ---- coefficient byte-code (qb_coeff.h) ----

@@ -529,6 +529,11 @@ class Comm(_Handle):
         check(_lib.load().qb_comm_allreduce_sum(self.handle, ptrs, views[0].size))
         return arrays
 
+    def allreduce_sum_device(self, device_pointers, count):
+        """in-place sum over the group of ``count`` doubles at one device pointer per member"""
+        ptrs = (C.c_void_p * self.nlocal)(*[int(p) for p in device_pointers])
+        check(_lib.load().qb_comm_allreduce_sum_device(self.handle, ptrs, int(count)))
+
     def reduce_expect(self, engines, neops, nt):
         """(sum_j e_j, sum_j (re^2, im^2)) over ALL trajectories of the group, [n_e][n_t] each:
         every engine (``None`` for a member that ran nothing) reduces the expectation values

@@ -83,7 +83,21 @@ def coefficient_to_program(c, system=None):
         i_code = next(i for i, x in enumerate(state) if isinstance(x, str))
         code, names = state[i_code], state[i_code + 1:]
         vals = state[:len(names)]
-        return coeffs.compile_expr(code, dict(zip(names, vals)))
+        prog = coeffs.compile_expr(code, dict(zip(names, vals)))
+        # the pickled members are ordered by attribute name (typed args: _arg_cpl*, _arg_dbl*,
+        # _arg_int*), which need not be the order of the names: check the compiled program
+        # against the coefficient itself before trusting the binding
+        for t in (0.0, 0.37, 1.9):
+            try:
+                want, got = complex(c(t)), complex(coeffs.evaluate(prog, t))
+            except (NotImplementedError, ArithmeticError, ValueError):
+                continue                      # instruction without a python mirror / singular point
+            if not (np.isfinite(want.real) and np.isfinite(want.imag)):
+                continue
+            if not abs(want - got) <= 1e-12 * max(1.0, abs(want)):
+                raise TypeError("string coefficient %r could not be bound to its argument "
+                                "values (typed arguments); evaluated by the host instead" % code)
+        return prog
     if name == "ConjCoefficient":
         return coefficient_to_program(_coeff_state(c)[1], system).conj()
     if name == "NormCoefficient":
@@ -134,8 +148,10 @@ def bind_qobjevo(qevo, system=None, allow_host=False):
                 and isinstance(el[1], _Coefficient):
             try:
                 prog = coefficient_to_program(el[1], system)
-            except TypeError:
+            except (TypeError, ValueError) as exc:
                 if not allow_host:
+                    if isinstance(exc, ValueError):
+                        raise TypeError(str(exc)) from exc
                     raise
                 prog = _HostCoefficient(el[1])        # python callable: evaluated by the host
             out.append((_data_to_host(el[0].data), prog))
@@ -945,18 +961,49 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
     multi = devices is not None and len(devices) > 1 and ntraj >= 2 * len(devices)
     store = int(want_states or want_final)
 
+    def fingerprint():
+        """identity of everything the device system is built from; the objects are kept alive
+        by the cache entry so that ids cannot be recycled.  ``solver.run(args=...)`` replaces
+        the coefficient objects of the rhs, which changes the key."""
+        objs = []
+        for q in [rhs.rhs] + list(rhs.c_ops) + list(rhs.n_ops):
+            for el in q.to_list():
+                objs.extend(el if isinstance(el, (list, tuple)) else [el])
+        objs.extend(e_dict.values())
+        return tuple(id(o) for o in objs), objs
+
+    opt_key = (method, floor, store, tuple(sorted((k, repr(v)) for k, v in iopt.items())),
+               tuple(repr(opts[k]) for k in ("norm_steps", "norm_t_tol", "norm_tol", "norm_min_step",
+                                             "mc_corr_eps")))
+
     def shard(lo, hi, device):
         if device is not None:
             E.set_device(device)
-        system = system_from_qobjevo(rhs.rhs, rhs.c_ops, rhs.n_ops, e_evos, allow_host=True)
-        if system.has_host:
-            raise TypeError("python-callable coefficients need a host evaluation per RHS call; the "
-                            "'b200' map runs whole batches on the device and cannot use them. Use "
-                            "string/array coefficients, or method='b200_vern7' with a stock map.")
+        # device system and engines are kept on the solver between runs (operators uploaded and
+        # converted once, state pool allocated once)
+        ids, objs = fingerprint()
+        cache = solver.__dict__.setdefault("_b200_cache", _DeviceCache())
+        key = (device, ids)
+        entry = cache.get(key)
+        if entry is None:
+            system = system_from_qobjevo(rhs.rhs, rhs.c_ops, rhs.n_ops, e_evos, allow_host=True)
+            if system.has_host:
+                raise TypeError("python-callable coefficients need a host evaluation per RHS call; the "
+                                "'b200' map runs whole batches on the device and cannot use them. Use "
+                                "string/array coefficients, or method='b200_vern7' with a stock map.")
+            for k in [k for k in cache if k[0] == device]:
+                del cache[k]                       # one system per device and solver
+            entry = cache[key] = dict(system=system, engines={}, refs=objs)
+        system = entry["system"]
         nslots = min(hi - lo, solve.default_nslots(N, method))
 
         def make_engine(max_collapses):
-            return E.Engine(
+            ek = (opt_key, max_collapses)
+            eng = entry["engines"].get(ek)
+            if eng is not None and eng.nslots >= min(hi - lo, nslots):
+                return eng
+            entry["engines"].clear()               # frees the previous state pool first
+            eng = entry["engines"][ek] = E.Engine(
                 system, method, nslots=nslots, atol=iopt['atol'], rtol=iopt['rtol'],
                 nsteps=int(iopt['nsteps']), first_step=float(iopt['first_step'] or 0),
                 min_step=float(iopt['min_step'] or 0), max_step=float(iopt['max_step'] or 0),
@@ -965,6 +1012,7 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
                 norm_t_tol=opts['norm_t_tol'], norm_tol=opts['norm_tol'],
                 norm_min_step=opts['norm_min_step'], mc_corr_eps=opts['mc_corr_eps'],
                 store_states=store, jump_prob_floor=floor, max_collapses=max_collapses)
+            return eng
 
         return _run_engine_batch(make_engine, psi0, tlist, np.ascontiguousarray(draws[lo:hi]),
                                  gens[lo:hi], _MAX_COLLAPSES)
@@ -1074,6 +1122,14 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
             if remaining is not None and remaining <= 0:
                 return True
     return False
+
+
+class _DeviceCache(dict):
+    """device systems / engines kept on a solver between runs; device handles do not travel,
+    so a pickled solver (process maps) starts with an empty cache"""
+
+    def __reduce__(self):
+        return (_DeviceCache, ())
 
 
 _MAX_COLLAPSES = 64       # initial capacity of the per-trajectory collapse record (grown on demand)

@@ -100,9 +100,10 @@ class EmulSystem:
         self.L.emul_set_functional(int(f))
 
     def rsell_stats(self, which):
-        out = (C.c_longlong * 5)()
+        out = (C.c_longlong * 6)()
         self.L.emul_rsell_stats(which, out)
-        return dict(slots=out[0], col_blocks=out[1], val_blocks=out[2], bytes=out[3], xor_slots=out[4])
+        return dict(slots=out[0], col_blocks=out[1], val_blocks=out[2], bytes=out[3], xor_slots=out[4],
+                    unique_descriptors=out[5])
 
     def matvec(self, which, x):
         x = np.ascontiguousarray(x, dtype=np.complex128)

@@ -61,13 +61,14 @@ static qb_c128 rowdot(const HostOp& A, int64_t r, const qb_c128* x) {
         return acc;
     }
     if (A.fmt == QB_FMT_RSELL) {
-        for (int k = A.rs.slice_ptr[sl]; k < A.rs.slice_ptr[sl + 1]; k++) {
+        const int* si = &A.rs.sinfo[(size_t)sl * 4];
+        for (int k = si[0]; k < si[0] + (si[1] & 4095); k++) {
             const QbSlotDesc& d = A.rs.desc[k];
             const int cr = d.rule & QB_RS_COL_MASK;
             const long long c = cr == QB_RS_COL_ADD ? r + d.delta : cr == QB_RS_COL_XOR ? (r ^ (long long)d.delta)
-                                                                   : A.rs.col[(size_t)d.cpos * 32 + lane];
+                                                                   : A.rs.col[(size_t)(si[3] + d.cpos) * 32 + lane];
             qb_c128 a = {d.vre, d.vim};
-            if (!(d.rule & QB_RS_VAL_CONST)) a = A.rs.val[(size_t)d.vpos * 32 + lane];
+            if (!(d.rule & QB_RS_VAL_CONST)) a = A.rs.val[(size_t)(si[2] + d.vpos) * 32 + lane];
             const qb_c128 b = x[c];
             acc.re += a.re * b.re - a.im * b.im; acc.im += a.re * b.im + a.im * b.re;
         }
@@ -139,13 +140,16 @@ double emul_diam_avg_lanes(int which) {
     return o.dh.ent.empty() ? 0.0 : (double)o.dh.val.size() / (double)o.dh.ent.size();
 }
 // RSELL statistics of element `which`: out = {slots, explicit column blocks, explicit value
-// blocks, device bytes, xor-rule slots}
+// blocks, device bytes, xor-rule slots, de-duplicated descriptors}
 void emul_rsell_stats(int which, long long* out) {
     const HostOp& o = g_sys.elems[which];
     long long nx = 0;
-    for (auto& d : o.rs.desc) nx += (d.rule & QB_RS_COL_MASK) == QB_RS_COL_XOR;
+    for (size_t sl = 0; sl * 4 < o.rs.sinfo.size(); sl++)
+        for (int k = o.rs.sinfo[sl * 4]; k < o.rs.sinfo[sl * 4] + (o.rs.sinfo[sl * 4 + 1] & 4095); k++)
+            nx += (o.rs.desc[k].rule & QB_RS_COL_MASK) == QB_RS_COL_XOR;
     out[0] = o.rs.stored(); out[1] = (long long)o.rs.col.size() / 32;
     out[2] = (long long)o.rs.val.size() / 32; out[3] = o.rs.bytes(); out[4] = nx;
+    out[5] = (long long)o.rs.desc.size();
 }
 // Adams corrector coefficients / error constants of order nq (qb_adams.h)
 void emul_adams_table(int nq, double* el, double* tq) {

@@ -60,6 +60,7 @@ def test_rsell_spin_chain_is_rule_compressed():
     st = s.rsell_stats(0)
     assert st["slots"] == (n // 32) * 9 and st["xor_slots"] == st["slots"]
     assert st["col_blocks"] == 0 and st["val_blocks"] == n // 32
+    assert st["unique_descriptors"] == 9        # every slice shares ONE descriptor list
     assert st["bytes"] < 0.25 * (A.nnz * 20)
     x = np.random.default_rng(1).random(n) + 1j * np.random.default_rng(2).random(n)
     np.testing.assert_allclose(s.matvec(0, x), A @ x, rtol=1e-13, atol=1e-13)
@@ -177,7 +178,8 @@ def test_coefficient_bytecode():
 
 
 @pytest.mark.parametrize("name,method,nslots", [("c3_tfim6_mc", "vern7", 24),
-                                               ("c3_tfim4_mc_strong", "vern9", 7)])
+                                               ("c3_tfim4_mc_strong", "vern9", 7),
+                                               ("c3_tfim4_mc_tsit5", "tsit5", 5)])
 def test_mcsolve_state_machine_tile_mode(name, method, nslots):
     """Fixed slot labels (explicit y_prev <- y_front copies, chunked expectation passes) as
     used by the trajectory-interleaved tile engine: same results as the relabelling mode."""
@@ -192,7 +194,7 @@ def test_mcsolve_state_machine_tile_mode(name, method, nslots):
         for i in range(int(g["n_eops"])):
             s.add_eop(*op_arrays(g, "eop%d" % i))
         ntraj = int(g["ntraj"])
-        r = s.run(1, {"vern7": 0, "vern9": 1}[method], g["psi0"], g["tlist"], ntraj=ntraj,
+        r = s.run(1, {"vern7": 0, "vern9": 1, "tsit5": 2}[method], g["psi0"], g["tlist"], ntraj=ntraj,
                   nslots=nslots, draws=g["draws"], opt=default_options(store_states=1))
     finally:
         lib().emul_set_tile_mode(0, 0)

@@ -66,3 +66,21 @@ def test_dense_heff_mcsolve_block_vs_oracle(dim, ntraj):
     r1 = eng1.run_mcsolve(psi0, tlist, draws)
     assert np.array_equal(r1.ncol, r.ncol)
     np.testing.assert_allclose(r1.expect, r.expect, rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("dim,ncols", [(1024, 256), (4096, 256)])
+def test_zgemm_dmma_baseline_dims_vs_numpy(dim, ncols):
+    """BASELINE config 5 sizes (dense H_eff dim 1024 / 4096 times a block of trajectories):
+    every output element against numpy's zgemm (matmul_dense, core/data/matmul.pyx:275-347)."""
+    rng = np.random.default_rng(dim)
+    A = (rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))) / np.sqrt(dim)
+    X = rng.standard_normal((dim, ncols)) + 1j * rng.standard_normal((dim, ncols))
+    dA = qb.DeviceDense.from_numpy(np.asfortranarray(A))
+    dX = qb.DeviceDense.from_numpy(np.asfortranarray(X))
+    dC = qb.DeviceDense.zeros(dim, ncols)
+    E.matmul(dA, dX, 1.0, dC)
+    ref = A @ X
+    # accumulation order differs (k-blocked DMMA vs BLAS): 1e-6 / 1e-8 is the north-star
+    # tolerance, observed ~1e-13
+    np.testing.assert_allclose(dC.to_numpy(), ref, rtol=1e-6, atol=1e-8)
+    assert np.abs(dC.to_numpy() - ref).max() < 1e-11

@@ -545,3 +545,44 @@ def test_b200_map_sharded_over_devices():
             np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-13)
         for a, b in zip(two.std_expect, one.std_expect):
             np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
+
+
+def test_c2_full_size_mesolve_vs_reference():
+    """BASELINE config 2 at full size (TFIM 10 spins, rho-vector 2^20) through qutip.mesolve:
+    the reference's own vern7 (matrix_form, so that the 24.6 M-nnz Liouvillian need not be
+    built on the host) against method='b200_vern7' on t in [0, 0.1]."""
+    H, c_ops, sz = tfim(10)
+    psi0 = basis([2] * 10, [0] * 10)
+    tl = np.linspace(0, 0.1, 3)
+    e_ops = [sz[0], sz[4] * sz[5]]
+    o = dict(OPT, matrix_form=True, store_states=False, store_final_state=True)
+    ref = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(o, method="vern7"))
+    out = mesolve(H, psi0, tl, c_ops, e_ops=e_ops, options=dict(o, method="b200_vern7"))
+    np.testing.assert_allclose(np.array(out.expect), np.array(ref.expect), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out.final_state.full(), ref.final_state.full(), rtol=RTOL, atol=ATOL)
+
+
+def test_c3_full_size_256_trajectories_vs_reference():
+    """BASELINE config 3 at full size (TFIM 14 spins, dim 16384): 256 trajectories of the
+    reference's own mcsolve (all host cores) against the b200 map -- jump counts and collapse
+    indices bit-exact, times to 1e-9, expectation values within 1e-8 / 1e-6."""
+    import os
+    H, c_ops, sz = tfim(14)
+    psi0 = basis([2] * 14, [0] * 14)
+    tl = np.linspace(0, 2, 21)
+    ntraj = 256
+    cores = len(os.sched_getaffinity(0))
+    o = dict(OPT, method="vern7", keep_runs_results=True)
+    ref = mcsolve(H, psi0, tl, c_ops, e_ops=[sz[0]], ntraj=ntraj, seeds=np.random.SeedSequence(7),
+                  options=dict(o, map="parallel" if cores > 1 else "serial", num_cpus=cores))
+    out = mcsolve(H, psi0, tl, c_ops, e_ops=[sz[0]], ntraj=ntraj, seeds=np.random.SeedSequence(7),
+                  options=dict(o, map="b200"))
+    # the process pool hands trajectories over in completion order: match them by seed
+    ro = np.argsort([s.spawn_key[-1] for s in ref.seeds])
+    oo = np.argsort([s.spawn_key[-1] for s in out.seeds])
+    assert len(ro) == len(oo) == ntraj
+    re_, oe_ = np.array(ref.runs_expect), np.array(out.runs_expect)
+    for i, j in zip(ro, oo):
+        assert list(out.col_which[j]) == list(ref.col_which[i])
+        np.testing.assert_allclose(out.col_times[j], ref.col_times[i], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(oe_[:, j], re_[:, i], rtol=RTOL, atol=ATOL)
