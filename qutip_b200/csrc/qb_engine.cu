@@ -499,11 +499,12 @@ struct QbTileArgs {
 
 template <bool CD>
 __global__ void __launch_bounds__(256, QB_TT_MINB)
-qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trows,
+qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trows, int nsb,
                     const __grid_constant__ QbTileArgs ta, const __grid_constant__ QbConstDesc cd)
 {
     extern __shared__ __align__(128) unsigned char qb_tile_smem[];
-    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ __align__(8) unsigned long long mbar;          // x tile
+    __shared__ __align__(8) unsigned long long wbar[8];       // per warp: staged epilogue sources
     const int N = ta.N;
     const int ntiles = (N + trows - 1) / trows;
     const int slot = blockIdx.x / ntiles;
@@ -523,33 +524,45 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
     const int vbase = slot * ta.V;
     const double2* const initp = E->init_states + (long long)E->traj[slot].init_idx * N;
     const double2* gx = nullptr;
-    // shared-window address of the staged tile, computed ONCE (volatile: the compiler would
-    // otherwise re-derive it from SR_CgaCtaId in front of every LDS to save a register)
+    // shared-window addresses, computed ONCE (volatile: the compiler would otherwise re-derive
+    // them from SR_CgaCtaId in front of every LDS to save a register)
     unsigned sxa;
     asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}"
                  : "=r"(sxa) : "l"(qb_tile_smem));
+    const unsigned wba = sxa + (unsigned)trows * 16u + (unsigned)(warp * nsb) * 1024u;   // this warp's source buffer
     const unsigned bar = qb_smem_u32(&mbar);
-    if (kind == QB_PASS_RHS) {
-        const int xs = gp->x;
-        gx = xs >= 0 ? ta.pool + (long long)(vbase + xs) * N : initp;
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned wb = qb_smem_u32(&wbar[warp]);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        for (int w = 0; w < nw; w++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(qb_smem_u32(&wbar[w])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (kind == QB_PASS_RHS) {
+            const int xs = gp->x;
+            const double2* xp = xs >= 0 ? ta.pool + (long long)(vbase + xs) * N : initp;
             const unsigned bytes = (unsigned)rows * 16u;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(sxa), "l"(gx + lo), "r"(bytes), "r"(bar) : "memory");
+                         :: "r"(sxa), "l"(xp + lo), "r"(bytes), "r"(bar) : "memory");
         }
-        __syncthreads();          // the barrier object is initialised before anybody polls it
     }
+    if (kind == QB_PASS_RHS) {
+        const int xs = gp->x;
+        gx = xs >= 0 ? ta.pool + (long long)(vbase + xs) * N : initp;
+    }
+    __syncthreads();              // the barrier objects are initialised before anybody uses them
     const int nsrc = gp->nsrc;
+    const int nb = min(nsrc, nsb);                      // sources staged by TMA; the rest is loaded directly
     const int red = gp->red;
     const bool werr = (red & QB_RED_WRMS) != 0;
     const int nelem = ta.nelem;
     const bool pow2 = (trows & (trows - 1)) == 0;       // tiles are aligned power-of-two blocks
     bool staged = false;
-    // a warp takes PAIRS of adjacent slices: everything warp-uniform (descriptor lists, pass
-    // descriptor, weights) is read once per pair
+    unsigned parity = 0;
+    // a warp takes PAIRS of adjacent slices (64 consecutive rows): everything warp-uniform
+    // (descriptor lists, pass descriptor, weights) is read once per pair, and the pair's rows
+    // of every epilogue source are ONE contiguous kilobyte -- fetched by one TMA bulk copy per
+    // source into the warp's own buffer, all in flight during the sweep, no register held
     const int npairs = (sl1 - sl0 + 1) >> 1;
     for (int pr = warp; pr < npairs; pr += nw) {
         const int sla = sl0 + 2 * pr;
@@ -557,16 +570,32 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
         const int slb = hasb ? sla + 1 : sla;
         const int r[2] = {sla * 32 + lane, slb * 32 + lane};
         const bool act[2] = {r[0] < N, hasb && r[1] < N};
-        // ---- request the first QB_TP sources of both rows
-        double2 pv[QB_TP][2];
-#pragma unroll
-        for (int u = 0; u < QB_TP; u++) {
-            const int s = gp->sw[u].src;
+        if (nb > 0) {
+            // lane i issues the copy of source i: the source indices are fetched with one
+            // coalesced load and all copies leave in one instruction
+            const int r0 = sla * 32;
+            const unsigned bytes = (unsigned)min(hasb ? 64 : 32, N - r0) * 16u;
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier reads of the buffer are done
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(wb), "r"(bytes * (unsigned)nb) : "memory");
+            }
+            __syncwarp();
+            if (lane < nb) {
+                const int s = gp->sw[lane].src;
+                const double2* p = (s >= 0 ? ta.pool + (long long)(vbase + s) * N : initp) + r0;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(wba + (unsigned)lane * 1024u), "l"(p), "r"(bytes), "r"(wb) : "memory");
+            }
+        }
+#ifdef QB_TAIL_PF
+        for (int i = nb; i < nsrc; i++) {       // sources beyond the staged ones: request them into L2
+            const int s = gp->sw[i].src;
             const double2* p = s >= 0 ? ta.pool + (long long)(vbase + max(s, 0)) * N : initp;
 #pragma unroll
             for (int j = 0; j < 2; j++)
-                pv[u][j] = (u < nsrc && act[j]) ? QB_LDV(p + r[j]) : make_double2(0.0, 0.0);
+                if (act[j]) asm volatile("prefetch.global.L2 [%0];" :: "l"(p + r[j]));
         }
+#endif
         // ---- operator sweep (x from the staged tile / global memory)
         double2 z[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
         if (kind == QB_PASS_RHS) {
@@ -605,17 +634,24 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
         // ---- fused linear combinations (sources in order, z last), stores, reductions
         double2 o1[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
         double2 o2[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+        if (nb > 0) {
+            while (!qb_mbar_try_wait(wb, parity)) { }
+            parity ^= 1u;
+            const unsigned la = wba + (unsigned)lane * 16u;
+            for (int i = 0; i < nb; i++) {
+                const double a = gp->sw[i].w1;
+                const double b = werr ? gp->w2[i] : 0.0;
 #pragma unroll
-        for (int u = 0; u < QB_TP; u++) {
-            const double a = gp->sw[u].w1;
-            const double b = werr ? gp->w2[u] : 0.0;
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                o1[j].x = fma(a, pv[u][j].x, o1[j].x); o1[j].y = fma(a, pv[u][j].y, o1[j].y);
-                o2[j].x = fma(b, pv[u][j].x, o2[j].x); o2[j].y = fma(b, pv[u][j].y, o2[j].y);
+                for (int j = 0; j < 2; j++) {
+                    const double2 v = act[j] ? qb_lds128(la + (unsigned)i * 1024u + (unsigned)j * 512u)
+                                             : make_double2(0.0, 0.0);
+                    o1[j].x = fma(a, v.x, o1[j].x); o1[j].y = fma(a, v.y, o1[j].y);
+                    o2[j].x = fma(b, v.x, o2[j].x); o2[j].y = fma(b, v.y, o2[j].y);
+                }
             }
+            __syncwarp();         // every lane has read its rows before the buffer is refilled
         }
-        for (int i = QB_TP; i < nsrc; i += 2) {
+        for (int i = nb; i < nsrc; i += 2) {
             double2 v[2][2];
 #pragma unroll
             for (int u = 0; u < 2; u++) {
@@ -1106,6 +1142,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     static_assert(sizeof(qb_options) == sizeof(QbOptions), "options layout");
     memcpy(&e->opt, opt, sizeof(QbOptions));
     if (e->opt.max_collapses < 1) e->opt.max_collapses = 1;
+    if (tableau == 3) { e->opt.atol *= QB_AD_TOL_SCALE; e->opt.rtol *= QB_AD_TOL_SCALE; }   // qb_adams.h
     QbEngineDev& h = e->h;
     if (tableau == 3) qb_adams_table(&h.ctl.tab);
     else h.ctl.tab = *QB_TABLEAUX[tableau];
@@ -1202,7 +1239,11 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         if (rows > nround) rows = nround;
         thr = std::max(32, std::min(256, thr)) & ~31;
         if (thr > rows) thr = rows;
-        e->tile_g = 1; e->tile_rows = rows; e->tile_threads = thr; e->tile_smem = (size_t)rows * 16;
+        const char* eb = getenv("QB_TILE_NSB");
+        int nsb = eb ? atoi(eb) : 6;                   // epilogue sources staged per warp (1 KB each)
+        nsb = std::max(0, std::min(nsb, QB_MAXSRC));
+        e->tile_g = 1; e->tile_rows = rows; e->tile_threads = thr; e->tile_ns = nsb;
+        e->tile_smem = (size_t)rows * 16 + (size_t)(thr / 32) * nsb * 1024;
         cudaError_t ce = cudaFuncSetAttribute(qb_pass_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qb_pass_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
         if (ce != cudaSuccess) { delete e; QB_FAIL(QB_E_CUDA, "tile kernel shared memory: %s", cudaGetErrorString(ce)); }
@@ -1294,10 +1335,10 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
             const int nt = (e->h.ctl.N + e->tile_rows - 1) / e->tile_rows;
             if (e->cdesc.n > 0)
                 qb_pass_tile_kernel<true><<<(unsigned)(nslots_used * nt), e->tile_threads, e->tile_smem, e->stream>>>(
-                    e->d, nslots_used, e->tile_rows, e->targs, e->cdesc);
+                    e->d, nslots_used, e->tile_rows, e->tile_ns, e->targs, e->cdesc);
             else
                 qb_pass_tile_kernel<false><<<(unsigned)(nslots_used * nt), e->tile_threads, e->tile_smem, e->stream>>>(
-                    e->d, nslots_used, e->tile_rows, e->targs, e->cdesc);
+                    e->d, nslots_used, e->tile_rows, e->tile_ns, e->targs, e->cdesc);
         }
         else if (use_shared) qb_pass_kernel_shared<<<(unsigned)grid_sh, QB_TILE_ROWS, 0, e->stream>>>(e->d);
         else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d, nslots_used);

@@ -277,13 +277,13 @@ __device__ __forceinline__ void qb_rowdot_rsell_tile(const QbTileElem& A, const 
 #pragma unroll
     for (int j = 0; j < RB; j++) sa[j] = (unsigned)(r[j] - lo) * 16u;
     int k = 0;
-    for (; k < nxor; k++) {
+    auto xslot = [&](int kk, double2 (&a)[RB]) {
         int delta;
         double2 cv, xv[RB];
-        if (CD) { delta = dsc[k].delta; cv = make_double2(dsc[k].vre, dsc[k].vim); }
+        if (CD) { delta = dsc[kk].delta; cv = make_double2(dsc[kk].vre, dsc[kk].vim); }
         else {
-            delta = __ldg(&dsc[k].delta);
-            cv = __ldg(reinterpret_cast<const double2*>(dsc + k) + 1);
+            delta = __ldg(&dsc[kk].delta);
+            cv = __ldg(reinterpret_cast<const double2*>(dsc + kk) + 1);
         }
         if (delta < tnom) {        // tnom: nominal (power-of-two) tile rows
 #pragma unroll
@@ -293,8 +293,29 @@ __device__ __forceinline__ void qb_rowdot_rsell_tile(const QbTileElem& A, const 
             for (int j = 0; j < RB; j++) xv[j] = __ldg(x + (r[j] ^ delta));
         }
 #pragma unroll
-        for (int j = 0; j < RB; j++) qb_fma(acc[j], cv, xv[j]);
+        for (int j = 0; j < RB; j++) qb_fma(a[j], cv, xv[j]);
+    };
+#ifdef QB_XPF       // measured neutral on C3 (tools/tile_ab.sh): off by default
+    // the partner rows outside the tile (the largest deltas, processed last) are L2 hits a few
+    // hundred cycles away: request them into L1 before the in-tile slots are swept
+    for (int kk = nxor - 1; kk >= 0; kk--) {
+        const int delta = CD ? dsc[kk].delta : __ldg(&dsc[kk].delta);
+        if (delta < tnom) break;
+#pragma unroll
+        for (int j = 0; j < RB; j++)
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(x + (r[j] ^ delta)));
     }
+#endif
+    // two independent accumulator sets halve the dependent DFMA chain of the sweep
+    double2 acc2[RB];
+#pragma unroll
+    for (int j = 0; j < RB; j++) acc2[j] = make_double2(0.0, 0.0);
+#ifdef QB_XACC2     // measured neutral on C3 (tools/tile_ab.sh): off by default
+    for (; k + 2 <= nxor; k += 2) { xslot(k, acc); xslot(k + 1, acc2); }
+#endif
+    for (; k < nxor; k++) xslot(k, acc);
+#pragma unroll
+    for (int j = 0; j < RB; j++) { acc[j].x += acc2[j].x; acc[j].y += acc2[j].y; }
     // other fast slots: column = (row ^ xd) + ad, one constant value
     for (; k < nfast; k++) {
         int ru, de, cp, vp;

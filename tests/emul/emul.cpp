@@ -184,6 +184,7 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
     if (tableau == 3) qb_adams_table(&g.tab);
     else g.tab = *QB_TABLEAUX[tableau];
     g.opt = *opt;
+    if (tableau == 3) { g.opt.atol *= QB_AD_TOL_SCALE; g.opt.rtol *= QB_AD_TOL_SCALE; }   // as qb_engine_create
     g.N = (int)N; g.ntiles = 1;
     g.nelem = (int)s.elems.size(); g.ncops = (int)s.cops.size(); g.neops = (int)s.eops.size();
     g.nargs = s.nargs; g.eop_functional = s.eop_functional;

@@ -201,7 +201,44 @@ def golden_matmul():
     save("matmul", **out)
 
 
+def golden_adams():
+    """zvode (the reference's method='adams', solver/integrator/scipy_integrator.py:20-196;
+    SciPy's compiled zvode, tied to the installed SciPy) on C1 and reduced C2 / C4: expectation
+    values and final states at the default tolerances and at tight ones, with zvode's own step
+    and RHS-evaluation counts.  The device-resident Adams method is a different member of the
+    ODEPACK family (no step-level parity): it is pinned against these solutions."""
+    import scipy
+    out = {"scipy_version": scipy.__version__}
+    N = 10
+    a = tensor(destroy(N), qeye(2)); sm = tensor(qeye(N), destroy(2))
+    H1 = 2 * np.pi * a.dag() * a + 2 * np.pi * sm.dag() * sm \
+        + 2 * np.pi * 0.05 * (a.dag() * sm + a * sm.dag())
+    cases = {"c1_jc": (H1, tensor(basis(N, 3), basis(2, 0)), np.linspace(0, 10, 101),
+                       [np.sqrt(0.1) * a, np.sqrt(0.05) * sm], [a.dag() * a, tensor(qeye(N), sigmaz())])}
+    H2, c2, sz = tfim(4)
+    cases["c2_tfim4"] = (H2, basis([2] * 4, [0] * 4), np.linspace(0, 1, 11), c2, [sz[0]])
+    Nc = 8
+    a4 = tensor(destroy(Nc), qeye(3)); b4 = tensor(qeye(Nc), destroy(3))
+    H0 = 5 * a4.dag() * a4 + 4.5 * b4.dag() * b4 - 0.15 * b4.dag() * b4.dag() * b4 * b4 \
+        + 0.1 * (a4.dag() * b4 + a4 * b4.dag())
+    Ht = QobjEvo([H0, [a4 + a4.dag(), "A*cos(w*t)"]], args={"A": 0.2, "w": 5.0})
+    cases["c4_driven"] = (Ht, tensor(basis(Nc, 0), basis(3, 0)), np.linspace(0, 5, 51),
+                          [np.sqrt(0.01) * a4, np.sqrt(0.02) * b4, np.sqrt(0.03) * b4.dag() * b4],
+                          [a4.dag() * a4, b4.dag() * b4])
+    for name, (H, psi0, tl, c_ops, e_ops) in cases.items():
+        for tag, tol in (("default", {}), ("tight", {"atol": 1e-12, "rtol": 1e-10, "nsteps": 100000})):
+            solver = qutip.MESolver(H, c_ops, options=dict(OPT, method="adams", **tol))
+            r = solver.run(psi0, tl, e_ops=e_ops)
+            iw = solver._integrator._ode_solver._integrator.iwork
+            out["%s_%s_expect" % (name, tag)] = np.array(r.expect)
+            out["%s_%s_final" % (name, tag)] = r.states[-1].full().ravel("F")
+            out["%s_%s_nst_nfe" % (name, tag)] = np.array([int(iw[10]), int(iw[11])])
+    save("adams_zvode", **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "adams":
+        return golden_adams()
     golden_matmul()
 
     # C1: damped Jaynes-Cummings, cavity N=10 (x) qubit  (SURVEY 8d)

@@ -92,3 +92,25 @@ def test_adams_max_order_and_failure_status():
     assert rf.stats[0][0] < r.stats[0][0]             # order 12 needs fewer RHS evaluations than order 2
     eng = qb.Engine(me_system_from_golden(g), "adams", nslots=1, nsteps=4)
     assert eng.run_mesolve(g["y0"], g["tlist"]).status[0] == -1
+
+
+@pytest.mark.parametrize("name", ["c1_jc", "c2_tfim4", "c4_driven"])
+def test_adams_pinned_against_zvode_golden(name):
+    """The device-resident Adams method against the reference's method='adams' (SciPy zvode)
+    golden runs (tests/golden/adams_zvode.npz): within 1e-8 / 1e-6 at tight tolerances; at the
+    default tolerances as close to the converged solution as zvode itself (up to a factor),
+    with a comparable number of RHS evaluations."""
+    z = load("adams_zvode")
+    g = load(name)
+    tight = z[name + "_tight_expect"]
+    sysm = me_system_from_golden(g, qb.FMT_AUTO)
+    eng = qb.Engine(sysm, "adams", nslots=1, store_states=1, nsteps=100000, atol=1e-12, rtol=1e-10)
+    r = eng.run_mesolve(g["y0"], g["tlist"])
+    assert r.status[0] == 1
+    np.testing.assert_allclose(r.expect[0], tight, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(r.states[0][-1], z[name + "_tight_final"], rtol=1e-6, atol=1e-8)
+    eng = qb.Engine(sysm, "adams", nslots=1, store_states=1, nsteps=2500)
+    r = eng.run_mesolve(g["y0"], g["tlist"])
+    zerr = max(np.abs(z[name + "_default_expect"] - tight).max(), 1e-7)
+    assert np.abs(r.expect[0] - tight).max() < 4 * zerr
+    assert r.stats[0][0] < 1.5 * int(z[name + "_default_nst_nfe"][1]) + 20
