@@ -47,6 +47,7 @@ int qb_dense_zeros(int64_t rows, int64_t cols, int fortran, qb_handle* out);
 int qb_dense_download(qb_handle h, void* host);
 int qb_dense_write(qb_handle h, const void* host);      /* overwrite from host memory */
 int qb_dense_copy(qb_handle h, qb_handle* out);
+int qb_dense_reshape(qb_handle h, int64_t rows, int64_t cols);   /* column-major buffer, same size, no copy */
 int qb_dense_info(qb_handle h, int64_t* rows, int64_t* cols, int* fortran, void** devptr);
 /* operator formats: 0 auto (rule-compressed sliced ELLPACK for small L2-resident operators
  * whose 32-row slices are diagonal structured -- no per-element column index, one constant per
@@ -92,6 +93,8 @@ int qb_matmul(qb_handle op, qb_handle x, double scale_re, double scale_im, qb_ha
  * qb_matmul routes here for dense operands with >= 8 columns. */
 int qb_zgemm(qb_handle a, qb_handle x, double scale_re, double scale_im, qb_handle out);
 int qb_zgemm_bench(qb_handle a, qb_handle x, qb_handle out, int iters, double* ms_total);
+/* measured FP64 tensor-core (DMMA) peak of the current device in TFLOP/s (register-only chains) */
+int qb_dmma_peak_bench(int iters, double* tflops);
 int qb_axpy(qb_handle x, double a_re, double a_im, qb_handle y);
 int qb_scal(qb_handle x, double a_re, double a_im);
 int qb_copy(qb_handle src, qb_handle dst);
@@ -120,6 +123,10 @@ int qb_system_add_collapse(qb_handle sys, qb_handle c_op, const qb_instr* cprog,
  * (tr(E rho) on a column-stacked rho, core/data/expect.pyx:146-158) */
 int qb_system_add_eop(qb_handle sys, qb_handle op, const qb_instr* prog, int nprog);
 int qb_system_set_eop_functional(qb_handle sys, int functional);
+/* mcsolve with a super-operator H (solver/mcsolve.py:481-490): the state is the column-stacked
+ * n x n rho (system size n*n), the jump logic compares tr(rho).real with the threshold
+ * (mcsolve.py:311-319), probabilities are tr(n_k rho), states are renormalised by their trace */
+int qb_system_set_mc_trace(qb_handle sys, int n);
 /* InterCoefficient tables (core/cy/coefficient.pyx:412-549): returns the spline id */
 int qb_system_add_spline(qb_handle sys, const double* tlist, const void* poly,
                          int n, int order, double dt, int* id);

@@ -39,17 +39,17 @@ class QbOptions(C.Structure):
 SYMBOLS = [
     "qb_version", "qb_last_error", "qb_device_count", "qb_set_device", "qb_synchronize",
     "qb_launch_count", "qb_device_mem_info",
-    "qb_dense_upload", "qb_dense_zeros", "qb_dense_download", "qb_dense_write", "qb_dense_copy", "qb_dense_info",
+    "qb_dense_upload", "qb_dense_zeros", "qb_dense_download", "qb_dense_write", "qb_dense_copy", "qb_dense_reshape", "qb_dense_info",
     "qb_csr_upload", "qb_dia_upload", "qb_kron_upload", "qb_sandwich_upload", "qb_op_info", "qb_free",
     "qb_matmul", "qb_axpy", "qb_scal", "qb_copy", "qb_zero", "qb_nrm2", "qb_wrms_error",
     "qb_inner", "qb_expect_ket", "qb_expect_dm", "qb_expect_super", "qb_trace_oper_ket",
     "qb_system_create", "qb_system_add_element", "qb_system_add_collapse", "qb_system_add_eop",
-    "qb_system_set_eop_functional", "qb_system_add_spline", "qb_options_default",
+    "qb_system_set_eop_functional", "qb_system_set_mc_trace", "qb_system_add_spline", "qb_options_default",
     "qb_engine_create", "qb_engine_run", "qb_engine_run_device", "qb_reduce_expect",
     "qb_engine_last_run_info", "qb_integ_set_state", "qb_integ_integrate",
     "qb_integ_get_state", "qb_integ_set_args", "qb_integ_stats", "qb_engine_rhs",
     "qb_engine_rhs_bench", "qb_engine_set_profiling", "qb_engine_profile",
-    "qb_zgemm", "qb_zgemm_bench", "qb_integ_pending_coef", "qb_integ_resume",
+    "qb_zgemm", "qb_zgemm_bench", "qb_dmma_peak_bench", "qb_integ_pending_coef", "qb_integ_resume",
     "qb_engine_rhs_coef",
     "qb_comm_nccl_version", "qb_comm_init_all", "qb_comm_unique_id", "qb_comm_init_rank",
     "qb_comm_info", "qb_comm_allreduce_sum", "qb_comm_allreduce_sum_device", "qb_comm_reduce_expect",
@@ -78,6 +78,7 @@ def load():
         "qb_dense_download": [vp, vp],
         "qb_dense_write": [vp, vp],
         "qb_dense_copy": [vp, pp],
+        "qb_dense_reshape": [vp, i64, i64],
         "qb_dense_info": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), pp],
         "qb_csr_upload": [vp, vp, vp, i64, i64, i64, i32, pp],
         "qb_dia_upload": [vp, vp, i64, i64, i64, i32, pp],
@@ -90,6 +91,7 @@ def load():
         "qb_axpy": [vp, dbl, dbl, vp],
         "qb_zgemm": [vp, vp, dbl, dbl, vp],
         "qb_zgemm_bench": [vp, vp, vp, i32, C.POINTER(dbl)],
+        "qb_dmma_peak_bench": [i32, C.POINTER(dbl)],
         "qb_scal": [vp, dbl, dbl],
         "qb_copy": [vp, vp],
         "qb_zero": [vp],
@@ -105,6 +107,7 @@ def load():
         "qb_system_add_collapse": [vp, vp, C.POINTER(QbInstr), i32, vp, C.POINTER(QbInstr), i32],
         "qb_system_add_eop": [vp, vp, C.POINTER(QbInstr), i32],
         "qb_system_set_eop_functional": [vp, i32],
+        "qb_system_set_mc_trace": [vp, i32],
         "qb_system_add_spline": [vp, vp, vp, i32, i32, dbl, C.POINTER(i32)],
         "qb_options_default": [C.POINTER(QbOptions)],
         "qb_engine_create": [vp, i32, i32, C.POINTER(QbOptions), pp],

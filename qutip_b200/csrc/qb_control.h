@@ -35,6 +35,9 @@ struct QbCtl {
                                 // slot patterns and can execute one pass together
     int exp_chunk;              // operators per EXPECT pass (<= QB_MAXRED / 2)
     int maxcoef;
+    int mc_trace;               // n > 0: mcsolve of a super-operator H on the column-stacked n x n rho:
+                                // the "norm" is tr(rho).real (mcsolve.py:311-319), collapse probabilities
+                                // are tr(n_k rho), states are renormalised by their trace
     int nt, ndraws;
     const QbProgRef* elem_prog;  // [nelem]
     const QbProgRef* cop_prog;   // [ncops]
@@ -53,6 +56,10 @@ struct QbCtl {
 };
 
 // ------------------------------------------------------------------ small helpers
+// the quantity MCIntegrator compares with its threshold: ||y||^2 (red[0]) for kets, tr(rho)
+// (red[3]) for a super-operator H; qb_mcz: the same for z (red[2] / red[4])
+QB_HD double qb_mcn(const QbCtl& g, const double* red) { return g.mc_trace ? red[3] : red[0]; }
+QB_HD double qb_mc_inv_norm(const QbCtl& g, double n) { return g.mc_trace ? 1.0 / n : 1.0 / sqrt(n); }
 QB_HD void qb_pass_clear(QbPass& p) {
     p.kind = QB_PASS_NONE; p.opset = 0; p.op_lo = 0; p.op_hi = 0; p.x = -1; p.zdst = -1;
     p.dst1 = -1; p.nsrc = 0; p.red = 0; p.out_index = 0; p.zscale = 1.0; p.w1z = 0.0;
@@ -197,11 +204,11 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
         }
         case QB_PC_SETCOPY_DONE: L = QL_SET_BEGIN; break;
         case QB_PC_SET_DONE:
-            c.norm2_y = red[0];
+            c.norm2_y = qb_mcn(g, red);
             L = QL_SET_DONE; break;
         case QB_PC_EST0_DONE: {     // :237-256
             double norm = sqrt(red[0]);
-            c.norm2_y = red[0];
+            c.norm2_y = qb_mcn(g, red);
             if (g.opt.first_step != 0.0) {           // FSAL with a given first step: k_fsal only
                 c.dt_safe = g.opt.first_step;
                 L = QL_SET_DONE; break;
@@ -340,7 +347,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             const double err = sqrt(red[1] / (double)g.N);
             c.t_front = c.t_prev + dt;
             c.dt_int = dt;
-            c.norm2_front = red[0];
+            c.norm2_front = qb_mcn(g, red);
             double factor;
             if (err == 0.0) factor = 10.0;
             else {
@@ -412,7 +419,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
         case QB_PC_DENSE_DONE:
             if (c.stage < S - 1) { dense_i = c.stage + 1; L = QL_DENSE_ISSUE; break; }
             c.status = QB_ST_INTERPOLATED;
-            c.t = c.int_t; c.sY = c.sI; c.norm2_y = red[0];
+            c.t = c.int_t; c.sY = c.sI; c.norm2_y = qb_mcn(g, red);
             L = QL_INT_DONE; break;
         case QL_INTERP_ISSUE: {     // _interpolate_step (:412-430) with k already complete
             const double dt = c.dt_int;
@@ -429,7 +436,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
         }
         case QB_PC_INTERP_DONE:
             c.status = QB_ST_INTERPOLATED;
-            c.t = c.int_t; c.sY = c.sI; c.norm2_y = red[0];
+            c.t = c.int_t; c.sY = c.sI; c.norm2_y = qb_mcn(g, red);
             L = QL_INT_DONE; break;
 
         case QL_INT_DONE:
@@ -470,7 +477,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             c.pc = QB_PC_AD_SET0_DONE; return 1;
         }
         case QB_PC_AD_SET0_DONE:
-            c.norm2_y = c.norm2_front = red[0];
+            c.norm2_y = c.norm2_front = qb_mcn(g, red);
             L = QL_AD_F0; break;
         case QL_AD_F0: {            // YH1 = f(t0, y0), unscaled (ad_hyh = 1); its weighted norm
             qb_pass_clear(p);
@@ -655,7 +662,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
             c.pc = QB_PC_AD_UPD_DONE; return 1;
         }
         case QB_PC_AD_UPD_DONE:
-            c.norm2_front = red[0];
+            c.norm2_front = qb_mcn(g, red);
             // the step is accepted
             c.ad_kflag = 0; c.ad_iredo = 0; c.ad_ncf = 0;
             c.ad_hu = c.ad_h; c.ad_tn += c.ad_h; c.ad_hyh = c.ad_h;
@@ -778,7 +785,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
         }
         case QB_PC_AD_INTERP_DONE:
             c.status = QB_ST_INTERPOLATED;
-            c.t = c.int_t; c.sY = c.sI; c.norm2_y = red[0];
+            c.t = c.int_t; c.sY = c.sI; c.norm2_y = qb_mcn(g, red);
             L = QL_INT_DONE; break;
 
         // ================================================================ mesolve driver
@@ -832,7 +839,7 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
                 qb_pass_clear(p);
                 p.kind = QB_PASS_COMBINE; p.dst1 = QB_SLOT_OUT; p.out_index = c.tl_idx;
                 double sc = 1.0;
-                if (c.mode == 1 && c.tl_idx > 0) sc = 1.0 / sqrt(c.norm2_y);
+                if (c.mode == 1 && c.tl_idx > 0) sc = qb_mc_inv_norm(g, c.norm2_y);
                 qb_pass_src(p, c.sY, sc, 0.0);
                 c.pc = QB_PC_STORE_DONE; return 1;
             }
@@ -911,10 +918,10 @@ QB_HD int qb_advance(const QbCtl& g, const QbTableau& T, QbTraj& c, QbPass& p,
         }
         case QB_PC_PROBS_DONE: L = QL_FAIL; c.status = QB_ST_BAD_PROGRAM; break;   // unused
         case QB_PC_APPLY_DONE: {    // mcsolve.py:394-406
-            const double new_norm = sqrt(red[2]);
+            const double new_norm = g.mc_trace ? red[4] : sqrt(red[2]);
             if (new_norm < g.opt.mc_corr_eps) {
                 // numerical-error collapse: keep the state, renormalise, no record, no draw
-                c.set_x = c.sY; c.set_scale = 1.0 / sqrt(c.norm2_y);
+                c.set_x = c.sY; c.set_scale = qb_mc_inv_norm(g, c.norm2_y);
             } else {
                 c.set_x = c.sTA; c.set_scale = 1.0 / new_norm;
                 if (c.ncol >= g.opt.max_collapses) { c.status = QB_ST_TOO_MANY_COLLAPSES; L = QL_FAIL; break; }

@@ -8,15 +8,17 @@
 //
 // Complex product as four real MMAs on split re/im planes staged in shared memory:
 //   Cr += Ar*Xr + (-Ai)*Xi ;  Ci += Ar*Xi + Ai*Xr
-// CTA tile 64 (rows) x 64 (columns/trajectories), K step 8, 8 warps as 4 (M) x 2 (N); each
-// warp owns 16 x 32 = 2 x 4 DMMA tiles (64 accumulator registers).  The columns of X and Z
+// CTA tile 64 (rows) x 64 (columns/trajectories), K step 16, 8 warps as 4 (M) x 2 (N); each
+// warp owns 16 x 32 = 2 x 4 DMMA tiles (64 accumulator registers).  The next K step's A and X
+// tiles are fetched into registers while the current one is multiplied (software double
+// buffering: the global loads overlap 64 DMMA per warp instead of preceding them).  The columns of X and Z
 // are addressed through per-column pointers, because inside the engine every trajectory's
 // vector lives in its own (relabelled) slot of the state pool.
 #include "qb_host.h"
 
 #define ZG_BM 64
 #define ZG_BN 64
-#define ZG_BK 8
+#define ZG_BK 16
 #define ZG_LD 68      // (2*LD) % 32 == 8 -> conflict-free fragment loads
 
 __device__ __forceinline__ void qb_dmma(double& d0, double& d1, double a, double b) {
@@ -57,22 +59,31 @@ qb_zgemm_dmma_kernel(const double2* __restrict__ A, int M, int K, long long lda,
 #pragma unroll
         for (int j = 0; j < 4; j++) { acc_re[i][j][0] = acc_re[i][j][1] = 0.0; acc_im[i][j][0] = acc_im[i][j][1] = 0.0; }
 
-    for (int k0 = 0; k0 < K; k0 += ZG_BK) {
-        // stage A tile (64 rows x 8 k) and X tile (8 k x 64 cols): 512 complex each, 2 per thread
+    // per thread 4 elements of the A tile (64 rows x 16 k) and 4 of the X tile (16 k x 64 cols)
+    double2 pa[4], px[4];
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 4; i++) {
             const int e = tid + i * 256;
             const int row = e & 63, kk = e >> 6;
-            double2 v = make_double2(0.0, 0.0);
-            if (m0 + row < M && k0 + kk < K) v = A[(long long)(m0 + row) + (long long)(k0 + kk) * lda];
-            As_re[kk][row] = v.x; As_im[kk][row] = v.y;
-            const int kx = e & 7, col = e >> 3;
-            double2 w = make_double2(0.0, 0.0);
+            pa[i] = make_double2(0.0, 0.0);
+            if (m0 + row < M && k0 + kk < K) pa[i] = A[(long long)(m0 + row) + (long long)(k0 + kk) * lda];
+            const int kx = e & 15, col = e >> 4;
+            px[i] = make_double2(0.0, 0.0);
             const double2* xp = s_x[col];
-            if (xp && k0 + kx < K) w = xp[k0 + kx];
-            Xs_re[kx][col] = w.x; Xs_im[kx][col] = w.y;
+            if (xp && k0 + kx < K) px[i] = xp[k0 + kx];
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += ZG_BK) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = tid + i * 256;
+            As_re[e >> 6][e & 63] = pa[i].x; As_im[e >> 6][e & 63] = pa[i].y;
+            Xs_re[e & 15][e >> 4] = px[i].x; Xs_im[e & 15][e >> 4] = px[i].y;
         }
         __syncthreads();
+        if (k0 + ZG_BK < K) fetch(k0 + ZG_BK);          // in flight during the multiply
 #pragma unroll
         for (int ks = 0; ks < ZG_BK; ks += 4) {
             const int kk = ks + (lane & 3);
@@ -167,5 +178,50 @@ extern "C" int qb_zgemm_bench(qb_handle ah, qb_handle xh, qb_handle oh, int iter
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (ms_total) *ms_total = ms;
+    return QB_OK;
+}
+
+// FP64 tensor-core (DMMA m8n8k4) peak of this device, measured: every warp of a full grid
+// issues independent register-only DMMA chains -- no memory traffic.  The roofline peak the
+// dense path is reported against (MEASURED_PEAKS.json holds no FP64 figure).
+__global__ void __launch_bounds__(256)
+qb_dmma_peak_kernel(int iters, double* sink)
+{
+    double acc[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { acc[i][0] = threadIdx.x * 1e-9; acc[i][1] = i * 1e-9; }
+    double a = 1.0 + threadIdx.x * 1e-6, b = 1.0 - threadIdx.x * 1e-6;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) qb_dmma(acc[i][0], acc[i][1], a, b);
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) t += acc[i][0] + acc[i][1];
+    if (t == 12345.678) sink[0] = t;                 // keeps the chains alive
+}
+extern "C" int qb_dmma_peak_bench(int iters, double* tflops) {
+    if (iters < 1 || !tflops) QB_FAIL(QB_E_ARG, "bad arguments");
+    int dev = 0, sms = 0;
+    QB_CUDA(cudaGetDevice(&dev));
+    QB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* sink = nullptr;
+    QB_CUDA(cudaMalloc((void**)&sink, 8));
+    cudaEvent_t e0, e1;
+    QB_CUDA(cudaEventCreate(&e0)); QB_CUDA(cudaEventCreate(&e1));
+    const int grid = sms * 8;
+    qb_dmma_peak_kernel<<<grid, 256>>>(16, sink);
+    QB_LAUNCH_CHECK();
+    QB_CUDA(cudaEventRecord(e0));
+    qb_dmma_peak_kernel<<<grid, 256>>>(iters, sink);
+    QB_LAUNCH_CHECK();
+    QB_CUDA(cudaEventRecord(e1));
+    QB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    // one m8n8k4 DMMA = 8*8*4 multiply-adds = 512 flop per warp instruction
+    const double flop = (double)grid * 8.0 * (double)iters * 16.0 * 512.0;
+    *tflops = flop / (ms * 1e-3) / 1e12;
     return QB_OK;
 }

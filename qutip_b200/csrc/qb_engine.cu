@@ -94,6 +94,17 @@ __device__ __forceinline__ const double2* qb_vsrc(const QbEngineDev* E, int slot
 #define QB_SH_T 4       // consecutive slices one CTA of the shared kernel walks through
 #endif
 
+// super-operator H mcsolve (trn = n > 0): part[3] = sum over the diagonal rows of rho of Re o1,
+// part[4] the same of z -- tr(rho) replaces ||psi||^2 in the jump logic (mcsolve.py:311-319)
+__device__ __forceinline__ void qb_trace_partials(int trn, long long r, bool active, double2 o1, double2 z,
+                                                  int lane, double* __restrict__ part)
+{
+    if (!trn) return;                                     // warp-uniform
+    const bool diag = active && (r % (trn + 1) == 0);
+    const double t1 = qb_warp_sum(diag ? o1.x : 0.0), t2 = qb_warp_sum(diag ? z.x : 0.0);
+    if (lane == 0) { part[3] = t1; part[4] = t2; }
+}
+
 // per-warp view of a slot's pass descriptor (read straight from L1/L2-resident global memory)
 struct QbWarpHdr {
     int kind, nsrc, zdst, dst1, red, xslot, my_src;
@@ -138,6 +149,9 @@ __device__ __forceinline__ void qb_pass_one_slice(
         const int opset = gp->opset, op_lo = gp->op_lo, nops = gp->op_hi - gp->op_lo;
         const QbOpDev* ops = (opset == QB_OPSET_EOPS) ? E->eops : E->nops;
         const bool functional = (opset == QB_OPSET_EOPS) && E->ctl.eop_functional;
+        // super-operator H (mcsolve.py:481-490): probabilities are tr(n_k rho), the diagonal
+        // rows of the column-stacked n_k rho
+        const int trn = (opset == QB_OPSET_NOPS) ? E->ctl.mc_trace : 0;
         const double2* x = QB_VS(h.xslot);
         double2 xr = make_double2(0.0, 0.0);
         if (active) xr = x[r];
@@ -145,6 +159,7 @@ __device__ __forceinline__ void qb_pass_one_slice(
             const double2 q = qb_rowdot<QB_UP>(ops[op_lo + m], sl, lane, r, active, x);
             double2 pr;
             if (functional) pr = q;
+            else if (trn) pr = (r % (trn + 1) == 0) ? q : make_double2(0.0, 0.0);
             else pr = make_double2(xr.x * q.x + xr.y * q.y, xr.x * q.y - xr.y * q.x);  // conj(x)*q
             if (!active) pr = make_double2(0.0, 0.0);
             const double sre = qb_warp_sum(pr.x), sim = qb_warp_sum(pr.y);
@@ -251,6 +266,7 @@ __device__ __forceinline__ void qb_pass_one_slice(
     if (h.red) {
         r0 = qb_warp_sum(r0); r1 = qb_warp_sum(r1); r2 = qb_warp_sum(r2);
         if (lane == 0) { part[0] = r0; part[1] = r1; part[2] = r2; }
+        qb_trace_partials(E->ctl.mc_trace, r, active, o1, z, lane, part);
     }
 #undef QB_VS
 }
@@ -333,6 +349,9 @@ __device__ __forceinline__ void qb_hot_epilogue(const QbEngineDev* __restrict__ 
             double* __restrict__ part = E->partials + (long long)(slot * E->nslices + sl) * E->red_stride;
             part[0] = r0; part[1] = r1; part[2] = r2;
         }
+        if (E->ctl.mc_trace)
+            qb_trace_partials(E->ctl.mc_trace, r, active, o1, z, lane,
+                              E->partials + (long long)(slot * E->nslices + sl) * E->red_stride);
     }
 }
 
@@ -492,7 +511,7 @@ struct QbTileArgs {
     const QbPass* pass;
     const qb_c128* coef;
     double* partials;
-    int N, V, nslices, red_stride, nelem, maxcoef;
+    int N, V, nslices, red_stride, nelem, maxcoef, mc_trace, tpad_;
     double atol, rtol;
     QbTileElem elem[QB_MAX_ELEMS];
 };
@@ -702,6 +721,9 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
                         (long long)(slot * ta.nslices + (j ? slb : sla)) * ta.red_stride;
                     part[0] = r0; part[1] = r1; part[2] = r2;
                 }
+                if (ta.mc_trace)
+                    qb_trace_partials(ta.mc_trace, r[j], act[j], o1[j], z[j], lane,
+                                      ta.partials + (long long)(slot * ta.nslices + (j ? slb : sla)) * ta.red_stride);
             }
         }
     }
@@ -745,7 +767,7 @@ qb_linmap_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
         const double2* p = sidx >= 0 ? slot_base + (long long)sidx * N : init_ptr;
         v[k] = (k < nsrc && active) ? QB_LDV(p + r) : make_double2(0.0, 0.0);
     }
-    double n0 = 0.0;
+    double n0 = 0.0, tr0 = 0.0;
     for (int j = 0; j < nout; j++) {
         double2 o = make_double2(0.0, 0.0);
 #pragma unroll
@@ -755,7 +777,7 @@ qb_linmap_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
         }
         if (active) {
             QB_STV(slot_base + (size_t)s_dst[j] * N_ + r, o);
-            if (j == 0) n0 = o.x * o.x + o.y * o.y;
+            if (j == 0) { n0 = o.x * o.x + o.y * o.y; tr0 = o.x; }
         }
     }
     if (gp->red) {
@@ -765,6 +787,14 @@ qb_linmap_kernel(const QbEngineDev* __restrict__ E, int nslots_used)
             if (lane == 0) {
                 double* __restrict__ part = E->partials + ((size_t)slot * E->nslices + sl) * E->red_stride;
                 part[0] = n0; part[1] = 0.0; part[2] = 0.0;
+            }
+            if (E->ctl.mc_trace) {
+                const bool diag = active && (r % (E->ctl.mc_trace + 1) == 0);
+                const double t1 = qb_warp_sum(diag ? tr0 : 0.0);
+                if (lane == 0) {
+                    double* __restrict__ part = E->partials + ((size_t)slot * E->nslices + sl) * E->red_stride;
+                    part[3] = t1; part[4] = 0.0;
+                }
             }
         }
     }
@@ -822,7 +852,7 @@ qb_partials_reduce_kernel(const QbEngineDev* __restrict__ E)
     const int kind = gp->kind;
     int nred = 0;
     if (kind == QB_PASS_EXPECT) nred = 2 * (gp->op_hi - gp->op_lo);
-    else if (kind != QB_PASS_NONE && gp->red) nred = 3;
+    else if (kind != QB_PASS_NONE && gp->red) nred = E->ctl.mc_trace ? 5 : 3;
     if (nred == 0) return;
     __shared__ double sh[8];
     const int nslices = E->nslices, stride = E->red_stride;
@@ -870,7 +900,7 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
     const int kind = gp->kind;
     int nred = 0;
     if (kind == QB_PASS_EXPECT) nred = 2 * (gp->op_hi - gp->op_lo);
-    else if (kind != QB_PASS_NONE && gp->red) nred = 3;
+    else if (kind != QB_PASS_NONE && gp->red) nred = E->ctl.mc_trace ? 5 : 3;
     const int nslices = E->nslices, stride = E->red_stride;
     const double* __restrict__ part = E->partials + (size_t)slot * nslices * stride;
     if (E->red_final) {
@@ -1111,6 +1141,13 @@ extern "C" int qb_system_set_eop_functional(qb_handle sys, int functional) {
     s->eop_functional = functional ? 1 : 0;
     return QB_OK;
 }
+extern "C" int qb_system_set_mc_trace(qb_handle sys, int n) {
+    QbSysH* s = qb_cast<QbSysH>(sys, QB_TAG_SYS);
+    if (!s) QB_FAIL(QB_E_TYPE, "not a system handle");
+    if (n < 0 || (n > 0 && (int64_t)n * n != s->N)) QB_FAIL(QB_E_SHAPE, "mc_trace needs a system of size n*n");
+    s->mc_trace = n;
+    return QB_OK;
+}
 extern "C" int qb_system_add_spline(qb_handle sys, const double* tlist, const void* poly,
                                     int n, int order, double dt, int* id) {
     QbSysH* s = qb_cast<QbSysH>(sys, QB_TAG_SYS);
@@ -1167,6 +1204,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     h.ctl.neops = (int)s->eops.size();
     h.ctl.nargs = s->nargs;
     h.ctl.eop_functional = s->eop_functional;
+    h.ctl.mc_trace = s->mc_trace;
     h.ctl.has_host_coef = 0;
     for (auto& pr : s->elem_prog)
         if (pr.size() == 1 && pr[0].op == QB_I_HOST) h.ctl.has_host_coef = 1;
@@ -1211,7 +1249,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     h.nslices = (int)((s->N + 31) / 32);
     {
         const int nops = std::max(h.ctl.ncops, h.ctl.neops);
-        h.red_stride = std::max(4, 2 * std::min(QB_MAXRED / 2, nops));
+        h.red_stride = std::max(6, 2 * std::min(QB_MAXRED / 2, nops));
     }
     QB_TRY(qb_dev_alloc(e, (size_t)nslots * h.nslices * h.red_stride, &h.partials));
     h.linmap = nullptr;
@@ -1250,7 +1288,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         memset(&e->targs, 0, sizeof e->targs);
         e->targs.pool = h.pool; e->targs.pass = h.pass; e->targs.coef = h.coef; e->targs.partials = h.partials;
         e->targs.N = h.ctl.N; e->targs.V = h.V; e->targs.nslices = h.nslices; e->targs.red_stride = h.red_stride;
-        e->targs.nelem = h.ctl.nelem; e->targs.maxcoef = h.ctl.maxcoef;
+        e->targs.nelem = h.ctl.nelem; e->targs.maxcoef = h.ctl.maxcoef; e->targs.mc_trace = h.ctl.mc_trace;
         e->targs.atol = e->opt.atol; e->targs.rtol = e->opt.rtol;
         for (size_t i = 0; i < s->elems.size(); i++) {
             e->targs.elem[i].sinfo = s->elems[i].sinfo; e->targs.elem[i].val = s->elems[i].val;

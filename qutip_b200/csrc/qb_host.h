@@ -57,6 +57,7 @@ struct QbSysH : QbObj {
     std::vector<QbOpDev> elems, cops, nops, eops;
     std::vector<std::vector<QbInstr>> elem_prog, cop_prog, nop_prog, eop_prog;
     int eop_functional = 0;
+    int mc_trace = 0;            // n: mcsolve norm is tr(rho) of the column-stacked n x n state
     std::vector<QbSpline> splines;
     std::vector<double> spool;
     QbSysH() : QbObj(QB_TAG_SYS) {}

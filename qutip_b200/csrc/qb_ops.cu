@@ -66,6 +66,16 @@ extern "C" int qb_dense_write(qb_handle h, const void* host) {
     QB_CUDA(cudaMemcpy(d->d, host, (size_t)d->size() * 16, cudaMemcpyHostToDevice));
     return QB_OK;
 }
+// re-interpret a column-major buffer with another shape of the same size (column stacking /
+// unstacking of rho: solver_base.py:134-147 stack_columns / unstack_columns), no copy
+extern "C" int qb_dense_reshape(qb_handle h, int64_t rows, int64_t cols) {
+    QbDenseH* d = qb_cast<QbDenseH>(h, QB_TAG_DENSE);
+    if (!d) QB_FAIL(QB_E_TYPE, "not a dense handle");
+    if (rows < 0 || cols < 0 || rows * cols != d->rows * d->cols) QB_FAIL(QB_E_SHAPE, "reshape changes the size");
+    if (!d->fortran && d->rows != 1 && d->cols != 1) QB_FAIL(QB_E_TYPE, "reshape needs a column-major buffer");
+    d->rows = rows; d->cols = cols; d->fortran = 1;
+    return QB_OK;
+}
 extern "C" int qb_dense_copy(qb_handle h, qb_handle* out) {
     QbDenseH* d = qb_cast<QbDenseH>(h, QB_TAG_DENSE);
     if (!d) QB_FAIL(QB_E_TYPE, "not a dense handle");

@@ -99,6 +99,12 @@ class DeviceDense(_Handle):
         check(_lib.load().qb_dense_copy(self.handle, C.byref(h)))
         return DeviceDense(h, self.shape, self.fortran)
 
+    def reshape(self, rows, cols):
+        """in-place change of shape of a column-major buffer (stack / unstack columns)"""
+        check(_lib.load().qb_dense_reshape(self.handle, int(rows), int(cols)))
+        self.shape, self.fortran = (int(rows), int(cols)), True
+        return self
+
     def write(self, arr):
         """overwrite the device buffer from a host array of the same size"""
         arr = as_c128(arr)
@@ -211,6 +217,13 @@ def zgemm_bench(a, x, out, iters=10):
     return ms.value
 
 
+def dmma_peak_tflops(iters=4096):
+    """measured FP64 tensor-core (DMMA m8n8k4) peak of the current device, TFLOP/s"""
+    t = C.c_double()
+    check(_lib.load().qb_dmma_peak_bench(int(iters), C.byref(t)))
+    return t.value
+
+
 def axpy(x, a, y):
     a = complex(a)
     check(_lib.load().qb_axpy(x.handle, a.real, a.imag, y.handle))
@@ -305,6 +318,12 @@ class System(_Handle):
     def set_functional(self, flag=True):
         check(_lib.load().qb_system_set_eop_functional(self.handle, int(flag)))
         self.functional = bool(flag)
+
+    def set_mc_trace(self, n):
+        """mcsolve of a super-operator H: the state is the column-stacked n x n rho and tr(rho)
+        takes the place of the squared norm (solver/mcsolve.py:311-319,481-490)"""
+        check(_lib.load().qb_system_set_mc_trace(self.handle, int(n)))
+        self.mc_trace = int(n)
 
     def add_spline(self, tlist, poly, dt=0.0):
         tlist = np.ascontiguousarray(tlist, dtype=np.float64)

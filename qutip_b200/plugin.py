@@ -674,6 +674,33 @@ def _matmul_dense_dense(left, right, scale=1):
     return B200Dense(E.matmul(left.dev, right.dev, scale))
 
 
+def _matmul_dag_dense_op(left, right, scale=1):
+    """scale * left @ right^dagger (matmul_dag, core/data/matmul.pyx:1084-1116; the product
+    LindbladMatrixForm and _BaseElement.adjoint_rmatmul_data_t are made of, _element.pyx:225-237).
+    For the square column-major rho and an n x n operator this is the matrix-free right product
+    (conj(A) (x) I) vec(rho) on the device (KRON side 1); other shapes go through
+    (A left^dagger)^dagger."""
+    if left.shape[1] != right.shape[1]:
+        raise ValueError("incompatible matrix shapes " + str(left.shape) + " and "
+                         + str(right.shape[::-1]))
+    n = right.shape[0]
+    if left.shape == (n, n) and right.shape == (n, n) and (left.dev.fortran or n == 1):
+        k = getattr(right, "_kron_right", None)
+        if k is None:
+            k = right._kron_right = E.DeviceOp.kron(sp.csr_matrix(right.host.as_scipy()), 1)
+        vec = left.dev.copy().reshape(n * n, 1)
+        return B200Dense(E.matmul(k, vec, scale).reshape(n, n))
+    out = E.matmul(right.dev, left.adjoint().dev, np.conj(complex(scale)))     # A left^dag conj(s)
+    return B200Dense(out).adjoint()
+
+
+def _matmul_dag_dense_dense(left, right, scale=1):
+    if left.shape[1] != right.shape[1]:
+        raise ValueError("incompatible matrix shapes " + str(left.shape) + " and "
+                         + str(right.shape[::-1]))
+    return _matmul_dense_dense(left, right.adjoint(), scale)
+
+
 def _add_dense(left, right, scale=1):
     if left.shape != right.shape:
         raise ValueError("incompatible matrix shapes " + str(left.shape) + " and "
@@ -759,6 +786,10 @@ def register():
     _data.matmul.add_specialisations([
         (B200Operator, B200Dense, B200Dense, _matmul_op_dense),
         (B200Dense, B200Dense, B200Dense, _matmul_dense_dense),
+    ])
+    _data.matmul_dag.add_specialisations([
+        (B200Dense, B200Operator, B200Dense, _matmul_dag_dense_op),
+        (B200Dense, B200Dense, B200Dense, _matmul_dag_dense_dense),
     ])
     _data.add.add_specialisations([(B200Dense, B200Dense, B200Dense, _add_dense)])
     _data.sub.add_specialisations([(B200Dense, B200Dense, B200Dense, _sub_dense)])
@@ -945,11 +976,21 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
         if not isinstance(e, (qutip.Qobj, QobjEvo)):
             raise TypeError("e_ops must be Qobj / QobjEvo for the 'b200' map (python callables "
                             "cannot run on the device)")
-    if rhs.rhs.issuper:
-        raise TypeError("superoperator Hamiltonians are not supported by the 'b200' map")
+    issuper = bool(rhs.rhs.issuper)
+    if issuper and any(not isinstance(e, qutip.Qobj) for e in e_dict.values()):
+        raise TypeError("time-dependent e_ops are not combined with a superoperator Hamiltonian in "
+                        "the 'b200' map")
     want_states = bool(opts["store_states"]) or (opts["store_states"] is None and not e_dict)
     want_final = bool(opts["store_final_state"])
-    e_evos = [QobjEvo(e) if isinstance(e, qutip.Qobj) else e for e in e_dict.values()]
+    if issuper:
+        # the trajectories evolve the column-stacked rho (mcsolve.py:481-490): tr(E rho) is the
+        # linear functional sum_r vec(E^T)[r] rho[r] (core/data/expect.pyx:146-158)
+        if any(not e.isoper for e in e_dict.values()):
+            raise TypeError("e_ops must be operators for a superoperator Hamiltonian in the 'b200' map")
+        e_evos = [QobjEvo(qutip.Qobj(sp.csr_matrix(solve.trace_functional(e.full()))))
+                  for e in e_dict.values()]
+    else:
+        e_evos = [QobjEvo(e) if isinstance(e, qutip.Qobj) else e for e in e_dict.values()]
     iopt = solver._integrator._integrator.options
     psi0 = _data.to(_data.Dense, state0).to_array().reshape(-1, order="F")
     tlist = np.asarray(tlist, dtype=float)
@@ -986,7 +1027,10 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
         key = (device, ids)
         entry = cache.get(key)
         if entry is None:
-            system = system_from_qobjevo(rhs.rhs, rhs.c_ops, rhs.n_ops, e_evos, allow_host=True)
+            system = system_from_qobjevo(rhs.rhs, rhs.c_ops, rhs.n_ops, e_evos, allow_host=True,
+                                         functional=issuper)
+            if issuper:
+                system.set_mc_trace(int(round(np.sqrt(N))))
             if system.has_host:
                 raise TypeError("python-callable coefficients need a host evaluation per RHS call; the "
                                 "'b200' map runs whole batches on the device and cannot use them. Use "

@@ -99,6 +99,9 @@ class EmulSystem:
     def set_functional(self, f):
         self.L.emul_set_functional(int(f))
 
+    def set_mc_trace(self, n):
+        self.L.emul_set_mc_trace(int(n))
+
     def rsell_stats(self, which):
         out = (C.c_longlong * 6)()
         self.L.emul_rsell_stats(which, out)

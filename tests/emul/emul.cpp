@@ -32,6 +32,7 @@ struct Sys {
     std::vector<HostOp> elems, cops, nops, eops;
     std::vector<std::vector<QbInstr>> elem_prog, cop_prog, nop_prog, eop_prog;
     int eop_functional = 0;
+    int mc_trace = 0;
 };
 Sys g_sys;
 // optional log of the pass classes each trajectory issues (scheduler studies): per pass one
@@ -135,6 +136,7 @@ void emul_add_eop(const void* d, const int32_t* c, const int32_t* r, int fmt) {
     g_sys.eop_prog.push_back({});
 }
 void emul_set_functional(int f) { g_sys.eop_functional = f; }
+void emul_set_mc_trace(int n) { g_sys.mc_trace = n; }
 double emul_diam_avg_lanes(int which) {
     const HostOp& o = g_sys.elems[which];
     return o.dh.ent.empty() ? 0.0 : (double)o.dh.val.size() / (double)o.dh.ent.size();
@@ -187,7 +189,7 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
     if (tableau == 3) { g.opt.atol *= QB_AD_TOL_SCALE; g.opt.rtol *= QB_AD_TOL_SCALE; }   // as qb_engine_create
     g.N = (int)N; g.ntiles = 1;
     g.nelem = (int)s.elems.size(); g.ncops = (int)s.cops.size(); g.neops = (int)s.eops.size();
-    g.nargs = s.nargs; g.eop_functional = s.eop_functional;
+    g.nargs = s.nargs; g.eop_functional = s.eop_functional; g.mc_trace = s.mc_trace;
     g.maxcoef = std::max(1, g.nelem);
     g.nt = nt; g.ndraws = ndraws;
     g.tile_mode = g_tile_mode; g.exp_chunk = g_exp_chunk;
@@ -279,6 +281,9 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
                     for (int64_t r = 0; r < N; r++) {
                         qb_c128 q = rowdot(ops[m], r, x);
                         if (fun) { sre += q.re; sim += q.im; }
+                        else if (p.opset == QB_OPSET_NOPS && g.mc_trace) {
+                            if (r % (g.mc_trace + 1) == 0) { sre += q.re; sim += q.im; }   // tr(n_k rho)
+                        }
                         else { sre += x[r].re * q.re + x[r].im * q.im; sim += x[r].re * q.im - x[r].im * q.re; }
                     }
                     rd[2 * (m - p.op_lo)] = sre; rd[2 * (m - p.op_lo) + 1] = sim;
@@ -298,10 +303,13 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
                         }
                         outs[j][r] = o;
                     }
-                double n0 = 0;
-                for (int64_t r = 0; r < N; r++) n0 += outs[0][r].re * outs[0][r].re + outs[0][r].im * outs[0][r].im;
+                double n0 = 0, tr0 = 0;
+                for (int64_t r = 0; r < N; r++) {
+                    n0 += outs[0][r].re * outs[0][r].re + outs[0][r].im * outs[0][r].im;
+                    if (g.mc_trace && r % (g.mc_trace + 1) == 0) tr0 += outs[0][r].re;
+                }
                 for (int j = 0; j < lm.nout; j++) memcpy(base + (size_t)lm.dst[j] * N, outs[j].data(), N * sizeof(qb_c128));
-                rd[0] = n0; rd[1] = 0; rd[2] = 0;
+                rd[0] = n0; rd[1] = 0; rd[2] = 0; rd[3] = tr0; rd[4] = 0;
                 continue;
             }
             // operator application into zbuf (x must not alias any destination)
@@ -324,7 +332,7 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
                     zbuf[r] = z;
                 }
             }
-            double r0 = 0, r1 = 0, r2 = 0;
+            double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
             qb_c128* base = pool.data() + (size_t)slot * V * N;
             for (int64_t r = 0; r < N; r++) {
                 const qb_c128 z = zbuf[r];
@@ -344,12 +352,13 @@ int emul_run(int mode, int tableau, const QbOptions* opt, int64_t ntraj, int nsl
                     r1 += q * q;
                 }
                 r2 += z.re * z.re + z.im * z.im;
+                if (g.mc_trace && r % (g.mc_trace + 1) == 0) { r3 += o1.re; r4 += z.re; }
             }
             if (p.zdst >= 0) memcpy(base + (size_t)p.zdst * N, zbuf.data(), N * sizeof(qb_c128));
             if (p.dst1 >= 0) memcpy(base + (size_t)p.dst1 * N, o1buf.data(), N * sizeof(qb_c128));
             else if (p.dst1 == QB_SLOT_OUT)
                 memcpy((qb_c128*)states + ((size_t)traj[slot].traj_id * nt + p.out_index) * N, o1buf.data(), N * sizeof(qb_c128));
-            rd[0] = r0; rd[1] = r1; rd[2] = r2;
+            rd[0] = r0; rd[1] = r1; rd[2] = r2; rd[3] = r3; rd[4] = r4;
         }
         control();
     }

@@ -127,8 +127,13 @@ def describe_coeff(c):
     raise NotImplementedError(cls)
 
 
-def golden_mcsolve(name, H, c_ops, psi0, tlist, e_ops, ntraj, seed, method="vern7"):
+def golden_mcsolve(name, H, c_ops, psi0, tlist, e_ops, ntraj, seed, method="vern7", super_h=False):
+    """super_h: the Hamiltonian is handed over as a super-operator (liouvillian(H)); the
+    trajectories then evolve the column-stacked density matrix, the jump logic runs on
+    tr(rho) and the collapse operators are spre(c) spost(c^dag) (solver/mcsolve.py:481-490)."""
     out = {}
+    if super_h:
+        H = liouvillian(H)
     solver = qutip.MCSolver(H, c_ops, options={"progress_bar": False, "method": method,
                                                "keep_runs_results": True,
                                                "store_final_state": True})
@@ -144,9 +149,11 @@ def golden_mcsolve(name, H, c_ops, psi0, tlist, e_ops, ntraj, seed, method="vern
     out["n_cops"] = len(c_ops)
     for i, e in enumerate(e_ops):
         pack_op("eop%d" % i, e.data, out)
+        out["eop%d_full" % i] = e.full()
     out["n_eops"] = len(e_ops)
     out["tlist"] = np.asarray(tlist, dtype=float)
-    out["psi0"] = psi0.full().ravel()
+    out["psi0"] = qutip.ket2dm(psi0).full().ravel("F") if super_h else psi0.full().ravel()
+    out["super_n"] = psi0.shape[0] if super_h else 0
     ss = np.random.SeedSequence(seed)
     r = solver.run(psi0, tlist, ntraj=ntraj, e_ops=e_ops, seeds=ss)
     out["seed"] = seed
@@ -159,7 +166,8 @@ def golden_mcsolve(name, H, c_ops, psi0, tlist, e_ops, ntraj, seed, method="vern
                                       + [np.zeros(0)])
     out["col_which"] = np.concatenate([np.asarray(c, dtype=np.int64) for c in r.col_which]
                                       + [np.zeros(0, dtype=np.int64)])
-    out["final_states"] = np.array([s.full().ravel() for s in r.runs_final_states])
+    out["final_states"] = np.array([s.full().ravel("F") if super_h else s.full().ravel()
+                                    for s in r.runs_final_states])
     # thresholds exactly as the reference draws them
     kids = np.random.SeedSequence(seed).spawn(ntraj)
     out["draws"] = np.stack([np.random.default_rng(k).random(64) for k in kids])
@@ -239,6 +247,10 @@ def golden_adams():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "adams":
         return golden_adams()
+    if len(sys.argv) > 1 and sys.argv[1] == "super":
+        H, c_ops, sz = tfim(3, gamma=0.8)
+        return golden_mcsolve("c3_tfim3_mc_super", H, c_ops, basis([2] * 3, [0] * 3), np.linspace(0, 3, 13),
+                              [sz[0], sz[1]], 16, 21, super_h=True)
     golden_matmul()
 
     # C1: damped Jaynes-Cummings, cavity N=10 (x) qubit  

@@ -206,3 +206,31 @@ def test_mcsolve_state_machine_tile_mode(name, method, nslots):
         assert np.array_equal(r["col_which"][j, :n], g["col_which"][cc[j]:cc[j + 1]])
     assert np.abs(np.transpose(r["expect"], (1, 0, 2)) - g["runs_expect"]).max() < 1e-9
     assert np.abs(r["states"][:, -1, :] - g["final_states"]).max() < 1e-9
+
+
+def test_mcsolve_super_operator_hamiltonian_state_machine():
+    """mcsolve with a super-operator H (solver/mcsolve.py:481-490): trajectories of the
+    column-stacked rho, thresholds compared with tr(rho) (mcsolve.py:311-319), probabilities
+    tr(n_k rho), renormalisation by the trace -- against the reference fixture."""
+    g = load("c3_tfim3_mc_super")
+    n = int(g["super_n"])
+    s = EmulSystem(len(g["psi0"]), 0, FMT_CSR)
+    s.add_element(*_sp_arrays(merged_constant_rhs(g)))
+    for i in range(int(g["n_cops"])):
+        s.add_collapse(op_arrays(g, "cop%d" % i), op_arrays(g, "nop%d" % i))
+    for i in range(int(g["n_eops"])):
+        s.add_eop(*_sp_arrays(functional_of(g["eop%d_full" % i])))
+    s.set_functional(1)
+    s.set_mc_trace(n)
+    ntraj = int(g["ntraj"])
+    r = s.run(1, 0, g["psi0"], g["tlist"], ntraj=ntraj, nslots=5, draws=g["draws"],
+              opt=default_options(store_states=1))
+    assert (r["status"] == 1).all()
+    assert np.array_equal(r["ncol"], g["col_count"]) and g["col_count"].sum() > 10
+    cc = np.concatenate([[0], np.cumsum(g["col_count"])])
+    for j in range(ntraj):
+        k = r["ncol"][j]
+        assert np.array_equal(r["col_which"][j, :k], g["col_which"][cc[j]:cc[j + 1]])
+        np.testing.assert_allclose(r["col_t"][j, :k], g["col_times"][cc[j]:cc[j + 1]], rtol=0, atol=1e-9)
+    assert np.abs(np.transpose(r["expect"], (1, 0, 2)) - g["runs_expect"]).max() < 1e-9
+    assert np.abs(r["states"][:, -1, :] - g["final_states"]).max() < 1e-9

@@ -233,3 +233,33 @@ def test_threshold_table_exhaustion_is_reported():
     assert (r.status == -12).any()           # QB_ST_RNG_EXHAUSTED, never silent
     ok = r.status == 1
     assert np.array_equal(r.ncol[ok], g["col_count"][ok])
+
+
+def test_mcsolve_super_operator_hamiltonian_vs_reference():
+    """mcsolve with a super-operator H (solver/mcsolve.py:481-490) on the device: tr(rho) in
+    place of the squared norm, tr(n_k rho) probabilities, renormalisation by the trace."""
+    from _emul import FMT_CSR  # noqa: F401
+    from _systems import functional_of, merged_constant_rhs
+    g = load("c3_tfim3_mc_super")
+    n = int(g["super_n"])
+    s = qb.System(len(g["psi0"]))
+    s.add_element(qb.DeviceOp.from_scipy(merged_constant_rhs(g)))
+    for i in range(int(g["n_cops"])):
+        s.add_collapse(dev_op(*op_arrays(g, "cop%d" % i)), dev_op(*op_arrays(g, "nop%d" % i)))
+    for i in range(int(g["n_eops"])):
+        s.add_eop(qb.DeviceOp.from_scipy(functional_of(g["eop%d_full" % i])))
+    s.set_functional(True)
+    s.set_mc_trace(n)
+    ntraj = int(g["ntraj"])
+    for method, nslots in (("vern7", 5), ("vern7", 16)):
+        eng = qb.Engine(s, method, nslots=nslots, store_states=1)
+        r = eng.run_mcsolve(g["psi0"], g["tlist"], g["draws"], ntraj=ntraj)
+        assert (r.status == 1).all()
+        assert np.array_equal(r.ncol, g["col_count"])
+        cc = np.concatenate([[0], np.cumsum(g["col_count"])])
+        for j in range(ntraj):
+            k = r.ncol[j]
+            assert np.array_equal(r.col_which[j, :k], g["col_which"][cc[j]:cc[j + 1]])
+            np.testing.assert_allclose(r.col_t[j, :k], g["col_times"][cc[j]:cc[j + 1]], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(np.transpose(r.expect, (1, 0, 2)), g["runs_expect"], rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(r.states[:, -1, :], g["final_states"], rtol=1e-6, atol=1e-8)

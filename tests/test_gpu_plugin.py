@@ -562,27 +562,107 @@ def test_c2_full_size_mesolve_vs_reference():
     np.testing.assert_allclose(out.final_state.full(), ref.final_state.full(), rtol=RTOL, atol=ATOL)
 
 
-def test_c3_full_size_256_trajectories_vs_reference():
+_C3_REF_SCRIPT = r"""
+import os, sys, warnings
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+warnings.filterwarnings("ignore")
+from qutip import basis, mcsolve, qeye, sigmam, sigmax, sigmaz, tensor
+n, ntraj = 14, int(sys.argv[3])
+sx, sz, sm = [], [], []
+for i in range(n):
+    ops = [qeye(2)] * n
+    ops[i] = sigmax(); sx.append(tensor(ops))
+    ops[i] = sigmaz(); sz.append(tensor(ops))
+    ops[i] = sigmam(); sm.append(tensor(ops))
+H = 0
+for i in range(n - 1):
+    H = H - sz[i] * sz[i + 1]
+for i in range(n):
+    H = H - sx[i]
+c_ops = [np.sqrt(0.1) * s for s in sm]
+cores = len(os.sched_getaffinity(0))
+ref = mcsolve(H, basis([2] * n, [0] * n), np.linspace(0, 2, 21), c_ops, e_ops=[sz[0]], ntraj=ntraj,
+              seeds=np.random.SeedSequence(7),
+              options={"progress_bar": False, "method": "vern7", "keep_runs_results": True,
+                       "map": "parallel" if cores > 1 else "serial", "num_cpus": cores})
+order = np.argsort([s.spawn_key[-1] for s in ref.seeds])
+np.savez(sys.argv[2], runs_expect=np.array(ref.runs_expect)[:, order],
+         ncol=np.array([len(ref.col_which[i]) for i in order]),
+         col_which=np.concatenate([np.asarray(ref.col_which[i], dtype=int) for i in order] + [np.zeros(0, dtype=int)]),
+         col_times=np.concatenate([np.asarray(ref.col_times[i], dtype=float) for i in order] + [np.zeros(0)]))
+"""
+
+
+def test_c3_full_size_256_trajectories_vs_reference(tmp_path):
     """BASELINE config 3 at full size (TFIM 14 spins, dim 16384): 256 trajectories of the
-    reference's own mcsolve (all host cores) against the b200 map -- jump counts and collapse
-    indices bit-exact, times to 1e-9, expectation values within 1e-8 / 1e-6."""
+    reference's own mcsolve (all host cores; run in a fresh interpreter because its process
+    pool forks) against the b200 map -- jump counts and collapse indices bit-exact, times to
+    1e-9, expectation values within 1e-8 / 1e-6."""
     import os
+    import subprocess
+    ntraj = 256
+    out_file = str(tmp_path / "c3_ref.npz")
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    subprocess.run([sys.executable, "-c", _C3_REF_SCRIPT, _ref, out_file, str(ntraj)], check=True,
+                   timeout=500, env=env)
+    ref = np.load(out_file)
     H, c_ops, sz = tfim(14)
     psi0 = basis([2] * 14, [0] * 14)
     tl = np.linspace(0, 2, 21)
-    ntraj = 256
-    cores = len(os.sched_getaffinity(0))
-    o = dict(OPT, method="vern7", keep_runs_results=True)
-    ref = mcsolve(H, psi0, tl, c_ops, e_ops=[sz[0]], ntraj=ntraj, seeds=np.random.SeedSequence(7),
-                  options=dict(o, map="parallel" if cores > 1 else "serial", num_cpus=cores))
     out = mcsolve(H, psi0, tl, c_ops, e_ops=[sz[0]], ntraj=ntraj, seeds=np.random.SeedSequence(7),
-                  options=dict(o, map="b200"))
-    # the process pool hands trajectories over in completion order: match them by seed
-    ro = np.argsort([s.spawn_key[-1] for s in ref.seeds])
+                  options=dict(OPT, method="vern7", keep_runs_results=True, map="b200"))
     oo = np.argsort([s.spawn_key[-1] for s in out.seeds])
-    assert len(ro) == len(oo) == ntraj
-    re_, oe_ = np.array(ref.runs_expect), np.array(out.runs_expect)
-    for i, j in zip(ro, oo):
-        assert list(out.col_which[j]) == list(ref.col_which[i])
-        np.testing.assert_allclose(out.col_times[j], ref.col_times[i], rtol=0, atol=1e-9)
-        np.testing.assert_allclose(oe_[:, j], re_[:, i], rtol=RTOL, atol=ATOL)
+    assert len(oo) == ntraj
+    cc = np.concatenate([[0], np.cumsum(ref["ncol"])])
+    oe_ = np.array(out.runs_expect)
+    for i, j in enumerate(oo):
+        assert list(out.col_which[j]) == list(ref["col_which"][cc[i]:cc[i + 1]])
+        np.testing.assert_allclose(out.col_times[j], ref["col_times"][cc[i]:cc[i + 1]], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(oe_[:, j], ref["runs_expect"][:, i], rtol=RTOL, atol=ATOL)
+
+
+def test_b200_map_super_operator_hamiltonian():
+    """mcsolve(liouvillian(H), ...) through the b200 map (solver/mcsolve.py:481-490,
+    311-319): same collapse records and expectation values as the reference's own run."""
+    H, c_ops, sz = tfim(3, gamma=0.8)
+    psi0 = basis([2] * 3, [0] * 3)
+    tl = np.linspace(0, 3, 13)
+    L = qutip.liouvillian(H)
+    o = dict(OPT, method="vern7", keep_runs_results=True, store_final_state=True)
+    kw = dict(e_ops=[sz[0], sz[1]], ntraj=16, seeds=np.random.SeedSequence(21))
+    ref = mcsolve(L, psi0, tl, c_ops, options=o, **kw)
+    kw["seeds"] = np.random.SeedSequence(21)
+    out = mcsolve(L, psi0, tl, c_ops, options=dict(o, map="b200"), **kw)
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    assert sum(len(w) for w in ref.col_which) > 10
+    for a, b in zip(out.col_times, ref.col_times):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=RTOL, atol=ATOL)
+    for x, y in zip(out.runs_final_states, ref.runs_final_states):
+        np.testing.assert_allclose(x.full(), y.full(), rtol=RTOL, atol=ATOL)
+
+
+def test_matmul_dag_specialisations():
+    """matmul_dag (core/data/matmul.pyx:1084-1116) registered for the device types: the
+    square rho @ A^dagger product runs matrix-free on the device, everything against numpy."""
+    from qutip.core import data as _data
+    rng = np.random.default_rng(4)
+    n = 24
+    A = (rng.random((n, n)) < 0.2) * (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    rho = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    dA = plugin.B200Operator(_data.to(_data.CSR, _data.Dense(A)))
+    drho = plugin.B200Dense(np.asfortranarray(rho))
+    out = _data.matmul_dag(drho, dA, 0.5 - 2j)
+    assert isinstance(out, plugin.B200Dense)
+    np.testing.assert_allclose(out.to_array(), (0.5 - 2j) * rho @ A.conj().T, rtol=1e-12, atol=1e-12)
+    B = rng.standard_normal((7, n)) + 1j * rng.standard_normal((7, n))
+    out = _data.matmul_dag(plugin.B200Dense(np.asfortranarray(B)), dA, 1.5j)      # non-square left
+    np.testing.assert_allclose(out.to_array(), 1.5j * B @ A.conj().T, rtol=1e-12, atol=1e-12)
+    C = rng.standard_normal((5, n)) + 1j * rng.standard_normal((5, n))
+    out = _data.matmul_dag(plugin.B200Dense(np.asfortranarray(B)), plugin.B200Dense(np.asfortranarray(C)))
+    np.testing.assert_allclose(out.to_array(), B @ C.conj().T, rtol=1e-12, atol=1e-12)
+    with pytest.raises(ValueError):
+        _data.matmul_dag(plugin.B200Dense(np.zeros((3, 4), dtype=complex)), dA)
+    # the dispatcher picks the device specialisation for the registered types
+    assert _data.matmul_dag[plugin.B200Dense, plugin.B200Operator, plugin.B200Dense] is not None
