@@ -345,7 +345,8 @@ class _B200Integrator(Integrator):
             self._system, self._tableau, nslots=1, atol=o['atol'], rtol=o['rtol'],
             nsteps=int(o['nsteps']), first_step=float(o['first_step'] or 0),
             min_step=float(o['min_step'] or 0), max_step=float(o['max_step'] or 0),
-            interpolate=int(bool(o.get('interpolate', True))), max_order=int(o.get('order', 0) or 0))
+            interpolate=int(bool(o.get('interpolate', True))), max_order=int(o.get('order', 0) or 0),
+            store_states=1)          # only used by run(tlist); the per-call protocol ignores it
         if self._system.has_host:
             objs = self._system.coeff_objects
             self._engine.host_coeffs = lambda t: [1.0 if c is None else complex(c(t)) for c in objs]
@@ -371,8 +372,10 @@ class _B200Integrator(Integrator):
             self._ncols = ncols
             self._build()
         self._shape = arr.shape
-        self._engine.set_state(t, np.ascontiguousarray(arr.reshape(-1, order="F")))
+        self._y_set = np.ascontiguousarray(arr.reshape(-1, order="F"))
+        self._engine.set_state(t, self._y_set)
         self._is_set = True
+        self._fresh_at = t           # no step taken since: run(tlist) may take the batched path
 
     def _wrap(self, y):
         return _data.Dense(y.reshape(self._shape, order="F"), copy=False)
@@ -381,7 +384,36 @@ class _B200Integrator(Integrator):
         t, y = self._engine.get_state()
         return t, self._wrap(y)
 
+    def run(self, tlist):
+        """``Integrator.run`` (solver/integrator/integrator.py:197-212; consumed by
+        ``Solver.run``, solver_base.py:218-220).  Right after ``set_state(tlist[0], ...)`` the
+        whole list is integrated by ONE device run -- the same sequence of ``integrate(t)``
+        calls the base class makes, without a host round trip per output time; otherwise
+        (python-evaluated coefficients, an integrator that has already stepped) the calls are
+        made one by one."""
+        tlist = np.asarray(tlist, dtype=float)
+        if (getattr(self, "_fresh_at", None) is None or len(tlist) < 3 or tlist[0] != self._fresh_at
+                or self._system.has_host or os.environ.get("QUTIP_B200_NO_BATCHED_RUN")):
+            for t in tlist[1:]:
+                yield self.integrate(t, False)
+            return
+        self._fresh_at = None
+        r = self._engine.run_mesolve(self._y_set, tlist)
+        st = int(r.status[0])
+        # states of the output times reached before a failure are handed over first, as the
+        # one-by-one loop would have done
+        good = len(tlist) if st == 1 else 0
+        for i in range(1, good):
+            yield float(tlist[i]), self._wrap(r.states[0, i].copy())
+        if st != 1:
+            # reproduce the failure through the protocol so that the exception (and the states
+            # yielded before it) are those of the reference's loop
+            self._engine.set_state(tlist[0], self._y_set)
+            for t in tlist[1:]:
+                yield self.integrate(t, False)
+
     def _run(self, t, step):
+        self._fresh_at = None
         t_out, status = self._engine.integrate(t, step)
         if status < 0:
             raise IntegratorException(E.STATUS_MESSAGES.get(status, "integration failed"))

@@ -54,4 +54,5 @@ def test_trajectories_sharded_over_two_devices_match_one_device():
     assert [list(t) for t in two.col_times] == [list(t) for t in one.col_times]
     np.testing.assert_array_equal(two.runs_expect, one.runs_expect)
     np.testing.assert_allclose(two.average_expect, one.average_expect, rtol=1e-12, atol=1e-13)
-    np.testing.assert_allclose(two.std_expect, one.std_expect, rtol=1e-9, atol=1e-12)
+    # std = sqrt(|<e^2> - <e>^2|): where it vanishes, rounding of the two sums enters as its square root
+    np.testing.assert_allclose(two.std_expect, one.std_expect, rtol=1e-9, atol=1e-7)
