@@ -174,9 +174,10 @@ struct RsellHost {
     }
 };
 
+// slices [sl_lo, sl_hi) into `out` (its own de-duplication map; lists[] = the unique lists)
 template <class RowFn>
-inline void build_rsell(int64_t nrows, int64_t ncols, RowFn row_fn, RsellHost& out) {
-    const int64_t nslices = (nrows + 31) / 32;
+inline void build_rsell_range(int64_t nrows, int64_t ncols, int64_t sl_lo, int64_t sl_hi, RowFn& row_fn,
+                              RsellHost& out, std::vector<std::pair<int, int>>& lists) {
     std::vector<std::vector<std::pair<int, qb_c128>>> rows(32);
     std::vector<QbSlotDesc> cur;          // descriptor list of the slice being built
     int vbase = 0, cbase = 0;
@@ -212,7 +213,7 @@ inline void build_rsell(int64_t nrows, int64_t ncols, RowFn row_fn, RsellHost& o
         }
         cur.push_back(d);
     };
-    for (int64_t sl = 0; sl < nslices; sl++) {
+    for (int64_t sl = sl_lo; sl < sl_hi; sl++) {
         const int64_t r0 = sl * 32;
         int width = 0; long long cnt = 0;
         for (int l = 0; l < 32; l++) {
@@ -290,12 +291,68 @@ inline void build_rsell(int64_t nrows, int64_t ncols, RowFn row_fn, RsellHost& o
             std::string keyb(reinterpret_cast<const char*>(cur.data()), cur.size() * sizeof(QbSlotDesc));
             auto it = seen.find(keyb);
             if (it != seen.end()) dstart = it->second;
-            else { seen.emplace(std::move(keyb), dstart); out.desc.insert(out.desc.end(), cur.begin(), cur.end()); }
+            else {
+                seen.emplace(std::move(keyb), dstart); lists.push_back({dstart, (int)cur.size()});
+                out.desc.insert(out.desc.end(), cur.begin(), cur.end());
+            }
         }
         out.slots += (long long)cur.size();
         out.sinfo.push_back(dstart);
         out.sinfo.push_back((int)(cur.size() & 4095) | ((nfast & 4095) << 12) | ((nxor & 255) << 24));
         out.sinfo.push_back(vbase); out.sinfo.push_back(cbase);
+    }
+}
+
+
+// all slices; large operators are converted by several threads (contiguous slice ranges,
+// merged in order: the result does not depend on the number of threads)
+template <class RowFn>
+inline void build_rsell(int64_t nrows, int64_t ncols, RowFn row_fn, RsellHost& out) {
+    const int64_t nslices = (nrows + 31) / 32;
+    int nthreads = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    if (nslices < 4096) nthreads = 1;
+    std::vector<RsellHost> parts(nthreads);
+    std::vector<std::vector<std::pair<int, int>>> lists(nthreads);
+    auto work = [&](int t) {
+        build_rsell_range(nrows, ncols, nslices * t / nthreads, nslices * (t + 1) / nthreads, row_fn,
+                          parts[t], lists[t]);
+    };
+    if (nthreads == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    if (nthreads == 1) { out = std::move(parts[0]); return; }
+    std::map<std::string, int> seen;
+    for (int t = 0; t < nthreads; t++) {
+        RsellHost& p = parts[t];
+        // unique lists of this part -> global position
+        std::map<int, int> remap;
+        for (auto& l : lists[t]) {
+            std::string key(reinterpret_cast<const char*>(p.desc.data() + l.first), (size_t)l.second * sizeof(QbSlotDesc));
+            auto it = seen.find(key);
+            int g;
+            if (it != seen.end()) g = it->second;
+            else {
+                g = (int)out.desc.size();
+                seen.emplace(std::move(key), g);
+                out.desc.insert(out.desc.end(), p.desc.begin() + l.first, p.desc.begin() + l.first + l.second);
+            }
+            remap[l.first] = g;
+        }
+        const int vb = (int)(out.val.size() / 32), cb = (int)(out.col.size() / 32);
+        for (size_t i = 0; i + 3 < p.sinfo.size(); i += 4) {
+            const int cnt = p.sinfo[i + 1] & 4095;
+            out.sinfo.push_back(cnt ? remap[p.sinfo[i]] : (int)out.desc.size());
+            out.sinfo.push_back(p.sinfo[i + 1]);
+            out.sinfo.push_back(p.sinfo[i + 2] + vb);
+            out.sinfo.push_back(p.sinfo[i + 3] + cb);
+        }
+        out.val.insert(out.val.end(), p.val.begin(), p.val.end());
+        out.col.insert(out.col.end(), p.col.begin(), p.col.end());
+        out.nnz += p.nnz; out.slots += p.slots; out.overflow = out.overflow || p.overflow;
+        p = RsellHost();
     }
 }
 

@@ -897,17 +897,22 @@ __device__ void qb_start_traj(QbEngineDev* E, QbTraj& c, int traj_id) {
     c.pc = E->mode ? QB_PC_MC_BEGIN : QB_PC_ME_BEGIN;
 }
 
-__global__ void __launch_bounds__(128)
+// BIG (systems with more than 2048 slices): one CTA of 1024 threads per slot sums the slot's
+// partials cooperatively in a fixed order before thread 0 runs the controller -- one launch
+// instead of qb_partials_reduce_kernel + a single-warp controller.
+template <bool BIG>
+__global__ void __launch_bounds__(BIG ? 1024 : 128)
 qb_control_kernel(QbEngineDev* __restrict__ E)
 {
-    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int slot = BIG ? (int)blockIdx.x : (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, w = BIG ? 0 : (int)(threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0 && E->work) *E->work = 0;
     if (slot >= E->nslots) return;
     QbTraj* gc = &E->traj[slot];
     if (gc->pc == QB_PC_IDLE) return;
     QbPass* gp = &E->pass[slot];
     __shared__ double sred[4][QB_MAXRED];
+    __shared__ double swarp[BIG ? 32 : 1];
 
     const int kind = gp->kind;
     int nred = 0;
@@ -915,7 +920,22 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
     else if (kind != QB_PASS_NONE && gp->red) nred = E->ctl.mc_trace ? 5 : 3;
     const int nslices = E->nslices, stride = E->red_stride;
     const double* __restrict__ part = E->partials + (size_t)slot * nslices * stride;
-    if (E->red_final) {
+    if (BIG) {
+        for (int k = 0; k < nred; k++) {
+            double s = 0.0;
+            for (int i = threadIdx.x; i < nslices; i += 1024) s += part[(size_t)i * stride + k];
+            s = qb_warp_sum(s);
+            if (lane == 0) swarp[BIG ? (threadIdx.x >> 5) : 0] = s;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int q = 0; q < 32; q++) t += swarp[BIG ? q : 0];
+                sred[0][k] = t;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x != 0) return;
+    } else if (E->red_final) {
         for (int k = 0; k < nred; k++) {      // lane c holds CTA c's sub-sum
             double sv = E->red_final[((size_t)slot * QB_RED_CTAS + lane) * QB_MAXRED + k];
             sv = qb_warp_sum(sv);
@@ -928,8 +948,7 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
         s = qb_warp_sum(s);
         if (lane == 0) sred[w][k] = s;
     }
-    __syncwarp();
-    if (lane != 0) return;
+    if (!BIG) { __syncwarp(); if (lane != 0) return; }
 
     QbTraj c = *gc;
     QbPass p;
@@ -1289,8 +1308,14 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         const int nround = (int)((s->N + 31) / 32 * 32);
         rows = std::max(32, std::min(rows, 8192)) & ~31;
         if (rows > nround) rows = nround;
+        // few slots of a large system: smaller tiles, so that the (persistent) grid draws enough
+        // work items to balance its last wave (C2: 1024 tiles of 1024 rows for 444 CTAs -> 4096 of 256)
+        if (!er)
+            while (rows > 256 && (rows & (rows - 1)) == 0 &&
+                   (long long)nslots * ((s->N + rows - 1) / rows) < 3552) rows >>= 1;
         thr = std::max(32, std::min(256, thr)) & ~31;
         if (thr > rows) thr = rows;
+        if (!et) thr = std::min(thr, std::max(32, (rows / 2) & ~31));     // a warp takes pairs of slices
         const char* eb = getenv("QB_TILE_NSB");
         int nsb = eb ? atoi(eb) : 6;                   // epilogue sources staged per warp (1 KB each)
         nsb = std::max(0, std::min(nsb, QB_MAXSRC));
@@ -1374,11 +1399,16 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
     const bool use_shared = e->h.ctl.nelem == 1 && e->h.elem[0].fmt == QB_FMT_SELL && !e->h.zbuf &&
                             nslots_used >= 8 && !e->no_shared;
     const long long grid_sh = (long long)((nslots_used + 7) / 8) * ((e->h.nslices + QB_SH_T - 1) / QB_SH_T);
+    // large systems in few slots: partial sums and controller fused in one launch per round.
+    // Measured on C2 (tools/prof_run.py c2): 4 us per round SLOWER than the 32-CTA reduction +
+    // single-warp controller (one SM reads 786 KB of partials alone) -- opt-in only.
+    const bool big_control = e->h.red_final != nullptr && nslots_used <= 64 && getenv("QB_BIG_CONTROL");
     long long rounds = 0;
     QB_CUDA(cudaMemsetAsync(e->h.vec_count, 0, sizeof(unsigned long long), e->stream));
     QB_CUDA(cudaEventRecord(e->ev0, e->stream));
     // the very first control launch turns the *_BEGIN entry points into passes
-    qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
+    if (big_control) qb_control_kernel<true><<<nslots_used, 1024, 0, e->stream>>>(e->d);
+    else qb_control_kernel<false><<<grid2, 128, 0, e->stream>>>(e->d);
     QB_LAUNCH_CHECK();
     auto enqueue_round = [&](bool timed) -> int {
         cudaEvent_t pa = nullptr, pb = nullptr;
@@ -1418,11 +1448,14 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
             QB_LAUNCH_CHECK();
         }
         if (timed) cudaEventRecord(pb, e->stream);
-        if (e->h.red_final) {
-            qb_partials_reduce_kernel<<<nslots_used * QB_RED_CTAS, 256, 0, e->stream>>>(e->d);
-            QB_LAUNCH_CHECK();
+        if (big_control) qb_control_kernel<true><<<nslots_used, 1024, 0, e->stream>>>(e->d);
+        else {
+            if (e->h.red_final) {
+                qb_partials_reduce_kernel<<<nslots_used * QB_RED_CTAS, 256, 0, e->stream>>>(e->d);
+                QB_LAUNCH_CHECK();
+            }
+            qb_control_kernel<false><<<grid2, 128, 0, e->stream>>>(e->d);
         }
-        qb_control_kernel<<<grid2, 128, 0, e->stream>>>(e->d);
         QB_LAUNCH_CHECK();
         return QB_OK;
     };
@@ -1460,13 +1493,13 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
             cudaGraphDestroy(g);
             if (ce != cudaSuccess) { e->graph = nullptr; QB_FAIL(QB_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)); }
             e->graph_slots = nslots_used;
-            g_qb_launches -= (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + (e->h.red_final ? 1 : 0) + (e->h.linmap ? 1 : 0));
+            g_qb_launches -= (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + ((e->h.red_final && !big_control) ? 1 : 0) + (e->h.linmap ? 1 : 0));
         }
         int pending = 0;              // chunks enqueued whose counter has not been read
         for (;;) {
             const int buf = (int)((rounds / QB_GRAPH_ROUNDS) & 1);
             QB_CUDA(cudaGraphLaunch(e->graph, e->stream));
-            g_qb_launches += (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + (e->h.red_final ? 1 : 0) + (e->h.linmap ? 1 : 0));
+            g_qb_launches += (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + ((e->h.red_final && !big_control) ? 1 : 0) + (e->h.linmap ? 1 : 0));
             QB_CUDA(cudaMemcpyAsync(e->h_active + buf, e->h.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
             QB_CUDA(cudaEventRecord(e->ev_chunk[buf], e->stream));
             rounds += QB_GRAPH_ROUNDS;

@@ -152,12 +152,19 @@ static int finish_rsell(QbOpH* h, RsellHost& rs, int64_t rows, int64_t cols) {
     return QB_OK;
 }
 // RSELL replaces SELL when the slices are diagonal structured: at most 1.75 stored lanes per
-// non-zero (every slot costs one gather for all 32 lanes) and L2-resident
-static bool want_rsell(const RsellHost& rs, int64_t rows, long long sell_padded) {
+// non-zero (every slot costs one gather for all 32 lanes) and L2-resident.  It also replaces
+// DIAM / CSR for LARGE operators (HBM streams) when rule compression at least halves the bytes
+// read per product -- e.g. the C2 Liouvillian: 60 MB instead of 402 MB (DIAM) / 497 MB (CSR),
+// because its Hamiltonian part is constant diagonals under the xor key.
+static bool want_rsell(const RsellHost& rs, int64_t rows, bool small_sell, long long sell_padded,
+                       long long other_bytes) {
     if (getenv("QB_NO_RSELL") || rs.nnz == 0 || rows < 32 || rs.overflow) return false;
     const long long stored = rs.stored() * 32;
-    return rs.bytes() <= (48ll << 20) && (double)stored <= 1.75 * (double)rs.nnz &&
-           stored <= sell_padded + sell_padded / 4;
+    if (small_sell)
+        return rs.bytes() <= (48ll << 20) && (double)stored <= 1.75 * (double)rs.nnz &&
+               stored <= sell_padded + sell_padded / 4;
+    if (getenv("QB_NO_BIG_RSELL")) return false;
+    return 2 * rs.bytes() <= other_bytes && (double)stored <= 2.5 * (double)rs.nnz;
 }
 // operators up to this size stay L2-resident when many trajectories re-read them: prefer
 // the instruction-lean SELL sweep; larger ones are HBM streams: prefer the compact DIAM
@@ -205,11 +212,13 @@ extern "C" int qb_csr_upload(const void* data, const int32_t* col, const int32_t
     }
     RsellHost rs;
     bool use_rsell = (format == 5);
-    if (format == 5 || (format == 0 && use_sell)) {
+    if (format == 5 || (format == 0 && nnz > 0 && rows >= 32)) {
         build_rsell(rows, cols, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o) {
             for (int p = rowptr[r]; p < rowptr[r + 1]; p++) o.push_back({col[p], v[p]});
         }, rs);
-        if (format == 0) use_rsell = want_rsell(rs, rows, (long long)sh.val.size());
+        const long long other = use_diam ? (long long)dh.val.size() * 16 + (long long)dh.ent.size() * 8
+                                         : (long long)nnz * 20;
+        if (format == 0) use_rsell = want_rsell(rs, rows, use_sell, (long long)sh.val.size(), other);
     }
     if (use_rsell) rc = finish_rsell(h, rs, rows, cols);
     else if (use_sell) rc = finish_sell(h, sh, rows, cols);
@@ -339,7 +348,7 @@ extern "C" int qb_dia_upload(const void* data, const int32_t* offsets, int64_t n
     }
     RsellHost rs;
     bool use_rsell = (format == 5);
-    if (format == 5 || (format == 0 && use_sell)) {
+    if (format == 5 || (format == 0 && !dh.val.empty() && rows >= 32)) {
         build_rsell(rows, cols, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o) {
             for (int k = 0; k < ndiag; k++) {
                 const int d = order[k];
@@ -350,7 +359,8 @@ extern "C" int qb_dia_upload(const void* data, const int32_t* offsets, int64_t n
                 o.push_back({(int)c, x});
             }
         }, rs);
-        if (format == 0) use_rsell = want_rsell(rs, rows, (long long)sh.val.size());
+        const long long other = (long long)dh.val.size() * (use_diam ? 16 : 20) + (long long)dh.ent.size() * 8;
+        if (format == 0) use_rsell = want_rsell(rs, rows, use_sell, (long long)sh.val.size(), other);
     }
     if (use_rsell) rc = finish_rsell(h, rs, rows, cols);
     else if (use_sell) rc = finish_sell(h, sh, rows, cols);
