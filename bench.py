@@ -229,10 +229,14 @@ def mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=False):
         "host_build_s": t_build, "upload_and_convert_s": t_upload,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": gbs / hbm_peak,
-                     "traffic": (ncu_traffic().get("c2_rhs_kernel_dram_bytes_per_launch")
+                     "traffic": (ncu_traffic().get("c2_rhs_kernel_%s_dram_bytes_per_launch" % info["format"])
                                  if not quick else None),
                      "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                     "kernel": "qb_rhs_kernel (DIAM SpMV)"},
+                     "kernel": "qb_rhs_kernel (%s SpMV)" % info["format"].upper(),
+                     "note": ("achieved = algorithmic CSR bytes of SURVEY 8d / time; the rule-compressed format "
+                              "(RSELL) stores %.0f MB for the %.0f MB CSR operator, so the figure may exceed the "
+                              "HBM peak -- `traffic` is what one launch really moves"
+                              % (info["device_bytes"] / 1e6, L.nnz * 20 / 1e6))},
     }
 
 

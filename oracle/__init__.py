@@ -3,7 +3,7 @@
 CPU restatement of the reference's algorithm for the hot path (numpy + a small C
 library).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` legs may import this package; the product package ``qutip_b200``
-never does (tests/test_layout.py greps for it).
+never does (tests/test_abi.py::test_product_never_imports_oracle greps for it).
 
 Parity status: PINNED.  The restatement is checked against outputs of the reference
 itself (the unmodified qutip 5.4.0.dev build in ``oracle/_ref``, see build_ref.py) via
