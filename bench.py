@@ -264,6 +264,16 @@ def plugin_figures(quick=False):
         return {"unavailable": repr(exc)[:200]}
 
 
+def plugin_c1_figures():
+    """C1 (BASELINE config 1) through qutip.mesolve: reference vern7 on the host vs b200_vern7."""
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "plugin_c1.py")],
+                             capture_output=True, text=True, timeout=300).stdout.strip().splitlines()
+        return json.loads(out[-1])
+    except Exception as exc:
+        return {"unavailable": repr(exc)[:200]}
+
+
 def extra_figures(qb, models, quick=False):
     """Secondary configs of BASELINE.json (C4 time-dependent mesolve, C5 sweep + dense ZGEMM).
     Parity of these paths is asserted in tests/; here only timings are recorded."""
@@ -558,6 +568,7 @@ def run_ours(args):
         except Exception as exc:
             line["extra_figures_error"] = repr(exc)[:300]
         line["plugin_matrix_form_c2"] = plugin_figures(quick=args.quick)
+        line["plugin_c1"] = plugin_c1_figures()
         line["mesolve"]["cpu_spmv_reference"] = reference_spmv(quick=args.quick)
     if world == 1 and not args.no_cpu:
         # reference CPU arm on a bounded sample, in a subprocess (it forks worker processes)

@@ -26,7 +26,7 @@ import numpy as np
 # op-codes: keep in sync with csrc/qb_types.h
 (I_CONST, I_T, I_ARG, I_ADD, I_SUB, I_MUL, I_DIV, I_NEG, I_CONJ, I_SIN, I_COS, I_TAN, I_EXP,
  I_LOG, I_SQRT, I_ABS, I_REAL, I_IMAG, I_POW, I_SINH, I_COSH, I_TANH, I_SPLINE, I_ASIN,
- I_ACOS, I_ATAN, I_NORM2, I_HEAVISIDE_GE, I_HOST) = range(29)
+ I_ACOS, I_ATAN, I_NORM2, I_HEAVISIDE_GE, I_HOST, I_MIN_RE, I_SQRT_RE) = range(31)
 
 _FUNCS = {
     "sin": I_SIN, "cos": I_COS, "tan": I_TAN, "exp": I_EXP, "log": I_LOG, "sqrt": I_SQRT,
@@ -70,9 +70,23 @@ class Program:
     def __mul__(self, other):
         return Program(self.instrs + other.instrs + [(I_MUL, 0, 0.0, 0.0)])
 
+    def sqrt_real(self):
+        """sqrt(real(.)) -- SqrtRealCoefficient (solver/cy/nm_mcsolve.pyx:80-119)"""
+        return Program(self.instrs + [(I_SQRT_RE, 0, 0.0, 0.0)])
+
     def scaled(self, z):
         z = complex(z)
         return Program(self.instrs + [(I_CONST, 0, z.real, z.imag), (I_MUL, 0, 0.0, 0.0)])
+
+
+def rate_shift(programs):
+    """2 * abs(min(0, real(c_1(t)), real(c_2(t)), ...)) -- RateShiftCoefficient
+    (solver/cy/nm_mcsolve.pyx:15-78)"""
+    instrs = [(I_CONST, 0, 0.0, 0.0)]
+    for p in programs:
+        instrs += list(p.instrs) + [(I_MIN_RE, 0, 0.0, 0.0)]
+    instrs += [(I_ABS, 0, 0.0, 0.0), (I_CONST, 0, 2.0, 0.0), (I_MUL, 0, 0.0, 0.0)]
+    return Program(instrs)
 
 
 def constant(z):
@@ -191,6 +205,11 @@ def evaluate(prog, t, args=()):
             b = st.pop(); a = st.pop()
             st.append({I_ADD: a + b, I_SUB: a - b, I_MUL: a * b,
                        I_DIV: a / b if op == I_DIV else 0, I_POW: a ** b if op == I_POW else 0}[op])
+        elif op == I_MIN_RE:
+            b = st.pop(); a = st.pop()
+            st.append(complex(min(a.real, b.real)))
+        elif op == I_SQRT_RE:
+            st.append(complex(np.sqrt(st.pop().real)))
         elif op in un:
             st.append(complex(un[op](st.pop())))
         else:

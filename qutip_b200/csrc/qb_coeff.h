@@ -129,7 +129,7 @@ QB_HD int qb_eval_prog(const QbInstr* code, int len, double t, const qb_c128* ar
             if (sp < 1) return -1;
             st[sp - 1] = qb_spline_eval(splines[in.iarg], spool, st[sp - 1].re); break;
         case QB_I_ADD: case QB_I_SUB: case QB_I_MUL: case QB_I_DIV: case QB_I_POW:
-        case QB_I_HEAVISIDE_GE:
+        case QB_I_HEAVISIDE_GE: case QB_I_MIN_RE:
             if (sp < 2) return -1;
             b = st[--sp]; a = st[sp - 1];
             if (in.op == QB_I_ADD) { r.re = a.re + b.re; r.im = a.im + b.im; }
@@ -137,6 +137,7 @@ QB_HD int qb_eval_prog(const QbInstr* code, int len, double t, const qb_c128* ar
             else if (in.op == QB_I_MUL) r = qb_cmul(a, b);
             else if (in.op == QB_I_DIV) r = qb_cdiv(a, b);
             else if (in.op == QB_I_POW) r = qb_cpow(a, b);
+            else if (in.op == QB_I_MIN_RE) { r.re = (b.re < a.re) ? b.re : a.re; r.im = 0.0; }
             else { r.re = (a.re >= b.re) ? 1.0 : 0.0; r.im = 0.0; }
             st[sp - 1] = r; break;
         default:
@@ -161,6 +162,7 @@ QB_HD int qb_eval_prog(const QbInstr* code, int len, double t, const qb_c128* ar
             case QB_I_ASIN: r.re = asin(a.re); r.im = 0.0; break;
             case QB_I_ACOS: r.re = acos(a.re); r.im = 0.0; break;
             case QB_I_ATAN: r.re = atan(a.re); r.im = 0.0; break;
+            case QB_I_SQRT_RE: r.re = sqrt(a.re); r.im = 0.0; break;
             default: return -1;
             }
             st[sp - 1] = r;

@@ -108,7 +108,9 @@ enum {
     QB_I_CONJ, QB_I_SIN, QB_I_COS, QB_I_TAN, QB_I_EXP, QB_I_LOG, QB_I_SQRT, QB_I_ABS,
     QB_I_REAL, QB_I_IMAG, QB_I_POW, QB_I_SINH, QB_I_COSH, QB_I_TANH, QB_I_SPLINE,
     QB_I_ASIN, QB_I_ACOS, QB_I_ATAN, QB_I_NORM2, QB_I_HEAVISIDE_GE,
-    QB_I_HOST     // value supplied by the host for the pending evaluation time (python callables)
+    QB_I_HOST,    // value supplied by the host for the pending evaluation time (python callables)
+    QB_I_MIN_RE,  // binary: min of the real parts (RateShiftCoefficient, solver/cy/nm_mcsolve.pyx:56-66)
+    QB_I_SQRT_RE  // unary: real sqrt of the real part (SqrtRealCoefficient, nm_mcsolve.pyx:113-115)
 };
 struct QbInstr { int op; int iarg; double re, im; };
 

@@ -108,6 +108,10 @@ def coefficient_to_program(c, system=None):
     if name == "MulCoefficient":
         s = _coeff_state(c)
         return coefficient_to_program(s[1], system) * coefficient_to_program(s[2], system)
+    if name == "RateShiftCoefficient":          # nm_mcsolve (solver/cy/nm_mcsolve.pyx:15-78)
+        return coeffs.rate_shift([coefficient_to_program(x, system) for x in c.__reduce__()[1][0]])
+    if name == "SqrtRealCoefficient":           # nm_mcsolve (solver/cy/nm_mcsolve.pyx:80-119)
+        return coefficient_to_program(_coeff_state(c)[1], system).sqrt_real()
     if name == "InterCoefficient":
         if system is None:
             raise TypeError("array coefficients need a system to hold the spline table")
@@ -879,9 +883,13 @@ def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, m
     inner = getattr(task, "func", task)                   # mcsolve._unpack_arguments wrapper
     solver = getattr(inner, "__self__", None)
     name = getattr(inner, "__name__", "")
-    # subclasses (NonMarkovianMCSolver: martingale weights per trajectory, nm_mcsolve.py:305-324)
-    # override the trajectory function; they run through their own code, one trajectory at a time
-    if type(solver) is not MCSolver or name not in ("_run_one_traj", "_run_one_traj_mixed"):
+    # NonMarkovianMCSolver (solver/nm_mcsolve.py): the same trajectories with rate-shifted collapse
+    # operators; the influence martingale of a trajectory depends only on its collapse record
+    # and is attached to the results afterwards (_b200_batch).  Other subclasses override the
+    # trajectory function and run through their own code, one trajectory at a time.
+    from qutip.solver.nm_mcsolve import NonMarkovianMCSolver
+    batched = type(solver) is MCSolver or (type(solver) is NonMarkovianMCSolver and name == "_run_one_traj")
+    if not batched or name not in ("_run_one_traj", "_run_one_traj_mixed"):
         results = []
         for v in values:
             out = task(v, *task_args, **task_kwargs)
@@ -1156,9 +1164,18 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
                 res.states = qs
             res._final_state = qs[-1]
         res.collapse = [(float(r.col_t[j, i]), int(r.col_which[j, i])) for i in range(r.ncol[j])]
+        if martingale is not None:
+            # NonMarkovianMCSolver._run_one_traj (nm_mcsolve.py:562-570): the influence martingale
+            # at the output times, from the solver's own InfluenceMartingale object (continuous
+            # part pre-computed by NonMarkovianMCSolver.run, discrete part from the collapses)
+            martingale.initialize(tlist[0], cache='keep')
+            for tc, ch in res.collapse:
+                martingale.add_collapse(tc, ch)
+            res.trace = [martingale.value(t) for t in tlist]
         return res
 
     first = 0
+    martingale = getattr(solver, "_martingale", None)
     target = getattr(reduce_func, "__self__", None)
     if _bulk_feed_ok(target, want_states, want_final) and ntraj > 1:
         # averages only: trajectory 0 goes through McResult.add (it sizes the accumulators),

@@ -666,3 +666,28 @@ def test_matmul_dag_specialisations():
         _data.matmul_dag(plugin.B200Dense(np.zeros((3, 4), dtype=complex)), dA)
     # the dispatcher picks the device specialisation for the registered types
     assert _data.matmul_dag[plugin.B200Dense, plugin.B200Operator, plugin.B200Dense] is not None
+
+
+def test_nm_mcsolve_b200_map_matches_reference():
+    """NonMarkovianMCSolver (solver/nm_mcsolve.py) through the b200 map: rate-shifted collapse
+    operators compiled to device coefficient programs (RateShiftCoefficient,
+    SqrtRealCoefficient), the influence martingale attached from the collapse records
+    (nm_mcsolve.py:562-570) -- same records, expectation values and traces as the reference."""
+    from qutip import nm_mcsolve, sigmap, coefficient
+    H = 0.5 * sigmaz() + 0.2 * sigmax()
+    ops_and_rates = [(sigmam(), coefficient("0.25*sin(2*t) + 0.05")), (sigmap(), 0.15)]
+    psi0 = (basis(2, 0) + 0.5 * basis(2, 1)).unit()
+    tl = np.linspace(0, 4, 17)
+    o = dict(OPT, method="vern7", keep_runs_results=True, store_final_state=True)
+    kw = dict(e_ops=[sigmaz(), sigmax()], ntraj=24)
+    ref = nm_mcsolve(H, psi0, tl, ops_and_rates, seeds=np.random.SeedSequence(3), options=o, **kw)
+    out = nm_mcsolve(H, psi0, tl, ops_and_rates, seeds=np.random.SeedSequence(3),
+                     options=dict(o, map="b200"), **kw)
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    assert sum(len(w) for w in ref.col_which) > 5
+    for a, b in zip(out.col_times, ref.col_times):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(np.array(out.runs_trace), np.array(ref.runs_trace), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(np.array(out.average_expect), np.array(ref.average_expect), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(np.array(out.average_trace), np.array(ref.average_trace), rtol=1e-9, atol=1e-12)
