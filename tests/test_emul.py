@@ -171,6 +171,18 @@ def test_coefficient_bytecode():
             assert rc == 0
             ref = coeffs.evaluate(p, t)
             assert abs(complex(out[0], out[1]) - ref) < 1e-13 * max(1, abs(ref))
+    # nm_mcsolve's rate shift 2*|min(0, r1, r2)| and sqrt(real(r + shift)) (solver/cy/nm_mcsolve.pyx)
+    r1, r2 = coeffs.compile_expr("0.25*sin(2*t)+0.05"), coeffs.compile_expr("0.15-0.1*t")
+    shift = coeffs.rate_shift([r1, r2])
+    for p, fn in ((shift, lambda t: 2 * abs(min(0.0, 0.25 * np.sin(2 * t) + 0.05, 0.15 - 0.1 * t))),
+                  ((r1 + shift).sqrt_real(),
+                   lambda t: np.sqrt(0.25 * np.sin(2 * t) + 0.05
+                                     + 2 * abs(min(0.0, 0.25 * np.sin(2 * t) + 0.05, 0.15 - 0.1 * t))))):
+        for t in (0.0, 0.9, 2.0, 2.6, 4.2):
+            out = (C.c_double * 2)()
+            assert L.emul_eval_prog(p.as_ctypes(), len(p), C.c_double(t), None, out) == 0
+            assert abs(complex(out[0], out[1]) - fn(t)) < 1e-13
+            assert abs(coeffs.evaluate(p, t) - fn(t)) < 1e-13
     with pytest.raises(TypeError):
         coeffs.compile_expr("__import__('os').system('x')")
     with pytest.raises(TypeError):
