@@ -530,7 +530,10 @@ def run_ours(args):
     traffic, traffic_src = None, None
     if tr.get("c3_pass_kernel_dram_bytes_per_launch") and n == C3["n_spins"] and tr.get("c3_slots") == nslots:
         traffic = tr["c3_pass_kernel_dram_bytes_per_launch"]
-        traffic_src = "profiles/r02_traffic.json (ncu --set full, dram read+write of one launch at %d slots)" % nslots
+        traffic_src = ("profiles/r02_traffic.json: ncu dram read+write, mean over launches 300..395 at %d slots "
+                       "(all slots active); the algorithmic bytes of those same launches are %.2f GB -- "
+                       "algorithmic_bytes_per_launch below averages over ALL rounds incl. the sparse tail"
+                       % (nslots, tr.get("c3_pass_kernel_algorithmic_bytes_same_launches", 0) / 1e9))
     roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
             "traffic_source": traffic_src,

@@ -220,6 +220,8 @@ int qb_engine_rhs_bench(qb_handle eng, double t, qb_handle x, qb_handle out, int
 int qb_engine_set_profiling(qb_handle eng, int on);
 int qb_engine_profile(qb_handle eng, double* pass_ms, int64_t* pass_launches,
                       double* state_vector_accesses);
+/* per pass launch of the last profiled run: time (ms) and cumulative state-vector accesses */
+int qb_engine_profile_rounds(qb_handle eng, double* ms, double* cum_vec, int64_t max, int64_t* n);
 
 /* ---- multi-GPU: the one collective of the sharded workloads -----------------------------
  * mcsolve trajectories (and sweep members) are independent given their seeds

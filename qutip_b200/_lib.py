@@ -48,7 +48,7 @@ SYMBOLS = [
     "qb_engine_create", "qb_engine_run", "qb_engine_run_device", "qb_reduce_expect",
     "qb_engine_last_run_info", "qb_integ_set_state", "qb_integ_integrate",
     "qb_integ_get_state", "qb_integ_set_args", "qb_integ_stats", "qb_engine_rhs",
-    "qb_engine_rhs_bench", "qb_engine_set_profiling", "qb_engine_profile",
+    "qb_engine_rhs_bench", "qb_engine_set_profiling", "qb_engine_profile", "qb_engine_profile_rounds",
     "qb_zgemm", "qb_zgemm_bench", "qb_dmma_peak_bench", "qb_integ_pending_coef", "qb_integ_resume",
     "qb_engine_rhs_coef",
     "qb_comm_nccl_version", "qb_comm_init_all", "qb_comm_unique_id", "qb_comm_init_rank",
@@ -129,6 +129,7 @@ def load():
         "qb_engine_rhs_bench": [vp, dbl, vp, vp, i32, C.POINTER(dbl)],
         "qb_engine_set_profiling": [vp, i32],
         "qb_engine_profile": [vp, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl)],
+        "qb_engine_profile_rounds": [vp, vp, vp, i64, C.POINTER(i64)],
         "qb_device_count": [C.POINTER(i32)],
         "qb_set_device": [i32],
         "qb_device_mem_info": [C.POINTER(i64), C.POINTER(i64)],

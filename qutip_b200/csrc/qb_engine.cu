@@ -583,6 +583,10 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
     }
     const int nsrc = gp->nsrc;
     const int nb = min(nsrc, nsb);                      // sources staged by TMA; the rest is loaded directly
+#ifdef QB_SRC_EVICT_FIRST
+    unsigned long long pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+#endif
     const int red = gp->red;
     const bool werr = (red & QB_RED_WRMS) != 0;
     const int nelem = ta.nelem;
@@ -611,8 +615,14 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
             if (lane < nb) {
                 const int s = gp->sw[lane].src;
                 const double2* p = (s >= 0 ? ta.pool + (long long)(vbase + s) * N : initp) + r0;
+#ifdef QB_SRC_EVICT_FIRST
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+                             "[%0], [%1], %2, [%3], %4;"
+                             :: "r"(wba + (unsigned)lane * 1024u), "l"(p), "r"(bytes), "r"(wb), "l"(pol_stream) : "memory");
+#else
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              :: "r"(wba + (unsigned)lane * 1024u), "l"(p), "r"(bytes), "r"(wb) : "memory");
+#endif
             }
         }
 #ifdef QB_TAIL_PF
@@ -1060,6 +1070,10 @@ struct QbEngH : QbObj {
     long long prof_pass_launches = 0;
     unsigned long long prof_vec_count = 0;
     std::vector<cudaEvent_t> prof_events;
+    std::vector<double> prof_round_ms;                  // per round of the last profiled run
+    std::vector<unsigned long long> prof_round_vec;     // cumulative vector accesses after the round
+    unsigned long long* prof_vec_host = nullptr;        // pinned
+    size_t prof_vec_cap = 0;
     int maxcoef = 1;
     int64_t last_ntraj = 0; int last_nt = 0;     // shape of the expectation values of the last qb_engine_run
     QbEngH() : QbObj(QB_TAG_ENG) { memset(&h, 0, sizeof h); }
@@ -1070,6 +1084,7 @@ struct QbEngH : QbObj {
         if (d_init) cudaFree(d_init);
         if (d_args) cudaFree(d_args);
         if (h_active) cudaFreeHost(h_active);
+        if (prof_vec_host) cudaFreeHost(prof_vec_host);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (graph) cudaGraphExecDestroy(graph);
@@ -1447,7 +1462,15 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
             qb_linmap_kernel<<<(unsigned)((long long)nslots_used * ntiles), QB_TILE_ROWS, 0, e->stream>>>(e->d, nslots_used);
             QB_LAUNCH_CHECK();
         }
-        if (timed) cudaEventRecord(pb, e->stream);
+        if (timed) {
+            cudaEventRecord(pb, e->stream);
+            // cumulative algorithmic vector accesses ISSUED up to here: the controller that follows
+            // adds the next round's, so the difference of two samples belongs to one pass launch
+            const size_t idx = e->prof_events.size() / 2 - 1;
+            if (idx < e->prof_vec_cap)
+                cudaMemcpyAsync(e->prof_vec_host + idx, e->h.vec_count, sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, e->stream);
+        }
         if (big_control) qb_control_kernel<true><<<nslots_used, 1024, 0, e->stream>>>(e->d);
         else {
             if (e->h.red_final) {
@@ -1459,6 +1482,12 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
         QB_LAUNCH_CHECK();
         return QB_OK;
     };
+    if (e->profiling && !e->prof_vec_host) {
+        e->prof_vec_cap = 8192;
+        if (cudaMallocHost((void**)&e->prof_vec_host, e->prof_vec_cap * sizeof(unsigned long long)) != cudaSuccess) {
+            e->prof_vec_host = nullptr; e->prof_vec_cap = 0;
+        }
+    }
     if (e->profiling || short_call) {
         // plain launches, one host look at the counter per chunk.  Used for per-pass
         // CUDA-event timing and for the Integrator protocol (qb_integ_*), whose calls often
@@ -1524,6 +1553,13 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
             float t = 0.f;
             cudaEventElapsedTime(&t, e->prof_events[i], e->prof_events[i + 1]);
             tot += t;
+        }
+        e->prof_round_ms.clear(); e->prof_round_vec.clear();
+        for (size_t i = 0; i + 1 < e->prof_events.size(); i += 2) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, e->prof_events[i], e->prof_events[i + 1]);
+            e->prof_round_ms.push_back(t);
+            e->prof_round_vec.push_back(i / 2 < e->prof_vec_cap ? e->prof_vec_host[i / 2] : 0ull);
         }
         e->prof_pass_ms = tot; e->prof_pass_launches = (long long)(e->prof_events.size() / 2);
         for (auto ev : e->prof_events) cudaEventDestroy(ev);
@@ -1922,6 +1958,19 @@ extern "C" int qb_engine_profile(qb_handle eng, double* pass_ms, int64_t* pass_l
     if (pass_ms) *pass_ms = e->prof_pass_ms;
     if (pass_launches) *pass_launches = e->prof_pass_launches;
     if (state_vector_accesses) *state_vector_accesses = (double)e->prof_vec_count;
+    return QB_OK;
+}
+// per pass launch of the last profiled run: CUDA-event time and the cumulative number of
+// algorithmic state-vector accesses issued when it ran (differences = that launch's accesses)
+extern "C" int qb_engine_profile_rounds(qb_handle eng, double* ms, double* cum_vec, int64_t max, int64_t* n) {
+    QbEngH* e = qb_cast<QbEngH>(eng, QB_TAG_ENG);
+    if (!e || !n) QB_FAIL(QB_E_TYPE, "not an engine handle");
+    const int64_t m = std::min<int64_t>(max, (int64_t)e->prof_round_ms.size());
+    for (int64_t i = 0; i < m; i++) {
+        if (ms) ms[i] = e->prof_round_ms[i];
+        if (cum_vec) cum_vec[i] = (double)e->prof_round_vec[i];
+    }
+    *n = (int64_t)e->prof_round_ms.size();
     return QB_OK;
 }
 // `iters` back-to-back RHS evaluations out = sum_k c_k(t) A_k x, timed with CUDA events on

@@ -483,6 +483,15 @@ class Engine(_Handle):
     def set_profiling(self, on=True):
         check(_lib.load().qb_engine_set_profiling(self.handle, int(on)))
 
+    def profile_rounds(self, max_rounds=8192):
+        """(ms, vector accesses) per pass launch of the last profiled run"""
+        ms = np.zeros(max_rounds); cum = np.zeros(max_rounds)
+        n = C.c_int64()
+        check(_lib.load().qb_engine_profile_rounds(self.handle, ptr(ms), ptr(cum), max_rounds, C.byref(n)))
+        k = min(max_rounds, n.value)
+        acc = np.diff(np.concatenate([[0.0], cum[:k]]))
+        return ms[:k], acc
+
     def profile(self):
         ms, n, v = C.c_double(), C.c_int64(), C.c_double()
         check(_lib.load().qb_engine_profile(self.handle, C.byref(ms), C.byref(n), C.byref(v)))
