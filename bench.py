@@ -180,12 +180,16 @@ def mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=False):
     rho0 = np.zeros(N, dtype=complex)
     rho0[0] = 1.0
     tlist = np.linspace(0, C2["t_end"], C2["nt"])
-    eng.set_profiling(True)
+    eng.run_mesolve(rho0, tlist[:2])                  # warm-up (graph capture)
     t0 = time.perf_counter()
-    r = eng.run_mesolve(rho0, tlist)
+    r = eng.run_mesolve(rho0, tlist)                  # timed as users run it: CUDA graphs, no per-round events
     wall = time.perf_counter() - t0
-    prof = eng.profile()
     nrhs = int(r.stats[0][0])
+    eng.set_profiling(True)                           # second run, plain launches: share of the pass kernel
+    rp = eng.run_mesolve(rho0, tlist)
+    prof = eng.profile()
+    prof_share = prof["pass_ms"] / rp.gpu_ms if rp.gpu_ms else None
+    eng.set_profiling(False)
     # the same run with the matrix-free Lindblad right-hand side (LindbladMatrixForm on the
     # device: I (x) H_nh, conj(H_nh) (x) I as Kronecker operators + the sparse jump part)
     solve = __import__("qutip_b200.solve", fromlist=["x"])
@@ -224,7 +228,7 @@ def mesolve_c2_figures(qb, models, hbm_peak, peak_src, quick=False):
         "spmv_ms": per * 1e3, "spmv_gbs": gbs, "rhs_evals_per_s_kernel": 1.0 / per,
         "mesolve_rhs_evals": nrhs, "mesolve_gpu_ms": r.gpu_ms, "mesolve_wall_s": wall,
         "mesolve_rhs_evals_per_s": nrhs / (r.gpu_ms * 1e-3),
-        "mesolve_pass_kernel_share": prof["pass_ms"] / r.gpu_ms if r.gpu_ms else None,
+        "mesolve_pass_kernel_share": prof_share,
         "expect_sz0_final": float(r.expect[0][0][-1].real),
         "host_build_s": t_build, "upload_and_convert_s": t_upload,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",

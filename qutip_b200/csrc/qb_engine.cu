@@ -44,6 +44,8 @@ struct QbEngineDev {
     int* queue_head;       // next trajectory id to start
     int* n_active;         // slots still working
     int* work;             // work counter of the persistent tile kernel (reset here every round)
+    int* act_list;         // slots whose pass the tile kernel executes this round, in slot order
+    int* act_count;
     int ntraj_total;
     int mode;
     int* out_status;
@@ -513,6 +515,8 @@ struct QbTileArgs {
     const qb_c128* coef;
     double* partials;
     int* work;                  // persistent mode: next (slot, tile) work item
+    const int* act_list;        // compacted list of the slots with a pass this round (qb_compact_kernel)
+    const int* act_count;
     int N, V, nslices, red_stride, nelem, maxcoef, mc_trace, tpad_;
     double atol, rtol;
     QbTileElem elem[QB_MAX_ELEMS];
@@ -529,7 +533,9 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
     __shared__ int s_work;
     const int N = ta.N;
     const int ntiles = (N + trows - 1) / trows;
-    const int total = nslots_used * ntiles;
+    // only the slots that have a pass this round are visited (their list is compacted by
+    // qb_compact_kernel after the controller): finished trajectories cost nothing in the tail
+    const int total = min(*ta.act_count, nslots_used) * ntiles;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     // shared-window addresses, computed ONCE (volatile: the compiler would otherwise re-derive
     // them from SR_CgaCtaId in front of every LDS to save a register)
@@ -555,8 +561,9 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
     __syncthreads();              // also: the barrier objects are initialised before anybody uses them
     const int work = s_work;
     if (work >= total) break;
-    const int slot = work / ntiles;
-    const int tile = work - slot * ntiles;
+    const int item = work / ntiles;
+    const int tile = work - item * ntiles;
+    const int slot = ta.act_list[item];
     const QbPass* __restrict__ gp = &ta.pass[slot];
     const int kind = gp->kind;
     if (kind == QB_PASS_NONE || kind == QB_PASS_LINMAP) continue;     // CTA-uniform
@@ -907,6 +914,35 @@ __device__ void qb_start_traj(QbEngineDev* E, QbTraj& c, int traj_id) {
     c.pc = E->mode ? QB_PC_MC_BEGIN : QB_PC_ME_BEGIN;
 }
 
+// Slots with a pass for the tile kernel, compacted in slot order (one block; runs after the
+// controller of every round).
+__global__ void __launch_bounds__(1024)
+qb_compact_kernel(QbEngineDev* __restrict__ E, int nslots_used)
+{
+    __shared__ int s_cnt[1024];
+    const int per = (nslots_used + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(nslots_used, lo + per);
+    int c = 0;
+    for (int s = lo; s < hi; s++) {
+        const int k = E->pass[s].kind;
+        c += (k != QB_PASS_NONE && k != QB_PASS_LINMAP);
+    }
+    s_cnt[threadIdx.x] = c;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {                  // inclusive scan
+        const int v = threadIdx.x >= d ? s_cnt[threadIdx.x - d] : 0;
+        __syncthreads();
+        s_cnt[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int pos = s_cnt[threadIdx.x] - c;
+    for (int s = lo; s < hi; s++) {
+        const int k = E->pass[s].kind;
+        if (k != QB_PASS_NONE && k != QB_PASS_LINMAP) E->act_list[pos++] = s;
+    }
+    if (threadIdx.x == 1023) *E->act_count = s_cnt[1023];
+}
+
 // BIG (systems with more than 2048 slices): one CTA of 1024 threads per slot sums the slot's
 // partials cooperatively in a fixed order before thread 0 runs the controller -- one launch
 // instead of qb_partials_reduce_kernel + a single-warp controller.
@@ -1064,6 +1100,7 @@ struct QbEngH : QbObj {
     int tile_g = 0, tile_rows = 0, tile_xw = 0, tile_ns = 0, tile_threads = 256;   // TMA-staged kernel (tile_g == 0: off)
     size_t tile_smem = 0;
     int tile_persist = 0;        // CTAs per SM of the persistent grid (0: one CTA per tile)
+    int act_identity = 0;        // act_list currently holds the identity list of this many slots
     QbConstDesc cdesc;          // descriptor lists in the constant bank (n == 0: read from global memory)
     QbTileArgs targs;
     double prof_pass_ms = 0.0;
@@ -1304,6 +1341,8 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
     QB_TRY(qb_dev_alloc(e, 1, &h.queue_head));
     QB_TRY(qb_dev_alloc(e, 1, &h.n_active));
     QB_TRY(qb_dev_alloc(e, 1, &h.work));
+    QB_TRY(qb_dev_alloc(e, (size_t)nslots, &h.act_list));
+    QB_TRY(qb_dev_alloc(e, 1, &h.act_count));
     QB_TRY(qb_dev_alloc(e, 1, &h.vec_count));
     h.zbuf = nullptr; h.xcols = nullptr; h.zcols = nullptr;
     h.red_final = nullptr;
@@ -1341,7 +1380,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         if (ce != cudaSuccess) { delete e; QB_FAIL(QB_E_CUDA, "tile kernel shared memory: %s", cudaGetErrorString(ce)); }
         memset(&e->targs, 0, sizeof e->targs);
         e->targs.pool = h.pool; e->targs.pass = h.pass; e->targs.coef = h.coef; e->targs.partials = h.partials;
-        e->targs.work = h.work;
+        e->targs.work = h.work; e->targs.act_list = h.act_list; e->targs.act_count = h.act_count;
         // persistent work-queue grid with as many CTAs per SM as fit (measured -3 % on C3 against one
         // CTA per tile); QB_TILE_PERSIST=0 restores the latter, =n forces n CTAs per SM
         e->tile_persist = getenv("QB_TILE_PERSIST") ? atoi(getenv("QB_TILE_PERSIST")) : -1;
@@ -1418,6 +1457,17 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
     // Measured on C2 (tools/prof_run.py c2): 4 us per round SLOWER than the 32-CTA reduction +
     // single-warp controller (one SM reads 786 KB of partials alone) -- opt-in only.
     const bool big_control = e->h.red_final != nullptr && nslots_used <= 64 && getenv("QB_BIG_CONTROL");
+    // the list of active slots is compacted every round when there are many slots (the tail of an
+    // mcsolve batch); few-slot systems keep the identity list and skip the extra launch
+    const bool compact = e->tile_g && nslots_used >= 64;
+    if (e->tile_g && !compact && e->act_identity != nslots_used) {
+        std::vector<int> idl(nslots_used);
+        for (int i = 0; i < nslots_used; i++) idl[i] = i;
+        QB_CUDA(cudaMemcpy(e->h.act_list, idl.data(), idl.size() * sizeof(int), cudaMemcpyHostToDevice));
+        QB_CUDA(cudaMemcpy(e->h.act_count, &nslots_used, sizeof(int), cudaMemcpyHostToDevice));
+        e->act_identity = nslots_used;
+    }
+    if (compact) e->act_identity = 0;
     long long rounds = 0;
     QB_CUDA(cudaMemsetAsync(e->h.vec_count, 0, sizeof(unsigned long long), e->stream));
     QB_CUDA(cudaEventRecord(e->ev0, e->stream));
@@ -1425,6 +1475,7 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
     if (big_control) qb_control_kernel<true><<<nslots_used, 1024, 0, e->stream>>>(e->d);
     else qb_control_kernel<false><<<grid2, 128, 0, e->stream>>>(e->d);
     QB_LAUNCH_CHECK();
+    if (compact) { qb_compact_kernel<<<1, 1024, 0, e->stream>>>(e->d, nslots_used); QB_LAUNCH_CHECK(); }
     auto enqueue_round = [&](bool timed) -> int {
         cudaEvent_t pa = nullptr, pb = nullptr;
         if (timed) {
@@ -1480,6 +1531,7 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
             qb_control_kernel<false><<<grid2, 128, 0, e->stream>>>(e->d);
         }
         QB_LAUNCH_CHECK();
+        if (compact) { qb_compact_kernel<<<1, 1024, 0, e->stream>>>(e->d, nslots_used); QB_LAUNCH_CHECK(); }
         return QB_OK;
     };
     if (e->profiling && !e->prof_vec_host) {
@@ -1522,13 +1574,13 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
             cudaGraphDestroy(g);
             if (ce != cudaSuccess) { e->graph = nullptr; QB_FAIL(QB_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)); }
             e->graph_slots = nslots_used;
-            g_qb_launches -= (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + ((e->h.red_final && !big_control) ? 1 : 0) + (e->h.linmap ? 1 : 0));
+            g_qb_launches -= (long long)QB_GRAPH_ROUNDS * (2 + (compact ? 1 : 0) + (e->h.zbuf ? 1 : 0) + ((e->h.red_final && !big_control) ? 1 : 0) + (e->h.linmap ? 1 : 0));
         }
         int pending = 0;              // chunks enqueued whose counter has not been read
         for (;;) {
             const int buf = (int)((rounds / QB_GRAPH_ROUNDS) & 1);
             QB_CUDA(cudaGraphLaunch(e->graph, e->stream));
-            g_qb_launches += (long long)QB_GRAPH_ROUNDS * (2 + (e->h.zbuf ? 1 : 0) + ((e->h.red_final && !big_control) ? 1 : 0) + (e->h.linmap ? 1 : 0));
+            g_qb_launches += (long long)QB_GRAPH_ROUNDS * (2 + (compact ? 1 : 0) + (e->h.zbuf ? 1 : 0) + ((e->h.red_final && !big_control) ? 1 : 0) + (e->h.linmap ? 1 : 0));
             QB_CUDA(cudaMemcpyAsync(e->h_active + buf, e->h.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
             QB_CUDA(cudaEventRecord(e->ev_chunk[buf], e->stream));
             rounds += QB_GRAPH_ROUNDS;
