@@ -497,7 +497,8 @@ def run_ours(args):
         e2e_times = []
         last = None
         for i in range(1 + args.steps):            # first call: untimed warm-up (qutip's lazy imports)
-            seeds = np.random.SeedSequence(C3["seed"]).spawn((args.warmup + i) * total + hi)[-ntraj:]
+            base = (args.warmup + i) * total + lo          # this rank's block of SeedSequence(7).spawn(...)
+            seeds = [np.random.SeedSequence(C3["seed"], spawn_key=(base + j,)) for j in range(ntraj)]
             barrier()
             t1 = time.perf_counter()
             last = solver.run(psi0_q, tlist, ntraj=ntraj, e_ops=eq, seeds=seeds)

@@ -31,7 +31,13 @@ def make_thresholds(seeds, ntraj, ndraws=64, bitgenerator=None, first=0):
                 for s in seeds[first:first + ntraj]]
     else:
         ss = seeds if isinstance(seeds, np.random.SeedSequence) else np.random.SeedSequence(seeds)
-        kids = ss.spawn(first + ntraj)[first:]
+        if ss.n_children_spawned == 0:
+            # child i of spawn() is SeedSequence(entropy, spawn_key + (i,)): build the block
+            # [first, first + ntraj) directly instead of spawning `first` children to drop them
+            kids = [np.random.SeedSequence(ss.entropy, spawn_key=tuple(ss.spawn_key) + (i,),
+                                           pool_size=ss.pool_size) for i in range(first, first + ntraj)]
+        else:
+            kids = ss.spawn(first + ntraj)[first:]
     out = np.empty((ntraj, ndraws), dtype=np.float64)
     for j, k in enumerate(kids):
         if bitgenerator:
