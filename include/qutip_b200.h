@@ -71,6 +71,20 @@ int qb_kron_upload(const void* data, const int32_t* col, const int32_t* rowptr, 
  * passed stacked row-wise as ONE CSR matrix of shape (nstack*n, n). */
 int qb_sandwich_upload(const void* data, const int32_t* col, const int32_t* rowptr,
                        int64_t n, int64_t nstack, int64_t nnz, qb_handle* out);
+/* Liouvillian assembled on the device (replaces the host kron / add chain of
+ * qutip.liouvillian, core/superoperator.py:116-142): A = -iH - 1/2 sum_k C_k^+ C_k (n x n CSR,
+ * built by the caller) and the nstack collapse operators stacked row-wise as one
+ * (nstack*n, n) CSR matrix give
+ *   L = I (x) A + conj(A) (x) I + sum_k conj(C_k) (x) C_k      (column-stacked, canonical CSR)
+ * one thread per row: count, scan, fill, sort, merge, tidy, compact.  tol: the reference's
+ * auto_tidyup_atol (components below it are zeroed, entries then exactly zero are dropped --
+ * core/data/csr.pxd:88-113; 0 drops exact zeros only).  format as qb_csr_upload;
+ * format 1 keeps the device CSR as it is (the operator never visits the host). */
+int qb_liouvillian_build(const void* a_data, const int32_t* a_col, const int32_t* a_rowptr, int64_t a_nnz,
+                         const void* c_data, const int32_t* c_col, const int32_t* c_rowptr, int64_t c_nnz,
+                         int64_t n, int64_t nstack, double tol, int format, qb_handle* out);
+/* copy a CSR-format operator back: data[nnz] complex128, col[nnz], rowptr[rows+1] (qb_op_info sizes) */
+int qb_op_csr_download(qb_handle h, void* data, int32_t* col, int32_t* rowptr);
 int qb_op_info(qb_handle h, int* fmt, int64_t* rows, int64_t* cols, int64_t* nnz,
                int64_t* device_bytes);
 int qb_free(qb_handle h);

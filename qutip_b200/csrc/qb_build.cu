@@ -1,0 +1,234 @@
+// qb_build.cu -- assemble the Liouvillian superoperator on the device.
+//
+// Replaces the host assembly qutip.liouvillian does with a chain of scipy-style kron / add
+// calls (reference: qutip/core/superoperator.py:116-142; data layer kron at
+// qutip/core/data/kron.pyx, add at qutip/core/data/add.pyx):
+//
+//   L = -i (I (x) H) + i (conj(H) (x) I) + sum_k [ conj(C_k) (x) C_k - 1/2 I (x) C_k^+C_k
+//                                                  - 1/2 (C_k^+C_k)^T (x) I ]
+//
+// on the column-stacked state (row index R = a*n + b for rho[b, a]).  With the n x n matrix
+// A = -iH - 1/2 sum_k C_k^+C_k (assembled by the caller: n x n work) this is
+//
+//   L[(a,b),(a',b')] = d_aa' A[b,b'] + conj(A)[a,a'] d_bb' + sum_k conj(C_k[a,a']) C_k[b,b'],
+//
+// so every row of L is the merge of three short lists.  One thread per row: count the
+// candidates, scan, write them, sort each row's run by column, sum duplicates, scan again and
+// compact into canonical CSR (sorted, no duplicates).  The n^2 x n^2 operator never exists on
+// the host unless a compressed format is asked for (the slice analysers of qb_diam.h run there).
+#include <cub/device/device_scan.cuh>
+#include <vector>
+#include "qb_host.h"
+
+namespace {
+struct LvIn {
+    const double2* av; const int* ac; const int* ap;      // A, n x n CSR
+    const double2* cv; const int* cc; const int* cp;      // C_k stacked row-wise, (nstack*n) x n CSR
+    int n, nstack;
+};
+
+__global__ void qb_lv_count_kernel(LvIn I, long long* __restrict__ ub) {
+    const long long R = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n2 = (long long)I.n * I.n;
+    if (R >= n2) return;
+    const int a = (int)(R / I.n), b = (int)(R % I.n);
+    long long c = (I.ap[b + 1] - I.ap[b]) + (I.ap[a + 1] - I.ap[a]);
+    for (int k = 0; k < I.nstack; k++) {
+        const int* p = I.cp + (size_t)k * I.n;
+        c += (long long)(p[a + 1] - p[a]) * (p[b + 1] - p[b]);
+    }
+    ub[R] = c;
+}
+
+// writes the candidates of row R at tcol/tval[off[R]..], sorts them by column (stable insertion
+// sort: the runs are a few dozen entries), sums duplicates in place, tidies, stores the count
+__global__ void qb_lv_fill_kernel(LvIn I, const long long* __restrict__ off, int* __restrict__ tcol,
+                                  double2* __restrict__ tval, int* __restrict__ cnt, double tol) {
+    const long long R = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n2 = (long long)I.n * I.n;
+    if (R >= n2) return;
+    const int n = I.n, a = (int)(R / n), b = (int)(R % n);
+    int* col = tcol + off[R];
+    double2* val = tval + off[R];
+    int m = 0;
+    for (int p = I.ap[b]; p < I.ap[b + 1]; p++) { col[m] = a * n + I.ac[p]; val[m] = I.av[p]; m++; }
+    for (int p = I.ap[a]; p < I.ap[a + 1]; p++) {
+        const double2 v = I.av[p];
+        col[m] = I.ac[p] * n + b; val[m] = make_double2(v.x, -v.y); m++;
+    }
+    for (int k = 0; k < I.nstack; k++) {
+        const int* rp = I.cp + (size_t)k * n;
+        for (int p = rp[a]; p < rp[a + 1]; p++) {
+            const double2 ca = I.cv[p];
+            const int ja = I.cc[p];
+            for (int q = rp[b]; q < rp[b + 1]; q++) {
+                const double2 cb = I.cv[q];
+                col[m] = ja * n + I.cc[q];
+                // conj(ca) * cb
+                val[m] = make_double2(ca.x * cb.x + ca.y * cb.y, ca.x * cb.y - ca.y * cb.x);
+                m++;
+            }
+        }
+    }
+    for (int i = 1; i < m; i++) {
+        const int c = col[i]; const double2 v = val[i];
+        int j = i - 1;
+        while (j >= 0 && col[j] > c) { col[j + 1] = col[j]; val[j + 1] = val[j]; j--; }
+        col[j + 1] = c; val[j + 1] = v;
+    }
+    int u = 0;
+    for (int i = 0; i < m; i++) {
+        if (u > 0 && col[u - 1] == col[i]) { val[u - 1].x += val[i].x; val[u - 1].y += val[i].y; }
+        else { col[u] = col[i]; val[u] = val[i]; u++; }
+    }
+    // the reference's accumulator (core/data/csr.pxd:88-113, used by add_csr): components below
+    // the tidy-up tolerance are zeroed, entries that are exactly zero afterwards are dropped
+    int w = 0;
+    for (int i = 0; i < u; i++) {
+        double2 v = val[i];
+        if (fabs(v.x) < tol) v.x = 0.0;
+        if (fabs(v.y) < tol) v.y = 0.0;
+        if (v.x != 0.0 || v.y != 0.0) { col[w] = col[i]; val[w] = v; w++; }
+    }
+    cnt[R] = w;
+}
+
+__global__ void qb_lv_compact_kernel(long long n2, const long long* __restrict__ off,
+                                     const int* __restrict__ rowptr, const int* __restrict__ tcol,
+                                     const double2* __restrict__ tval, int* __restrict__ col,
+                                     double2* __restrict__ val) {
+    // one warp per row: coalesced copy of the row's unique run
+    const long long R = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (R >= n2) return;
+    const int p0 = rowptr[R], m = rowptr[R + 1] - p0;
+    const long long s = off[R];
+    for (int i = lane; i < m; i += 32) { col[p0 + i] = tcol[s + i]; val[p0 + i] = tval[s + i]; }
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+static int check_csr(const int32_t* col, const int32_t* rowptr, int64_t rows, int64_t cols, int64_t nnz,
+                     const char* what) {
+    if (rowptr[0] != 0 || rowptr[rows] != nnz) QB_FAIL(QB_E_ARG, "%s: row_index does not match nnz", what);
+    for (int64_t r = 0; r < rows; r++)
+        if (rowptr[r + 1] < rowptr[r]) QB_FAIL(QB_E_ARG, "%s: row_index not monotone", what);
+    for (int64_t p = 0; p < nnz; p++)
+        if (col[p] < 0 || col[p] >= cols) QB_FAIL(QB_E_ARG, "%s: column index out of range", what);
+    return QB_OK;
+}
+template <class T> static int upload(DevBuf& b, const T* src, size_t count) {
+    QB_CUDA(cudaMalloc(&b.p, std::max<size_t>(16, count * sizeof(T))));
+    if (count) QB_CUDA(cudaMemcpy(b.p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    return QB_OK;
+}
+}  // namespace
+
+extern "C" int qb_liouvillian_build(const void* a_data, const int32_t* a_col, const int32_t* a_rowptr,
+                                    int64_t a_nnz, const void* c_data, const int32_t* c_col,
+                                    const int32_t* c_rowptr, int64_t c_nnz, int64_t n, int64_t nstack,
+                                    double tol, int format, qb_handle* out) {
+    if (!out || n <= 0 || nstack < 0 || !a_rowptr || a_nnz < 0 || c_nnz < 0 ||
+        (a_nnz > 0 && (!a_data || !a_col)) || (nstack > 0 && !c_rowptr) || (c_nnz > 0 && (!c_data || !c_col)))
+        QB_FAIL(QB_E_ARG, "bad Liouvillian arguments");
+    if (n > 46340) QB_FAIL(QB_E_ARG, "n*n exceeds int32 row indices");
+    if (!(tol >= 0.0)) QB_FAIL(QB_E_ARG, "tidy-up tolerance must be >= 0");
+    if (format != 0 && format != 1 && format != 2 && format != 3 && format != 5)
+        QB_FAIL(QB_E_ARG, "unknown operator format %d", format);
+    int rc;
+    if ((rc = check_csr(a_col, a_rowptr, n, n, a_nnz, "A"))) return rc;
+    if (nstack > 0 && (rc = check_csr(c_col, c_rowptr, n * nstack, n, c_nnz, "C"))) return rc;
+    static const int32_t zero_ptr[1] = {0};
+    DevBuf av, ac, ap, cv, cc, cp;
+    if ((rc = upload(av, static_cast<const double2*>(a_data), (size_t)a_nnz)) ||
+        (rc = upload(ac, a_col, (size_t)a_nnz)) || (rc = upload(ap, a_rowptr, (size_t)n + 1)) ||
+        (rc = upload(cv, static_cast<const double2*>(c_data), (size_t)c_nnz)) ||
+        (rc = upload(cc, c_col, (size_t)c_nnz)) ||
+        (rc = upload(cp, nstack > 0 ? c_rowptr : zero_ptr, nstack > 0 ? (size_t)(n * nstack) + 1 : 1)))
+        return rc;
+    LvIn I{av.as<double2>(), ac.as<int>(), ap.as<int>(), cv.as<double2>(), cc.as<int>(), cp.as<int>(),
+           (int)n, (int)nstack};
+    const long long n2 = (long long)n * n;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((n2 + threads - 1) / threads);
+
+    DevBuf ub, off, cnt, scan_tmp;
+    QB_CUDA(cudaMalloc(&ub.p, (size_t)(n2 + 1) * sizeof(long long)));
+    QB_CUDA(cudaMalloc(&off.p, (size_t)(n2 + 1) * sizeof(long long)));
+    QB_CUDA(cudaMemset(ub.p, 0, (size_t)(n2 + 1) * sizeof(long long)));
+    qb_lv_count_kernel<<<blocks, threads>>>(I, ub.as<long long>());
+    QB_LAUNCH_CHECK();
+    size_t tmp_bytes = 0, tmp2 = 0;
+    QB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ub.as<long long>(), off.as<long long>(), n2 + 1));
+    QB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, (int*)nullptr, (int*)nullptr, n2 + 1));
+    tmp_bytes = std::max(tmp_bytes, tmp2);
+    QB_CUDA(cudaMalloc(&scan_tmp.p, std::max<size_t>(16, tmp_bytes)));
+    QB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, tmp_bytes, ub.as<long long>(), off.as<long long>(), n2 + 1));
+    g_qb_launches++;
+    long long total_ub = 0;
+    QB_CUDA(cudaMemcpy(&total_ub, off.as<long long>() + n2, sizeof total_ub, cudaMemcpyDeviceToHost));
+    if (total_ub > 0x7fffffffll) QB_FAIL(QB_E_ARG, "Liouvillian too large for int32 indices");
+
+    DevBuf tcol, tval, rowptr;
+    QB_CUDA(cudaMalloc(&tcol.p, std::max<size_t>(16, (size_t)total_ub * sizeof(int))));
+    QB_CUDA(cudaMalloc(&tval.p, std::max<size_t>(16, (size_t)total_ub * sizeof(double2))));
+    QB_CUDA(cudaMalloc(&cnt.p, (size_t)(n2 + 1) * sizeof(int)));
+    QB_CUDA(cudaMalloc(&rowptr.p, (size_t)(n2 + 1) * sizeof(int)));
+    QB_CUDA(cudaMemset(cnt.p, 0, (size_t)(n2 + 1) * sizeof(int)));
+    qb_lv_fill_kernel<<<blocks, threads>>>(I, off.as<long long>(), tcol.as<int>(), tval.as<double2>(),
+                                           cnt.as<int>(), tol);
+    QB_LAUNCH_CHECK();
+    QB_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, tmp_bytes, cnt.as<int>(), rowptr.as<int>(), n2 + 1));
+    g_qb_launches++;
+    int nnz = 0;
+    QB_CUDA(cudaMemcpy(&nnz, rowptr.as<int>() + n2, sizeof nnz, cudaMemcpyDeviceToHost));
+
+    DevBuf col, val;
+    QB_CUDA(cudaMalloc(&col.p, std::max<size_t>(16, (size_t)nnz * sizeof(int))));
+    QB_CUDA(cudaMalloc(&val.p, std::max<size_t>(16, (size_t)nnz * sizeof(double2))));
+    {
+        const unsigned wblocks = (unsigned)((n2 * 32 + 255) / 256);
+        qb_lv_compact_kernel<<<wblocks, 256>>>(n2, off.as<long long>(), rowptr.as<int>(), tcol.as<int>(),
+                                               tval.as<double2>(), col.as<int>(), val.as<double2>());
+        QB_LAUNCH_CHECK();
+    }
+    QB_CUDA(cudaDeviceSynchronize());
+
+    if (format == 1) {                     // CSR: the device arrays are the operator
+        QbOpH* h = new QbOpH();
+        h->dev.fmt = QB_FMT_CSR; h->dev.nrows = (int)n2; h->dev.ncols = (int)n2; h->dev.nnz = nnz;
+        h->dev.val = val.as<qb_c128>(); h->dev.col = col.as<int>(); h->dev.rowptr = rowptr.as<int>();
+        h->owned = {val.p, col.p, rowptr.p};
+        h->device_bytes = (int64_t)nnz * 20 + (n2 + 1) * 4;
+        val.p = col.p = rowptr.p = nullptr;
+        *out = h;
+        return QB_OK;
+    }
+    // compressed formats: the slice analysers (diagonal masks / column rules) run on the host
+    std::vector<qb_c128> hv((size_t)nnz);
+    std::vector<int32_t> hc((size_t)nnz), hp((size_t)n2 + 1);
+    if (nnz) {
+        QB_CUDA(cudaMemcpy(hv.data(), val.p, (size_t)nnz * sizeof(double2), cudaMemcpyDeviceToHost));
+        QB_CUDA(cudaMemcpy(hc.data(), col.p, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    QB_CUDA(cudaMemcpy(hp.data(), rowptr.p, (size_t)(n2 + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    return qb_csr_upload(hv.data(), hc.data(), hp.data(), n2, n2, nnz, format, out);
+}
+
+extern "C" int qb_op_csr_download(qb_handle hh, void* data, int32_t* col, int32_t* rowptr) {
+    QbOpH* h = qb_cast<QbOpH>(hh, QB_TAG_OP);
+    if (!h) QB_FAIL(QB_E_TYPE, "qb_op_csr_download: not an operator handle");
+    if (h->dev.fmt != QB_FMT_CSR) QB_FAIL(QB_E_TYPE, "qb_op_csr_download: operator is not stored as CSR");
+    if (!rowptr || (h->dev.nnz > 0 && (!data || !col))) QB_FAIL(QB_E_ARG, "null output buffer");
+    QB_CUDA(cudaSetDevice(h->device));
+    const size_t nnz = (size_t)h->dev.nnz;
+    if (nnz) {
+        QB_CUDA(cudaMemcpy(data, h->dev.val, nnz * sizeof(double2), cudaMemcpyDeviceToHost));
+        QB_CUDA(cudaMemcpy(col, h->dev.col, nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    QB_CUDA(cudaMemcpy(rowptr, h->dev.rowptr, ((size_t)h->dev.nrows + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    return QB_OK;
+}

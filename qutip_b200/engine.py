@@ -184,6 +184,56 @@ class DeviceOp(_Handle):
         return cls(h, (n * n, n * n))
 
     @classmethod
+    def liouvillian(cls, H=None, c_ops=(), fmt=FMT_AUTO, tol=0.0):
+        """The Liouvillian ``qutip.liouvillian(H, c_ops)`` (core/superoperator.py:116-142) of
+        n x n matrices, assembled ON THE DEVICE: only the n x n effective generator
+        ``A = -iH - 1/2 sum C^dagger C`` is formed on the host; the Kronecker rows are counted,
+        filled, sorted and merged by one thread per row.  ``fmt=FMT_CSR`` keeps the device CSR
+        as it is; the compressed formats pass through the host slice analysers.  ``tol`` is the
+        reference's ``auto_tidyup_atol`` (0: drop exact zeros only, as scipy's sparse add does)."""
+        import scipy.sparse as sp
+        c_ops = [sp.csr_matrix(c, dtype=np.complex128) for c in c_ops]
+        if H is None and not c_ops:
+            raise ValueError("The liouvillian need an Hamiltonian and/or c_ops")
+        n = (sp.csr_matrix(H) if H is not None else c_ops[0]).shape[0]
+        a = sp.csr_matrix((n, n), dtype=np.complex128)
+        if H is not None:
+            H = sp.csr_matrix(H, dtype=np.complex128)
+            if H.shape != (n, n):
+                raise ValueError("H must be square")
+            a = a + (-1j) * H
+        for c in c_ops:
+            if c.shape != (n, n):
+                raise ValueError("collapse operators must all be n x n")
+            a = a - 0.5 * (c.conj().T @ c)
+        a = sp.csr_matrix(a)
+        a.sum_duplicates()
+        a.sort_indices()
+        if c_ops:
+            cs = sp.vstack(c_ops, format="csr")
+            cs.sum_duplicates()
+            cs.sort_indices()
+        else:
+            cs = sp.csr_matrix((0, n), dtype=np.complex128)
+        ad, ac, ap = as_c128(a.data), a.indices.astype(np.int32), a.indptr.astype(np.int32)
+        cd, cc, cp = as_c128(cs.data), cs.indices.astype(np.int32), cs.indptr.astype(np.int32)
+        h = C.c_void_p()
+        check(_lib.load().qb_liouvillian_build(ptr(ad), ptr(ac), ptr(ap), int(ap[-1]),
+                                               ptr(cd), ptr(cc), ptr(cp), int(cp[-1]) if len(cp) else 0,
+                                               n, len(c_ops), float(tol), fmt, C.byref(h)))
+        return cls(h, (n * n, n * n))
+
+    def to_scipy(self):
+        """Copy a CSR-format operator back to the host (scipy.sparse.csr_matrix)."""
+        import scipy.sparse as sp
+        inf = self.info()
+        data = np.empty(inf["nnz"], dtype=np.complex128)
+        col = np.empty(inf["nnz"], dtype=np.int32)
+        rowptr = np.empty(inf["rows"] + 1, dtype=np.int32)
+        check(_lib.load().qb_op_csr_download(self.handle, ptr(data), ptr(col), ptr(rowptr)))
+        return sp.csr_matrix((data, col, rowptr), shape=(inf["rows"], inf["cols"]))
+
+    @classmethod
     def from_scipy(cls, m, fmt=FMT_AUTO):
         import scipy.sparse as sp
         if isinstance(m, (sp.dia_matrix, sp.dia_array)):

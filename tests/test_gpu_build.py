@@ -1,0 +1,117 @@
+"""Liouvillian assembled on the device (qb_liouvillian_build) against the reference's
+construction: qutip.liouvillian (core/superoperator.py:116-142) where the reference build
+travels with the repo, the scipy restatement in qutip_b200.models otherwise -- structure
+(canonical CSR, same pattern) and values."""
+import time
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import qutip_b200 as qb
+from qutip_b200 import models
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_sparse(rng, n, density):
+    m = sp.random(n, n, density=density, random_state=np.random.RandomState(int(rng.integers(1 << 30))),
+                  format="csr", dtype=float)
+    m = m.astype(complex)
+    m.data = m.data + 1j * rng.standard_normal(m.nnz)
+    return sp.csr_matrix(m)
+
+
+def _same(got, want, rtol=1e-13):
+    got = sp.csr_matrix(got); want = sp.csr_matrix(want)
+    got.sort_indices(); want.sum_duplicates(); want.sort_indices()
+    assert got.shape == want.shape
+    diff = (got - want)
+    scale = max(1e-300, np.abs(want.data).max() if want.nnz else 1.0)
+    assert (np.abs(diff.data).max() if diff.nnz else 0.0) <= rtol * scale
+    # canonical: sorted, no duplicates
+    for r in range(0, got.shape[0], max(1, got.shape[0] // 64)):
+        c = got.indices[got.indptr[r]:got.indptr[r + 1]]
+        assert (np.diff(c) > 0).all()
+
+
+@pytest.mark.parametrize("n,nc,density", [(2, 0, 1.0), (3, 1, 1.0), (5, 2, 0.6), (12, 3, 0.3), (33, 4, 0.1),
+                                          (64, 1, 0.05)])
+def test_liouvillian_matches_restatement(n, nc, density):
+    rng = np.random.default_rng(100 + n)
+    H = _rand_sparse(rng, n, density)
+    H = sp.csr_matrix(H + H.conj().T)
+    c_ops = [_rand_sparse(rng, n, density) for _ in range(nc)]
+    want = models.liouvillian(H, c_ops)
+    op = qb.DeviceOp.liouvillian(H, c_ops, qb.FMT_CSR)
+    got = op.to_scipy()
+    _same(got, want)
+    assert got.nnz == want.nnz and np.array_equal(got.indices, want.indices)
+
+
+def test_liouvillian_one_by_one_cancels():
+    # n = 1: |c|^2 - |c|^2 cancels; scipy's sum order may leave rounding noise, the reference's
+    # tidy-up (and ours) drops it
+    c = sp.csr_matrix(np.array([[0.3 - 0.7j]]))
+    got = qb.DeviceOp.liouvillian(sp.csr_matrix(np.array([[2.0 + 0j]])), [c], qb.FMT_CSR, tol=1e-14).to_scipy()
+    assert got.shape == (1, 1) and got.nnz == 0
+
+
+def test_liouvillian_dissipator_only_and_errors():
+    rng = np.random.default_rng(5)
+    c_ops = [_rand_sparse(rng, 7, 0.5) for _ in range(2)]
+    want = models.liouvillian(sp.csr_matrix((7, 7), dtype=complex), c_ops)
+    _same(qb.DeviceOp.liouvillian(None, c_ops, qb.FMT_CSR).to_scipy(), want)
+    with pytest.raises(ValueError):
+        qb.DeviceOp.liouvillian(None, [])
+    with pytest.raises(ValueError):
+        qb.DeviceOp.liouvillian(sp.identity(3), [sp.identity(4)])
+    with pytest.raises(qb.QbError):          # not a CSR-format operator
+        qb.DeviceOp.liouvillian(sp.identity(64, dtype=complex, format="csr"), [], qb.FMT_RSELL).to_scipy()
+
+
+def test_liouvillian_against_reference_constructor():
+    qutip = pytest.importorskip("qutip")
+    N = 6
+    a = qutip.tensor(qutip.destroy(N), qutip.qeye(2))
+    sm = qutip.tensor(qutip.qeye(N), qutip.sigmam())
+    H = a.dag() * a + 0.5 * sm.dag() * sm + 0.3 * (a.dag() * sm + a * sm.dag())
+    c_ops = [np.sqrt(0.2) * a, np.sqrt(0.05) * sm, np.sqrt(0.01) * a.dag()]
+    want = qutip.liouvillian(H, c_ops).to("CSR").data.as_scipy()
+    got = qb.DeviceOp.liouvillian(H.to("CSR").data.as_scipy(), [c.to("CSR").data.as_scipy() for c in c_ops],
+                                  qb.FMT_CSR, tol=qutip.settings.core["auto_tidyup_atol"]).to_scipy()
+    _same(got, want)
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+
+
+def test_liouvillian_compressed_format_same_product():
+    H, c_ops, _ = models.tfim(6)
+    want = models.liouvillian(H, c_ops)
+    op = qb.DeviceOp.liouvillian(H, c_ops)            # auto format: host slice analysers
+    N = want.shape[0]
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    y = qb.matmul(op, qb.DeviceDense.from_numpy(x)).to_numpy().ravel()
+    ref = want @ x
+    assert np.abs(y - ref).max() < 1e-13 * np.abs(ref).max()
+    assert op.info()["nnz"] == want.nnz
+
+
+def test_c2_liouvillian_full_size_on_device():
+    """C2: 2^20 x 2^20, 24.6 M non-zeros -- assembled on the device, bit-for-bit pattern of the
+    host construction, values within rounding of the different summation order."""
+    H, c_ops, _ = models.tfim(10)
+    t0 = time.perf_counter()
+    op = qb.DeviceOp.liouvillian(H, c_ops, qb.FMT_CSR)
+    qb.synchronize()
+    t_dev = time.perf_counter() - t0
+    info = op.info()
+    assert info["rows"] == 2 ** 20 and info["nnz"] == 24641535
+    t0 = time.perf_counter()
+    want = models.liouvillian(H, c_ops)
+    t_host = time.perf_counter() - t0
+    got = op.to_scipy()
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    assert np.abs(got.data - want.data).max() <= 1e-14 * np.abs(want.data).max()
+    print("C2 Liouvillian assembly: device %.3f s, host (scipy kron/add) %.3f s" % (t_dev, t_host))
+    assert t_dev < t_host

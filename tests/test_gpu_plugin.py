@@ -668,14 +668,22 @@ def test_matmul_dag_specialisations():
     assert _data.matmul_dag[plugin.B200Dense, plugin.B200Operator, plugin.B200Dense] is not None
 
 
-def test_nm_mcsolve_b200_map_matches_reference():
+@pytest.mark.parametrize("rate,tight", [("-0.08 + 0.05*sin(2*t)", True), ("0.25*sin(2*t) + 0.05", False)])
+def test_nm_mcsolve_b200_map_matches_reference(rate, tight):
     """NonMarkovianMCSolver (solver/nm_mcsolve.py) through the b200 map: rate-shifted collapse
     operators compiled to device coefficient programs (RateShiftCoefficient,
     SqrtRealCoefficient), the influence martingale attached from the collapse records
-    (nm_mcsolve.py:562-570) -- same records, expectation values and traces as the reference."""
+    (nm_mcsolve.py:562-570) -- same records, expectation values and traces as the reference.
+
+    The second rate changes sign: the shifted rates have kinks at t = 1.67 and 3.04, and behind
+    a kink the adaptive step sequence is ill-conditioned -- the REFERENCE run against itself with
+    the rate perturbed by 2 ulp (`0.25*sin(2*t)*(1+4e-16) + 0.05`) moves the collapse times of
+    trajectories 0, 12 and 15 by 3e-9 ... 3.5e-7 and the expectation values by 5e-8 (measured
+    here with oracle/_ref), so that case is compared at the reference's own collapse-time
+    resolution norm_t_tol = 1e-6; the smooth (always negative) rate is compared tightly."""
     from qutip import nm_mcsolve, sigmap, coefficient
     H = 0.5 * sigmaz() + 0.2 * sigmax()
-    ops_and_rates = [(sigmam(), coefficient("0.25*sin(2*t) + 0.05")), (sigmap(), 0.15)]
+    ops_and_rates = [(sigmam(), coefficient(rate)), (sigmap(), 0.15)]
     psi0 = (basis(2, 0) + 0.5 * basis(2, 1)).unit()
     tl = np.linspace(0, 4, 17)
     o = dict(OPT, method="vern7", keep_runs_results=True, store_final_state=True)
@@ -685,9 +693,13 @@ def test_nm_mcsolve_b200_map_matches_reference():
                      options=dict(o, map="b200"), **kw)
     assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
     assert sum(len(w) for w in ref.col_which) > 5
+    t_atol = 1e-9 if tight else 2e-6
+    e_rtol, e_atol = (RTOL, ATOL) if tight else (1e-5, 1e-6)
     for a, b in zip(out.col_times, ref.col_times):
-        np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)
-    np.testing.assert_allclose(np.array(out.runs_trace), np.array(ref.runs_trace), rtol=1e-9, atol=1e-12)
-    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=RTOL, atol=ATOL)
-    np.testing.assert_allclose(np.array(out.average_expect), np.array(ref.average_expect), rtol=RTOL, atol=ATOL)
-    np.testing.assert_allclose(np.array(out.average_trace), np.array(ref.average_trace), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(a, b, rtol=0, atol=t_atol)
+    np.testing.assert_allclose(np.array(out.runs_trace), np.array(ref.runs_trace), rtol=1e-9 if tight else 1e-6,
+                               atol=1e-12)
+    np.testing.assert_allclose(np.array(out.runs_expect), np.array(ref.runs_expect), rtol=e_rtol, atol=e_atol)
+    np.testing.assert_allclose(np.array(out.average_expect), np.array(ref.average_expect), rtol=e_rtol, atol=e_atol)
+    np.testing.assert_allclose(np.array(out.average_trace), np.array(ref.average_trace),
+                               rtol=1e-9 if tight else 1e-6, atol=1e-12)
