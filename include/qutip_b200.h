@@ -83,6 +83,11 @@ int qb_sandwich_upload(const void* data, const int32_t* col, const int32_t* rowp
 int qb_liouvillian_build(const void* a_data, const int32_t* a_col, const int32_t* a_rowptr, int64_t a_nnz,
                          const void* c_data, const int32_t* c_col, const int32_t* c_rowptr, int64_t c_nnz,
                          int64_t n, int64_t nstack, double tol, int format, qb_handle* out);
+/* Format conversion of a CSR-format operator (the `_data.to(Dia, CSR)` family of
+ * core/data/convert.pyx:208-329, csr.pyx:710, dia.pyx:364): format 2 (diagonal-masked slices)
+ * is produced on the device -- one warp per 32-row slice merges its rows by diagonal offset;
+ * the column-rule / padding analysers of formats 0, 3, 5 run on the host. */
+int qb_op_convert(qb_handle h, int format, qb_handle* out);
 /* copy a CSR-format operator back: data[nnz] complex128, col[nnz], rowptr[rows+1] (qb_op_info sizes) */
 int qb_op_csr_download(qb_handle h, void* data, int32_t* col, int32_t* rowptr);
 int qb_op_info(qb_handle h, int* fmt, int64_t* rows, int64_t* cols, int64_t* nnz,

@@ -106,6 +106,46 @@ __global__ void qb_lv_compact_kernel(long long n2, const long long* __restrict__
     for (int i = lane; i < m; i += 32) { col[p0 + i] = tcol[s + i]; val[p0 + i] = tval[s + i]; }
 }
 
+
+// ---- CSR -> DIAM on the device (the host analyser is qbdiam::emit_slice): one warp per 32-row
+// slice merges its 32 sorted rows by diagonal offset -- the minimum offset over the lanes is
+// the next entry, the lanes that hold it form its mask, their values are packed in lane order.
+// Canonical CSR (sorted columns, no duplicates) only.
+template <bool FILL>
+__global__ void qb_diam_slices_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                      const double2* __restrict__ val, int nrows, int nslices,
+                                      int* __restrict__ ent_cnt, long long* __restrict__ val_cnt,
+                                      const int* __restrict__ slice_ptr, const long long* __restrict__ slice_vbase,
+                                      int2* __restrict__ ent, double2* __restrict__ oval) {
+    const int sl = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (sl >= nslices) return;
+    const long long r = (long long)sl * 32 + lane;
+    int p = 0, pe = 0;
+    if (r < nrows) { p = rowptr[r]; pe = rowptr[r + 1]; }
+    const unsigned lt = (1u << lane) - 1u;
+    int ne = 0;
+    long long nv = 0;
+    const int e0 = FILL ? slice_ptr[sl] : 0;
+    const long long v0 = FILL ? slice_vbase[sl] : 0;
+    for (;;) {
+        const int off = p < pe ? col[p] - (int)r : 0x7fffffff;
+        int m = off;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if (m == 0x7fffffff) break;
+        const bool hit = off == m;
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (FILL) {
+            if (lane == 0) ent[e0 + ne] = make_int2(m, (int)mask);
+            if (hit) oval[v0 + nv + __popc(mask & lt)] = val[p];
+        }
+        if (hit) p++;
+        ne++; nv += __popc(mask);
+    }
+    if (!FILL && lane == 0) { ent_cnt[sl] = ne; val_cnt[sl] = nv; }
+}
+
 struct DevBuf {
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -126,6 +166,9 @@ template <class T> static int upload(DevBuf& b, const T* src, size_t count) {
     return QB_OK;
 }
 }  // namespace
+
+static int qb_diam_from_device_csr(const double2* val, const int* col, const int* rowptr, int64_t rows,
+                                   int64_t cols, int64_t nnz, qb_handle* out);
 
 extern "C" int qb_liouvillian_build(const void* a_data, const int32_t* a_col, const int32_t* a_rowptr,
                                     int64_t a_nnz, const void* c_data, const int32_t* c_col,
@@ -207,7 +250,9 @@ extern "C" int qb_liouvillian_build(const void* a_data, const int32_t* a_col, co
         *out = h;
         return QB_OK;
     }
-    // compressed formats: the slice analysers (diagonal masks / column rules) run on the host
+    if (format == 2)                       // diagonal-masked slices: converted on the device too
+        return qb_diam_from_device_csr(val.as<double2>(), col.as<int>(), rowptr.as<int>(), n2, n2, nnz, out);
+    // the other compressed formats: the padding / column-rule analysers run on the host
     std::vector<qb_c128> hv((size_t)nnz);
     std::vector<int32_t> hc((size_t)nnz), hp((size_t)n2 + 1);
     if (nnz) {
@@ -231,4 +276,85 @@ extern "C" int qb_op_csr_download(qb_handle hh, void* data, int32_t* col, int32_
     }
     QB_CUDA(cudaMemcpy(rowptr, h->dev.rowptr, ((size_t)h->dev.nrows + 1) * sizeof(int), cudaMemcpyDeviceToHost));
     return QB_OK;
+}
+
+// device CSR arrays -> DIAM operator, everything on the device
+static int qb_diam_from_device_csr(const double2* val, const int* col, const int* rowptr, int64_t rows,
+                                   int64_t cols, int64_t nnz, qb_handle* out) {
+    const int nslices = (int)((rows + 31) / 32);
+    DevBuf ecnt, vcnt, sptr, vbase, tmp;
+    QB_CUDA(cudaMalloc(&ecnt.p, (size_t)(nslices + 1) * sizeof(int)));
+    QB_CUDA(cudaMalloc(&vcnt.p, (size_t)(nslices + 1) * sizeof(long long)));
+    QB_CUDA(cudaMalloc(&sptr.p, (size_t)(nslices + 1) * sizeof(int)));
+    QB_CUDA(cudaMalloc(&vbase.p, (size_t)(nslices + 1) * sizeof(long long)));
+    QB_CUDA(cudaMemset(ecnt.p, 0, (size_t)(nslices + 1) * sizeof(int)));
+    QB_CUDA(cudaMemset(vcnt.p, 0, (size_t)(nslices + 1) * sizeof(long long)));
+    const unsigned blocks = (unsigned)(((long long)nslices * 32 + 255) / 256);
+    if (nslices > 0) {
+        qb_diam_slices_kernel<false><<<blocks, 256>>>(rowptr, col, val, (int)rows, nslices, ecnt.as<int>(),
+                                                      vcnt.as<long long>(), nullptr, nullptr, nullptr, nullptr);
+        QB_LAUNCH_CHECK();
+    }
+    size_t t1 = 0, t2 = 0;
+    QB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t1, ecnt.as<int>(), sptr.as<int>(), nslices + 1));
+    QB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t2, vcnt.as<long long>(), vbase.as<long long>(), nslices + 1));
+    QB_CUDA(cudaMalloc(&tmp.p, std::max<size_t>(16, std::max(t1, t2))));
+    QB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, t1, ecnt.as<int>(), sptr.as<int>(), nslices + 1));
+    QB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, t2, vcnt.as<long long>(), vbase.as<long long>(), nslices + 1));
+    g_qb_launches += 2;
+    int nent = 0;
+    long long nval = 0;
+    QB_CUDA(cudaMemcpy(&nent, sptr.as<int>() + nslices, sizeof nent, cudaMemcpyDeviceToHost));
+    QB_CUDA(cudaMemcpy(&nval, vbase.as<long long>() + nslices, sizeof nval, cudaMemcpyDeviceToHost));
+    if (nval != nnz) QB_FAIL(QB_E_STATE, "DIAM conversion lost entries (CSR not canonical?)");
+    DevBuf ent, oval;
+    QB_CUDA(cudaMalloc(&ent.p, std::max<size_t>(16, (size_t)nent * sizeof(int2))));
+    QB_CUDA(cudaMalloc(&oval.p, std::max<size_t>(16, (size_t)nval * sizeof(double2))));
+    if (nslices > 0) {
+        qb_diam_slices_kernel<true><<<blocks, 256>>>(rowptr, col, val, (int)rows, nslices, nullptr, nullptr,
+                                                     sptr.as<int>(), vbase.as<long long>(), ent.as<int2>(),
+                                                     oval.as<double2>());
+        QB_LAUNCH_CHECK();
+    }
+    QB_CUDA(cudaDeviceSynchronize());
+    QbOpH* h = new QbOpH();
+    h->dev.fmt = QB_FMT_DIAM; h->dev.nrows = (int)rows; h->dev.ncols = (int)cols; h->dev.nnz = nval;
+    h->avg_lanes = nent ? (double)nval / (double)nent : 0.0;
+    h->dev.slice_ptr = sptr.as<int>();
+    h->dev.ent_off = ent.as<int>();
+    h->dev.ent_mask = nullptr;
+    h->dev.slice_vbase = vbase.as<long long>();
+    h->dev.val = oval.as<qb_c128>();
+    h->owned = {sptr.p, ent.p, vbase.p, oval.p};
+    h->device_bytes = (int64_t)std::max<size_t>(16, (size_t)(nslices + 1) * sizeof(int)) +
+                      (int64_t)std::max<size_t>(16, (size_t)nent * sizeof(int2)) +
+                      (int64_t)std::max<size_t>(16, (size_t)(nslices + 1) * sizeof(long long)) +
+                      (int64_t)std::max<size_t>(16, (size_t)nval * sizeof(double2));
+    h->dev.pad_ = h->device_bytes > (int64_t)96 << 20 ? 1 : 0;     // streamed, as finish_diam decides
+    sptr.p = ent.p = vbase.p = oval.p = nullptr;
+    *out = h;
+    return QB_OK;
+}
+
+// Format conversion of a CSR-format operator (the reference's `_data.to(Dia, CSR)` family,
+// core/data/convert.pyx:208-329 + csr.pyx:710 / dia.pyx:364): DIAM is produced on the device,
+// the rule / padding analysers of the other formats run on the host.
+extern "C" int qb_op_convert(qb_handle hh, int format, qb_handle* out) {
+    QbOpH* h = qb_cast<QbOpH>(hh, QB_TAG_OP);
+    if (!h || !out) QB_FAIL(QB_E_TYPE, "qb_op_convert: not an operator handle");
+    if (h->dev.fmt != QB_FMT_CSR) QB_FAIL(QB_E_TYPE, "qb_op_convert: source operator is not stored as CSR");
+    QB_CUDA(cudaSetDevice(h->device));
+    if (format == 2)
+        return qb_diam_from_device_csr(reinterpret_cast<const double2*>(h->dev.val), h->dev.col, h->dev.rowptr,
+                                       h->dev.nrows, h->dev.ncols, h->dev.nnz, out);
+    if (format != 0 && format != 1 && format != 3 && format != 5) QB_FAIL(QB_E_ARG, "unknown operator format %d", format);
+    const size_t nnz = (size_t)h->dev.nnz;
+    std::vector<qb_c128> hv(nnz);
+    std::vector<int32_t> hc(nnz), hp((size_t)h->dev.nrows + 1);
+    if (nnz) {
+        QB_CUDA(cudaMemcpy(hv.data(), h->dev.val, nnz * sizeof(double2), cudaMemcpyDeviceToHost));
+        QB_CUDA(cudaMemcpy(hc.data(), h->dev.col, nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    QB_CUDA(cudaMemcpy(hp.data(), h->dev.rowptr, hp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    return qb_csr_upload(hv.data(), hc.data(), hp.data(), h->dev.nrows, h->dev.ncols, (int64_t)nnz, format, out);
 }

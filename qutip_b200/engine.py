@@ -223,6 +223,13 @@ class DeviceOp(_Handle):
                                                n, len(c_ops), float(tol), fmt, C.byref(h)))
         return cls(h, (n * n, n * n))
 
+    def convert(self, fmt):
+        """A CSR-format operator in another device format (``FMT_DIAM``: converted on the
+        device; the others pass through the host analysers)."""
+        h = C.c_void_p()
+        check(_lib.load().qb_op_convert(self.handle, int(fmt), C.byref(h)))
+        return type(self)(h, self.shape)
+
     def to_scipy(self):
         """Copy a CSR-format operator back to the host (scipy.sparse.csr_matrix)."""
         import scipy.sparse as sp

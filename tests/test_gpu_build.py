@@ -123,3 +123,43 @@ def test_c2_liouvillian_full_size_on_device():
     assert np.abs(got.data - want.data).max() <= 1e-14 * np.abs(want.data).max()
     print("C2 Liouvillian assembly: device %.3f s, host (scipy kron/add) %.3f s" % (t_dev, t_host))
     assert t_dev < t_host
+
+
+@pytest.mark.parametrize("n,density", [(7, 0.5), (32, 0.2), (100, 0.05), (257, 0.02)])
+def test_csr_to_diam_on_device_matches_host_analyser(n, density):
+    rng = np.random.default_rng(n)
+    m = _rand_sparse(rng, n, density) + sp.diags(rng.standard_normal(n) + 0j, 0) \
+        + sp.diags(rng.standard_normal(n - 3) + 0j, 3)
+    m = sp.csr_matrix(m)
+    m.sum_duplicates(); m.sort_indices()
+    host = qb.DeviceOp.from_scipy(m, qb.FMT_DIAM)
+    dev = qb.DeviceOp.from_scipy(m, qb.FMT_CSR).convert(qb.FMT_DIAM)
+    hi, di = host.info(), dev.info()
+    assert di["format"] == "diam" and di["nnz"] == hi["nnz"] == m.nnz
+    assert abs(di["device_bytes"] - hi["device_bytes"]) <= 16
+    x = rng.standard_normal((n, 3)) + 1j * rng.standard_normal((n, 3))
+    dx = qb.DeviceDense.from_numpy(np.asfortranarray(x))
+    yh = E.matmul(host, dx).to_numpy()
+    yd = E.matmul(dev, dx).to_numpy()
+    assert np.array_equal(yh, yd)                       # same entries in the same order: bit-equal
+    np.testing.assert_allclose(yd, m @ x, rtol=1e-13, atol=1e-13)
+    # through the host analysers: RSELL / SELL / auto
+    for fmt in (qb.FMT_SELL, qb.FMT_RSELL, qb.FMT_AUTO):
+        y = E.matmul(qb.DeviceOp.from_scipy(m, qb.FMT_CSR).convert(fmt), dx).to_numpy()
+        np.testing.assert_allclose(y, m @ x, rtol=1e-13, atol=1e-13)
+    with pytest.raises(qb.QbError):
+        host.convert(qb.FMT_CSR)
+
+
+def test_c2_liouvillian_device_build_to_diam_never_visits_host():
+    H, c_ops, _ = models.tfim(8)
+    want = models.liouvillian(H, c_ops)
+    want.eliminate_zeros()
+    op = qb.DeviceOp.liouvillian(H, c_ops, qb.FMT_DIAM)
+    assert op.info()["format"] == "diam" and op.info()["nnz"] == want.nnz
+    N = want.shape[0]
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    y = E.matmul(op, qb.DeviceDense.from_numpy(x)).to_numpy().ravel()
+    ref = want @ x
+    assert np.abs(y - ref).max() < 1e-13 * np.abs(ref).max()
