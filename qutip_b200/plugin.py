@@ -850,6 +850,13 @@ def register():
         solver.add_integrator(B200Adams, "b200_adams")
         solver.add_integrator(B200Zvode, "b200_zvode")
     _qparallel._maps["b200"] = b200_map
+    import os
+    if os.environ.get("QUTIP_B200_DEFAULT_MAP") == "1":
+        # acceptance runs of the reference's own mcsolve tests: every MCSolver / nm_mcsolve
+        # call that does not name a map takes the device map
+        from qutip.solver.nm_mcsolve import NonMarkovianMCSolver
+        for cls in (MCSolver, NonMarkovianMCSolver):
+            cls.solver_options = dict(cls.solver_options, map="b200")
     _registered = True
 
 
@@ -1012,25 +1019,31 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
     method = _device_method(opts["method"])
     rhs = solver.rhs
     e_dict = e_ops if isinstance(e_ops, dict) else dict(enumerate(e_ops or []))
-    for k, e in e_dict.items():
-        if not isinstance(e, (qutip.Qobj, QobjEvo)):
-            raise TypeError("e_ops must be Qobj / QobjEvo for the 'b200' map (python callables "
-                            "cannot run on the device)")
+    # python-callable e_ops f(t, state) (solver/result.py:29-77) cannot run on the device: the
+    # trajectories' states are brought back and the callables evaluated on them, the operator
+    # e_ops stay device-side expectation passes
+    host_keys = [k for k, e in e_dict.items() if not isinstance(e, (qutip.Qobj, QobjEvo))]
+    for k in host_keys:
+        if not callable(e_dict[k]):
+            raise TypeError("e_ops must be Qobj, QobjEvo or callables f(t, state)")
+    dev_dict = {k: e for k, e in e_dict.items() if k not in host_keys}
+    dev_index = {k: m for m, k in enumerate(dev_dict)}
     issuper = bool(rhs.rhs.issuper)
-    if issuper and any(not isinstance(e, qutip.Qobj) for e in e_dict.values()):
+    if issuper and any(not isinstance(e, qutip.Qobj) for e in dev_dict.values()):
         raise TypeError("time-dependent e_ops are not combined with a superoperator Hamiltonian in "
                         "the 'b200' map")
     want_states = bool(opts["store_states"]) or (opts["store_states"] is None and not e_dict)
     want_final = bool(opts["store_final_state"])
+    need_states = want_states or bool(host_keys)
     if issuper:
         # the trajectories evolve the column-stacked rho (mcsolve.py:481-490): tr(E rho) is the
         # linear functional sum_r vec(E^T)[r] rho[r] (core/data/expect.pyx:146-158)
-        if any(not e.isoper for e in e_dict.values()):
+        if any(not e.isoper for e in dev_dict.values()):
             raise TypeError("e_ops must be operators for a superoperator Hamiltonian in the 'b200' map")
         e_evos = [QobjEvo(qutip.Qobj(sp.csr_matrix(solve.trace_functional(e.full()))))
-                  for e in e_dict.values()]
+                  for e in dev_dict.values()]
     else:
-        e_evos = [QobjEvo(e) if isinstance(e, qutip.Qobj) else e for e in e_dict.values()]
+        e_evos = [QobjEvo(e) if isinstance(e, qutip.Qobj) else e for e in dev_dict.values()]
     iopt = solver._integrator._integrator.options
     psi0 = _data.to(_data.Dense, state0).to_array().reshape(-1, order="F")
     tlist = np.asarray(tlist, dtype=float)
@@ -1040,7 +1053,7 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
     draws = np.stack([g.random(ndraws) for g in gens])
     devices = _map_devices()
     multi = devices is not None and len(devices) > 1 and ntraj >= 2 * len(devices)
-    store = int(want_states or want_final)
+    store = int(need_states or want_final)
 
     def fingerprint():
         """identity of everything the device system is built from; the objects are kept alive
@@ -1050,7 +1063,7 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
         for q in [rhs.rhs] + list(rhs.c_ops) + list(rhs.n_ops):
             for el in q.to_list():
                 objs.extend(el if isinstance(el, (list, tuple)) else [el])
-        objs.extend(e_dict.values())
+        objs.extend(dev_dict.values())
         return tuple(id(o) for o in objs), objs
 
     opt_key = (method, floor, store, tuple(sorted((k, repr(v)) for k, v in iopt.items())),
@@ -1127,9 +1140,9 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
         if errors:
             raise errors[0]
         live = [q for q in parts if q is not None]
-        if e_dict:
+        if dev_dict:
             sums = comm.reduce_expect([None if q is None else q.engine for q in parts],
-                                      len(e_dict), len(tlist))
+                                      len(dev_dict), len(tlist))
         comm.free()
         width = max(q.col_t.shape[1] for q in live)
 
@@ -1148,18 +1161,24 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
         if st == -10:
             raise RuntimeError(E.STATUS_MESSAGES[-10])
         raise IntegratorException(E.STATUS_MESSAGES.get(st, "integration failed"))
-    herm = [bool(e.isherm) if isinstance(e, qutip.Qobj) else False for e in e_dict.values()]
+    herm = [bool(e.isherm) if isinstance(e, qutip.Qobj) else False for e in dev_dict.values()]
     w_traj = (1 - floor) * weight                                        # mcsolve.py:565
 
     def make_result(j):
         res = solver._trajectory_resultclass(e_dict, solver.options)
         res.times = list(tlist)
-        for m, k in enumerate(res.e_data):
-            vals = r.expect[j, m]
-            res.e_data[k].extend((vals.real if herm[m] else vals).tolist())
-        if want_states or want_final:
+        qs = None
+        if need_states or want_final:
             qs = [solver._restore_state(_data.Dense(r.states[j, i].reshape(-1, 1)), copy=False)
-                  for i in (range(len(tlist)) if want_states else [len(tlist) - 1])]
+                  for i in (range(len(tlist)) if need_states else [len(tlist) - 1])]
+        for k in res.e_data:
+            if k in dev_index:
+                m = dev_index[k]
+                vals = r.expect[j, m]
+                res.e_data[k].extend((vals.real if herm[m] else vals).tolist())
+            else:                                   # callable e_op on the downloaded states
+                res.e_data[k].extend([e_dict[k](t, q) for t, q in zip(tlist, qs)])
+        if want_states or want_final:
             if want_states:
                 res.states = qs
             res._final_state = qs[-1]
@@ -1177,7 +1196,7 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
     first = 0
     martingale = getattr(solver, "_martingale", None)
     target = getattr(reduce_func, "__self__", None)
-    if _bulk_feed_ok(target, want_states, want_final) and ntraj > 1:
+    if _bulk_feed_ok(target, need_states, want_final) and ntraj > 1:
         # averages only: trajectory 0 goes through McResult.add (it sizes the accumulators),
         # the others are added to the running sums in bulk -- what _TrajectorySum.reduce_expect
         # (multitrajresult.py:1116-1124) and _McBaseResult._add_collapse do one by one
@@ -1192,7 +1211,7 @@ def _b200_batch(solver, state0, tlist, e_ops, seeds, floor, weight, reduce_func,
             target.seeds.extend(seeds[sel])
             target._trajectories_weight_info.extend([w_traj] * room)
             target.num_trajectories += room
-            for m in range(len(e_dict)):
+            for m in range(len(dev_dict)):
                 vals = r.expect[sel, m]
                 vals = vals.real if herm[m] else vals
                 if sums is not None and room == ntraj - 1 and not np.iscomplexobj(vals):

@@ -32,3 +32,24 @@ def test_reference_solver_tests_with_b200_methods():
     assert m and int(m.group(1)) >= 30, out[-2000:]
     unexpected = [f for f in failed if "TDDecay[func-" not in f]
     assert not unexpected, unexpected
+
+
+def test_reference_mcsolve_tests_with_b200_as_default_map():
+    """The reference's own mcsolve and nm_mcsolve test files with `map="b200"` as the DEFAULT map
+    (QUTIP_B200_DEFAULT_MAP=1): every MCSolver / NonMarkovianMCSolver run of those tests that does
+    not name a map goes through the device batches -- seeds, collapse records, photocurrent,
+    improved sampling, mixed states, callable e_ops, target tolerances, timeouts, states.
+    The only tolerated failures use a python-function rate (`coefficient(rate_function)`), which
+    the batched map rejects with TypeError by design (no host evaluation inside a device batch)."""
+    ref = oracle.ref_path()
+    if ref is None:
+        pytest.skip("reference build not present")
+    env = dict(os.environ, PYTHONPATH=ref + os.pathsep + ROOT, QUTIP_B200_DEFAULT_MAP="1", OMP_NUM_THREADS="1")
+    files = [os.path.join(ref, "qutip", "tests", "solver", f) for f in ("test_mcsolve.py", "test_nm_mcsolve.py")]
+    out = subprocess.run([sys.executable, "-m", "pytest", "-p", "qutip_b200.plugin", "-q", "-p", "no:cacheprovider"]
+                         + files, env=env, capture_output=True, text=True, timeout=1500).stdout
+    failed = re.findall(r"^FAILED (\S+)", out, flags=re.M)
+    m = re.search(r"(\d+) passed", out)
+    assert m and int(m.group(1)) >= 240, out[-2000:]
+    unexpected = [f for f in failed if "test_nm_mcsolve.py::test_mixed_equals_merged" not in f]
+    assert not unexpected, unexpected
