@@ -57,13 +57,15 @@ SYMBOLS = [
 ]
 
 _lib = None
+_load_pid = None
 
 
 def load():
     """Load the shared library (no CUDA call is made by loading)."""
-    global _lib
+    global _lib, _load_pid
     if _lib is not None:
         return _lib
+    _load_pid = os.getpid()
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             "qutip_b200: %s is missing. Build it with `python -c \"import __graft_entry__ as g; "
@@ -156,7 +158,12 @@ def load():
 
 def check(rc):
     if rc != 0:
-        raise QbError(rc, load().qb_last_error().decode("utf-8", "replace"))
+        msg = load().qb_last_error().decode("utf-8", "replace")
+        if _load_pid is not None and os.getpid() != _load_pid and "initialization error" in msg:
+            msg += (" -- this process was forked after CUDA had been initialised in its parent and CUDA "
+                    "contexts do not survive fork(): use the 'spawn' start method for process maps, or "
+                    "options={'map': 'serial'} / {'map': 'b200'}")
+        raise QbError(rc, msg)
 
 
 def ptr(a):

@@ -53,3 +53,27 @@ def test_reference_mcsolve_tests_with_b200_as_default_map():
     assert m and int(m.group(1)) >= 240, out[-2000:]
     unexpected = [f for f in failed if "test_nm_mcsolve.py::test_mixed_equals_merged" not in f]
     assert not unexpected, unexpected
+
+
+def test_reference_solver_tests_with_b200_vern7_as_default_method():
+    """The reference's mesolve / sesolve / propagator test files with `b200_vern7` as THE default
+    method of MESolver / SESolver / MCSolver (QUTIP_B200_DEFAULT_METHOD): every solver call of
+    those tests that does not name a method integrates on the device.  Deselected by name are the
+    forms DESIGN.md declares host-only -- operator-valued python functions (`func` ids, the
+    piecewise propagator tests' `H_func`) and feedback arguments -- which raise TypeError by
+    design.  The full run over six test files (tools/ref_suite_b200_method.sh) is recorded in
+    DESIGN.md section 4."""
+    ref = oracle.ref_path()
+    if ref is None:
+        pytest.skip("reference build not present")
+    env = dict(os.environ, PYTHONPATH=ref + os.pathsep + ROOT, QUTIP_B200_DEFAULT_METHOD="b200_vern7",
+               OMP_NUM_THREADS="1")
+    files = [os.path.join(ref, "qutip", "tests", "solver", f)
+             for f in ("test_mesolve.py", "test_sesolve.py", "test_propagator.py")]
+    out = subprocess.run([sys.executable, "-m", "pytest", "-p", "qutip_b200.plugin", "-q", "-p", "no:cacheprovider",
+                          "-k", "not func and not feedback and not Piecewise"] + files,
+                         env=env, capture_output=True, text=True, timeout=1500).stdout
+    failed = re.findall(r"^FAILED (\S+)", out, flags=re.M)
+    m = re.search(r"(\d+) passed", out)
+    assert m and int(m.group(1)) >= 150, out[-2000:]
+    assert not failed, failed
