@@ -703,3 +703,37 @@ def test_nm_mcsolve_b200_map_matches_reference(rate, tight):
     np.testing.assert_allclose(np.array(out.average_expect), np.array(ref.average_expect), rtol=e_rtol, atol=e_atol)
     np.testing.assert_allclose(np.array(out.average_trace), np.array(ref.average_trace),
                                rtol=1e-9 if tight else 1e-6, atol=1e-12)
+
+
+def test_heom_and_bloch_redfield_solvers_reuse_the_device_integrators():
+    """Solver subclasses outside mesolve/mcsolve whose right-hand side is a constant QobjEvo --
+    HEOMSolver's hierarchy generator (solver/heom/bofin_solvers.py:699-703, 929-940: one large
+    sparse matrix acting on the stacked ADOs) and BRSolver's Bloch-Redfield tensor
+    (solver/brmesolve.py:323-333) -- resolve `b200_*` through Solver.avail_integrators and run
+    the same QobjEvo.matmul_data hot path on the device."""
+    from qutip.solver.heom import DrudeLorentzBath, HEOMSolver
+    H = 0.5 * sigmaz() + 0.25 * sigmax()
+    bath = DrudeLorentzBath(sigmaz(), lam=0.05, gamma=0.5, T=1.0, Nk=2)
+    rho0 = basis(2, 0) * basis(2, 0).dag()
+    tl = np.linspace(0, 5, 21)
+    res = {}
+    for m in ("vern7", "b200_vern7", "b200_adams"):
+        o = dict(OPT, method=m, store_states=True)
+        if "adams" not in m:
+            o.update(atol=1e-10, rtol=1e-8)
+        res[m] = HEOMSolver(H, bath, max_depth=4, options=o).run(rho0, tl, e_ops=[sigmaz(), sigmax()])
+    np.testing.assert_allclose(np.array(res["b200_vern7"].expect), np.array(res["vern7"].expect),
+                               rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(res["b200_vern7"].states[-1].full(), res["vern7"].states[-1].full(),
+                               rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(np.array(res["b200_adams"].expect), np.array(res["vern7"].expect),
+                               rtol=1e-4, atol=1e-5)
+    from qutip import brmesolve
+    a = destroy(6)
+    Hb = a.dag() * a + 0.1 * (a + a.dag())
+    a_ops = [(a + a.dag(), "0.05 * (w > 0)")]
+    psi0 = basis(6, 3)
+    tlb = np.linspace(0, 4, 17)
+    ref = brmesolve(Hb, psi0, tlb, a_ops, e_ops=[a.dag() * a], options=dict(OPT, method="vern7"))
+    out = brmesolve(Hb, psi0, tlb, a_ops, e_ops=[a.dag() * a], options=dict(OPT, method="b200_vern7"))
+    np.testing.assert_allclose(out.expect[0], ref.expect[0], rtol=RTOL, atol=ATOL)
