@@ -277,6 +277,11 @@ __device__ __forceinline__ void qb_rowdot_rsell_tile(const QbTileElem& A, const 
 #pragma unroll
     for (int j = 0; j < RB; j++) sa[j] = (unsigned)(r[j] - lo) * 16u;
     int k = 0;
+#ifdef QB_XSHFL
+    double2 own[RB];
+#pragma unroll
+    for (int j = 0; j < RB; j++) own[j] = nxor > 0 ? qb_lds128(sxa + sa[j]) : make_double2(0.0, 0.0);
+#endif
     auto xslot = [&](int kk, double2 (&a)[RB]) {
         int delta;
         double2 cv, xv[RB];
@@ -285,6 +290,15 @@ __device__ __forceinline__ void qb_rowdot_rsell_tile(const QbTileElem& A, const 
             delta = __ldg(&dsc[kk].delta);
             cv = __ldg(reinterpret_cast<const double2*>(dsc + kk) + 1);
         }
+#ifdef QB_XSHFL     // partner rows inside the warp's own 32 rows: warp shuffles instead of gathers
+        if (delta < 32) {
+#pragma unroll
+            for (int j = 0; j < RB; j++) {
+                xv[j].x = __shfl_xor_sync(0xffffffffu, own[j].x, delta);
+                xv[j].y = __shfl_xor_sync(0xffffffffu, own[j].y, delta);
+            }
+        } else
+#endif
         if (delta < tnom) {        // tnom: nominal (power-of-two) tile rows
 #pragma unroll
             for (int j = 0; j < RB; j++) xv[j] = qb_lds128(sxa + (sa[j] ^ ((unsigned)delta << 4)));

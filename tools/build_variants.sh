@@ -8,7 +8,7 @@ while [ $# -ge 2 ]; do
   (
     d=$(mktemp -d)
     F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2,-pthread $flags"
-    for f in qb_ops qb_engine qb_dense qb_comm; do $NVCC $F -c $f.cu -o $d/$f.o & done
+    for f in qb_ops qb_engine qb_dense qb_comm qb_build; do $NVCC $F -c $f.cu -o $d/$f.o & done
     wait
     $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../lib_$name.so $d/*.o -lcudart -ldl
     rm -rf $d; echo "built lib_$name.so"
