@@ -848,11 +848,18 @@ def register():
     _data.trace_oper_ket.add_specialisations([(B200Dense, _trace_oper_ket_dense)])
     _data.inner.add_specialisations([(B200Dense, B200Dense, _inner_dense)])
 
-    # the base class too: every Solver subclass whose right-hand side is a QobjEvo (HEOMSolver's
-    # hierarchy generator, BRSolver's constant Bloch-Redfield tensor, FMESolver ...) resolves the
-    # device methods through Solver.avail_integrators (solver_base.py:462-470)
-    from qutip.solver.solver_base import Solver as _SolverBase
-    for solver in (_SolverBase, MESolver, SESolver, MCSolver):
+    # also the other Solver subclasses whose right-hand side is a QobjEvo: HEOMSolver's hierarchy
+    # generator, BRSolver's constant Bloch-Redfield tensor, FMESolver.  (Not the Solver base class:
+    # its integrators must accept arbitrary python callables, tests/solver/test_integrator.py.)
+    solvers = [MESolver, SESolver, MCSolver]
+    try:
+        from qutip.solver.brmesolve import BRSolver
+        from qutip.solver.floquet import FMESolver
+        from qutip.solver.heom.bofin_solvers import HEOMSolver
+        solvers += [BRSolver, FMESolver, HEOMSolver]
+    except ImportError:                                   # pragma: no cover
+        pass
+    for solver in solvers:
         solver.add_integrator(B200Vern7, "b200_vern7")
         solver.add_integrator(B200Vern9, "b200_vern9")
         solver.add_integrator(B200Tsit5, "b200_tsit5")

@@ -709,7 +709,7 @@ def test_heom_and_bloch_redfield_solvers_reuse_the_device_integrators():
     """Solver subclasses outside mesolve/mcsolve whose right-hand side is a constant QobjEvo --
     HEOMSolver's hierarchy generator (solver/heom/bofin_solvers.py:699-703, 929-940: one large
     sparse matrix acting on the stacked ADOs) and BRSolver's Bloch-Redfield tensor
-    (solver/brmesolve.py:323-333) -- resolve `b200_*` through Solver.avail_integrators and run
+    (solver/brmesolve.py:323-333) -- have `b200_*` registered (`add_integrator`) and run
     the same QobjEvo.matmul_data hot path on the device."""
     from qutip.solver.heom import DrudeLorentzBath, HEOMSolver
     H = 0.5 * sigmaz() + 0.25 * sigmax()
