@@ -23,11 +23,13 @@
   (pure and mixed initial states, improved sampling).
 
 Anything that cannot run on the device (python-function coefficients or operators,
-feedback arguments, non-Qobj e_ops in the batched map) raises ``TypeError`` naming the
-stock method to use instead -- there is no CPU fallback in this package.
+feedback arguments) raises ``TypeError`` naming the stock method to use instead -- there is no
+CPU fallback in this package.  Python-callable ``e_ops`` in the batched map are evaluated by
+the host on the trajectories' downloaded states (they are host code by definition).
 """
 import os
 import threading
+import warnings
 
 import numpy as np
 import scipy.sparse as sp
@@ -913,11 +915,17 @@ def b200_map(task, values, task_args=None, task_kwargs=None, reduce_func=None, m
     name = getattr(inner, "__name__", "")
     # NonMarkovianMCSolver (solver/nm_mcsolve.py): the same trajectories with rate-shifted collapse
     # operators; the influence martingale of a trajectory depends only on its collapse record
-    # and is attached to the results afterwards (_b200_batch).  Other subclasses override the
-    # trajectory function and run through their own code, one trajectory at a time.
+    # and is attached to the results afterwards (_b200_batch), for pure and mixed initial states
+    # (_run_one_traj_mixed only picks the state and multiplies the weight, mcsolve.py:752-792).
+    # Other subclasses override the trajectory function and run through their own code, one
+    # trajectory at a time, with a RuntimeWarning.
     from qutip.solver.nm_mcsolve import NonMarkovianMCSolver
-    batched = type(solver) is MCSolver or (type(solver) is NonMarkovianMCSolver and name == "_run_one_traj")
+    batched = type(solver) in (MCSolver, NonMarkovianMCSolver)
     if not batched or name not in ("_run_one_traj", "_run_one_traj_mixed"):
+        if name.startswith("_run_one_traj"):
+            warnings.warn("the 'b200' map batches MCSolver / NonMarkovianMCSolver trajectories on the device; "
+                          "%s.%s is run one trajectory at a time through the solver's own code"
+                          % (type(solver).__name__, name), RuntimeWarning, stacklevel=2)
         results = []
         for v in values:
             out = task(v, *task_args, **task_kwargs)

@@ -737,3 +737,27 @@ def test_heom_and_bloch_redfield_solvers_reuse_the_device_integrators():
     ref = brmesolve(Hb, psi0, tlb, a_ops, e_ops=[a.dag() * a], options=dict(OPT, method="vern7"))
     out = brmesolve(Hb, psi0, tlb, a_ops, e_ops=[a.dag() * a], options=dict(OPT, method="b200_vern7"))
     np.testing.assert_allclose(out.expect[0], ref.expect[0], rtol=RTOL, atol=ATOL)
+
+
+def test_nm_mcsolve_mixed_initial_states_b200_map():
+    """NonMarkovianMCSolver with a mixed initial state (solver/multitraj.py:285-352 picks the
+    state per trajectory, nm_mcsolve.py:562-570 adds the martingale): batched on the device per
+    initial state, identical to the reference run with the same seeds."""
+    from qutip import NonMarkovianMCSolver, coefficient, sigmap
+    H = 0.5 * sigmaz() + 0.2 * sigmax()
+    ops_and_rates = [(sigmam(), coefficient("-0.08 + 0.05*sin(2*t)")), (sigmap(), 0.15)]
+    ics = [(basis(2, 1), 0.25), ((basis(2, 1) + basis(2, 0)).unit(), 0.75)]
+    tl = np.linspace(0, 3, 13)
+    res = {}
+    for mp in ("serial", "b200"):
+        o = dict(OPT, method="vern7", map=mp, keep_runs_results=True)
+        solver = NonMarkovianMCSolver(H, ops_and_rates, options=o)
+        res[mp] = solver.run(ics, tl, [6, 18], e_ops=[sigmaz(), sigmax()], seeds=np.random.SeedSequence(11))
+    ref, out = res["serial"], res["b200"]
+    assert [list(w) for w in out.col_which] == [list(w) for w in ref.col_which]
+    assert sum(len(w) for w in ref.col_which) > 3
+    for a, b in zip(out.col_times, ref.col_times):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(np.array(out.runs_trace), np.array(ref.runs_trace), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(np.array(out.average_expect), np.array(ref.average_expect), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(np.array(out.average_trace), np.array(ref.average_trace), rtol=1e-9, atol=1e-12)
