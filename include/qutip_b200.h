@@ -83,6 +83,11 @@ int qb_sandwich_upload(const void* data, const int32_t* col, const int32_t* rowp
 int qb_liouvillian_build(const void* a_data, const int32_t* a_col, const int32_t* a_rowptr, int64_t a_nnz,
                          const void* c_data, const int32_t* c_col, const int32_t* c_rowptr, int64_t c_nnz,
                          int64_t n, int64_t nstack, double tol, int format, qb_handle* out);
+/* Kronecker product A (x) B of two CSR matrices assembled on the device (core/data/kron.pyx,
+ * kron_csr): one warp per output row; canonical CSR when A and B are.  format as above. */
+int qb_kron_build(const void* a_data, const int32_t* a_col, const int32_t* a_rowptr, int64_t a_rows,
+                  int64_t a_cols, const void* b_data, const int32_t* b_col, const int32_t* b_rowptr,
+                  int64_t b_rows, int64_t b_cols, int format, qb_handle* out);
 /* Format conversion of a CSR-format operator (the `_data.to(Dia, CSR)` family of
  * core/data/convert.pyx:208-329, csr.pyx:710, dia.pyx:364): format 2 (diagonal-masked slices)
  * is produced on the device -- one warp per 32-row slice merges its rows by diagonal offset;

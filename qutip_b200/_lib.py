@@ -40,7 +40,7 @@ SYMBOLS = [
     "qb_version", "qb_last_error", "qb_device_count", "qb_set_device", "qb_synchronize",
     "qb_launch_count", "qb_device_mem_info",
     "qb_dense_upload", "qb_dense_zeros", "qb_dense_download", "qb_dense_write", "qb_dense_copy", "qb_dense_reshape", "qb_dense_info",
-    "qb_csr_upload", "qb_dia_upload", "qb_kron_upload", "qb_sandwich_upload", "qb_liouvillian_build", "qb_op_csr_download", "qb_op_convert",
+    "qb_csr_upload", "qb_dia_upload", "qb_kron_upload", "qb_sandwich_upload", "qb_liouvillian_build", "qb_op_csr_download", "qb_op_convert", "qb_kron_build",
     "qb_op_info", "qb_free",
     "qb_matmul", "qb_axpy", "qb_scal", "qb_copy", "qb_zero", "qb_nrm2", "qb_wrms_error",
     "qb_inner", "qb_expect_ket", "qb_expect_dm", "qb_expect_super", "qb_trace_oper_ket",
@@ -90,6 +90,7 @@ def load():
         "qb_liouvillian_build": [vp, vp, vp, i64, vp, vp, vp, i64, i64, i64, dbl, i32, pp],
         "qb_op_csr_download": [vp, vp, vp, vp],
         "qb_op_convert": [vp, i32, pp],
+        "qb_kron_build": [vp, vp, vp, i64, i64, vp, vp, vp, i64, i64, i32, pp],
         "qb_op_info": [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
                        C.POINTER(i64)],
         "qb_free": [vp],

@@ -146,6 +146,42 @@ __global__ void qb_diam_slices_kernel(const int* __restrict__ rowptr, const int*
     if (!FILL && lane == 0) { ent_cnt[sl] = ne; val_cnt[sl] = nv; }
 }
 
+
+// ---- Kronecker product C = A (x) B in canonical CSR (core/data/kron.pyx: kron_csr): row
+// ia * rowsB + ib holds nnzA(ia) * nnzB(ib) entries, column ca * colsB + cb, value a * b --
+// sorted and duplicate-free when A and B are.  One warp per output row.
+__global__ void qb_kron_rowptr_kernel(const int* __restrict__ ap, const int* __restrict__ bp,
+                                      long long rows, int rows_b, long long* __restrict__ cnt) {
+    const long long R = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (R >= rows) return;
+    const int ia = (int)(R / rows_b), ib = (int)(R % rows_b);
+    cnt[R] = (long long)(ap[ia + 1] - ap[ia]) * (bp[ib + 1] - bp[ib]);
+}
+__global__ void qb_kron_fill_kernel(const double2* __restrict__ av, const int* __restrict__ ac,
+                                    const int* __restrict__ ap, const double2* __restrict__ bv,
+                                    const int* __restrict__ bc, const int* __restrict__ bp,
+                                    long long rows, int rows_b, int cols_b,
+                                    const long long* __restrict__ off, int* __restrict__ rowptr,
+                                    int* __restrict__ col, double2* __restrict__ val) {
+    const long long R = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (R > rows) return;
+    if (R == rows) { if (lane == 0) rowptr[rows] = (int)off[rows]; return; }
+    const int ia = (int)(R / rows_b), ib = (int)(R % rows_b);
+    const int a0 = ap[ia], na = ap[ia + 1] - a0, b0 = bp[ib], nb = bp[ib + 1] - b0;
+    const long long o = off[R];
+    if (lane == 0) rowptr[R] = (int)o;
+    const int m = na * nb;
+    for (int i = lane; i < m; i += 32) {
+        const int pa = a0 + i / nb, pb = b0 + i % nb;
+        const double2 a = av[pa], b = bv[pb];
+        col[o + i] = ac[pa] * cols_b + bc[pb];
+        // unfused products, as the reference's scalar C multiply (no FMA contraction): bit-equal
+        val[o + i] = make_double2(__dsub_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)),
+                                  __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
+    }
+}
+
 struct DevBuf {
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -357,4 +393,66 @@ extern "C" int qb_op_convert(qb_handle hh, int format, qb_handle* out) {
     }
     QB_CUDA(cudaMemcpy(hp.data(), h->dev.rowptr, hp.size() * sizeof(int), cudaMemcpyDeviceToHost));
     return qb_csr_upload(hv.data(), hc.data(), hp.data(), h->dev.nrows, h->dev.ncols, (int64_t)nnz, format, out);
+}
+
+// Kronecker product of two CSR matrices, assembled on the device (core/data/kron.pyx kron_csr;
+// format as qb_csr_upload: 1 keeps the device CSR, 2 converts on the device, others via the host).
+extern "C" int qb_kron_build(const void* a_data, const int32_t* a_col, const int32_t* a_rowptr,
+                             int64_t a_rows, int64_t a_cols, const void* b_data, const int32_t* b_col,
+                             const int32_t* b_rowptr, int64_t b_rows, int64_t b_cols, int format,
+                             qb_handle* out) {
+    if (!out || !a_rowptr || !b_rowptr || a_rows < 0 || a_cols < 0 || b_rows < 0 || b_cols < 0)
+        QB_FAIL(QB_E_ARG, "bad Kronecker product arguments");
+    if (format != 0 && format != 1 && format != 2 && format != 3 && format != 5)
+        QB_FAIL(QB_E_ARG, "unknown operator format %d", format);
+    const int64_t a_nnz = a_rowptr[a_rows], b_nnz = b_rowptr[b_rows];
+    if ((a_nnz > 0 && (!a_data || !a_col)) || (b_nnz > 0 && (!b_data || !b_col)))
+        QB_FAIL(QB_E_ARG, "bad Kronecker product arguments");
+    const long long rows = (long long)a_rows * b_rows, cols = (long long)a_cols * b_cols;
+    const long long nnz = (long long)a_nnz * b_nnz;
+    if (rows > 0x7ffffffeLL || cols > 0x7fffffffLL || nnz > 0x7fffffffLL)
+        QB_FAIL(QB_E_ARG, "Kronecker product too large for int32 indices");
+    int rc;
+    if ((rc = check_csr(a_col, a_rowptr, a_rows, a_cols, a_nnz, "A")) ||
+        (rc = check_csr(b_col, b_rowptr, b_rows, b_cols, b_nnz, "B"))) return rc;
+    DevBuf av, ac, ap, bv, bc, bp, cnt, off, tmp, rowptr, col, val;
+    if ((rc = upload(av, static_cast<const double2*>(a_data), (size_t)a_nnz)) ||
+        (rc = upload(ac, a_col, (size_t)a_nnz)) || (rc = upload(ap, a_rowptr, (size_t)a_rows + 1)) ||
+        (rc = upload(bv, static_cast<const double2*>(b_data), (size_t)b_nnz)) ||
+        (rc = upload(bc, b_col, (size_t)b_nnz)) || (rc = upload(bp, b_rowptr, (size_t)b_rows + 1)))
+        return rc;
+    QB_CUDA(cudaMalloc(&cnt.p, (size_t)(rows + 1) * sizeof(long long)));
+    QB_CUDA(cudaMalloc(&off.p, (size_t)(rows + 1) * sizeof(long long)));
+    QB_CUDA(cudaMemset(cnt.p, 0, (size_t)(rows + 1) * sizeof(long long)));
+    if (rows > 0 && b_rows > 0) {
+        qb_kron_rowptr_kernel<<<(unsigned)((rows + 255) / 256), 256>>>(ap.as<int>(), bp.as<int>(), rows,
+                                                                      (int)b_rows, cnt.as<long long>());
+        QB_LAUNCH_CHECK();
+    }
+    size_t tb = 0;
+    QB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.as<long long>(), off.as<long long>(), rows + 1));
+    QB_CUDA(cudaMalloc(&tmp.p, std::max<size_t>(16, tb)));
+    QB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.as<long long>(), off.as<long long>(), rows + 1));
+    g_qb_launches++;
+    QB_CUDA(cudaMalloc(&rowptr.p, (size_t)(rows + 1) * sizeof(int)));
+    QB_CUDA(cudaMalloc(&col.p, std::max<size_t>(16, (size_t)nnz * sizeof(int))));
+    QB_CUDA(cudaMalloc(&val.p, std::max<size_t>(16, (size_t)nnz * sizeof(double2))));
+    qb_kron_fill_kernel<<<(unsigned)(((rows + 1) * 32 + 255) / 256), 256>>>(
+        av.as<double2>(), ac.as<int>(), ap.as<int>(), bv.as<double2>(), bc.as<int>(), bp.as<int>(), rows,
+        (int)std::max<int64_t>(1, b_rows), (int)b_cols, off.as<long long>(), rowptr.as<int>(), col.as<int>(),
+        val.as<double2>());
+    QB_LAUNCH_CHECK();
+    QB_CUDA(cudaDeviceSynchronize());
+    if (format == 2)
+        return qb_diam_from_device_csr(val.as<double2>(), col.as<int>(), rowptr.as<int>(), rows, cols, nnz, out);
+    QbOpH* h = new QbOpH();
+    h->dev.fmt = QB_FMT_CSR; h->dev.nrows = (int)rows; h->dev.ncols = (int)cols; h->dev.nnz = nnz;
+    h->dev.val = val.as<qb_c128>(); h->dev.col = col.as<int>(); h->dev.rowptr = rowptr.as<int>();
+    h->owned = {val.p, col.p, rowptr.p};
+    h->device_bytes = (int64_t)nnz * 20 + (rows + 1) * 4;
+    val.p = col.p = rowptr.p = nullptr;
+    if (format == 1) { *out = h; return QB_OK; }
+    rc = qb_op_convert(h, format, out);
+    delete h;
+    return rc;
 }

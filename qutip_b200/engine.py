@@ -223,6 +223,23 @@ class DeviceOp(_Handle):
                                                n, len(c_ops), float(tol), fmt, C.byref(h)))
         return cls(h, (n * n, n * n))
 
+    @classmethod
+    def kron_product(cls, a, b, fmt=FMT_CSR):
+        """``kron(a, b)`` (core/data/kron.pyx) of two sparse matrices assembled on the device;
+        ``fmt=FMT_CSR`` / ``FMT_DIAM`` never visit the host."""
+        import scipy.sparse as sp
+        mats = []
+        for m in (a, b):
+            m = sp.csr_matrix(m, dtype=np.complex128)
+            m.sum_duplicates()
+            m.sort_indices()
+            mats.append((as_c128(m.data), m.indices.astype(np.int32), m.indptr.astype(np.int32), m.shape))
+        (ad, ac, ap, ash), (bd, bc, bp, bsh) = mats
+        h = C.c_void_p()
+        check(_lib.load().qb_kron_build(ptr(ad), ptr(ac), ptr(ap), ash[0], ash[1], ptr(bd), ptr(bc), ptr(bp),
+                                        bsh[0], bsh[1], int(fmt), C.byref(h)))
+        return cls(h, (ash[0] * bsh[0], ash[1] * bsh[1]))
+
     def convert(self, fmt):
         """A CSR-format operator in another device format (``FMT_DIAM``: converted on the
         device; the others pass through the host analysers)."""

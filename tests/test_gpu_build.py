@@ -2,12 +2,14 @@
 construction: qutip.liouvillian (core/superoperator.py:116-142) where the reference build
 travels with the repo, the scipy restatement in qutip_b200.models otherwise -- structure
 (canonical CSR, same pattern) and values."""
+import sys
 import time
 
 import numpy as np
 import pytest
 import scipy.sparse as sp
 
+import oracle
 import qutip_b200 as qb
 from qutip_b200 import engine as E, models
 
@@ -72,8 +74,6 @@ def test_liouvillian_dissipator_only_and_errors():
 
 
 def test_liouvillian_against_reference_constructor():
-    import sys
-    import oracle
     ref = oracle.ref_path()
     if ref is None:
         pytest.skip("reference build (oracle/_ref) not present")
@@ -163,3 +163,43 @@ def test_c2_liouvillian_device_build_to_diam_never_visits_host():
     y = E.matmul(op, qb.DeviceDense.from_numpy(x)).to_numpy().ravel()
     ref = want @ x
     assert np.abs(y - ref).max() < 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("sa,sb", [((3, 4), (5, 2)), ((1, 1), (7, 7)), ((6, 6), (1, 3)), ((40, 33), (9, 20))])
+def test_kron_product_on_device(sa, sb):
+    rng = np.random.default_rng(sa[0] * 100 + sb[0])
+
+    def rnd(shape):
+        m = sp.random(shape[0], shape[1], density=0.3, format="csr", dtype=float,
+                      random_state=np.random.RandomState(int(rng.integers(1 << 30)))).astype(complex)
+        m.data = m.data + 1j * rng.standard_normal(m.nnz)
+        return sp.csr_matrix(m)
+
+    a, b = rnd(sa), rnd(sb)
+    want = sp.kron(a, b, format="csr")
+    want.sum_duplicates(); want.sort_indices()
+    got = qb.DeviceOp.kron_product(a, b).to_scipy()
+    assert got.shape == want.shape and got.nnz == want.nnz
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    np.testing.assert_allclose(got.data, want.data, rtol=4e-16, atol=0)
+    ref = oracle.ref_path()
+    if ref is not None:                                  # the reference's own kron_csr: bit-equal
+        if ref not in sys.path:
+            sys.path.insert(0, ref)
+        from qutip.core import data as _data
+        q = _data.kron(_data.CSR(a), _data.CSR(b)).as_scipy()
+        q.sort_indices()
+        assert np.array_equal(q.indices, got.indices) and np.array_equal(q.data, got.data)
+    if min(want.shape) >= 1 and want.shape[0] == want.shape[1]:
+        x = rng.standard_normal(want.shape[1]) + 0j
+        y = E.matmul(qb.DeviceOp.kron_product(a, b, qb.FMT_DIAM), qb.DeviceDense.from_numpy(x)).to_numpy().ravel()
+        np.testing.assert_allclose(y, want @ x, rtol=1e-13, atol=1e-13)
+
+
+def test_kron_product_empty_and_errors():
+    z = sp.csr_matrix((4, 4), dtype=complex)
+    got = qb.DeviceOp.kron_product(z, sp.identity(3, dtype=complex, format="csr")).to_scipy()
+    assert got.shape == (12, 12) and got.nnz == 0
+    with pytest.raises(qb.QbError):
+        qb.DeviceOp.kron_product(sp.identity(70000, dtype=complex, format="csr"),
+                                 sp.identity(70000, dtype=complex, format="csr"))
