@@ -18,6 +18,7 @@
 #include "qb_host.h"
 #include "qb_kernels.cuh"
 #include "qb_tableaux.h"
+#include <cooperative_groups.h>
 
 // the tableaux (and the generated Adams coefficient table) live in constant memory: the controller's single active lane reads them
 // through the constant cache instead of serial global loads
@@ -92,6 +93,10 @@ __device__ __forceinline__ const double2* qb_vsrc(const QbEngineDev* E, int slot
 #ifndef QB_MINB
 #define QB_MINB 4
 #endif
+#define QB_RED_CTAS 32
+#ifndef QB_COOP_MAX_SLOTS
+#define QB_COOP_MAX_SLOTS 63     // the cooperative form serves runs below the compaction threshold
+#endif
 #define QB_SH_MAXW 40   // widest SELL slice the shared kernel stages (40*32*20 B = 25.6 KB)
 #ifndef QB_SH_T
 #define QB_SH_T 4       // consecutive slices one CTA of the shared kernel walks through
@@ -135,6 +140,7 @@ __device__ __forceinline__ void qb_load_hdr(const QbEngineDev* __restrict__ E, i
 // latency overlaps it; partial reductions go to partials[slot][slice][k].
 // sval/scol != nullptr: the slice of the (single, SELL) RHS operator is staged in shared
 // memory by the caller and shared by the CTA's warps (= 8 trajectories).
+template <bool COH = false>
 __device__ __forceinline__ void qb_pass_one_slice(
     const QbEngineDev* __restrict__ E, int slot, int sl, int lane, const QbWarpHdr& h,
     const double2* __restrict__ sval, const int* __restrict__ scol, int sw)
@@ -159,7 +165,7 @@ __device__ __forceinline__ void qb_pass_one_slice(
         double2 xr = make_double2(0.0, 0.0);
         if (active) xr = x[r];
         for (int m = 0; m < nops; m++) {
-            const double2 q = qb_rowdot<QB_UP>(ops[op_lo + m], sl, lane, r, active, x);
+            const double2 q = qb_rowdot<QB_UP, COH>(ops[op_lo + m], sl, lane, r, active, x);
             double2 pr;
             if (functional) pr = q;
             else if (trn) pr = (r % (trn + 1) == 0) ? q : make_double2(0.0, 0.0);
@@ -210,13 +216,13 @@ __device__ __forceinline__ void qb_pass_one_slice(
             z.y = c.re * q.y + c.im * q.x;
         } else
         for (int e = 0; e < nelem; e++) {
-            const double2 q = qb_rowdot<QB_UP>(E->elem[e], sl, lane, r, active, x);
+            const double2 q = qb_rowdot<QB_UP, COH>(E->elem[e], sl, lane, r, active, x);
             const qb_c128 c = cf[e];
             z.x += c.re * q.x - c.im * q.y;
             z.y += c.re * q.y + c.im * q.x;
         }
     } else if (kind == QB_PASS_APPLY) {
-        const double2 q = qb_rowdot<QB_UP>(E->cops[gp->op_lo], sl, lane, r, active, QB_VS(h.xslot));
+        const double2 q = qb_rowdot<QB_UP, COH>(E->cops[gp->op_lo], sl, lane, r, active, QB_VS(h.xslot));
         const qb_c128 c = E->coef[(size_t)slot * E->ctl.maxcoef];
         z = make_double2(c.re * q.x - c.im * q.y, c.re * q.y + c.im * q.x);
     }
@@ -418,12 +424,13 @@ __device__ __forceinline__ void qb_pass_slice_hot_multi(const QbEngineDev* __res
     }
 }
 
+template <bool COH = false>
 static __device__ __noinline__ void qb_pass_slice_generic(const QbEngineDev* E, int slot, int sl,
                                                           int lane)
 {
     QbWarpHdr h;
     qb_load_hdr(E, slot, lane, h);
-    qb_pass_one_slice(E, slot, sl, lane, h, nullptr, nullptr, 0);
+    qb_pass_one_slice<COH>(E, slot, sl, lane, h, nullptr, nullptr, 0);
 }
 
 #ifndef QB_G
@@ -517,25 +524,33 @@ struct QbTileArgs {
     int* work;                  // persistent mode: next (slot, tile) work item
     const int* act_list;        // compacted list of the slots with a pass this round (qb_compact_kernel)
     const int* act_count;
+    int* coop_rounds;           // cooperative form: rounds executed (added up by block 0)
     int N, V, nslices, red_stride, nelem, maxcoef, mc_trace, tpad_;
     double atol, rtol;
     QbTileElem elem[QB_MAX_ELEMS];
 };
 
-template <bool CD>
+// COOP: the cooperative multi-round form for systems in few slots (a single mesolve, a handful
+// of trajectories): ONE launch runs up to max_rounds rounds of (pass, partial sums, controller)
+// separated by grid barriers instead of three kernel launches per round.  Correct (the engine
+// tests pass with it) but not faster -- see qb_drive; opt-in only.  State written in one phase is read in the next by other
+// SMs: no non-coherent (ld.global.nc) loads of mutable data in this instantiation.
+__device__ void qb_control_slot_coop(QbEngineDev* E, int slot, int lane, double* sred_row);
+__device__ void qb_partials_reduce_coop(const QbEngineDev* E, int b);
+
+template <bool CD, bool COOP>
 __global__ void __launch_bounds__(256, QB_TT_MINB)
 qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trows, int nsb, int persist,
-                    const __grid_constant__ QbTileArgs ta, const __grid_constant__ QbConstDesc cd)
+                    const __grid_constant__ QbTileArgs ta, const __grid_constant__ QbConstDesc cd,
+                    int max_rounds)
 {
     extern __shared__ __align__(128) unsigned char qb_tile_smem[];
     __shared__ __align__(8) unsigned long long mbar;          // x tile
     __shared__ __align__(8) unsigned long long wbar[8];       // per warp: staged epilogue sources
     __shared__ int s_work;
+    __shared__ double s_red[COOP ? 8 : 1][QB_MAXRED];
     const int N = ta.N;
     const int ntiles = (N + trows - 1) / trows;
-    // only the slots that have a pass this round are visited (their list is compacted by
-    // qb_compact_kernel after the controller): finished trajectories cost nothing in the tail
-    const int total = min(*ta.act_count, nslots_used) * ntiles;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     // shared-window addresses, computed ONCE (volatile: the compiler would otherwise re-derive
     // them from SR_CgaCtaId in front of every LDS to save a register)
@@ -553,6 +568,11 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
     }
     const bool pow2 = (trows & (trows - 1)) == 0;       // tiles are aligned power-of-two blocks
     unsigned parity = 0, xparity = 0;
+    int round = 0;
+    for (;; round++) {                            // one iteration unless COOP
+    // only the slots that have a pass this round are visited (their list is compacted by
+    // qb_compact_kernel after the controller): finished trajectories cost nothing in the tail
+    const int total = min(*ta.act_count, nslots_used) * ntiles;
     // persist: the grid is one wave of CTAs that draw (slot, tile) work items from a counter
     // (reset by the control kernel) -- no CTA launch / barrier set-up per tile
     for (bool first = true;; first = false) {
@@ -571,7 +591,7 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
     const int rows = min(trows, N - lo);
     const int sl0 = lo >> 5, sl1 = (lo + rows + 31) >> 5;
     if (kind != QB_PASS_RHS && kind != QB_PASS_COMBINE) {             // EXPECT / APPLY: rare
-        for (int sl = sl0 + warp; sl < sl1; sl += nw) qb_pass_slice_generic(E, slot, sl, lane);
+        for (int sl = sl0 + warp; sl < sl1; sl += nw) qb_pass_slice_generic<COOP>(E, slot, sl, lane);
         continue;
     }
     const int vbase = slot * ta.V;
@@ -583,6 +603,7 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
         if (threadIdx.x == 0) {
             const unsigned bytes = (unsigned)rows * 16u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier reads of the tile are done
+            if (COOP) asm volatile("fence.proxy.async.global;" ::: "memory");   // x was written in this launch
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          :: "r"(sxa), "l"(gx + lo), "r"(bytes), "r"(bar) : "memory");
@@ -620,6 +641,7 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
             }
             __syncwarp();
             if (lane < nb) {
+                if (COOP) asm volatile("fence.proxy.async.global;" ::: "memory");   // sources were written in this launch
                 const int s = gp->sw[lane].src;
                 const double2* p = (s >= 0 ? ta.pool + (long long)(vbase + s) * N : initp) + r0;
 #ifdef QB_SRC_EVICT_FIRST
@@ -653,15 +675,15 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
                 double2 q[2];
                 if (hasb && sa.x == sb.x && sa.y == sb.y) {
                     const int vb[2] = {sa.z, sb.z}, cb[2] = {sa.w, sb.w};
-                    qb_rowdot_rsell_tile<2, CD>(A, cdp, sa.x, sa.y, vb, cb, r, lane, gx, sxa, lo, rows, trows, pow2, q);
+                    qb_rowdot_rsell_tile<2, CD, COOP>(A, cdp, sa.x, sa.y, vb, cb, r, lane, gx, sxa, lo, rows, trows, pow2, q);
                 } else {
                     double2 q1[1];
                     const int va[1] = {sa.z}, ca[1] = {sa.w}, ra[1] = {r[0]};
-                    qb_rowdot_rsell_tile<1, CD>(A, cdp, sa.x, sa.y, va, ca, ra, lane, gx, sxa, lo, rows, trows, pow2, q1);
+                    qb_rowdot_rsell_tile<1, CD, COOP>(A, cdp, sa.x, sa.y, va, ca, ra, lane, gx, sxa, lo, rows, trows, pow2, q1);
                     q[0] = q1[0]; q[1] = make_double2(0.0, 0.0);
                     if (hasb) {
                         const int vb1[1] = {sb.z}, cb1[1] = {sb.w}, rb1[1] = {r[1]};
-                        qb_rowdot_rsell_tile<1, CD>(A, cdp, sb.x, sb.y, vb1, cb1, rb1, lane, gx, sxa, lo, rows, trows, pow2, q1);
+                        qb_rowdot_rsell_tile<1, CD, COOP>(A, cdp, sb.x, sb.y, vb1, cb1, rb1, lane, gx, sxa, lo, rows, trows, pow2, q1);
                         q[1] = q1[0];
                     }
                 }
@@ -755,6 +777,23 @@ qb_pass_tile_kernel(const QbEngineDev* __restrict__ E, int nslots_used, int trow
     }
     if (kind == QB_PASS_RHS) xparity ^= 1u;       // the x-tile barrier completed one more phase
     }   // work loop
+    if (!COOP) break;
+    // ---- the rest of the round: partial sums, controller, each behind a grid barrier
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    grid.sync();
+    QbEngineDev* Ew = const_cast<QbEngineDev*>(E);
+    if (Ew->red_final) {
+        for (int b = blockIdx.x; b < nslots_used * QB_RED_CTAS; b += gridDim.x) qb_partials_reduce_coop(E, b);
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ta.work = 0;
+    for (int slot = blockIdx.x * nw + warp; slot < nslots_used; slot += gridDim.x * nw)
+        qb_control_slot_coop(Ew, slot, lane, s_red[COOP ? warp : 0]);
+    grid.sync();
+    if (*reinterpret_cast<volatile int*>(Ew->n_active) <= 0 || round + 1 >= max_rounds) break;
+    }   // rounds
+    // (every CTA leaves the loop in the same round)
+    if (COOP && blockIdx.x == 0 && threadIdx.x == 0 && ta.coop_rounds) *ta.coop_rounds += round + 1;
 }
 
 // LINMAP passes (Adams prediction / update): V[dst[j]] = sum_k w[j][k] V[src[k]] for up to 14
@@ -871,35 +910,40 @@ qb_pass_kernel_shared(const QbEngineDev* __restrict__ E)
 // Large systems (N/32 > 2048 slices): QB_RED_CTAS CTAs per slot sum the per-warp partials in
 // a fixed order (the control kernel's warp then adds the QB_RED_CTAS sub-sums), so that the
 // control kernel's single warp does not walk tens of thousands of partials serially.
-#define QB_RED_CTAS 32
-__global__ void __launch_bounds__(256)
-qb_partials_reduce_kernel(const QbEngineDev* __restrict__ E)
+
+__device__ __forceinline__ void qb_partials_reduce_body(const QbEngineDev* __restrict__ E, int b)
 {
-    const int slot = blockIdx.x / QB_RED_CTAS, c = blockIdx.x - slot * QB_RED_CTAS;
+    const int slot = b / QB_RED_CTAS, c = b - slot * QB_RED_CTAS;
     const QbPass* gp = &E->pass[slot];
     const int kind = gp->kind;
     int nred = 0;
     if (kind == QB_PASS_EXPECT) nred = 2 * (gp->op_hi - gp->op_lo);
     else if (kind != QB_PASS_NONE && gp->red) nred = E->ctl.mc_trace ? 5 : 3;
-    if (nred == 0) return;
-    __shared__ double sh[8];
+    if (nred == 0) return;                           // CTA-uniform
+    __shared__ double sh[32];
     const int nslices = E->nslices, stride = E->red_stride;
     const int chunk = (nslices + QB_RED_CTAS - 1) / QB_RED_CTAS;
     const int i0 = c * chunk, i1 = min(nslices, i0 + chunk);
-    const double* __restrict__ part = E->partials + (size_t)slot * nslices * stride;
+    const double* part = E->partials + (size_t)slot * nslices * stride;
+    const int nthr = (int)blockDim.x, nwarps = nthr >> 5;
     for (int k = 0; k < nred; k++) {
         double s = 0.0;
-        for (int i = i0 + threadIdx.x; i < i1; i += 256) s += part[(size_t)i * stride + k];
+        for (int i = i0 + threadIdx.x; i < i1; i += nthr) s += part[(size_t)i * stride + k];
         s = qb_warp_sum(s);
         if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
         __syncthreads();
         if (threadIdx.x == 0) {
             double t = 0.0;
-            for (int w = 0; w < 8; w++) t += sh[w];
+            for (int w = 0; w < nwarps; w++) t += sh[w];
             E->red_final[((size_t)slot * QB_RED_CTAS + c) * QB_MAXRED + k] = t;
         }
         __syncthreads();
     }
+}
+__global__ void __launch_bounds__(256)
+qb_partials_reduce_kernel(const QbEngineDev* __restrict__ E)
+{
+    qb_partials_reduce_body(E, (int)blockIdx.x);
 }
 
 // ------------------------------------------------------------------ control kernel
@@ -943,65 +987,18 @@ qb_compact_kernel(QbEngineDev* __restrict__ E, int nslots_used)
     if (threadIdx.x == 1023) *E->act_count = s_cnt[1023];
 }
 
-// BIG (systems with more than 2048 slices): one CTA of 1024 threads per slot sums the slot's
-// partials cooperatively in a fixed order before thread 0 runs the controller -- one launch
-// instead of qb_partials_reduce_kernel + a single-warp controller.
-template <bool BIG>
-__global__ void __launch_bounds__(BIG ? 1024 : 128)
-qb_control_kernel(QbEngineDev* __restrict__ E)
+// the scalar part of a round for one slot: consume the reduced partials, advance the state
+// machine until it issues the next pass (or retires / refills the slot)
+__device__ __forceinline__ void qb_control_advance(QbEngineDev* __restrict__ E, int slot, double* sred_row)
 {
-    const int slot = BIG ? (int)blockIdx.x : (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31, w = BIG ? 0 : (int)(threadIdx.x >> 5);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && E->work) *E->work = 0;
-    if (slot >= E->nslots) return;
     QbTraj* gc = &E->traj[slot];
-    if (gc->pc == QB_PC_IDLE) return;
     QbPass* gp = &E->pass[slot];
-    __shared__ double sred[4][QB_MAXRED];
-    __shared__ double swarp[BIG ? 32 : 1];
-
-    const int kind = gp->kind;
-    int nred = 0;
-    if (kind == QB_PASS_EXPECT) nred = 2 * (gp->op_hi - gp->op_lo);
-    else if (kind != QB_PASS_NONE && gp->red) nred = E->ctl.mc_trace ? 5 : 3;
-    const int nslices = E->nslices, stride = E->red_stride;
-    const double* __restrict__ part = E->partials + (size_t)slot * nslices * stride;
-    if (BIG) {
-        for (int k = 0; k < nred; k++) {
-            double s = 0.0;
-            for (int i = threadIdx.x; i < nslices; i += 1024) s += part[(size_t)i * stride + k];
-            s = qb_warp_sum(s);
-            if (lane == 0) swarp[BIG ? (threadIdx.x >> 5) : 0] = s;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double t = 0.0;
-                for (int q = 0; q < 32; q++) t += swarp[BIG ? q : 0];
-                sred[0][k] = t;
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x != 0) return;
-    } else if (E->red_final) {
-        for (int k = 0; k < nred; k++) {      // lane c holds CTA c's sub-sum
-            double sv = E->red_final[((size_t)slot * QB_RED_CTAS + lane) * QB_MAXRED + k];
-            sv = qb_warp_sum(sv);
-            if (lane == 0) sred[w][k] = sv;
-        }
-    } else
-    for (int k = 0; k < nred; k++) {
-        double s = 0.0;
-        for (int i = lane; i < nslices; i += 32) s += part[(size_t)i * stride + k];
-        s = qb_warp_sum(s);
-        if (lane == 0) sred[w][k] = s;
-    }
-    if (!BIG) { __syncwarp(); if (lane != 0) return; }
-
     QbTraj c = *gc;
     QbPass p;
     qb_c128* coef = E->coef + (size_t)slot * E->ctl.maxcoef;
     double* probs = E->probs + (size_t)slot * (E->ctl.ncops > 0 ? E->ctl.ncops : 1);
     for (;;) {
-        const int issued = qb_advance(E->ctl, c_tabs[E->tableau_id], c, p, sred[w], coef, probs,
+        const int issued = qb_advance(E->ctl, c_tabs[E->tableau_id], c, p, sred_row, coef, probs,
                                       &E->linmap[slot]);
         if (issued) {
             c.n_pass++;
@@ -1033,6 +1030,86 @@ qb_control_kernel(QbEngineDev* __restrict__ E)
         E->zcols[slot] = zrow;
         E->xcols[slot] = (p.kind == QB_PASS_RHS) ? qb_vsrc(E, slot, p.x, c.init_idx) : zrow;
     }
+}
+
+// BIG (systems with more than 2048 slices): one CTA of 1024 threads per slot sums the slot's
+// partials cooperatively in a fixed order before thread 0 runs the controller -- one launch
+// instead of qb_partials_reduce_kernel + a single-warp controller.
+// one warp = one slot: sum the slot's partials (or the pre-reduced sub-sums) in a fixed order,
+// then lane 0 runs the controller
+__device__ __forceinline__ void qb_control_slot_warp(QbEngineDev* __restrict__ E, int slot, int lane,
+                                                     double* sred_row)
+{
+    if (E->traj[slot].pc == QB_PC_IDLE) return;
+    const QbPass* gp = &E->pass[slot];
+    const int kind = gp->kind;
+    int nred = 0;
+    if (kind == QB_PASS_EXPECT) nred = 2 * (gp->op_hi - gp->op_lo);
+    else if (kind != QB_PASS_NONE && gp->red) nred = E->ctl.mc_trace ? 5 : 3;
+    const int nslices = E->nslices, stride = E->red_stride;
+    const double* part = E->partials + (size_t)slot * nslices * stride;
+    if (E->red_final) {
+        for (int k = 0; k < nred; k++) {      // lane c holds CTA c's sub-sum
+            double sv = E->red_final[((size_t)slot * QB_RED_CTAS + lane) * QB_MAXRED + k];
+            sv = qb_warp_sum(sv);
+            if (lane == 0) sred_row[k] = sv;
+        }
+    } else
+    for (int k = 0; k < nred; k++) {
+        double s = 0.0;
+        for (int i = lane; i < nslices; i += 32) s += part[(size_t)i * stride + k];
+        s = qb_warp_sum(s);
+        if (lane == 0) sred_row[k] = s;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    qb_control_advance(E, slot, sred_row);
+}
+
+__device__ __noinline__ void qb_control_slot_coop(QbEngineDev* E, int slot, int lane, double* sred_row)
+{
+    qb_control_slot_warp(E, slot, lane, sred_row);
+}
+__device__ __noinline__ void qb_partials_reduce_coop(const QbEngineDev* E, int b)
+{
+    qb_partials_reduce_body(E, b);
+}
+
+template <bool BIG>
+__global__ void __launch_bounds__(BIG ? 1024 : 128)
+qb_control_kernel(QbEngineDev* __restrict__ E)
+{
+    const int slot = BIG ? (int)blockIdx.x : (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, w = BIG ? 0 : (int)(threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && E->work) *E->work = 0;
+    if (slot >= E->nslots) return;
+    __shared__ double sred[4][QB_MAXRED];
+    __shared__ double swarp[BIG ? 32 : 1];
+    if (!BIG) { qb_control_slot_warp(E, slot, lane, sred[w]); return; }
+    QbTraj* gc = &E->traj[slot];
+    if (gc->pc == QB_PC_IDLE) return;
+    QbPass* gp = &E->pass[slot];
+    const int kind = gp->kind;
+    int nred = 0;
+    if (kind == QB_PASS_EXPECT) nred = 2 * (gp->op_hi - gp->op_lo);
+    else if (kind != QB_PASS_NONE && gp->red) nred = E->ctl.mc_trace ? 5 : 3;
+    const int nslices = E->nslices, stride = E->red_stride;
+    const double* __restrict__ part = E->partials + (size_t)slot * nslices * stride;
+    for (int k = 0; k < nred; k++) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nslices; i += 1024) s += part[(size_t)i * stride + k];
+        s = qb_warp_sum(s);
+        if (lane == 0) swarp[BIG ? (threadIdx.x >> 5) : 0] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int q = 0; q < 32; q++) t += swarp[BIG ? q : 0];
+            sred[0][k] = t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    qb_control_advance(E, slot, sred[0]);
 }
 
 // one RHS evaluation on plain device vectors (micro-benchmark / data-layer matmul of a
@@ -1100,6 +1177,7 @@ struct QbEngH : QbObj {
     int tile_g = 0, tile_rows = 0, tile_xw = 0, tile_ns = 0, tile_threads = 256;   // TMA-staged kernel (tile_g == 0: off)
     size_t tile_smem = 0;
     int tile_persist = 0;        // CTAs per SM of the persistent grid (0: one CTA per tile)
+    int coop_occ = 0;            // CTAs per SM of the cooperative multi-round form (0: unavailable)
     int act_identity = 0;        // act_list currently holds the identity list of this many slots
     QbConstDesc cdesc;          // descriptor lists in the constant bank (n == 0: read from global memory)
     QbTileArgs targs;
@@ -1375,8 +1453,10 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         nsb = std::max(0, std::min(nsb, QB_MAXSRC));
         e->tile_g = 1; e->tile_rows = rows; e->tile_threads = thr; e->tile_ns = nsb;
         e->tile_smem = (size_t)rows * 16 + (size_t)(thr / 32) * nsb * 1024;
-        cudaError_t ce = cudaFuncSetAttribute(qb_pass_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qb_pass_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
+        cudaError_t ce = cudaFuncSetAttribute(qb_pass_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qb_pass_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qb_pass_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qb_pass_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
         if (ce != cudaSuccess) { delete e; QB_FAIL(QB_E_CUDA, "tile kernel shared memory: %s", cudaGetErrorString(ce)); }
         memset(&e->targs, 0, sizeof e->targs);
         e->targs.pool = h.pool; e->targs.pass = h.pass; e->targs.coef = h.coef; e->targs.partials = h.partials;
@@ -1398,9 +1478,21 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         if (e->tile_persist < 0) {
             int occ = 0;
             cudaError_t co = (total <= QB_CD_MAX && !getenv("QB_NO_CDESC"))
-                ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qb_pass_tile_kernel<true>, e->tile_threads, e->tile_smem)
-                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qb_pass_tile_kernel<false>, e->tile_threads, e->tile_smem);
+                ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qb_pass_tile_kernel<true, false>, e->tile_threads, e->tile_smem)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qb_pass_tile_kernel<false, false>, e->tile_threads, e->tile_smem);
             e->tile_persist = (co == cudaSuccess && occ > 0) ? occ : 0;
+        }
+        {   // cooperative multi-round form: its grid must be co-resident
+            int occ = 0, dev = 0, coop_ok = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev);
+            cudaError_t co = (total <= QB_CD_MAX && !getenv("QB_NO_CDESC"))
+                ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qb_pass_tile_kernel<true, true>, e->tile_threads, e->tile_smem)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qb_pass_tile_kernel<false, true>, e->tile_threads, e->tile_smem);
+            e->coop_occ = (co == cudaSuccess && coop_ok && !getenv("QB_NO_COOP")) ? occ : 0;
+            if (e->coop_occ > 0) {
+                if (qb_dev_alloc(e, 1, &e->targs.coop_rounds)) e->coop_occ = 0;
+            }
         }
         if (total <= QB_CD_MAX && !getenv("QB_NO_CDESC")) {
             int off = 0;
@@ -1500,11 +1592,11 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
                 grid = std::min<unsigned>(grid, (unsigned)(sms * e->tile_persist));
             }
             if (e->cdesc.n > 0)
-                qb_pass_tile_kernel<true><<<grid, e->tile_threads, e->tile_smem, e->stream>>>(
-                    e->d, nslots_used, e->tile_rows, e->tile_ns, e->tile_persist > 0, e->targs, e->cdesc);
+                qb_pass_tile_kernel<true, false><<<grid, e->tile_threads, e->tile_smem, e->stream>>>(
+                    e->d, nslots_used, e->tile_rows, e->tile_ns, e->tile_persist > 0, e->targs, e->cdesc, 1);
             else
-                qb_pass_tile_kernel<false><<<grid, e->tile_threads, e->tile_smem, e->stream>>>(
-                    e->d, nslots_used, e->tile_rows, e->tile_ns, e->tile_persist > 0, e->targs, e->cdesc);
+                qb_pass_tile_kernel<false, false><<<grid, e->tile_threads, e->tile_smem, e->stream>>>(
+                    e->d, nslots_used, e->tile_rows, e->tile_ns, e->tile_persist > 0, e->targs, e->cdesc, 1);
         }
         else if (use_shared) qb_pass_kernel_shared<<<(unsigned)grid_sh, QB_TILE_ROWS, 0, e->stream>>>(e->d);
         else qb_pass_kernel<<<(unsigned)grid1, QB_TILE_ROWS, 0, e->stream>>>(e->d, nslots_used);
@@ -1540,6 +1632,47 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
             e->prof_vec_host = nullptr; e->prof_vec_cap = 0;
         }
     }
+    // few slots of an all-RSELL system: the cooperative multi-round kernel -- one launch runs
+    // rounds (pass, partial sums, controller) behind grid barriers until every slot has retired,
+    // for batched runs and for the Integrator protocol alike (no idle rounds, no host polling)
+    // Measured (tools/coop_ab.sh, tools/plugin_c1.py) and left OFF: a grid barrier among tens to
+    // hundreds of CTAs costs as much as a kernel boundary inside a CUDA graph -- C4 (57 tiles)
+    // 58.5 -> 71.8 ms, C2 (4096 tiles) 8.9 k -> 6.8 k RHS evaluations/s -- and for a one-CTA grid
+    // (C1, N = 400) the plug-in wall time is unchanged within noise (13.9-14.0 ms either way: the
+    // round is bound by its dependent loads, not by the launches).  QB_COOP_MAX_CTAS=n enables it
+    // for grids of up to n CTAs.
+    const int coop_nt = e->tile_g ? (e->h.ctl.N + e->tile_rows - 1) / e->tile_rows : 0;
+    static const int coop_max_ctas = getenv("QB_COOP_MAX_CTAS") ? atoi(getenv("QB_COOP_MAX_CTAS")) : 0;
+    const bool coop = e->tile_g && e->coop_occ > 0 && !compact && !e->profiling && !e->h.linmap &&
+                      !e->h.zbuf && !big_control && nslots_used <= QB_COOP_MAX_SLOTS &&
+                      (long long)nslots_used * coop_nt <= coop_max_ctas;
+    if (coop) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int nt = coop_nt;
+        unsigned grid = (unsigned)std::min<long long>((long long)nslots_used * nt, (long long)sms * e->coop_occ);
+        grid = std::max(grid, 1u);
+        QB_CUDA(cudaMemsetAsync(e->targs.coop_rounds, 0, sizeof(int), e->stream));
+        for (;;) {
+            const QbEngineDev* dE = e->d;
+            int a_slots = nslots_used, a_rows = e->tile_rows, a_nsb = e->tile_ns, a_persist = 1, a_max = 4096;
+            void* args[] = {(void*)&dE, (void*)&a_slots, (void*)&a_rows, (void*)&a_nsb, (void*)&a_persist,
+                            (void*)&e->targs, (void*)&e->cdesc, (void*)&a_max};
+            const void* fn = e->cdesc.n > 0 ? (const void*)qb_pass_tile_kernel<true, true>
+                                            : (const void*)qb_pass_tile_kernel<false, true>;
+            QB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(e->tile_threads), args, e->tile_smem, e->stream));
+            g_qb_launches++;
+            QB_CUDA(cudaMemcpyAsync(e->h_active, e->h.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+            QB_CUDA(cudaStreamSynchronize(e->stream));
+            if (*e->h_active <= 0) break;
+            if (rounds > 2000000000LL) QB_FAIL(QB_E_STATE, "engine did not terminate");
+            rounds += a_max;
+        }
+        int done = 0;
+        QB_CUDA(cudaMemcpy(&done, e->targs.coop_rounds, sizeof(int), cudaMemcpyDeviceToHost));
+        rounds = done;
+    } else
     if (e->profiling || short_call) {
         // plain launches, one host look at the counter per chunk.  Used for per-pass
         // CUDA-event timing and for the Integrator protocol (qb_integ_*), whose calls often

@@ -197,9 +197,21 @@ __device__ __forceinline__ double2 qb_lds128(unsigned addr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
+// COH: x is re-written by other SMs while this kernel runs (the cooperative multi-round kernel),
+// so its gathers must not take the non-coherent (ld.global.nc) path; every out-of-tile row is
+// gathered by exactly one lane per slot, so bypassing L1 (ld.global.cg) costs no reuse
+template <bool COH>
+__device__ __forceinline__ double2 qb_ldx(const double2* p) {
+    if (COH) {
+        double2 v;
+        asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+        return v;
+    }
+    return __ldg(p);
+}
 // generic form (stand-alone kernels, rare passes): (A x)[r] for the lane's row r of slice sl,
 // descriptors and x from global memory
-template <int U = QB_RS_U>
+template <int U = QB_RS_U, bool COH = false>
 __device__ __forceinline__ double2 qb_rowdot_rsell(const QbOpDev& A, int sl, int lane, int r,
                                                    const double2* __restrict__ x)
 {
@@ -224,14 +236,14 @@ __device__ __forceinline__ double2 qb_rowdot_rsell(const QbOpDev& A, int sl, int
 #pragma unroll
         for (int u = 0; u < U; u++) slot(k + u, cc[u], vv[u]);
 #pragma unroll
-        for (int u = 0; u < U; u++) xx[u] = __ldg(x + cc[u]);
+        for (int u = 0; u < U; u++) xx[u] = qb_ldx<COH>(x + cc[u]);
 #pragma unroll
         for (int u = 0; u < U; u++) qb_fma(acc, vv[u], xx[u]);
     }
     for (; k < s1; k++) {
         int c; double2 v;
         slot(k, c, v);
-        qb_fma(acc, v, __ldg(x + c));
+        qb_fma(acc, v, qb_ldx<COH>(x + c));
     }
     return acc;
 }
@@ -243,7 +255,7 @@ __device__ __forceinline__ double2 qb_rowdot_rsell(const QbOpDev& A, int sl, int
 // that window are gathered with conflict-free LDS.128 (no L1 tag stage / replays), the
 // others from global memory.
 struct QbTileElem { const int* sinfo; const qb_c128* val; const int* col; const QbSlotDesc* sdesc; };
-template <int RB, bool CD>
+template <int RB, bool CD, bool COH = false>
 __device__ __forceinline__ void qb_rowdot_rsell_tile(const QbTileElem& A, const QbSlotDesc* __restrict__ cdesc,
                                                      int dstart, int dcount, const int (&vb)[RB],
                                                      const int (&cb)[RB], const int (&r)[RB], int lane,
@@ -268,7 +280,7 @@ __device__ __forceinline__ void qb_rowdot_rsell_tile(const QbTileElem& A, const 
     auto gather = [&](int c) -> double2 {
         const unsigned o = (unsigned)(c - lo);
         if (o < (unsigned)trows) return qb_lds128(sxa + o * 16u);
-        return __ldg(x + c);
+        return qb_ldx<COH>(x + c);
     };
     // xor slots with a constant value on a power-of-two tile: the partner row is at the own
     // tile offset ^ (delta * 16) when delta < tile rows (warp-uniform branch), else in global
@@ -304,7 +316,7 @@ __device__ __forceinline__ void qb_rowdot_rsell_tile(const QbTileElem& A, const 
             for (int j = 0; j < RB; j++) xv[j] = qb_lds128(sxa + (sa[j] ^ ((unsigned)delta << 4)));
         } else {
 #pragma unroll
-            for (int j = 0; j < RB; j++) xv[j] = __ldg(x + (r[j] ^ delta));
+            for (int j = 0; j < RB; j++) xv[j] = qb_ldx<COH>(x + (r[j] ^ delta));
         }
 #pragma unroll
         for (int j = 0; j < RB; j++) qb_fma(a[j], cv, xv[j]);
@@ -363,7 +375,7 @@ __device__ __forceinline__ void qb_rowdot_rsell_tile(const QbTileElem& A, const 
 }
 
 // (A x)[r] for the lane's row r of slice sl, any format.  `active` lanes have r < nrows.
-template <int U = QB_U1>
+template <int U = QB_U1, bool COH = false>
 __device__ __forceinline__ double2 qb_rowdot(const QbOpDev& A, int sl, int lane, long long r,
                                              bool active, const double2* __restrict__ x)
 {
@@ -396,7 +408,7 @@ __device__ __forceinline__ double2 qb_rowdot(const QbOpDev& A, int sl, int lane,
     } else if (A.fmt == QB_FMT_KRON) {
         acc = qb_rowdot_kron(A, sl, lane, r, active, x);
     } else if (A.fmt == QB_FMT_RSELL) {
-        acc = qb_rowdot_rsell(A, sl, lane, (int)r, x);
+        acc = qb_rowdot_rsell<QB_RS_U, COH>(A, sl, lane, (int)r, x);
     } else {
         if (active) {
             const double2* __restrict__ a = reinterpret_cast<const double2*>(A.dense) + r;
