@@ -182,9 +182,24 @@ extern "C" int qb_csr_upload(const void* data, const int32_t* col, const int32_t
         if (col[p] < 0 || col[p] >= cols) QB_FAIL(QB_E_ARG, "column index out of range");
     QbOpH* h = new QbOpH();
     int rc = QB_OK;
+    auto row_fn = [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o) {
+        for (int p = rowptr[r]; p < rowptr[r + 1]; p++) o.push_back({col[p], v[p]});
+    };
+    // a large operator (an HBM stream) can neither be SELL nor needs the DIAM analysis when the
+    // rule compression already wins against DIAM's lower bound of 16 B per non-zero: the three
+    // analysers each walk all non-zeros, so skipping two of them halves the conversion time of
+    // e.g. the C2 Liouvillian.  The decisions are the same as with all three built.
+    const bool big = (long long)nnz * 20 > QB_SELL_MAX_BYTES;
+    RsellHost rs;
+    bool use_rsell = (format == 5), rsell_built = false;
+    if (format == 0 && big && nnz > 0 && rows >= 32) {
+        build_rsell(rows, cols, row_fn, rs);
+        rsell_built = true;
+        use_rsell = want_rsell(rs, rows, false, 0, (long long)nnz * 16);
+    }
     bool use_diam = (format == 2);
     DiamHost dh;
-    if (format != 1) {
+    if (format != 1 && !use_rsell && format != 5 && format != 3) {
         build_diam(rows, [&](int64_t sl, std::vector<Entry>& es) {
             const int64_t r0 = sl * 32, r1 = std::min<int64_t>(rows, r0 + 32);
             for (int64_t r = r0; r < r1; r++)
@@ -201,21 +216,15 @@ extern "C" int qb_csr_upload(const void* data, const int32_t* col, const int32_t
     // format 3: force SELL; auto: SELL for small (L2-resident) operators with little padding
     bool use_sell = (format == 3);
     SellHost sh;
-    if (format == 3 || format == 0) {
-        build_sell(rows, cols, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o) {
-            for (int p = rowptr[r]; p < rowptr[r + 1]; p++) o.push_back({col[p], v[p]});
-        }, sh);
+    if (format == 3 || (format == 0 && !big && !use_rsell)) {
+        build_sell(rows, cols, row_fn, sh);
         const long long padded = (long long)sh.val.size();
         if (format == 0)
             use_sell = nnz > 0 && rows >= 32 && padded * 20 <= QB_SELL_MAX_BYTES &&
                        (double)padded <= 1.5 * (double)nnz;
     }
-    RsellHost rs;
-    bool use_rsell = (format == 5);
-    if (format == 5 || (format == 0 && nnz > 0 && rows >= 32)) {
-        build_rsell(rows, cols, [&](int64_t r, std::vector<std::pair<int, qb_c128>>& o) {
-            for (int p = rowptr[r]; p < rowptr[r + 1]; p++) o.push_back({col[p], v[p]});
-        }, rs);
+    if (format == 5 || (format == 0 && !use_rsell && nnz > 0 && rows >= 32)) {
+        if (!rsell_built) build_rsell(rows, cols, row_fn, rs);
         const long long other = use_diam ? (long long)dh.val.size() * 16 + (long long)dh.ent.size() * 8
                                          : (long long)nnz * 20;
         if (format == 0) use_rsell = want_rsell(rs, rows, use_sell, (long long)sh.val.size(), other);
