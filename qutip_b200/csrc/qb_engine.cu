@@ -1455,8 +1455,10 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
         e->tile_smem = (size_t)rows * 16 + (size_t)(thr / 32) * nsb * 1024;
         cudaError_t ce = cudaFuncSetAttribute(qb_pass_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qb_pass_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
+#ifdef QB_ENABLE_COOP
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qb_pass_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qb_pass_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem);
+#endif
         if (ce != cudaSuccess) { delete e; QB_FAIL(QB_E_CUDA, "tile kernel shared memory: %s", cudaGetErrorString(ce)); }
         memset(&e->targs, 0, sizeof e->targs);
         e->targs.pool = h.pool; e->targs.pass = h.pass; e->targs.coef = h.coef; e->targs.partials = h.partials;
@@ -1482,6 +1484,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qb_pass_tile_kernel<false, false>, e->tile_threads, e->tile_smem);
             e->tile_persist = (co == cudaSuccess && occ > 0) ? occ : 0;
         }
+#ifdef QB_ENABLE_COOP
         {   // cooperative multi-round form: its grid must be co-resident
             int occ = 0, dev = 0, coop_ok = 0;
             cudaGetDevice(&dev);
@@ -1494,6 +1497,7 @@ extern "C" int qb_engine_create(qb_handle sys, int tableau, int nslots, const qb
                 if (qb_dev_alloc(e, 1, &e->targs.coop_rounds)) e->coop_occ = 0;
             }
         }
+#endif
         if (total <= QB_CD_MAX && !getenv("QB_NO_CDESC")) {
             int off = 0;
             for (size_t i = 0; i < s->elems.size(); i++) {
@@ -1640,12 +1644,14 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
     // 58.5 -> 71.8 ms, C2 (4096 tiles) 8.9 k -> 6.8 k RHS evaluations/s -- and for a one-CTA grid
     // (C1, N = 400) the plug-in wall time is unchanged within noise (13.9-14.0 ms either way: the
     // round is bound by its dependent loads, not by the launches).  QB_COOP_MAX_CTAS=n enables it
-    // for grids of up to n CTAs.
+    // for grids of up to n CTAs in a build with -DQB_ENABLE_COOP (QB_NVCC_EXTRA); the default
+    // build does not instantiate it.
     const int coop_nt = e->tile_g ? (e->h.ctl.N + e->tile_rows - 1) / e->tile_rows : 0;
     static const int coop_max_ctas = getenv("QB_COOP_MAX_CTAS") ? atoi(getenv("QB_COOP_MAX_CTAS")) : 0;
     const bool coop = e->tile_g && e->coop_occ > 0 && !compact && !e->profiling && !e->h.linmap &&
                       !e->h.zbuf && !big_control && nslots_used <= QB_COOP_MAX_SLOTS &&
                       (long long)nslots_used * coop_nt <= coop_max_ctas;
+#ifdef QB_ENABLE_COOP
     if (coop) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
@@ -1673,6 +1679,9 @@ static int qb_drive(QbEngH* e, int nslots_used, bool short_call = false) {
         QB_CUDA(cudaMemcpy(&done, e->targs.coop_rounds, sizeof(int), cudaMemcpyDeviceToHost));
         rounds = done;
     } else
+#else
+    (void)coop;
+#endif
     if (e->profiling || short_call) {
         // plain launches, one host look at the counter per chunk.  Used for per-pass
         // CUDA-event timing and for the Integrator protocol (qb_integ_*), whose calls often
