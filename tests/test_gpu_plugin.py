@@ -761,3 +761,24 @@ def test_nm_mcsolve_mixed_initial_states_b200_map():
     np.testing.assert_allclose(np.array(out.runs_trace), np.array(ref.runs_trace), rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(np.array(out.average_expect), np.array(ref.average_expect), rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(np.array(out.average_trace), np.array(ref.average_trace), rtol=1e-9, atol=1e-12)
+
+
+def test_floquet_markov_solver_reuses_the_device_integrators():
+    """FMESolver (solver/floquet.py:785-): the Floquet-Markov tensor is a constant QobjEvo, so
+    `method="b200_vern7"` integrates it on the device -- same result as the stock vern7."""
+    from qutip import fmmesolve, num
+    delta, eps0, A = 2 * np.pi, 2 * np.pi, 0.5 * 2 * np.pi
+    omega = np.sqrt(delta ** 2 + eps0 ** 2)
+    T = 2 * np.pi / omega
+    tl = np.linspace(0.0, 2 * T, 41)
+    psi0 = (basis(2, 0) + 0.3j * basis(2, 1)).unit()
+    H = [-eps0 / 2.0 * sigmaz() - delta / 2.0 * sigmax(), [A / 2.0 * sigmax(), "sin(w * t)"]]
+
+    def spectrum(w):
+        return (w > 0) * w * 0.5 * 0.25 / (2 * np.pi)
+
+    res = {}
+    for m in ("vern7", "b200_vern7"):
+        res[m] = fmmesolve(H, psi0, tl, [sigmax()], [spectrum], T, e_ops=[num(2)], args={"w": omega},
+                           options=dict(OPT, method=m)).expect[0]
+    np.testing.assert_allclose(res["b200_vern7"], res["vern7"], rtol=RTOL, atol=ATOL)
