@@ -318,6 +318,14 @@ __device__ __forceinline__ void qb_rowdot_rsell_tile(const QbTileElem& A, const 
 #pragma unroll
             for (int j = 0; j < RB; j++) xv[j] = qb_ldx<COH>(x + (r[j] ^ delta));
         }
+#ifdef QB_XIMAG     // constants of Hamiltonian parts are purely imaginary (-i H): two DFMA instead of four
+        if (cv.x == 0.0) {             // warp-uniform (constant bank / uniform load)
+#pragma unroll
+            for (int j = 0; j < RB; j++) {
+                a[j].x = fma(-cv.y, xv[j].y, a[j].x); a[j].y = fma(cv.y, xv[j].x, a[j].y);
+            }
+        } else
+#endif
 #pragma unroll
         for (int j = 0; j < RB; j++) qb_fma(a[j], cv, xv[j]);
     };
