@@ -88,3 +88,46 @@ def test_matrix_form_is_bound_as_superoperator():
     sup = plugin._device_qevo(lmf)
     ref = qutip.liouvillian(H(0), [0.3 * a])
     assert np.abs(sup(0).full() - ref.full()).max() < 1e-14
+
+
+def test_integrators_registered_on_other_qobjevo_solvers_but_not_on_the_base_class():
+    """HEOMSolver / BRSolver / FMESolver integrate a constant QobjEvo: they list the device
+    methods; the Solver base class does not (its integrators must accept arbitrary callables,
+    tests/solver/test_integrator.py parametrises over them)."""
+    from qutip.solver.brmesolve import BRSolver
+    from qutip.solver.floquet import FMESolver
+    from qutip.solver.heom.bofin_solvers import HEOMSolver
+    from qutip.solver.solver_base import Solver
+    for cls in (BRSolver, FMESolver, HEOMSolver):
+        assert "b200_vern7" in cls.avail_integrators() and "b200_adams" in cls.avail_integrators()
+    assert not any(k.startswith("b200") for k in Solver.avail_integrators())
+
+
+def test_nm_mcsolve_rate_coefficients_compile_to_device_programs():
+    """The rate-shifted collapse operators of NonMarkovianMCSolver (solver/nm_mcsolve.py:400-440:
+    sqrt(rate + shift) with shift = 2 |min(0, rates)|, solver/cy/nm_mcsolve.pyx) are bound
+    without host evaluation, and the compiled programs reproduce the reference coefficients."""
+    from qutip import NonMarkovianMCSolver, coefficient, sigmam, sigmap, sigmax, sigmaz
+    H = 0.5 * sigmaz() + 0.2 * sigmax()
+    rates = [(sigmam(), coefficient("0.25*sin(2*t) + 0.05")), (sigmap(), 0.15)]
+    solver = NonMarkovianMCSolver(H, rates, options={"progress_bar": False})
+    checked = 0
+    for q in list(solver.rhs.c_ops) + list(solver.rhs.n_ops) + [solver.rhs.rhs]:
+        for el in q.to_list():
+            if isinstance(el, (list, tuple)):
+                prog = plugin.coefficient_to_program(el[1])
+                for t in (0.0, 0.4, 1.7, 2.3, 3.9):          # both signs of the first rate
+                    want = complex(el[1](t))
+                    got = complex(coeffs.evaluate(prog, t))
+                    assert abs(want - got) <= 1e-13 * max(1.0, abs(want))
+                    checked += 1
+    assert checked >= 10
+
+
+def test_python_rate_function_is_rejected_for_device_batches():
+    from qutip import NonMarkovianMCSolver, coefficient, sigmam, sigmax
+    solver = NonMarkovianMCSolver(sigmax(), [(sigmam(), coefficient(lambda t: -1 + t))],
+                                  options={"progress_bar": False})
+    el = [e for e in solver.rhs.c_ops[0].to_list() if isinstance(e, (list, tuple))][0]
+    with pytest.raises(TypeError):
+        plugin.coefficient_to_program(el[1])
