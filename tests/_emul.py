@@ -83,11 +83,16 @@ class EmulSystem:
         prog = prog or Program()
         self.L.emul_add_element(_p(d), _p(c), _p(r), self.fmt, prog.as_ctypes(), len(prog))
 
-    def add_collapse(self, c_op, n_op):
+    def add_collapse(self, c_op, n_op, cprog=None, nprog=None):
         cd, cc, cr = _csr(*c_op)
         nd, nc, nr = _csr(*n_op)
         self._keep += [cd, cc, cr, nd, nc, nr]
-        self.L.emul_add_collapse(_p(cd), _p(cc), _p(cr), _p(nd), _p(nc), _p(nr), self.fmt)
+        if cprog is None and nprog is None:
+            self.L.emul_add_collapse(_p(cd), _p(cc), _p(cr), _p(nd), _p(nc), _p(nr), self.fmt)
+        else:
+            cprog, nprog = cprog or Program(), nprog or Program()
+            self.L.emul_add_collapse_td(_p(cd), _p(cc), _p(cr), _p(nd), _p(nc), _p(nr), self.fmt,
+                                        cprog.as_ctypes(), len(cprog), nprog.as_ctypes(), len(nprog))
         self.ncops += 1
 
     def add_eop(self, kind, shape, arrs):

@@ -131,6 +131,14 @@ void emul_add_collapse(const void* cd, const int32_t* cc, const int32_t* cr,
     g_sys.nops.push_back(make_op((const qb_c128*)nd, nc, nr, g_sys.N, g_sys.N, fmt));
     g_sys.cop_prog.push_back({}); g_sys.nop_prog.push_back({});
 }
+// collapse operator with time-dependent coefficients: c(t) C and n(t) C^dagger C
+void emul_add_collapse_td(const void* cd, const int32_t* cc, const int32_t* cr,
+                          const void* nd, const int32_t* nc, const int32_t* nr, int fmt,
+                          const QbInstr* cp, int ncp, const QbInstr* npg, int nnp) {
+    g_sys.cops.push_back(make_op((const qb_c128*)cd, cc, cr, g_sys.N, g_sys.N, fmt));
+    g_sys.nops.push_back(make_op((const qb_c128*)nd, nc, nr, g_sys.N, g_sys.N, fmt));
+    g_sys.cop_prog.push_back(prog(cp, ncp)); g_sys.nop_prog.push_back(prog(npg, nnp));
+}
 void emul_add_eop(const void* d, const int32_t* c, const int32_t* r, int fmt) {
     g_sys.eops.push_back(make_op((const qb_c128*)d, c, r, g_sys.N, g_sys.N, fmt));
     g_sys.eop_prog.push_back({});

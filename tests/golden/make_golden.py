@@ -244,7 +244,78 @@ def golden_adams():
     save("adams_zvode", **out)
 
 
+
+def golden_nm_mcsolve(name="nm_two_level", ntraj=32, seed=3):
+    """nm_mcsolve (solver/nm_mcsolve.py) on a two-level system with one always-negative rate
+    (smooth shifted rates: well conditioned, see tests/test_gpu_plugin.py) and one constant rate.
+    Stored: the effective system the reference integrates (elements of H_eff, rate-shifted
+    collapse operators c_k(t) C_k and n_k(t) C_k^dagger C_k) with every coefficient as the
+    byte-code `qutip_b200.plugin.coefficient_to_program` compiles it to (tests/test_plugin_cpu.py
+    checks those programs against the reference coefficients), and the reference's per-trajectory
+    collapse records, un-weighted expectation values and influence martingales."""
+    sys.path.insert(0, ROOT)
+    import qutip_b200.plugin as plugin
+    from qutip import NonMarkovianMCSolver, coefficient, sigmap
+    H = 0.5 * sigmaz() + 0.2 * sigmax()
+    ops_and_rates = [(sigmam(), coefficient("-0.08 + 0.05*sin(2*t)")), (sigmap(), 0.15)]
+    psi0 = (basis(2, 0) + 0.5 * basis(2, 1)).unit()
+    tlist = np.linspace(0, 4, 17)
+    e_ops = [sigmaz(), sigmax()]
+    solver = NonMarkovianMCSolver(H, ops_and_rates, options={"progress_bar": False, "method": "vern7",
+                                                              "keep_runs_results": True,
+                                                              "store_final_state": True})
+    out = {}
+
+    def pack_terms(prefix, qevo):
+        """constant elements merged (as the device binding does), each td element with its program"""
+        n = 0
+        const = None
+        for el in qevo.to_list():
+            if isinstance(el, qutip.Qobj):
+                const = el if const is None else const + el
+        for el in qevo.to_list():
+            if isinstance(el, (list, tuple)):
+                pack_op("%s%d" % (prefix, n), el[0].to("CSR").data, out)
+                out["%s%d_prog" % (prefix, n)] = np.array(plugin.coefficient_to_program(el[1]).instrs, dtype=float)
+                n += 1
+        if const is not None:
+            pack_op("%s%d" % (prefix, n), const.to("CSR").data, out)
+            out["%s%d_prog" % (prefix, n)] = np.zeros((0, 4))
+            n += 1
+        return n
+
+    out["n_elements"] = pack_terms("el", solver.rhs.rhs)
+    for i, (c, n) in enumerate(zip(solver.rhs.c_ops, solver.rhs.n_ops)):
+        assert pack_terms("cop%d_" % i, c) == 1 and pack_terms("nop%d_" % i, n) == 1
+    out["n_cops"] = len(solver.rhs.c_ops)
+    for i, e in enumerate(e_ops):
+        pack_op("eop%d" % i, e.to("CSR").data, out)
+    out["n_eops"] = len(e_ops)
+    out["tlist"] = tlist
+    out["psi0"] = psi0.full().ravel()
+    r = solver.run(psi0, tlist, ntraj=ntraj, e_ops=e_ops, seeds=np.random.SeedSequence(seed))
+    out["seed"], out["ntraj"] = seed, ntraj
+    # NonMarkovianMCSolver's own defaults differ from MCSolver's (nm_mcsolve.py:352-372)
+    out["norm_steps"], out["norm_min_step"] = solver.options["norm_steps"], solver.options["norm_min_step"]
+    out["norm_tol"], out["norm_t_tol"] = solver.options["norm_tol"], solver.options["norm_t_tol"]
+    out["raw_expect"] = np.array([[np.asarray(tr.e_data[k]) for k in range(len(e_ops))]
+                                  for tr in r.trajectories])          # [ntraj][n_e][nt], un-weighted
+    out["runs_trace"] = np.array(r.runs_trace)
+    out["avg_expect"] = np.array(r.average_expect)
+    out["col_count"] = np.array([len(c) for c in r.col_times])
+    out["col_times"] = np.concatenate([np.asarray(c, dtype=float) for c in r.col_times] + [np.zeros(0)])
+    out["col_which"] = np.concatenate([np.asarray(c, dtype=np.int64) for c in r.col_which]
+                                      + [np.zeros(0, dtype=np.int64)])
+    out["final_states"] = np.array([s.full().ravel() if s.isket else s.full().ravel("F")
+                                    for s in r.runs_final_states])
+    kids = np.random.SeedSequence(seed).spawn(ntraj)
+    out["draws"] = np.stack([np.random.default_rng(k).random(64) for k in kids])
+    save(name, **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "nm":
+        return golden_nm_mcsolve()
     if len(sys.argv) > 1 and sys.argv[1] == "adams":
         return golden_adams()
     if len(sys.argv) > 1 and sys.argv[1] == "super":

@@ -246,3 +246,42 @@ def test_mcsolve_super_operator_hamiltonian_state_machine():
         np.testing.assert_allclose(r["col_t"][j, :k], g["col_times"][cc[j]:cc[j + 1]], rtol=0, atol=1e-9)
     assert np.abs(np.transpose(r["expect"], (1, 0, 2)) - g["runs_expect"]).max() < 1e-9
     assert np.abs(r["states"][:, -1, :] - g["final_states"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("fmt", [FMT_DIAM, FMT_CSR])
+def test_nm_mcsolve_state_machine(fmt):
+    """nm_mcsolve (solver/nm_mcsolve.py): rate-shifted collapse operators with time-dependent
+    coefficients c_k(t) = sqrt(rate_k + shift), n_k(t) = |c_k|^2 and the matching H_eff terms,
+    as compiled device programs (MIN_RE / SQRT_RE byte-code) -- the reference's trajectories
+    (fixture nm_two_level, generated by make_golden.py nm): collapse records, un-weighted
+    expectation values and final states.  The influence martingale is host post-processing of
+    the collapse records (plugin._b200_batch) and is checked on the GPU against the reference."""
+    g = load("nm_two_level")
+    N = len(g["psi0"])
+    s = EmulSystem(N, 0, fmt)
+
+    def prog(key):
+        a = g[key]
+        return coeffs.Program([(int(op), int(ia), float(re), float(im)) for op, ia, re, im in a]) if len(a) else None
+
+    for i in range(int(g["n_elements"])):
+        s.add_element(*op_arrays(g, "el%d" % i), prog=prog("el%d_prog" % i))
+    for i in range(int(g["n_cops"])):
+        s.add_collapse(op_arrays(g, "cop%d_0" % i), op_arrays(g, "nop%d_0" % i),
+                       cprog=prog("cop%d_0_prog" % i), nprog=prog("nop%d_0_prog" % i))
+    for i in range(int(g["n_eops"])):
+        s.add_eop(*op_arrays(g, "eop%d" % i))
+    ntraj = int(g["ntraj"])
+    # the collapse search runs with NonMarkovianMCSolver's own defaults (norm_steps 5, norm_min_step 0)
+    opt = default_options(store_states=1, norm_steps=int(g["norm_steps"]), norm_min_step=float(g["norm_min_step"]),
+                          norm_tol=float(g["norm_tol"]), norm_t_tol=float(g["norm_t_tol"]))
+    r = s.run(1, 0, g["psi0"], g["tlist"], ntraj=ntraj, nslots=5, draws=g["draws"], opt=opt)
+    assert (r["status"] == 1).all()
+    assert np.array_equal(r["ncol"], g["col_count"]) and g["col_count"].sum() >= 8
+    cc = np.concatenate([[0], np.cumsum(g["col_count"])])
+    for j in range(ntraj):
+        n = r["ncol"][j]
+        assert np.array_equal(r["col_which"][j, :n], g["col_which"][cc[j]:cc[j + 1]])
+        np.testing.assert_allclose(r["col_t"][j, :n], g["col_times"][cc[j]:cc[j + 1]], rtol=0, atol=1e-9)
+    assert np.abs(r["expect"] - g["raw_expect"]).max() < 1e-8
+    assert np.abs(r["states"][:, -1, :] - g["final_states"]).max() < 1e-8
