@@ -313,7 +313,53 @@ def golden_nm_mcsolve(name="nm_two_level", ntraj=32, seed=3):
     save(name, **out)
 
 
+def golden_mcsolve_improved(name="c3_tfim4_mc_improved", ntraj=16, seed=9):
+    """mcsolve with options["improved_sampling"] (solver/mcsolve.py:716-747): the no-jump trajectory
+    is integrated first, its survival probability p becomes the floor of every trajectory's FIRST
+    threshold (mcsolve.py:276-279) and the trajectories carry the weight 1 - p (:565)."""
+    H, c_ops, sz = tfim(4, gamma=0.25)
+    psi0 = basis([2] * 4, [0] * 4)
+    tlist = np.linspace(0, 2, 11)
+    e_ops = [sz[0], sz[2]]
+    solver = qutip.MCSolver(H, c_ops, options={"progress_bar": False, "method": "vern7",
+                                               "keep_runs_results": True, "store_final_state": True,
+                                               "improved_sampling": True})
+    out = {}
+    els = solver.rhs().to_list()
+    for i, el in enumerate(els):
+        pack_op("el%d" % i, el.data, out)
+        out["el%d_coeff" % i] = ""
+    out["n_elements"] = len(els)
+    for i, (c, n) in enumerate(zip(solver._c_ops, solver._n_ops)):
+        pack_op("cop%d" % i, c.to_list()[0].data, out)
+        pack_op("nop%d" % i, n.to_list()[0].data, out)
+    out["n_cops"] = len(c_ops)
+    for i, e in enumerate(e_ops):
+        pack_op("eop%d" % i, e.data, out)
+    out["n_eops"] = len(e_ops)
+    out["tlist"] = tlist
+    out["psi0"] = psi0.full().ravel()
+    r = solver.run(psi0, tlist, ntraj=ntraj, e_ops=e_ops, seeds=np.random.SeedSequence(seed))
+    det = r.deterministic_trajectories[0]
+    out["no_jump_expect"] = np.array([np.asarray(det.e_data[k]) for k in range(len(e_ops))])
+    out["no_jump_prob"] = float(r.deterministic_weights[0]) if hasattr(r, "deterministic_weights") \
+        else float(solver._no_jump_simulation(solver._prepare_state(psi0), tlist, e_ops)[1])
+    out["seed"], out["ntraj"] = seed, ntraj
+    out["raw_expect"] = np.array([[np.asarray(tr.e_data[k]) for k in range(len(e_ops))] for tr in r.trajectories])
+    out["avg_expect"] = np.array(r.average_expect)
+    out["col_count"] = np.array([len(c) for c in r.col_times])
+    out["col_times"] = np.concatenate([np.asarray(c, dtype=float) for c in r.col_times] + [np.zeros(0)])
+    out["col_which"] = np.concatenate([np.asarray(c, dtype=np.int64) for c in r.col_which]
+                                      + [np.zeros(0, dtype=np.int64)])
+    out["final_states"] = np.array([s.full().ravel() for s in r.runs_final_states])
+    kids = np.random.SeedSequence(seed).spawn(ntraj)
+    out["draws"] = np.stack([np.random.default_rng(k).random(64) for k in kids])
+    save(name, **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "improved":
+        return golden_mcsolve_improved()
     if len(sys.argv) > 1 and sys.argv[1] == "nm":
         return golden_nm_mcsolve()
     if len(sys.argv) > 1 and sys.argv[1] == "adams":

@@ -285,3 +285,34 @@ def test_nm_mcsolve_state_machine(fmt):
         np.testing.assert_allclose(r["col_t"][j, :n], g["col_times"][cc[j]:cc[j + 1]], rtol=0, atol=1e-9)
     assert np.abs(r["expect"] - g["raw_expect"]).max() < 1e-8
     assert np.abs(r["states"][:, -1, :] - g["final_states"]).max() < 1e-8
+
+
+def test_mcsolve_improved_sampling_state_machine():
+    """options["improved_sampling"] (solver/mcsolve.py:716-747): the first threshold of every
+    trajectory is floored at the no-jump probability (mcsolve.py:276-279) -- the reference's
+    trajectories (fixture c3_tfim4_mc_improved) against `jump_prob_floor`; the no-jump trajectory
+    itself is the `no_jump` option (threshold 0)."""
+    g = load("c3_tfim4_mc_improved")
+    s = EmulSystem(len(g["psi0"]), 0, FMT_DIAM)
+    s.add_element(*_sp_arrays(merged_constant_rhs(g)))
+    for i in range(int(g["n_cops"])):
+        s.add_collapse(op_arrays(g, "cop%d" % i), op_arrays(g, "nop%d" % i))
+    for i in range(int(g["n_eops"])):
+        s.add_eop(*op_arrays(g, "eop%d" % i))
+    ntraj = int(g["ntraj"])
+    p = float(g["no_jump_prob"])
+    assert 0.05 < p < 0.95
+    r = s.run(1, 0, g["psi0"], g["tlist"], ntraj=ntraj, nslots=6, draws=g["draws"],
+              opt=default_options(store_states=1, jump_prob_floor=p))
+    assert (r["status"] == 1).all()
+    assert np.array_equal(r["ncol"], g["col_count"]) and (g["col_count"] >= 1).all()
+    cc = np.concatenate([[0], np.cumsum(g["col_count"])])
+    for j in range(ntraj):
+        n = r["ncol"][j]
+        assert np.array_equal(r["col_which"][j, :n], g["col_which"][cc[j]:cc[j + 1]])
+        np.testing.assert_allclose(r["col_t"][j, :n], g["col_times"][cc[j]:cc[j + 1]], rtol=0, atol=1e-9)
+    assert np.abs(r["expect"] - g["raw_expect"]).max() < 1e-9
+    assert np.abs(r["states"][:, -1, :] - g["final_states"]).max() < 1e-9
+    # the deterministic no-jump trajectory and its survival probability
+    r0 = s.run(1, 0, g["psi0"], g["tlist"], ntraj=1, draws=g["draws"][:1], opt=default_options(store_states=1, no_jump=1))
+    assert r0["ncol"][0] == 0 and np.abs(r0["expect"][0] - g["no_jump_expect"]).max() < 1e-9
